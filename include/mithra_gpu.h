@@ -1,0 +1,229 @@
+/* mithra_gpu.h -- C ABI of the B200-native MITHRA time-march (libmithra_gpu.so).
+ *
+ * This is the drop-in boundary for the hot path named by BASELINE.json: the Lorentz-boosted-frame
+ * FDTD/PIC loop of MITHRA 2.0.  The reference has no FFI; its boundary is the C++ class surface
+ * Solver / FdTd / FdTdSC (reference src/solver.h:25-178, src/fdtd.h:18-66, src/fdtdSC.h:18-66).  Every entry
+ * point below replaces one of those methods (cited per function); the host-side classes in
+ * mithra_b200/host/ keep the reference's names and call straight into this ABI.
+ *
+ * Conventions
+ *   - plain C, opaque handle, no C++/torch types; all pointers are HOST pointers unless named d_*;
+ *   - every function returns 0 on success, non-zero on failure; mithra_gpu_last_error() gives the text.
+ *     (The reference's convention is "print and exit(1)"; the host classes do exactly that on non-zero.)
+ *   - there is NO CPU fallback: without a CUDA device mithra_gpu_create fails.
+ *   - host-side array layouts are the reference's own:
+ *       vector field  : double[np*N0*N1][3], node m = N1*N0*k + N1*i + j      (solver.cpp:674, fieldvector.h:25)
+ *       scalar field  : double[np*N0*N1]
+ *       E / B         : float [np*N0*N1][3]                                    (solver.h:244-245)
+ *       particles     : double[n][11] = { q, rnp[3], rnm[3], gb[3], e }        (stdinclude.h:130-144)
+ *     The device layout (component-planar, padded rows) is private to the library, see DESIGN.md.
+ */
+#ifndef MITHRA_GPU_H_
+#define MITHRA_GPU_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MITHRA_GPU_ABI_VERSION      1
+#define MITHRA_MAX_UNDULATORS       16
+#define MITHRA_MAX_EXTFIELDS        8
+#define MITHRA_MAX_POWER_PLANES     256
+#define MITHRA_MAX_POWER_LAMBDAS    64
+#define MITHRA_MAX_SCREENS          64
+
+/* enum values are the reference's (stdinclude.h:18-40) */
+enum { MITHRA_SOLVER_FD = 0, MITHRA_SOLVER_NSFD = 1 };
+enum { MITHRA_UNDULATOR_STATIC = 0, MITHRA_UNDULATOR_OPTICAL = 1 };
+enum { MITHRA_SIGNAL_NEUMANN = 0, MITHRA_SIGNAL_GAUSSIAN = 1, MITHRA_SIGNAL_SECANT = 2, MITHRA_SIGNAL_FLATTOP = 3, MITHRA_SIGNAL_INVGAUSSIAN = 4 };
+enum { MITHRA_BEAM_PLANEWAVE = 0, MITHRA_BEAM_PLANEWAVETRUNCATED = 1, MITHRA_BEAM_GAUSSIAN = 2, MITHRA_BEAM_SUPERGAUSSIAN = 3,
+       MITHRA_BEAM_STANDINGPLANEWAVE = 4, MITHRA_BEAM_STANDINGPLANEWAVETRUNCATED = 5, MITHRA_BEAM_STANDINGGAUSSIAN = 6,
+       MITHRA_BEAM_STANDINGSUPERGAUSSIAN = 7 };
+
+/* Signal (classes.h Signal; classes.cpp:534-575), already converted to solver units. */
+typedef struct MithraSignal
+{
+  int    type;
+  double t0, s, f0, cep;
+  int    nR;
+  double sigma_inv_g[2];          /* inverse-gaussian only (classes.cpp:559-572)                     */
+} MithraSignal;
+
+/* One analytic beam: Seed, optical Undulator or ExtField share this shape (classes.h:208-262, 303-352, 383-427). */
+typedef struct MithraBeam
+{
+  int          seed_type;
+  double       position[3], direction[3], polarization[3];
+  double       amplitude;
+  double       radius[2];
+  double       l;                 /* wavelength                                                      */
+  double       zR[2];             /* Rayleigh lengths                                                */
+  int          order[2];
+  MithraSignal signal;
+} MithraBeam;
+
+/* Undulator module (classes.h:265-352), after Solver::setSimulationParameters (sorted, shifted, boosted). */
+typedef struct MithraUndulator
+{
+  int        type;                /* MITHRA_UNDULATOR_*                                              */
+  double     k, lu, rb, theta;
+  double     length;              /* number of periods (unsigned in the reference)                   */
+  double     dist;                /* bunch-head to entrance distance; [0].dist gates the e flag      */
+  MithraBeam beam;                /* used when type == OPTICAL                                       */
+} MithraUndulator;
+
+/* Radiation-power sampling group (one FEL-OUTPUT/radiation-power block; radiation.cpp:18-121). */
+typedef struct MithraPower
+{
+  int    enabled;
+  int    N;                                     /* planes                                            */
+  double z[MITHRA_MAX_POWER_PLANES];            /* boosted plane positions                           */
+  int    Nl;                                    /* wavelengths                                       */
+  double w[MITHRA_MAX_POWER_LAMBDAS];           /* angular frequencies 2 pi / dt_lambda              */
+  int    Nf;                                    /* DFT window length                                 */
+  double pc;                                    /* power prefactor                                   */
+} MithraPower;
+
+/* Screens (solver.cpp:2145-2257). */
+typedef struct MithraScreens
+{
+  int    enabled;
+  int    N;
+  double pos[MITHRA_MAX_SCREENS];               /* lab-frame positions, sorted                       */
+} MithraScreens;
+
+/* Everything Solver::initialize() derives on the host (solver.cpp:547-842, 1050-1059) and the device needs. */
+typedef struct MithraGpuParams
+{
+  int    abi_version;
+
+  /* mesh and slab (solver.cpp:601-689) */
+  int    N0, N1, N2;              /* global node counts                                              */
+  int    np, k0;                  /* local planes and index of the first one                         */
+  int    rank, size;              /* slab index / number of slabs                                    */
+  double dx, dy, dz, dt;
+  double xmin, xmax, ymin, ymax, zmin, zmax;
+  double zp[2];                   /* ownership interval [zp0, zp1)                                   */
+  double Lz;                      /* mesh_.meshLength_[2] (period of the z wrap, solver.cpp:1440)    */
+
+  /* solver switches (classes.h Mesh) */
+  int    solver;                  /* MITHRA_SOLVER_*                                                 */
+  int    space_charge;
+  int    truncation_order;
+
+  /* update coefficients (solver.cpp:729-824) */
+  double a[6], alpha, beta_nsfd;
+  double bB[5], cB[5], dB[5], eE[5], fE[5], gE[5], hC[17];
+
+  /* frame (solver.cpp:168-176, 322) and units (solver.cpp:59-61) */
+  double c0, gamma, beta, dt_shift;
+
+  /* bunch update (solver.cpp:268-275, 1053-1059) */
+  double dt_bunch;                /* bunch_.timeStep_                                                */
+  int    n_update_bunch;          /* nUpdateBunch_                                                   */
+  double r1, r2, dtb;
+
+  /* analytic fields seen by the particles */
+  int             n_undulators;
+  MithraUndulator undulator[MITHRA_MAX_UNDULATORS];
+  int             n_ext_fields;
+  MithraBeam      ext_field[MITHRA_MAX_EXTFIELDS];
+
+  /* seed injected through the TF/SF shell (fdtd.cpp:307-373); amplitude 0 disables it */
+  int        seed_enabled;
+  MithraBeam seed;
+
+  /* diagnostics */
+  MithraPower   power;
+  MithraScreens screens;
+
+  /* capacity hints (0 = library default) */
+  size_t max_particles;           /* capacity of the particle arrays                                 */
+  size_t max_screen_records;      /* capacity of the per-screen record buffers                       */
+  int    device;                  /* CUDA device ordinal, -1 = current                               */
+} MithraGpuParams;
+
+typedef struct MithraGpu MithraGpu;
+
+/* Counters of work done, used by bench.py. */
+typedef struct MithraGpuCounters
+{
+  unsigned long long field_steps;
+  unsigned long long cell_updates;        /* nodes advanced by fieldUpdate                            */
+  unsigned long long particle_pushes;     /* particle sub-steps                                       */
+  unsigned long long kernel_launches;     /* kernels of this library launched                         */
+} MithraGpuCounters;
+
+const char* mithra_gpu_last_error (void);
+int         mithra_gpu_abi_version (void);
+int         mithra_gpu_device_count (void);
+
+/* Solver::Solver + Solver::initializeMesh allocation part (solver.cpp:14-62, 646-658). */
+int  mithra_gpu_create  (const MithraGpuParams* params, MithraGpu** out);
+void mithra_gpu_destroy (MithraGpu* h);
+
+/* Solver state in: an_, anm1_, the current in anp1_ (may be NULL = zero) and, with space charge, fn_, fnm1_,
+ * the charge in fnp1_ (solver.cpp:646-658, 828-839).                                                 */
+int mithra_gpu_upload_fields (MithraGpu* h, const double* an, const double* anm1, const double* jn,
+			      const double* fn, const double* fnm1, const double* rho);
+/* Any pointer may be NULL. anp1/fnp1 name what the reference keeps in anp1_/fnp1_ at that moment: the new
+ * potential after mithra_gpu_field_update, the deposited current/charge after mithra_gpu_current_update. */
+int mithra_gpu_download_fields (MithraGpu* h, double* anp1, double* an, double* anm1,
+				double* fnp1, double* fn, double* fnm1);
+/* en_, bn_ as float[.][3]; nodes never evaluated in this step hold 0; mask (may be NULL) flags evaluated nodes. */
+int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsigned char* mask);
+
+/* chargeVectorn_ (solver.h:271). */
+int mithra_gpu_upload_particles   (MithraGpu* h, const double* aos11, size_t n);
+int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_t capacity, size_t* n);
+int mithra_gpu_num_particles      (MithraGpu* h, size_t* n);
+
+/* time_, timeBunch_, nTime_ (solver.h:265-275). */
+int mithra_gpu_set_time (MithraGpu* h, double time, double time_bunch, unsigned int n_time);
+int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bunch, unsigned int* n_time);
+
+/* --- one entry point per reference method of the time march ------------------------------------------- */
+int mithra_gpu_field_update        (MithraGpu* h);   /* FdTd::fieldUpdate  fdtd.cpp:231-800 / fdtdSC.cpp:260-1087 */
+int mithra_gpu_bunch_update        (MithraGpu* h);   /* rnm = rnp + nUpdateBunch x Solver::bunchUpdate, solver.cpp:1311-1325 */
+int mithra_gpu_screen_profile      (MithraGpu* h);   /* Solver::screenProfile solver.cpp:2205-2257        */
+int mithra_gpu_power_sample        (MithraGpu* h);   /* Solver::powerSample  radiation.cpp:127-232        */
+int mithra_gpu_field_shift         (MithraGpu* h);   /* FdTd::fieldShift     fdtd.cpp:806-812             */
+int mithra_gpu_current_reset       (MithraGpu* h);   /* FdTd::currentReset   fdtd.cpp:23-32               */
+int mithra_gpu_current_update      (MithraGpu* h);   /* FdTd::currentUpdate  fdtd.cpp:38-185              */
+int mithra_gpu_current_communicate (MithraGpu* h);   /* FdTd::currentCommunicate fdtd.cpp:191-225         */
+int mithra_gpu_advance_time        (MithraGpu* h);   /* solver.cpp:1396-1399                              */
+
+/* The body of the second while loop of Solver::solve (solver.cpp:1300-1399), nsteps times, without host
+ * synchronisation between steps.                                                                       */
+int mithra_gpu_step (MithraGpu* h, int nsteps);
+/* Same, bracketed by CUDA events on the library's stream; *ms = elapsed device time.                  */
+int mithra_gpu_step_timed (MithraGpu* h, int nsteps, float* ms);
+int mithra_gpu_synchronize (MithraGpu* h);
+
+/* Radiated power: one row of N*Nl doubles (pG[k*Nl+l], radiation.cpp:209-218) per sampled step since the
+ * last fetch; *nrows rows are copied (at most capacity_rows).                                          */
+int mithra_gpu_fetch_power (MithraGpu* h, double* rows, size_t capacity_rows, size_t* nrows);
+/* Screen crossings: records of 6 doubles { x, y, t, gbx, gby, gbz_lab } (solver.cpp:2229-2252) since the
+ * last fetch, in particle order within a step.                                                        */
+int mithra_gpu_fetch_screen (MithraGpu* h, int screen, double* rec6, size_t capacity, size_t* n);
+
+int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
+
+/* Per-kernel timing of the last mithra_gpu_step_profiled call (device ms by CUDA events around each
+ * kernel group): stencil, boundary, clear, eval_eb, push, deposit, power, screens.                    */
+#define MITHRA_GPU_NPHASES 8
+int mithra_gpu_step_profiled (MithraGpu* h, int nsteps, float ms[MITHRA_GPU_NPHASES]);
+
+/* --- z-slab exchange between the GPUs of one box (one process per GPU) -------------------------------- */
+/* Export an opaque blob (CUDA IPC handles of the ghost mailboxes) to hand to both z-neighbours ...     */
+int mithra_gpu_ipc_export  (MithraGpu* h, void* blob, size_t capacity, size_t* nbytes);
+/* ... and connect with the blobs of rank-1 (NULL on rank 0) and rank+1 (NULL on the last rank).        */
+int mithra_gpu_ipc_connect (MithraGpu* h, const void* blob_prev, const void* blob_next);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

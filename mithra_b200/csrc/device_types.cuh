@@ -1,0 +1,83 @@
+/* device_types.cuh -- device-side parameter blocks and index helpers of the B200 MITHRA time-march.
+ *
+ * Device layout (private to the library, see DESIGN.md "Data layout in HBM"):
+ *   potentials : component-planar doubles, comp c in {Ax, Ay, Az [, phi]}:
+ *                  idx(c,k,i,j) = (c*np + k) * Pp + i*N1 + j,   Pp = roundup(N0*N1, 16)   (128-byte planes)
+ *                three time levels (n+1, n, n-1) are three such allocations that rotate (FdTd::fieldShift).
+ *   current    : J = {Jx, Jy, Jz [, rho]} in the same layout, in its own allocation (the reference aliases it
+ *                onto anp1_, fdtd.cpp:27,244); only the device-tracked bounding box of the deposits is read
+ *                by the stencil and cleared afterwards.
+ *   E, B       : one float4 pair per node (Ex,Ey,Ez,0 | Bx,By,Bz,0), node m = N0*N1*k + N1*i + j -- the
+ *                reference's FieldVector<float> en_, bn_ (solver.h:244-245) interleaved for the 8-node gather.
+ *   particles  : struct-of-arrays of doubles q, r[3], rm[3], gb[3], e (reference Charge, stdinclude.h:130-144).
+ */
+#ifndef MITHRA_DEVICE_TYPES_CUH_
+#define MITHRA_DEVICE_TYPES_CUH_
+
+#include <cuda_runtime.h>
+#include "../../include/mithra_gpu.h"
+
+namespace mithra
+{
+  /* Bounding box of node indices, inclusive; empty when lo > hi. Lives in device memory.              */
+  struct Box { int lo[3]; int hi[3]; };   /* axis 0 = i (x), 1 = j (y), 2 = k (z, local plane index)   */
+
+  /* Field-side constants, passed to kernels by value.                                                 */
+  struct FieldDev
+  {
+    int    N0, N1, np, k0;
+    int    P;                     /* N0*N1                                                              */
+    long   Pp;                    /* padded plane stride (doubles)                                      */
+    int    ncomp;                 /* 3, or 4 with space charge                                          */
+    int    rank, size;
+    int    nsfd;                  /* 1 = NSFD, 0 = FD                                                   */
+    int    order;                 /* truncation order                                                   */
+    double a[6], alpha, beta;
+    double bB[5], cB[5], dB[5], eE[5], fE[5], gE[5], hC[17];
+    double dt, dx2, dy2, dz2;     /* uf_.dt, 2dx, 2dy, 2dz (solver.cpp:714-722)                         */
+  };
+
+  /* One static-undulator module with the per-module constants of Solver::undulatorField precomputed on
+   * the host in the reference's operation order (solver.cpp:1805-1812).                               */
+  struct UndulatorDev
+  {
+    int    type;
+    double b0, ku, ct, st, rb, len;     /* len = length_ * lu_                                          */
+    double r0_prev, r0_next;            /* gaps to the neighbouring modules (beam.cc:35,60)             */
+    int    has_prev, has_next;
+    MithraBeam beam;
+  };
+
+  /* Bunch-side constants, kept in device memory (too large for the kernel-argument space).            */
+  struct BunchDev
+  {
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+    double zp0, zp1, Lz;
+    double dx, dy, dz;
+    double c0, gamma, beta, dt_shift;
+    double r1, r2, dtb, dt_bunch, dt_field;
+    int    N0, N1, np, k0, P;
+    long   Pp;
+    int    ncomp;
+    int    n_und;
+    double und0_dist;                   /* undulator_[0].dist_ (entrance flag, solver.cpp:1510-1511)    */
+    UndulatorDev und[MITHRA_MAX_UNDULATORS];
+    int    n_ext;
+    MithraBeam ext[MITHRA_MAX_EXTFIELDS];
+  };
+
+  /* Particle struct-of-arrays.                                                                        */
+  struct ParticlesDev
+  {
+    double* q;
+    double* r[3];
+    double* rm[3];
+    double* gb[3];
+    double* e;
+  };
+
+  __host__ __device__ inline long fidx (const long Pp, const int np, const int N1, int c, int k, int i, int j)
+  { return ((long) c * np + k) * Pp + (long) i * N1 + j; }
+}
+
+#endif

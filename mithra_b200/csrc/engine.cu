@@ -1,0 +1,821 @@
+/* engine.cu -- device state and the C ABI (include/mithra_gpu.h) of the B200-native MITHRA time-march.
+ *
+ * One MithraGpu handle owns one z-slab on one GPU: three rotating levels of the potentials, the current
+ * buffer, the E/B node array, the particle struct-of-arrays, the power ring buffer and the screen records.
+ * All work of a time step is enqueued on one stream without host synchronisation; the order is the
+ * reference's (Solver::solve, solver.cpp:1300-1399).
+ *
+ * There is no CPU path in this file: every entry point either launches sm_100a kernels or fails.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mithra_gpu.h"
+#include "device_types.cuh"
+#include "kernels_field.cuh"
+#include "kernels_bunch.cuh"
+#include "kernels_seed.cuh"
+#include "exchange.cuh"
+
+using namespace mithra;
+
+/* ---------------------------------------------------------------------------------------------------- */
+
+static thread_local std::string g_error;
+
+static int fail (const char* fmt, ...)
+{
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_error = buf;
+  return 1;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+enum Phase { PH_STENCIL = 0, PH_BOUNDARY, PH_CLEAR, PH_EVAL, PH_PUSH, PH_DEPOSIT, PH_POWER, PH_SCREEN };
+
+struct MithraGpu
+{
+  MithraGpuParams prm;
+  FieldDev        fd;
+  BunchDev        bd;
+  int             device;
+  int             num_sms;
+  cudaStream_t    stream;
+
+  /* potentials */
+  size_t          level_doubles;          /* ncomp * np * Pp                                              */
+  double*         A[3];                   /* rotating: A[ip1], A[in], A[im1]                              */
+  int             ip1, in, im1;
+  bool            anp1_is_current;        /* reference view: anp1_ currently holds J (after fieldShift)    */
+  double*         J;
+  Box*            d_jbox;
+  unsigned int*   d_done;
+
+  /* E/B */
+  float4*         eb;
+  Box*            d_pbox;                 /* particle cell box (filled by push / particle_box)            */
+  Box*            d_ebox;                 /* node box evaluated by eval_eb_box                            */
+  Box             h_ebox_last;
+
+  /* particles */
+  BunchDev*       d_bd;
+  ParticlesDev    P;
+  double*         pstore;                 /* one allocation of 11 * capacity doubles                      */
+  size_t          pcap, pn;
+  unsigned int*   d_noutside;
+
+  /* power */
+  PowerDev        pw;
+  double*         d_fdt;
+  double2*        d_ep;
+  double*         d_partial;
+  int             power_blocks;
+  double*         d_rows;                 /* [rows_cap][N*Nl]                                             */
+  size_t          rows_cap, rows_used;
+  std::vector<double> h_rows;             /* rows already flushed to the host                             */
+  int             power_k[MITHRA_MAX_POWER_PLANES];
+  double          power_dzr[MITHRA_MAX_POWER_PLANES];
+  bool            power_mine[MITHRA_MAX_POWER_PLANES];
+
+  /* screens */
+  double*         d_scr_pos;
+  double*         d_scr_rec;
+  unsigned int*   d_scr_cur;
+  unsigned int    scr_cap;
+  std::vector<unsigned int> scr_fetched;  /* records already handed out per screen                        */
+
+  /* seed */
+  SeedDev*        d_seed;
+
+  /* slab exchange */
+  Exchange        xch;
+
+  /* time */
+  double          time, timem1, timep1, time_bunch;
+  unsigned int    n_time, n_time_bunch;
+
+  MithraGpuCounters cnt;
+
+  /* profiling */
+  bool            profiling;
+  cudaEvent_t     pev[2];
+  float           pms[MITHRA_GPU_NPHASES];
+};
+
+/* ---------------------------------------------------------------------------------------------------- */
+
+extern "C" const char* mithra_gpu_last_error (void) { return g_error.c_str(); }
+extern "C" int mithra_gpu_abi_version (void) { return MITHRA_GPU_ABI_VERSION; }
+extern "C" int mithra_gpu_device_count (void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static inline int grid_for (long n, int block, int cap)
+{
+  long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int) g;
+}
+
+struct PhaseTimer
+{
+  MithraGpu* h; int ph;
+  PhaseTimer (MithraGpu* h_, int ph_) : h(h_), ph(ph_) { if (h->profiling) cudaEventRecord(h->pev[0], h->stream); }
+  ~PhaseTimer ()
+  {
+    if (!h->profiling) return;
+    cudaEventRecord(h->pev[1], h->stream); cudaEventSynchronize(h->pev[1]);
+    float ms = 0.f; cudaEventElapsedTime(&ms, h->pev[0], h->pev[1]); h->pms[ph] += ms;
+  }
+};
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* layout conversion kernels (host AoS <-> device component-planar)                                      */
+
+__global__ void aos_to_planar (const double* __restrict__ src, double* __restrict__ dst, int ncomp_src, int c0, int nc,
+			       long nodes, int P, long Pp, int np)
+{
+  for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < nodes * nc; t += (long) gridDim.x * blockDim.x)
+    {
+      const long m = t / nc; const int c = (int) (t - m * nc);
+      const long k = m / P, r = m - k * P;
+      dst[((long) (c0 + c) * np + k) * Pp + r] = src[m * ncomp_src + c];
+    }
+}
+
+__global__ void planar_to_aos (const double* __restrict__ src, double* __restrict__ dst, int ncomp_dst, int c0, int nc,
+			       long nodes, int P, long Pp, int np)
+{
+  for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < nodes * nc; t += (long) gridDim.x * blockDim.x)
+    {
+      const long m = t / nc; const int c = (int) (t - m * nc);
+      const long k = m / P, r = m - k * P;
+      dst[m * ncomp_dst + c] = src[((long) (c0 + c) * np + k) * Pp + r];
+    }
+}
+
+__global__ void set_box (Box* b, int l0, int l1, int l2, int h0, int h1, int h2)
+{ b->lo[0] = l0; b->lo[1] = l1; b->lo[2] = l2; b->hi[0] = h0; b->hi[1] = h1; b->hi[2] = h2; }
+
+/* node box for the E/B evaluation from the particle cell box: pad by the cells a particle can cross in one
+ * field step, add the +1 upper node, clamp to the interior transversally; then empty the particle box.   */
+__global__ void make_eb_box (const Box* __restrict__ pbox_in, Box* __restrict__ ebox, Box* __restrict__ pbox_reset,
+			     int padx, int pady, int padz, int N0, int N1, int np)
+{
+  Box p = *pbox_in;
+  Box e;
+  if (p.hi[0] < p.lo[0]) { e.lo[0] = e.lo[1] = e.lo[2] = 0; e.hi[0] = e.hi[1] = e.hi[2] = -1; }
+  else
+    {
+      e.lo[0] = max(1, p.lo[0] - padx); e.hi[0] = min(N0 - 2, p.hi[0] + 1 + padx);
+      e.lo[1] = max(1, p.lo[1] - pady); e.hi[1] = min(N1 - 2, p.hi[1] + 1 + pady);
+      e.lo[2] = max(0, p.lo[2] - padz); e.hi[2] = min(np - 1, p.hi[2] + 1 + padz);
+    }
+  *ebox = e;
+  if (pbox_reset)
+    {
+      pbox_reset->lo[0] = pbox_reset->lo[1] = pbox_reset->lo[2] = 0x7fffffff;
+      pbox_reset->hi[0] = pbox_reset->hi[1] = pbox_reset->hi[2] = -1;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+
+static void fill_field_dev (const MithraGpuParams& p, FieldDev& f)
+{
+  memset(&f, 0, sizeof(f));
+  f.N0 = p.N0; f.N1 = p.N1; f.np = p.np; f.k0 = p.k0;
+  f.P  = p.N0 * p.N1;
+  f.Pp = ((long) f.P + 15) / 16 * 16;
+  f.ncomp = p.space_charge ? 4 : 3;
+  f.rank = p.rank; f.size = p.size;
+  f.nsfd = (p.solver == MITHRA_SOLVER_NSFD) ? 1 : 0;
+  f.order = p.truncation_order;
+  memcpy(f.a, p.a, sizeof(f.a)); f.alpha = p.alpha; f.beta = p.beta_nsfd;
+  memcpy(f.bB, p.bB, sizeof(f.bB)); memcpy(f.cB, p.cB, sizeof(f.cB)); memcpy(f.dB, p.dB, sizeof(f.dB));
+  memcpy(f.eE, p.eE, sizeof(f.eE)); memcpy(f.fE, p.fE, sizeof(f.fE)); memcpy(f.gE, p.gE, sizeof(f.gE));
+  memcpy(f.hC, p.hC, sizeof(f.hC));
+  f.dt = p.dt; f.dx2 = 2.0 * p.dx; f.dy2 = 2.0 * p.dy; f.dz2 = 2.0 * p.dz;
+}
+
+static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDev& b)
+{
+  const double PI = 3.1415926535, EC = 1.602e-19, EM = 9.109e-31;      /* stdinclude.h:43-52 */
+  memset(&b, 0, sizeof(b));
+  b.xmin = p.xmin; b.xmax = p.xmax; b.ymin = p.ymin; b.ymax = p.ymax; b.zmin = p.zmin; b.zmax = p.zmax;
+  b.zp0 = p.zp[0]; b.zp1 = p.zp[1]; b.Lz = p.Lz;
+  b.dx = p.dx; b.dy = p.dy; b.dz = p.dz;
+  b.c0 = p.c0; b.gamma = p.gamma; b.beta = p.beta; b.dt_shift = p.dt_shift;
+  b.r1 = p.r1; b.r2 = p.r2; b.dtb = p.dtb; b.dt_bunch = p.dt_bunch; b.dt_field = p.dt;
+  b.N0 = p.N0; b.N1 = p.N1; b.np = p.np; b.k0 = p.k0; b.P = f.P; b.Pp = f.Pp; b.ncomp = f.ncomp;
+  b.n_und = p.n_undulators;
+  b.und0_dist = p.n_undulators > 0 ? p.undulator[0].dist : 0.0;
+  for (int u = 0; u < p.n_undulators; u++)
+    {
+      const MithraUndulator& U = p.undulator[u];
+      UndulatorDev& D = b.und[u];
+      D.type = U.type;
+      /* solver.cpp:1805-1812, same operation order */
+      D.b0 = ( U.lu != 0.0 ) ? EM * p.c0 * 2 * PI / U.lu * U.k / EC : 0.0;
+      D.ku = ( U.lu != 0.0 ) ? 2 * PI / U.lu : 0.0;
+      D.ct = cos( U.theta ); D.st = sin( U.theta );
+      D.rb = U.rb; D.len = U.length * U.lu;
+      D.has_prev = (u > 0); D.has_next = (u + 1 < p.n_undulators);
+      /* beam.cc:35 and :60 */
+      D.r0_prev = D.has_prev ? p.undulator[u - 1].rb + p.undulator[u - 1].length * p.undulator[u - 1].lu - U.rb : 0.0;
+      D.r0_next = D.has_next ? p.undulator[u + 1].rb - U.rb - U.length * U.lu : 0.0;
+      D.beam = U.beam;
+    }
+  b.n_ext = p.n_ext_fields;
+  for (int u = 0; u < p.n_ext_fields; u++) b.ext[u] = p.ext_field[u];
+}
+
+extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out)
+{
+  if (!params || !out) return fail("mithra_gpu_create: null argument");
+  if (params->abi_version != MITHRA_GPU_ABI_VERSION) return fail("mithra_gpu_create: ABI version %d, library has %d", params->abi_version, MITHRA_GPU_ABI_VERSION);
+  if (params->N0 < 5 || params->N1 < 5 || params->np < 5) return fail("mithra_gpu_create: mesh too small (%d x %d x %d local planes)", params->N0, params->N1, params->np);
+  if (params->n_undulators > MITHRA_MAX_UNDULATORS || params->n_ext_fields > MITHRA_MAX_EXTFIELDS) return fail("mithra_gpu_create: too many undulators / external fields");
+  if (params->power.enabled && (params->power.N > MITHRA_MAX_POWER_PLANES || params->power.Nl > MITHRA_MAX_POWER_LAMBDAS || params->power.Nf < 1)) return fail("mithra_gpu_create: power sampling out of range");
+  if (params->screens.enabled && params->screens.N > MITHRA_MAX_SCREENS) return fail("mithra_gpu_create: too many screens");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    { cudaGetLastError(); return fail("mithra_gpu_create: no CUDA device available; this library has no CPU path"); }
+
+  MithraGpu* h = new MithraGpu();
+  h->prm = *params;
+  h->device = params->device;
+  if (h->device < 0) CU(cudaGetDevice(&h->device));
+  CU(cudaSetDevice(h->device));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major < 10) { delete h; return fail("mithra_gpu_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); }
+  h->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->pev[0])); CU(cudaEventCreate(&h->pev[1]));
+  h->profiling = false; memset(h->pms, 0, sizeof(h->pms));
+
+  fill_field_dev(*params, h->fd);
+  fill_bunch_dev(*params, h->fd, h->bd);
+  const FieldDev& f = h->fd;
+
+  h->level_doubles = (size_t) f.ncomp * f.np * f.Pp;
+  for (int l = 0; l < 3; l++) { CU(cudaMalloc(&h->A[l], h->level_doubles * sizeof(double))); CU(cudaMemsetAsync(h->A[l], 0, h->level_doubles * sizeof(double), h->stream)); }
+  CU(cudaMalloc(&h->J, h->level_doubles * sizeof(double))); CU(cudaMemsetAsync(h->J, 0, h->level_doubles * sizeof(double), h->stream));
+  h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
+  CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
+  CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
+  set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+  set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+  set_box<<<1, 1, 0, h->stream>>>(h->d_ebox, 0, 0, 0, -1, -1, -1);
+  h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
+
+  const size_t nodes = (size_t) f.np * f.P;
+  CU(cudaMalloc(&h->eb, nodes * 2 * sizeof(float4))); CU(cudaMemsetAsync(h->eb, 0, nodes * 2 * sizeof(float4), h->stream));
+
+  CU(cudaMalloc(&h->d_bd, sizeof(BunchDev))); CU(cudaMemcpyAsync(h->d_bd, &h->bd, sizeof(BunchDev), cudaMemcpyHostToDevice, h->stream));
+  h->pcap = params->max_particles ? params->max_particles : (size_t) 1 << 20;
+  h->pn = 0;
+  CU(cudaMalloc(&h->pstore, h->pcap * 11 * sizeof(double)));
+  {
+    double* s = h->pstore; const size_t c = h->pcap;
+    h->P.q = s; for (int a = 0; a < 3; a++) { h->P.r[a] = s + (1 + a) * c; h->P.rm[a] = s + (4 + a) * c; h->P.gb[a] = s + (7 + a) * c; } h->P.e = s + 10 * c;
+  }
+  CU(cudaMalloc(&h->d_noutside, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_noutside, 0, sizeof(unsigned int), h->stream));
+
+  /* power sampling, radiation.cpp:18-121 */
+  memset(&h->pw, 0, sizeof(h->pw));
+  h->d_fdt = 0; h->d_ep = 0; h->d_partial = 0; h->d_rows = 0; h->rows_cap = 0; h->rows_used = 0; h->power_blocks = 0;
+  if (params->power.enabled)
+    {
+      const MithraPower& pp = params->power;
+      PowerDev& pw = h->pw;
+      pw.N = pp.N; pw.Nl = pp.Nl; pw.Nf = pp.Nf; pw.ni = f.N0 - 4; pw.nj = f.N1 - 4; pw.npx = pw.ni * pw.nj;
+      pw.pc = pp.pc; pw.gamma = params->gamma; pw.beta = params->beta; pw.c0 = params->c0;
+      int nmine = 0;
+      for (int k = 0; k < pp.N; k++)
+	{
+	  h->power_mine[k] = ( pp.z[k] < params->zp[1] && pp.z[k] >= params->zp[0] );
+	  double c; h->power_dzr[k] = modf( ( pp.z[k] - params->zmin ) / params->dz, &c ); h->power_k[k] = (int) c - params->k0;
+	  if (h->power_mine[k]) nmine++;
+	}
+      const size_t ring = (size_t) pp.N * pp.Nf * 4 * pw.npx;
+      CU(cudaMalloc(&h->d_fdt, ring * sizeof(double))); CU(cudaMemsetAsync(h->d_fdt, 0, ring * sizeof(double), h->stream));
+      std::vector<double2> ep((size_t) pp.Nl * pp.Nf);
+      for (int l = 0; l < pp.Nl; l++)
+	for (int m = 0; m < pp.Nf; m++)
+	  { ep[(size_t) l * pp.Nf + m].x = cos( pp.w[l] * m * params->dt ); ep[(size_t) l * pp.Nf + m].y = sin( pp.w[l] * m * params->dt ); }
+      CU(cudaMalloc(&h->d_ep, ep.size() * sizeof(double2))); CU(cudaMemcpy(h->d_ep, ep.data(), ep.size() * sizeof(double2), cudaMemcpyHostToDevice));
+      h->power_blocks = (pw.npx + MITHRA_POWER_PX - 1) / MITHRA_POWER_PX;
+      CU(cudaMalloc(&h->d_partial, (size_t) pp.N * pp.Nl * h->power_blocks * sizeof(double)));
+      CU(cudaMemsetAsync(h->d_partial, 0, (size_t) pp.N * pp.Nl * h->power_blocks * sizeof(double), h->stream));
+      h->rows_cap = 4096;
+      CU(cudaMalloc(&h->d_rows, h->rows_cap * pp.N * pp.Nl * sizeof(double)));
+    }
+
+  /* screens */
+  h->d_scr_pos = 0; h->d_scr_rec = 0; h->d_scr_cur = 0; h->scr_cap = 0;
+  if (params->screens.enabled && params->screens.N > 0)
+    {
+      const int ns = params->screens.N;
+      h->scr_cap = (unsigned int) (params->max_screen_records ? params->max_screen_records : std::max<size_t>(h->pcap, 1024));
+      CU(cudaMalloc(&h->d_scr_pos, ns * sizeof(double))); CU(cudaMemcpy(h->d_scr_pos, params->screens.pos, ns * sizeof(double), cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&h->d_scr_rec, (size_t) ns * h->scr_cap * 8 * sizeof(double)));
+      CU(cudaMalloc(&h->d_scr_cur, ns * sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_scr_cur, 0, ns * sizeof(unsigned int), h->stream));
+      h->scr_fetched.assign(ns, 0u);
+    }
+
+  /* seed */
+  h->d_seed = 0;
+  if (params->seed_enabled)
+    {
+      SeedDev sd; memset(&sd, 0, sizeof(sd));
+      sd.beam = params->seed; sd.c0 = params->c0; sd.gamma = params->gamma; sd.beta = params->beta; sd.dt_shift = params->dt_shift;
+      sd.xmin = params->xmin; sd.ymin = params->ymin; sd.zmin = params->zmin; sd.dx = params->dx; sd.dy = params->dy; sd.dz = params->dz;
+      CU(cudaMalloc(&h->d_seed, sizeof(SeedDev))); CU(cudaMemcpy(h->d_seed, &sd, sizeof(SeedDev), cudaMemcpyHostToDevice));
+    }
+
+  exchange_init(h->xch);
+
+  h->time = 0.0; h->timem1 = - params->dt; h->timep1 = params->dt; h->time_bunch = 0.0; h->n_time = 0; h->n_time_bunch = 0;
+  memset(&h->cnt, 0, sizeof(h->cnt));
+  CU(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+extern "C" void mithra_gpu_destroy (MithraGpu* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  exchange_destroy(h->xch);
+  for (int l = 0; l < 3; l++) cudaFree(h->A[l]);
+  cudaFree(h->J); cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
+  cudaFree(h->eb); cudaFree(h->d_bd); cudaFree(h->pstore); cudaFree(h->d_noutside);
+  cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
+  cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed);
+  cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+#define USE(h) do { if (!(h)) return fail("null handle"); CU(cudaSetDevice((h)->device)); } while (0)
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* state transfer                                                                                        */
+
+static int upload_vec (MithraGpu* h, const double* src, double* dst, int ncomp_src, int c0, int nc)
+{
+  const FieldDev& f = h->fd;
+  const long nodes = (long) f.np * f.P;
+  double* tmp = 0;
+  CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_src * sizeof(double)));
+  CU(cudaMemcpyAsync(tmp, src, (size_t) nodes * ncomp_src * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  aos_to_planar<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(tmp, dst, ncomp_src, c0, nc, nodes, f.P, f.Pp, f.np);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
+static int download_vec (MithraGpu* h, const double* src, double* dst, int ncomp_dst, int c0, int nc)
+{
+  const FieldDev& f = h->fd;
+  const long nodes = (long) f.np * f.P;
+  double* tmp = 0;
+  CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_dst * sizeof(double)));
+  planar_to_aos<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, tmp, ncomp_dst, c0, nc, nodes, f.P, f.Pp, f.np);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(dst, tmp, (size_t) nodes * ncomp_dst * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
+extern "C" int mithra_gpu_upload_fields (MithraGpu* h, const double* an, const double* anm1, const double* jn,
+					 const double* fn, const double* fnm1, const double* rho)
+{
+  USE(h);
+  const FieldDev& f = h->fd;
+  if (an)   TRY(upload_vec(h, an,   h->A[h->in],  3, 0, 3));
+  if (anm1) TRY(upload_vec(h, anm1, h->A[h->im1], 3, 0, 3));
+  if (jn)   TRY(upload_vec(h, jn,   h->J,         3, 0, 3));
+  if (f.ncomp == 4)
+    {
+      if (fn)   TRY(upload_vec(h, fn,   h->A[h->in],  1, 3, 1));
+      if (fnm1) TRY(upload_vec(h, fnm1, h->A[h->im1], 1, 3, 1));
+      if (rho)  TRY(upload_vec(h, rho,  h->J,         1, 3, 1));
+    }
+  if (jn || rho)
+    set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0, 0, 0, f.N0 - 1, f.N1 - 1, f.np - 1);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->anp1_is_current = true;
+  return 0;
+}
+
+extern "C" int mithra_gpu_download_fields (MithraGpu* h, double* anp1, double* an, double* anm1,
+					   double* fnp1, double* fn, double* fnm1)
+{
+  USE(h);
+  const FieldDev& f = h->fd;
+  const double* np1 = h->anp1_is_current ? h->J : h->A[h->ip1];
+  if (anp1) TRY(download_vec(h, np1,          anp1, 3, 0, 3));
+  if (an)   TRY(download_vec(h, h->A[h->in],  an,   3, 0, 3));
+  if (anm1) TRY(download_vec(h, h->A[h->im1], anm1, 3, 0, 3));
+  if (f.ncomp == 4)
+    {
+      if (fnp1) TRY(download_vec(h, np1,          fnp1, 1, 3, 1));
+      if (fn)   TRY(download_vec(h, h->A[h->in],  fn,   1, 3, 1));
+      if (fnm1) TRY(download_vec(h, h->A[h->im1], fnm1, 1, 3, 1));
+    }
+  return 0;
+}
+
+extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsigned char* mask)
+{
+  USE(h);
+  const FieldDev& f = h->fd;
+  const size_t nodes = (size_t) f.np * f.P;
+  std::vector<float4> tmp(nodes * 2);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(tmp.data(), h->eb, nodes * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
+  Box b; CU(cudaMemcpy(&b, h->d_ebox, sizeof(Box), cudaMemcpyDeviceToHost));
+  for (size_t m = 0; m < nodes; m++)
+    {
+      const int k = (int) (m / f.P), r = (int) (m % f.P), i = r / f.N1, j = r % f.N1;
+      bool in = ( i >= b.lo[0] && i <= b.hi[0] && j >= b.lo[1] && j <= b.hi[1] && k >= b.lo[2] && k <= b.hi[2] );
+      if (in && f.size > 1 && ((k == 0 && f.rank != 0) || (k == f.np - 1 && f.rank != f.size - 1))) in = h->xch.connected;
+      if (mask) mask[m] = in ? 1 : 0;
+      if (en) { en[3 * m] = in ? tmp[2 * m].x : 0.f; en[3 * m + 1] = in ? tmp[2 * m].y : 0.f; en[3 * m + 2] = in ? tmp[2 * m].z : 0.f; }
+      if (bn) { bn[3 * m] = in ? tmp[2 * m + 1].x : 0.f; bn[3 * m + 1] = in ? tmp[2 * m + 1].y : 0.f; bn[3 * m + 2] = in ? tmp[2 * m + 1].z : 0.f; }
+    }
+  return 0;
+}
+
+static int refresh_particle_box (MithraGpu* h)
+{
+  set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+  if (h->pn > 0)
+    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->d_pbox);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 2;
+  return 0;
+}
+
+extern "C" int mithra_gpu_upload_particles (MithraGpu* h, const double* aos11, size_t n)
+{
+  USE(h);
+  if (n > h->pcap) return fail("mithra_gpu_upload_particles: %zu particles exceed the capacity %zu (MithraGpuParams.max_particles)", n, h->pcap);
+  std::vector<double> soa(11 * n);
+  for (size_t i = 0; i < n; i++)
+    for (int c = 0; c < 11; c++) soa[(size_t) c * n + i] = aos11[i * 11 + c];
+  CU(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < 11; c++)
+    if (n) CU(cudaMemcpy(h->pstore + (size_t) c * h->pcap, soa.data() + (size_t) c * n, n * sizeof(double), cudaMemcpyHostToDevice));
+  h->pn = n;
+  TRY(refresh_particle_box(h));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_t capacity, size_t* n)
+{
+  USE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  if (n) *n = h->pn;
+  if (!aos11) return 0;
+  if (capacity < h->pn) return fail("mithra_gpu_download_particles: capacity %zu < %zu particles", capacity, h->pn);
+  const size_t np = h->pn;
+  std::vector<double> soa(11 * np);
+  for (int c = 0; c < 11; c++)
+    if (np) CU(cudaMemcpy(soa.data() + (size_t) c * np, h->pstore + (size_t) c * h->pcap, np * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < np; i++)
+    for (int c = 0; c < 11; c++) aos11[i * 11 + c] = soa[(size_t) c * np + i];
+  return 0;
+}
+
+extern "C" int mithra_gpu_num_particles (MithraGpu* h, size_t* n) { USE(h); if (n) *n = h->pn; return 0; }
+
+extern "C" int mithra_gpu_set_time (MithraGpu* h, double time, double time_bunch, unsigned int n_time)
+{
+  USE(h);
+  h->time = time; h->timem1 = time - h->prm.dt; h->timep1 = time + h->prm.dt; h->time_bunch = time_bunch; h->n_time = n_time;
+  return 0;
+}
+
+extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bunch, unsigned int* n_time)
+{
+  USE(h);
+  if (time) *time = h->time; if (time_bunch) *time_bunch = h->time_bunch; if (n_time) *n_time = h->n_time;
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* the time march                                                                                        */
+
+template <bool NSFD>
+static void launch_stencil (MithraGpu* h)
+{
+  const FieldDev& f = h->fd;
+  constexpr int BX = 128, KC = 32;
+  dim3 grid((f.P + BX - 1) / BX, (f.np - 2 + KC - 1) / KC, f.ncomp);
+  stencil_interior<NSFD, BX, KC><<<grid, BX, 0, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox);
+}
+
+extern "C" int mithra_gpu_field_update (MithraGpu* h)
+{
+  USE(h);
+  const FieldDev& f = h->fd;
+  double* ap = h->A[h->ip1]; const double* a = h->A[h->in]; const double* am = h->A[h->im1];
+  {
+    PhaseTimer t(h, PH_STENCIL);
+    if (f.nsfd) launch_stencil<true>(h); else launch_stencil<false>(h);
+    CU(cudaGetLastError());
+    h->cnt.kernel_launches += 1;
+  }
+  {
+    PhaseTimer t(h, PH_BOUNDARY);
+    if (h->d_seed)
+      {
+	TRY(seed_inject(h->d_seed, f, ap, h->time, h->stream, h->num_sms));
+	h->cnt.kernel_launches += 1;
+      }
+    const long nface = (2L * (f.N1 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.N1 - 2)) * f.ncomp;
+    boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am);
+    h->cnt.kernel_launches += 1;
+    if (f.order == 2)
+      {
+	const long nedge = (4L * (f.np - 2) + 4L * (f.N0 - 2) + 4L * (f.N1 - 2)) * f.ncomp;
+	boundary_edges<<<grid_for(nedge, 256, h->num_sms * 4), 256, 0, h->stream>>>(f, ap, a, am);
+	boundary_corners<<<1, 32, 0, h->stream>>>(f, ap, a, am);
+	h->cnt.kernel_launches += 2;
+      }
+    CU(cudaGetLastError());
+    if (h->xch.connected) { TRY(exchange_potentials(h->xch, f, ap, h->stream)); h->cnt.kernel_launches += 2; }
+  }
+  {
+    PhaseTimer t(h, PH_EVAL);
+    const double cdt = h->prm.c0 * h->prm.dt;
+    const int padx = (int) ceil(cdt / h->prm.dx), pady = (int) ceil(cdt / h->prm.dy), padz = (int) ceil(cdt / h->prm.dz);
+    make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
+    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+    else              eval_eb_box<false><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+    CU(cudaGetLastError());
+    h->cnt.kernel_launches += 2;
+    if (h->xch.connected) { TRY(exchange_eb(h->xch, f, h->eb, h->stream)); h->cnt.kernel_launches += 2; }
+  }
+  h->anp1_is_current = false;
+  h->cnt.cell_updates += (unsigned long long) f.np * f.P;
+  return 0;
+}
+
+extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
+{
+  USE(h);
+  PhaseTimer t(h, PH_PUSH);
+  const int nsub = h->prm.n_update_bunch;
+  if (h->pn > 0)
+    {
+      /* the particle box is rebuilt by the push (it is read by the next field update)                      */
+      set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+      const int grid = (int) ((h->pn + 127) / 128);
+      if (!h->xch.connected)
+	{
+	  push_particles<<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
+	  h->cnt.kernel_launches += 2;
+	}
+      else
+	return fail("mithra_gpu_bunch_update: slab migration is not wired yet");
+      CU(cudaGetLastError());
+    }
+  for (int s = 0; s < nsub; s++) { h->time_bunch += h->prm.dt_bunch; ++h->n_time_bunch; }
+  h->cnt.particle_pushes += (unsigned long long) h->pn * nsub;
+  return 0;
+}
+
+extern "C" int mithra_gpu_screen_profile (MithraGpu* h)
+{
+  USE(h);
+  if (!h->d_scr_pos || h->pn == 0) return 0;
+  PhaseTimer t(h, PH_SCREEN);
+  screen_cross<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->time_bunch, h->prm.screens.N,
+								     h->d_scr_pos, h->d_scr_rec, h->d_scr_cur, h->scr_cap, (double) h->n_time);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  return 0;
+}
+
+static int flush_power_rows (MithraGpu* h)
+{
+  if (h->rows_used == 0) return 0;
+  const size_t w = (size_t) h->pw.N * h->pw.Nl;
+  const size_t old = h->h_rows.size();
+  h->h_rows.resize(old + h->rows_used * w);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(h->h_rows.data() + old, h->d_rows, h->rows_used * w * sizeof(double), cudaMemcpyDeviceToHost));
+  h->rows_used = 0;
+  return 0;
+}
+
+extern "C" int mithra_gpu_power_sample (MithraGpu* h)
+{
+  USE(h);
+  if (!h->d_fdt) return 0;
+  PhaseTimer t(h, PH_POWER);
+  const FieldDev& f = h->fd;
+  if (h->rows_used == h->rows_cap) TRY(flush_power_rows(h));
+  const int slot = (int) (h->n_time % (unsigned int) h->pw.Nf);
+  const double* np1 = h->A[h->ip1]; const double* an = h->A[h->in];
+  for (int k = 0; k < h->pw.N; k++)
+    {
+      if (!h->power_mine[k]) continue;
+      if (f.ncomp == 4)
+	power_dft<true ><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
+      else
+	power_dft<false><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
+      h->cnt.kernel_launches += 1;
+    }
+  const int nout = h->pw.N * h->pw.Nl;
+  power_finish<<<(nout + 63) / 64, 64, 0, h->stream>>>(h->pw, h->d_partial, h->power_blocks, h->d_rows + h->rows_used * nout);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  h->rows_used++;
+  return 0;
+}
+
+extern "C" int mithra_gpu_field_shift (MithraGpu* h)
+{
+  USE(h);
+  const int t = h->im1; h->im1 = h->in; h->in = h->ip1; h->ip1 = t;
+  h->anp1_is_current = true;
+  return 0;
+}
+
+extern "C" int mithra_gpu_current_reset (MithraGpu* h)
+{
+  USE(h);
+  PhaseTimer t(h, PH_CLEAR);
+  clear_current_box<<<h->num_sms * 2, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  return 0;
+}
+
+extern "C" int mithra_gpu_current_update (MithraGpu* h)
+{
+  USE(h);
+  PhaseTimer t(h, PH_DEPOSIT);
+  if (h->pn == 0) return 0;
+  const int grid = (int) ((h->pn + 127) / 128);
+  if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->J, h->d_jbox);
+  else                  deposit_current<false><<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->J, h->d_jbox);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  return 0;
+}
+
+extern "C" int mithra_gpu_current_communicate (MithraGpu* h)
+{
+  USE(h);
+  if (h->xch.connected) { TRY(exchange_current(h->xch, h->fd, h->J, h->d_jbox, h->stream)); h->cnt.kernel_launches += 2; }
+  return 0;
+}
+
+extern "C" int mithra_gpu_advance_time (MithraGpu* h)
+{
+  USE(h);
+  h->timem1 += h->prm.dt; h->time += h->prm.dt; h->timep1 += h->prm.dt; ++h->n_time;
+  h->cnt.field_steps += 1;
+  return 0;
+}
+
+extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
+{
+  USE(h);
+  for (int s = 0; s < nsteps; s++)
+    {
+      TRY(mithra_gpu_field_update(h));
+      TRY(mithra_gpu_bunch_update(h));
+      TRY(mithra_gpu_screen_profile(h));
+      TRY(mithra_gpu_power_sample(h));
+      TRY(mithra_gpu_field_shift(h));
+      TRY(mithra_gpu_current_reset(h));
+      TRY(mithra_gpu_current_update(h));
+      TRY(mithra_gpu_current_communicate(h));
+      TRY(mithra_gpu_advance_time(h));
+    }
+  return 0;
+}
+
+extern "C" int mithra_gpu_synchronize (MithraGpu* h)
+{
+  USE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mithra_gpu_step_timed (MithraGpu* h, int nsteps, float* ms)
+{
+  USE(h);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  int r = mithra_gpu_step(h, nsteps);
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  float t = 0.f; CU(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return r;
+}
+
+extern "C" int mithra_gpu_step_profiled (MithraGpu* h, int nsteps, float ms[MITHRA_GPU_NPHASES])
+{
+  USE(h);
+  CU(cudaStreamSynchronize(h->stream));
+  memset(h->pms, 0, sizeof(h->pms));
+  h->profiling = true;
+  int r = mithra_gpu_step(h, nsteps);
+  h->profiling = false;
+  CU(cudaStreamSynchronize(h->stream));
+  if (ms) memcpy(ms, h->pms, sizeof(h->pms));
+  return r;
+}
+
+extern "C" int mithra_gpu_fetch_power (MithraGpu* h, double* rows, size_t capacity_rows, size_t* nrows)
+{
+  USE(h);
+  if (!h->d_fdt) { if (nrows) *nrows = 0; return 0; }
+  TRY(flush_power_rows(h));
+  const size_t w = (size_t) h->pw.N * h->pw.Nl;
+  const size_t have = h->h_rows.size() / w;
+  const size_t take = std::min(have, capacity_rows);
+  if (rows && take) memcpy(rows, h->h_rows.data(), take * w * sizeof(double));
+  if (rows) h->h_rows.erase(h->h_rows.begin(), h->h_rows.begin() + take * w);
+  if (nrows) *nrows = rows ? take : have;
+  return 0;
+}
+
+extern "C" int mithra_gpu_fetch_screen (MithraGpu* h, int screen, double* rec6, size_t capacity, size_t* n)
+{
+  USE(h);
+  if (n) *n = 0;
+  if (!h->d_scr_pos) return 0;
+  if (screen < 0 || screen >= h->prm.screens.N) return fail("mithra_gpu_fetch_screen: screen %d out of range", screen);
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned int cur = 0;
+  CU(cudaMemcpy(&cur, h->d_scr_cur + screen, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  if (cur > h->scr_cap) return fail("mithra_gpu_fetch_screen: screen %d overflowed its %u-record buffer (MithraGpuParams.max_screen_records)", screen, h->scr_cap);
+  const unsigned int done = h->scr_fetched[screen];
+  const size_t fresh = cur - done;
+  if (!rec6) { if (n) *n = fresh; return 0; }
+  if (capacity < fresh) return fail("mithra_gpu_fetch_screen: capacity %zu < %zu records", capacity, fresh);
+  std::vector<double> raw(fresh * 8);
+  if (fresh) CU(cudaMemcpy(raw.data(), h->d_scr_rec + ((size_t) screen * h->scr_cap + done) * 8, fresh * 8 * sizeof(double), cudaMemcpyDeviceToHost));
+  /* restore the reference's order: by step, then by particle index */
+  std::vector<size_t> order(fresh);
+  for (size_t i = 0; i < fresh; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    if (raw[a * 8 + 7] != raw[b * 8 + 7]) return raw[a * 8 + 7] < raw[b * 8 + 7];
+    return raw[a * 8 + 6] < raw[b * 8 + 6]; });
+  for (size_t i = 0; i < fresh; i++) memcpy(rec6 + i * 6, raw.data() + order[i] * 8, 6 * sizeof(double));
+  h->scr_fetched[screen] = cur;
+  if (n) *n = fresh;
+  return 0;
+}
+
+extern "C" int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out)
+{
+  USE(h);
+  if (out) *out = h->cnt;
+  return 0;
+}
+
+extern "C" int mithra_gpu_ipc_export (MithraGpu* h, void* blob, size_t capacity, size_t* nbytes)
+{
+  USE(h);
+  return exchange_export(h->xch, h->fd, h->A, h->J, h->eb, blob, capacity, nbytes) ? fail("mithra_gpu_ipc_export: %s", exchange_error()) : 0;
+}
+
+extern "C" int mithra_gpu_ipc_connect (MithraGpu* h, const void* blob_prev, const void* blob_next)
+{
+  USE(h);
+  return exchange_connect(h->xch, h->fd, blob_prev, blob_next) ? fail("mithra_gpu_ipc_connect: %s", exchange_error()) : 0;
+}

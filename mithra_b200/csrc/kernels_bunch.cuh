@@ -1,0 +1,464 @@
+/* kernels_bunch.cuh -- particle-side sm_100a kernels: Boris push with analytic undulator / external fields and
+ * trilinear E,B gather, charge-conserving ZigZag deposition, bounding boxes, screens and radiated power.
+ *
+ * Reference: Solver::bunchUpdate solver.cpp:1424-1576, undulatorField / externalField solver.cpp:1798-1947,
+ * FdTd::currentUpdate fdtd.cpp:38-185 (+rho fdtdSC.cpp:141-160), Solver::screenProfile solver.cpp:2205-2257,
+ * Solver::powerSample radiation.cpp:127-232.
+ *
+ * Index arithmetic (cell index, weights, ownership) uses true IEEE division, modf / floor and no FMA
+ * contraction (-fmad=false), exactly as the reference does, so particle-to-cell assignment is bit-exact for
+ * identical positions.
+ */
+#ifndef MITHRA_KERNELS_BUNCH_CUH_
+#define MITHRA_KERNELS_BUNCH_CUH_
+
+#include "device_types.cuh"
+#include "beams.cuh"
+
+namespace mithra
+{
+  /* pmod, stdinclude.cpp:88-93 */
+  __device__ __forceinline__ double pmod (double a, double b)
+  {
+    double x = fmod(a, b);
+    x += ( x < 0.0 ) ? b : 0.0;
+    return x;
+  }
+
+  __device__ __forceinline__ void warp_box_merge (Box* box, bool valid, int i0, int i1, int j0, int j1, int k0, int k1)
+  {
+    const unsigned full = 0xffffffffu;
+    int lo0 = valid ? i0 : 0x7fffffff, lo1 = valid ? j0 : 0x7fffffff, lo2 = valid ? k0 : 0x7fffffff;
+    int hi0 = valid ? i1 : -1,         hi1 = valid ? j1 : -1,         hi2 = valid ? k1 : -1;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      {
+	lo0 = min(lo0, __shfl_xor_sync(full, lo0, o)); lo1 = min(lo1, __shfl_xor_sync(full, lo1, o)); lo2 = min(lo2, __shfl_xor_sync(full, lo2, o));
+	hi0 = max(hi0, __shfl_xor_sync(full, hi0, o)); hi1 = max(hi1, __shfl_xor_sync(full, hi1, o)); hi2 = max(hi2, __shfl_xor_sync(full, hi2, o));
+      }
+    if ((threadIdx.x & 31) == 0 && hi0 >= lo0)
+      {
+	atomicMin(&box->lo[0], lo0); atomicMin(&box->lo[1], lo1); atomicMin(&box->lo[2], lo2);
+	atomicMax(&box->hi[0], hi0); atomicMax(&box->hi[1], hi1); atomicMax(&box->hi[2], hi2);
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Bounding box (cell indices) of the particles that will gather mesh fields, used to size the E/B
+   * evaluation of the next step.  The host pads it by the distance a particle can travel in one field step.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(256)
+  particle_box (const BunchDev* __restrict__ bp, ParticlesDev P, long n, Box* __restrict__ box)
+  {
+    const BunchDev& b = *bp;
+    for (long base = (long) blockIdx.x * blockDim.x; base < n; base += (long) gridDim.x * blockDim.x)
+      {
+	const long t = base + threadIdx.x;
+	bool valid = false; int i = 0, j = 0, k = 0;
+	if (t < n)
+	  {
+	    const double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
+	    if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
+	      {
+		i = (int) floor( ( x - b.xmin ) / b.dx );
+		j = (int) floor( ( y - b.ymin ) / b.dy );
+		k = (int) floor( ( z - b.zmin ) / b.dz ) - b.k0;
+		valid = true;
+	      }
+	  }
+	warp_box_merge(box, valid, i, i, j, j, k, k);
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Push: `nsub` consecutive sub-steps of Solver::bunchUpdate for every particle (solver.cpp:1437-1549).
+   * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312).
+   * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(128)
+  push_particles (const BunchDev* __restrict__ bp, ParticlesDev P, long n, const float4* __restrict__ eb,
+		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside)
+  {
+    const BunchDev& b = *bp;
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool boxvalid = false; int bi = 0, bj = 0, bk = 0;
+
+    if (t < n)
+      {
+	double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
+	double gx = P.gb[0][t], gy = P.gb[1][t], gz = P.gb[2][t];
+	double e = P.e[t];
+	if (first_of_step) { P.rm[0][t] = x; P.rm[1][t] = y; P.rm[2][t] = z; }
+
+	double tb = time_bunch;
+	for (int s = 0; s < nsub; s++, tb += b.dt_bunch)
+	  {
+	    /* ownership with the periodic z wrap (solver.cpp:1440-1441)                                    */
+	    double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;
+	    if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) continue;
+
+	    const bool b1x = ( x < b.xmax - b.dx && x > b.xmin + b.dx );
+	    const bool b1y = ( y < b.ymax - b.dy && y > b.ymin + b.dy );
+	    const bool b1z = ( z < b.zp1 && z >= b.zp0 );
+
+	    V3 et = v3(0.0, 0.0, 0.0), bt = v3(0.0, 0.0, 0.0);
+
+	    /* undulatorField, solver.cpp:1798-1880                                                         */
+	    for (int u = 0; u < b.n_und; u++)
+	      {
+		const UndulatorDev& U = b.und[u];
+		if (U.type == MITHRA_UNDULATOR_STATIC)
+		  {
+		    const double lz = b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) ) - U.rb;
+		    const double ly = x * U.ct + y * U.st;
+		    static_undulator(U, b.gamma, b.c0 * b.beta, lz, ly, et, bt);
+		  }
+		else
+		  {
+		    const V3 rl = v3(x, y, b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) ));
+		    const double t0 = b.gamma * ( tb + b.dt_shift + b.beta / b.c0 * z );
+		    const V3 rv = v3(rl.x - U.beam.position[0], rl.y - U.beam.position[1], rl.z - U.beam.position[2]);
+		    const double zz = dot3(rv, v3a(U.beam.direction));
+		    V3 eT, bT;
+		    beam_fields(U.beam, b.c0, rv, zz, t0 - zz / b.c0, t0 + zz / b.c0, eT, bT);
+		    bt.x += b.gamma * ( bT.x + b.beta / b.c0 * eT.y );
+		    bt.y += b.gamma * ( bT.y - b.beta / b.c0 * eT.x );
+		    bt.z += bT.z;
+		    et.x += b.gamma * ( eT.x - b.beta * b.c0 * bT.y );
+		    et.y += b.gamma * ( eT.y + b.beta * b.c0 * bT.x );
+		    et.z += eT.z;
+		  }
+	      }
+
+	    /* externalField, solver.cpp:1886-1947                                                          */
+	    if (b.n_ext > 0)
+	      {
+		const V3 rl = v3(x, y, b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) ));
+		const double t0 = b.gamma * ( tb + b.dt_shift + b.beta / b.c0 * z );
+		for (int u = 0; u < b.n_ext; u++)
+		  {
+		    const MithraBeam& S = b.ext[u];
+		    const V3 rv = v3(rl.x - S.position[0], rl.y - S.position[1], rl.z - S.position[2]);
+		    const double zz = dot3(rv, v3a(S.direction));
+		    V3 eT, bT;
+		    beam_fields(S, b.c0, rv, zz, t0 - zz / b.c0, t0 + zz / b.c0, eT, bT);
+		    bt.x += b.gamma * ( bT.x + b.beta / b.c0 * eT.y );
+		    bt.y += b.gamma * ( bT.y - b.beta / b.c0 * eT.x );
+		    bt.z += bT.z;
+		    et.x += b.gamma * ( eT.x - b.beta * b.c0 * bT.y );
+		    et.y += b.gamma * ( eT.y + b.beta * b.c0 * bT.x );
+		    et.z += eT.z;
+		  }
+	      }
+
+	    if (e == 1.0)
+	      {
+		if (b1x && b1y && b1z)
+		  {
+		    double d1;
+		    const double dxr = modf( ( x - b.xmin ) / b.dx, &d1 ); const int i = (int) d1;
+		    const double dyr = modf( ( y - b.ymin ) / b.dy, &d1 ); const int j = (int) d1;
+		    const double dzr = modf( ( z - b.zmin ) / b.dz, &d1 ); const int k = (int) d1;
+		    const long m = (long) ( k - b.k0 ) * b.P + (long) i * b.N1 + j;
+		    const long N1 = b.N1, Pn = b.P;
+		    const long off[8] = { 0, N1, 1, N1 + 1, Pn, Pn + N1, Pn + 1, Pn + N1 + 1 };
+		    const double w[8] = {
+		      ( 1.0 - dxr ) * ( 1.0 - dyr ) * ( 1.0 - dzr ),         dxr   * ( 1.0 - dyr ) * ( 1.0 - dzr ),
+		      ( 1.0 - dxr ) *         dyr   * ( 1.0 - dzr ),         dxr   *         dyr   * ( 1.0 - dzr ),
+		      ( 1.0 - dxr ) * ( 1.0 - dyr ) *         dzr,           dxr   * ( 1.0 - dyr ) *         dzr,
+		      ( 1.0 - dxr ) *         dyr   *         dzr,           dxr   *         dyr   *         dzr };
+		    float4 fe[8], fb[8];
+		    #pragma unroll
+		    for (int q = 0; q < 8; q++) { fe[q] = __ldg(&eb[2 * (m + off[q])]); fb[q] = __ldg(&eb[2 * (m + off[q]) + 1]); }
+		    #pragma unroll
+		    for (int q = 0; q < 8; q++) { et.x += w[q] * fe[q].x; et.y += w[q] * fe[q].y; et.z += w[q] * fe[q].z; }
+		    #pragma unroll
+		    for (int q = 0; q < 8; q++) { bt.x += w[q] * fb[q].x; bt.y += w[q] * fb[q].y; bt.z += w[q] * fb[q].z; }
+		  }
+		else if ( !b1x && !b1y && b1z )
+		  atomicAdd(n_outside, 1u);
+	      }
+	    else if (b.n_und > 0)
+	      {
+		const double lz = b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) );
+		e = ( lz > - b.und0_dist ) ? 1.0 : 0.0;
+	      }
+	    else
+	      e = 1.0;
+
+	    /* Boris rotation, solver.cpp:1519-1541                                                         */
+	    const double mx = gx + b.r1 * et.x, my = gy + b.r1 * et.y, mz = gz + b.r1 * et.z;          /* gb-   */
+	    double cx = my * bt.z - mz * bt.y, cy = mz * bt.x - mx * bt.z, cz = mx * bt.y - my * bt.x;
+	    const double d1 = sqrt( 1.0 + ( mx * mx + my * my + mz * mz ) );
+	    const double f1 = b.r2 / d1;
+	    const double px = f1 * cx + mx, py = f1 * cy + my, pz = f1 * cz + mz;                      /* gb'   */
+	    cx = py * bt.z - pz * bt.y; cy = pz * bt.x - px * bt.z; cz = px * bt.y - py * bt.x;
+	    const double f2 = 2.0 / ( d1 / b.r2 + b.r2 / d1 * ( bt.x * bt.x + bt.y * bt.y + bt.z * bt.z ) );
+	    const double lx = f2 * cx + mx, ly = f2 * cy + my, lzz = f2 * cz + mz;                     /* gb+   */
+	    gx = lx + b.r1 * et.x; gy = ly + b.r1 * et.y; gz = lzz + b.r1 * et.z;
+
+	    const double f3 = b.dtb / sqrt( 1.0 + ( gx * gx + gy * gy + gz * gz ) );
+	    const double drx = f3 * gx, dry = f3 * gy, drz = f3 * gz;
+	    x += drx; y += dry; z += drz;
+	  }
+
+	P.r[0][t] = x; P.r[1][t] = y; P.r[2][t] = z;
+	P.gb[0][t] = gx; P.gb[1][t] = gy; P.gb[2][t] = gz;
+	P.e[t] = e;
+
+	if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
+	  {
+	    bi = (int) floor( ( x - b.xmin ) / b.dx );
+	    bj = (int) floor( ( y - b.ymin ) / b.dy );
+	    bk = (int) floor( ( z - b.zmin ) / b.dz ) - b.k0;
+	    boxvalid = true;
+	  }
+      }
+    warp_box_merge(pbox, boxvalid, bi, bi, bj, bj, bk, bk);
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * ZigZag deposition of one particle (fdtd.cpp:47-184): relay point, two segments, each scattering the three
+   * current components to the 8 nodes of its cell (+ rho at the end point with space charge,
+   * fdtdSC.cpp:141-160).  FP64 atomics straight to L2 (RED.ADD.F64); the box of touched nodes is merged
+   * per warp.
+   * ------------------------------------------------------------------------------------------------ */
+  __device__ __forceinline__ void scatter_segment (const BunchDev& b, double* __restrict__ jn, long m, double q,
+						   double mx, double my, double mz, double jx, double jy, double jz)
+  {
+    double c;
+    const double dxp = modf( ( mx - b.xmin ) / b.dx, &c );
+    const double dyp = modf( ( my - b.ymin ) / b.dy, &c );
+    const double dzp = modf( ( mz - b.zmin ) / b.dz, &c );
+    const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
+    const long N1 = b.N1, Pp = b.Pp, cs = (long) b.np * b.Pp;
+    const long o[8] = { m, m + N1, m + 1, m + N1 + 1, m + Pp, m + Pp + N1, m + Pp + 1, m + Pp + N1 + 1 };
+    double* J0 = jn; double* J1 = jn + cs; double* J2 = jn + 2 * cs;
+    const double h = q * 0.5;
+
+    atomicAdd(J0 + o[0], h * y1 * z1 * jx); atomicAdd(J0 + o[1], h * y1 * z1 * jx);
+    atomicAdd(J0 + o[2], h * y2 * z1 * jx); atomicAdd(J0 + o[3], h * y2 * z1 * jx);
+    atomicAdd(J0 + o[4], h * y1 * z2 * jx); atomicAdd(J0 + o[5], h * y1 * z2 * jx);
+    atomicAdd(J0 + o[6], h * y2 * z2 * jx); atomicAdd(J0 + o[7], h * y2 * z2 * jx);
+
+    atomicAdd(J1 + o[0], h * x1 * z1 * jy); atomicAdd(J1 + o[1], h * x2 * z1 * jy);
+    atomicAdd(J1 + o[2], h * x1 * z1 * jy); atomicAdd(J1 + o[3], h * x2 * z1 * jy);
+    atomicAdd(J1 + o[4], h * x1 * z2 * jy); atomicAdd(J1 + o[5], h * x2 * z2 * jy);
+    atomicAdd(J1 + o[6], h * x1 * z2 * jy); atomicAdd(J1 + o[7], h * x2 * z2 * jy);
+
+    atomicAdd(J2 + o[0], h * x1 * y1 * jz); atomicAdd(J2 + o[1], h * x2 * y1 * jz);
+    atomicAdd(J2 + o[2], h * x1 * y2 * jz); atomicAdd(J2 + o[3], h * x2 * y2 * jz);
+    atomicAdd(J2 + o[4], h * x1 * y1 * jz); atomicAdd(J2 + o[5], h * x2 * y1 * jz);
+    atomicAdd(J2 + o[6], h * x1 * y2 * jz); atomicAdd(J2 + o[7], h * x2 * y2 * jz);
+  }
+
+  template <bool SC>
+  __global__ void __launch_bounds__(128)
+  deposit_current (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox)
+  {
+    const BunchDev& b = *bp;
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false; int i0 = 0, i1 = 0, j0 = 0, j1 = 0, k0 = 0, k1 = 0;
+
+    if (t < n)
+      {
+	const double rpx = P.r[0][t],  rpy = P.r[1][t],  rpz = P.r[2][t];
+	const double rmx = P.rm[0][t], rmy = P.rm[1][t], rmz = P.rm[2][t];
+
+	const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
+			   rpz < b.zp1 && rpz >= b.zp0 );
+	const bool bmf = ( rmx < b.xmax - b.dx && rmx > b.xmin + b.dx && rmy < b.ymax - b.dy && rmy > b.ymin + b.dy &&
+			   rmz < b.zp1 && rmz >= b.zp0 );
+	if (bpf || bmf)
+	  {
+	    const double q = P.q[t];
+	    const int ip = (int) floor( ( rpx - b.xmin ) / b.dx ), jp = (int) floor( ( rpy - b.ymin ) / b.dy ), kp = (int) floor( ( rpz - b.zmin ) / b.dz );
+	    const int im = (int) floor( ( rmx - b.xmin ) / b.dx ), jm = (int) floor( ( rmy - b.ymin ) / b.dy ), km = (int) floor( ( rmz - b.zmin ) / b.dz );
+
+	    /* relay point, fdtd.cpp:80-85 */
+	    const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
+	    const double ry = fmin( min(jm, jp) * b.dy + b.dy + b.ymin, fmax( max(jm, jp) * b.dy + b.ymin, 0.5 * ( rmy + rpy ) ) );
+	    const double rz = fmin( min(km, kp) * b.dz + b.dz + b.zmin, fmax( max(km, kp) * b.dz + b.zmin, 0.5 * ( rmz + rpz ) ) );
+
+	    valid = true;
+	    i0 = 0x7fffffff; j0 = 0x7fffffff; k0 = 0x7fffffff; i1 = j1 = k1 = -1;
+	    if (bpf)
+	      {
+		const long m = (long) ( kp - b.k0 ) * b.Pp + (long) ip * b.N1 + jp;
+		scatter_segment(b, jn, m, q, 0.5 * ( rpx + rx ), 0.5 * ( rpy + ry ), 0.5 * ( rpz + rz ), rpx - rx, rpy - ry, rpz - rz);
+		if (SC)
+		  {
+		    double c;
+		    const double dxp = modf( ( rpx - b.xmin ) / b.dx, &c ), dyp = modf( ( rpy - b.ymin ) / b.dy, &c ), dzp = modf( ( rpz - b.zmin ) / b.dz, &c );
+		    const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
+		    double* R = jn + 3 * (long) b.np * b.Pp + m;
+		    const long N1 = b.N1, Pp = b.Pp;
+		    atomicAdd(R,               q * x1 * y1 * z1); atomicAdd(R + N1,          q * x2 * y1 * z1);
+		    atomicAdd(R + 1,           q * x1 * y2 * z1); atomicAdd(R + N1 + 1,      q * x2 * y2 * z1);
+		    atomicAdd(R + Pp,          q * x1 * y1 * z2); atomicAdd(R + Pp + N1,     q * x2 * y1 * z2);
+		    atomicAdd(R + Pp + 1,      q * x1 * y2 * z2); atomicAdd(R + Pp + N1 + 1, q * x2 * y2 * z2);
+		  }
+		i0 = min(i0, ip); i1 = max(i1, ip + 1); j0 = min(j0, jp); j1 = max(j1, jp + 1); k0 = min(k0, kp - b.k0); k1 = max(k1, kp - b.k0 + 1);
+	      }
+	    if (bmf)
+	      {
+		const long m = (long) ( km - b.k0 ) * b.Pp + (long) im * b.N1 + jm;
+		scatter_segment(b, jn, m, q, 0.5 * ( rmx + rx ), 0.5 * ( rmy + ry ), 0.5 * ( rmz + rz ), rx - rmx, ry - rmy, rz - rmz);
+		i0 = min(i0, im); i1 = max(i1, im + 1); j0 = min(j0, jm); j1 = max(j1, jm + 1); k0 = min(k0, km - b.k0); k1 = max(k1, km - b.k0 + 1);
+	      }
+	  }
+      }
+    warp_box_merge(jbox, valid, i0, i1, j0, j1, k0, k1);
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Screens (solver.cpp:2205-2257).  One thread per particle, loop over screens; a crossing appends a record
+   * { x, y, t, gbx, gby, gbz_lab, particle index, step } to the screen's buffer through an atomic cursor.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(256)
+  screen_cross (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double time_bunch, int nscreens,
+		const double* __restrict__ pos, double* __restrict__ rec, unsigned int* __restrict__ cursor,
+		unsigned int capacity, double step_id)
+  {
+    const BunchDev& b = *bp;
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double xp = P.r[0][t], yp = P.r[1][t], zp = P.r[2][t];
+    const double zr = pmod( zp - b.zmin, b.Lz ) + b.zmin;
+    if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) return;
+    const double xm = P.rm[0][t], ym = P.rm[1][t], zm = P.rm[2][t];
+    const double lzm = b.gamma * ( zm + b.beta * b.c0 * ( time_bunch - b.dt_field + b.dt_shift ) );
+    const double lzp = b.gamma * ( zp + b.beta * b.c0 * ( time_bunch + b.dt_shift ) );
+    for (int s = 0; s < nscreens; s++)
+      {
+	const double lzs = pos[s];
+	if (lzm >= lzs) continue;
+	if (lzp <  lzs) continue;
+	const unsigned int slot = atomicAdd(&cursor[s], 1u);
+	if (slot >= capacity) continue;
+	double* r = rec + ( (size_t) s * capacity + slot ) * 8;
+	const double fr = ( lzs - lzm ) / ( lzp - lzm );
+	r[0] = xm + fr * ( xp - xm );
+	r[1] = ym + fr * ( yp - ym );
+	const double tm = b.gamma * ( time_bunch + b.dt_shift - b.dt_field + b.beta / b.c0 * zm );
+	const double tp = b.gamma * ( time_bunch + b.dt_shift              + b.beta / b.c0 * zp );
+	r[2] = tm + fr * ( tp - tm );
+	const double gx = P.gb[0][t], gy = P.gb[1][t], gz = P.gb[2][t];
+	r[3] = gx; r[4] = gy;
+	r[5] = b.gamma * ( gz + b.beta * sqrt( 1.0 + ( gx * gx + gy * gy + gz * gz ) ) );
+	r[6] = (double) t; r[7] = step_id;
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Radiated power (radiation.cpp:154-215).  One CTA = PX pixels x MS window slices.  The thread whose slice
+   * owns the current ring slot interpolates E,B between the two z planes, boosts to the lab frame and stores
+   * the 4 values in the ring; every thread then accumulates its share of the length-Nf DFT sums.  Slices are
+   * combined in shared memory in a fixed order and each CTA writes one partial per wavelength; power_finish
+   * adds the partials in order (deterministic) and appends pc * sum to the output row.
+   *
+   * ring layout: fdt[plane][slot][4][npx]   (pixel fastest => coalesced), twiddles ep[l][m] = exp(+i w_l m dt).
+   * ------------------------------------------------------------------------------------------------ */
+  struct PowerDev
+  {
+    int    N, Nl, Nf, npx, ni, nj;          /* planes, wavelengths, window, pixels = ni*nj                  */
+    double pc;
+    double gamma, beta, c0;
+  };
+
+  #define MITHRA_POWER_PX 32
+  #define MITHRA_POWER_MS 8
+
+  template <bool SC>
+  __global__ void __launch_bounds__(MITHRA_POWER_PX * MITHRA_POWER_MS)
+  power_dft (const FieldDev f, const PowerDev pw, const double* __restrict__ anp1, const double* __restrict__ an,
+	     double* __restrict__ fdt, const double2* __restrict__ ep, int plane, int kplane, double dzr, int slot,
+	     double* __restrict__ partial)
+  {
+    __shared__ double red[4][2][MITHRA_POWER_MS][MITHRA_POWER_PX];
+    __shared__ double pix[MITHRA_POWER_PX];
+    const int lp = threadIdx.x % MITHRA_POWER_PX, ms = threadIdx.x / MITHRA_POWER_PX;
+    const int px = blockIdx.x * MITHRA_POWER_PX + lp;
+    const bool live = px < pw.npx;
+    double* ring = fdt + (size_t) plane * pw.Nf * 4 * pw.npx;
+
+    double cur[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (live && (slot % MITHRA_POWER_MS) == ms)
+      {
+	const int i = 2 + px / pw.nj, j = 2 + px % pw.nj;
+	/* fieldEvaluate on mi and mi + N1N0 with the z-end copy rule (planes 0 / np-1)                     */
+	int ka = kplane, kb = kplane + 1;
+	if (ka == 0 && f.rank == 0) ka = 1;
+	if (kb == f.np - 1 && f.rank == f.size - 1) kb = f.np - 2;
+	const EB A = eval_eb_node<SC>(f, anp1, an, i, j, ka);
+	const EB B = eval_eb_node<SC>(f, anp1, an, i, j, kb);
+	const double et0 = ( 1.0 - dzr ) * A.e[0] + dzr * B.e[0];
+	const double et1 = ( 1.0 - dzr ) * A.e[1] + dzr * B.e[1];
+	const double bt0 = ( 1.0 - dzr ) * A.b[0] + dzr * B.b[0];
+	const double bt1 = ( 1.0 - dzr ) * A.b[1] + dzr * B.b[1];
+	cur[0] = pw.gamma * ( et0 + pw.c0 * pw.beta * bt1 );
+	cur[1] = pw.gamma * ( et1 - pw.c0 * pw.beta * bt0 );
+	cur[2] = pw.gamma * ( bt0 - pw.beta / pw.c0 * et1 );
+	cur[3] = pw.gamma * ( bt1 + pw.beta / pw.c0 * et0 );
+	#pragma unroll
+	for (int q = 0; q < 4; q++) ring[( (size_t) slot * 4 + q ) * pw.npx + px] = cur[q];
+      }
+
+    for (int l = 0; l < pw.Nl; l++)
+      {
+	double s[4][2] = { { 0.0, 0.0 }, { 0.0, 0.0 }, { 0.0, 0.0 }, { 0.0, 0.0 } };
+	if (live)
+	  for (int m = ms; m < pw.Nf; m += MITHRA_POWER_MS)
+	    {
+	      const double2 w = ep[(size_t) l * pw.Nf + m];
+	      double v[4];
+	      if (m == slot) { v[0] = cur[0]; v[1] = cur[1]; v[2] = cur[2]; v[3] = cur[3]; }
+	      else
+		{
+		  #pragma unroll
+		  for (int q = 0; q < 4; q++) v[q] = ring[( (size_t) m * 4 + q ) * pw.npx + px];
+		}
+	      /* ew1 += f0 ep; bw1 += f3 em; ew2 += f1 ep; bw2 += f2 em   (em = conj ep)                      */
+	      s[0][0] += v[0] * w.x; s[0][1] += v[0] * w.y;
+	      s[1][0] += v[3] * w.x; s[1][1] -= v[3] * w.y;
+	      s[2][0] += v[1] * w.x; s[2][1] += v[1] * w.y;
+	      s[3][0] += v[2] * w.x; s[3][1] -= v[2] * w.y;
+	    }
+	#pragma unroll
+	for (int q = 0; q < 4; q++) { red[q][0][ms][lp] = s[q][0]; red[q][1][ms][lp] = s[q][1]; }
+	__syncthreads();
+	if (ms == 0)
+	  {
+	    double t[4][2];
+	    #pragma unroll
+	    for (int q = 0; q < 4; q++)
+	      {
+		double re = 0.0, im = 0.0;
+		for (int a = 0; a < MITHRA_POWER_MS; a++) { re += red[q][0][a][lp]; im += red[q][1][a][lp]; }
+		t[q][0] = re; t[q][1] = im;
+	      }
+	    /* Re(ew1 bw1) - Re(ew2 bw2) */
+	    pix[lp] = live ? ( ( t[0][0] * t[1][0] - t[0][1] * t[1][1] ) - ( t[2][0] * t[3][0] - t[2][1] * t[3][1] ) ) : 0.0;
+	  }
+	__syncthreads();
+	if (threadIdx.x == 0)
+	  {
+	    double acc = 0.0;
+	    for (int a = 0; a < MITHRA_POWER_PX; a++) acc += pix[a];
+	    partial[( (size_t) plane * pw.Nl + l ) * gridDim.x + blockIdx.x] = acc;
+	  }
+	__syncthreads();
+      }
+  }
+
+  __global__ void power_finish (const PowerDev pw, const double* __restrict__ partial, int nblocks, double* __restrict__ row)
+  {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pw.N * pw.Nl) return;
+    double acc = 0.0;
+    for (int a = 0; a < nblocks; a++) acc += partial[(size_t) t * nblocks + a];
+    row[t] = pw.pc * acc;
+  }
+}
+
+#endif

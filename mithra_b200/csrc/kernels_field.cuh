@@ -1,0 +1,388 @@
+/* kernels_field.cuh -- field-side sm_100a kernels: the 3-level leap-frog update of A (and phi), the
+ * absorbing boundaries, the current-box clear and the E/B evaluation.
+ *
+ * Arithmetic follows the reference's association order operation by operation and the translation unit is
+ * compiled with -fmad=false, so for identical inputs the potentials are BIT-IDENTICAL to the reference CPU
+ * build (x86-64 g++ -O3 has no FMA contraction either).  Reference formulas:
+ *   interior  : AdvanceField::advance{Magnetic,Scalar}Potential{NSFD,FD}   database.cpp:44-134
+ *   faces     : AdvanceField::advanceBoundary{F,S}                          database.cpp:137-176
+ *   edges     : AdvanceField::advanceEdge{F,S}                              database.cpp:179-229
+ *   corners   : AdvanceField::advanceCorner{F,S}                            database.cpp:232-288
+ *   call sites: FdTd::fieldUpdate                                           fdtd.cpp:231-725
+ *   E/B       : FdTd::fieldEvaluate / FdTdSC::fieldEvaluate                 fdtd.cpp:818-845, fdtdSC.cpp:1110-1141
+ */
+#ifndef MITHRA_KERNELS_FIELD_CUH_
+#define MITHRA_KERNELS_FIELD_CUH_
+
+#include "device_types.cuh"
+
+namespace mithra
+{
+  /* ------------------------------------------------------------------------------------------------
+   * Interior stencil, z-marching register pipeline.
+   *
+   * grid  = ( ceil(P / BX), ceil((np-2) / KC), ncomp ),  block = BX threads.
+   * A thread owns one in-plane position p = i*N1 + j of one component and marches KC planes in +z, keeping
+   * the 5-point cross of the planes k-1, k, k+1 of A^n in registers: each A^n value is loaded once per
+   * thread, in-plane neighbours come out of L1 (they are the centre loads of the neighbouring lanes /
+   * warps of the same CTA).  A^{n-1} and J are streamed (read once), A^{n+1} is streamed out.
+   * J is only read inside the deposit bounding box `jbox`; outside of it the source term is exactly zero.
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool NSFD, int BX, int KC>
+  __global__ void __launch_bounds__(BX)
+  stencil_interior (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+		    const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox)
+  {
+    const int p = blockIdx.x * BX + threadIdx.x;
+    if (p >= f.P) return;
+    const int i = p / f.N1, j = p - i * f.N1;
+    if (i < 1 || i > f.N0 - 2 || j < 1 || j > f.N1 - 2) return;
+
+    const int c  = blockIdx.z;
+    const int ks = 1 + blockIdx.y * KC;
+    const int ke = min(ks + KC, f.np - 1);               /* exclusive                                    */
+    if (ks >= ke) return;
+
+    const long   cb  = (long) c * f.np * f.Pp;
+    const double* A  = an   + cb + p;
+    const double* Am = anm1 + cb + p;
+    const double* Jn = jn   + cb + p;
+    double*       Ap = anp1 + cb + p;
+    const int    N1  = f.N1;
+    const long   Pp  = f.Pp;
+
+    const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
+    const double as = (c < 3) ? f.a[4] : f.a[5];
+    const double alpha = f.alpha, beta = f.beta;
+
+    /* is this column inside the deposit box at all?                                                     */
+    const Box bx = *jbox;
+    const bool inxy = (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+
+    /* planes k-1 (suffix m), k (suffix 0), k+1 (suffix p) of the 5-point cross                          */
+    double cm, c0, cp, xpm, xp0, xpp, xmm, xm0, xmp, ypm, yp0, ypp, ymm, ym0, ymp;
+    {
+      const double* q = A + (long) (ks - 1) * Pp;
+      cm = q[0];
+      if (NSFD) { xpm = q[N1]; xmm = q[-N1]; ypm = q[1]; ymm = q[-1]; }
+      q += Pp;
+      c0 = q[0]; xp0 = q[N1]; xm0 = q[-N1]; yp0 = q[1]; ym0 = q[-1];
+    }
+
+    for (int k = ks; k < ke; k++)
+      {
+	const double* q = A + (long) (k + 1) * Pp;
+	cp = q[0];
+	if (NSFD) { xpp = q[N1]; xmp = q[-N1]; ypp = q[1]; ymp = q[-1]; }
+	const double vm1 = Am[(long) k * Pp];
+	double src = 0.0;
+	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = Jn[(long) k * Pp];
+
+	double r;
+	if (NSFD)
+	  r = a0 * c0 - vm1 + alpha * (
+	      a1 * ( xp0 + xm0 + beta * ( xpp + xpm + xmp + xmm ) ) +
+	      a2 * ( yp0 + ym0 + beta * ( ypp + ypm + ymp + ymm ) ) ) +
+	      a3 * ( cp + cm ) +
+	      as * src;
+	else
+	  r = a0 * c0 - vm1 +
+	      a1 * ( xp0 + xm0 ) +
+	      a2 * ( yp0 + ym0 ) +
+	      a3 * ( cp + cm ) +
+	      as * src;
+	Ap[(long) k * Pp] = r;
+
+	cm = c0; c0 = cp;
+	if (NSFD) { xpm = xp0; xmm = xm0; ypm = yp0; ymm = ym0; xp0 = xpp; xm0 = xmp; yp0 = ypp; ym0 = ymp; }
+	else      { const double* q0 = A + (long) (k + 1) * Pp; xp0 = q0[N1]; xm0 = q0[-N1]; yp0 = q0[1]; ym0 = q0[-1]; }
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Faces.  A+_s = B0 (A-_s + A+_n) + B1 A-_n + B2 (A_s + A_n)
+   *              + B3 (A_{n+t1} + A_{n-t1} + A_{s+t1} + A_{s-t1}) + B4 (same along t2)
+   * s = face node, n = s + dn its inward neighbour; x faces: (t1,t2) = (y,z), y faces: (x,z), z: (x,y).
+   * ------------------------------------------------------------------------------------------------ */
+  __device__ __forceinline__ void face_update (double* __restrict__ ap, const double* __restrict__ a,
+					       const double* __restrict__ am, long s, long dn, long d1, long d2,
+					       const double* B)
+  {
+    const long n = s + dn;
+    ap[s] = B[0] * ( am[s] + ap[n] ) +
+	    B[1] * am[n] +
+	    B[2] * ( a[s] + a[n] ) +
+	    B[3] * ( a[n + d1] + a[n - d1] + a[s + d1] + a[s - d1] ) +
+	    B[4] * ( a[n + d2] + a[n - d2] + a[s + d2] + a[s - d2] );
+  }
+
+  /* grid-stride over all face nodes of all components; faces are enumerated x-, x+, y-, y+, [z-], [z+].  */
+  __global__ void __launch_bounds__(256)
+  boundary_faces (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+		  const double* __restrict__ anm1)
+  {
+    const long nx = (long) (f.N1 - 2) * (f.np - 2);       /* per x face                                  */
+    const long ny = (long) (f.N0 - 2) * (f.np - 2);
+    const long nz = (long) (f.N0 - 2) * (f.N1 - 2);
+    const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
+    const long per = 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0);
+    const long tot = per * f.ncomp;
+    const long N1 = f.N1, Pp = f.Pp;
+
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int  c = (int) (t / per);
+	long       r = t - (long) c * per;
+	const long cb = (long) c * f.np * Pp;
+	double*       ap = anp1 + cb;
+	const double* a  = an   + cb;
+	const double* am = anm1 + cb;
+
+	if (r < 2 * nx)
+	  {
+	    const bool hi = r >= nx; if (hi) r -= nx;
+	    /* j fastest so that a warp walks along a row                                              */
+	    const int k = 1 + (int) (r / (f.N1 - 2)), j = 1 + (int) (r % (f.N1 - 2));
+	    const int i = hi ? f.N0 - 1 : 0;
+	    face_update(ap, a, am, (long) k * Pp + i * N1 + j, hi ? -N1 : N1, 1, Pp, f.bB);
+	    continue;
+	  }
+	r -= 2 * nx;
+	if (r < 2 * ny)
+	  {
+	    const bool hi = r >= ny; if (hi) r -= ny;
+	    const int k = 1 + (int) (r / (f.N0 - 2)), i = 1 + (int) (r % (f.N0 - 2));
+	    const int j = hi ? f.N1 - 1 : 0;
+	    face_update(ap, a, am, (long) k * Pp + i * N1 + j, hi ? -1 : 1, N1, Pp, f.cB);
+	    continue;
+	  }
+	r -= 2 * ny;
+	{
+	  bool hi;
+	  if (zlo && r < nz) hi = false; else { hi = true; if (zlo) r -= nz; }
+	  const int i = 1 + (int) (r / (f.N1 - 2)), j = 1 + (int) (r % (f.N1 - 2));
+	  const int k = hi ? f.np - 1 : 0;
+	  face_update(ap, a, am, (long) k * Pp + i * N1 + j, hi ? -Pp : Pp, N1, 1, f.dB);
+	}
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Edges (second-order truncation only).  For the edge node e with inward neighbours u, v and diagonal d,
+   * running along w:
+   *   A+_e = E0 (A+_u + A-_v) + E1 (A-_u + A+_v) + E2 (A-_e + A+_d) + E3 (A_e + A_u + A_v + A_d)
+   *        + E4 ( sum over {e,u,v,d} at w-1, then at w+1 ) - A-_d
+   * z edges (eE): u = i-neighbour, v = j-neighbour; x edges (fE): u = j, v = k; y edges (gE): u = k, v = i.
+   * ------------------------------------------------------------------------------------------------ */
+  __device__ __forceinline__ void edge_update (double* __restrict__ ap, const double* __restrict__ a,
+					       const double* __restrict__ am, long e, long du, long dv, long dw,
+					       const double* E)
+  {
+    const long u = e + du, v = e + dv, d = e + du + dv;
+    ap[e] = E[0] * ( ap[u] + am[v] ) +
+	    E[1] * ( am[u] + ap[v] ) +
+	    E[2] * ( am[e] + ap[d] ) +
+	    E[3] * ( a[e] + a[u] + a[v] + a[d] ) +
+	    E[4] * ( a[e - dw] + a[u - dw] + a[v - dw] + a[d - dw] + a[e + dw] + a[u + dw] + a[v + dw] + a[d + dw] ) -
+	    am[d];
+  }
+
+  __global__ void __launch_bounds__(256)
+  boundary_edges (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+		  const double* __restrict__ anm1)
+  {
+    const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
+    const long nze = 4L * (f.np - 2);
+    const int  nends = (zlo ? 1 : 0) + (zhi ? 1 : 0);
+    const long nxe = 2L * nends * (f.N0 - 2);
+    const long nye = 2L * nends * (f.N1 - 2);
+    const long per = nze + nxe + nye;
+    const long tot = per * f.ncomp;
+    const long N1 = f.N1, Pp = f.Pp;
+
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int  c = (int) (t / per);
+	long       r = t - (long) c * per;
+	const long cb = (long) c * f.np * Pp;
+	double*       ap = anp1 + cb;
+	const double* a  = an   + cb;
+	const double* am = anm1 + cb;
+
+	if (r < nze)
+	  {
+	    const int q = (int) (r & 3); const int k = 1 + (int) (r >> 2);
+	    const bool ihi = q & 1, jhi = q & 2;
+	    const long e = (long) k * Pp + (ihi ? f.N0 - 1 : 0) * N1 + (jhi ? f.N1 - 1 : 0);
+	    edge_update(ap, a, am, e, ihi ? -N1 : N1, jhi ? -1 : 1, Pp, f.eE);
+	    continue;
+	  }
+	r -= nze;
+	if (r < nxe)
+	  {
+	    /* x edges: enumerate (end, jhi, i)                                                          */
+	    const long per_end = 2L * (f.N0 - 2);
+	    int end = (int) (r / per_end); r -= end * per_end;
+	    const bool khi = zlo ? (end == 1) : true;
+	    const bool jhi = r >= (f.N0 - 2); if (jhi) r -= (f.N0 - 2);
+	    const int i = 1 + (int) r;
+	    const long e = (long) (khi ? f.np - 1 : 0) * Pp + i * N1 + (jhi ? f.N1 - 1 : 0);
+	    edge_update(ap, a, am, e, jhi ? -1 : 1, khi ? -Pp : Pp, N1, f.fE);
+	    continue;
+	  }
+	r -= nxe;
+	{
+	  const long per_end = 2L * (f.N1 - 2);
+	  int end = (int) (r / per_end); r -= end * per_end;
+	  const bool khi = zlo ? (end == 1) : true;
+	  const bool ihi = r >= (f.N1 - 2); if (ihi) r -= (f.N1 - 2);
+	  const int j = 1 + (int) r;
+	  const long e = (long) (khi ? f.np - 1 : 0) * Pp + (ihi ? f.N0 - 1 : 0) * N1 + j;
+	  edge_update(ap, a, am, e, khi ? -Pp : Pp, ihi ? -N1 : N1, 1, f.gE);
+	}
+      }
+  }
+
+  /* Corners: A+_c = -[ h16 A_c + h8 A-_c + sum_{n=1..7} ( h_n A+_n + h16 A_n + h_{8+n} A-_n ) ] / h0,
+   * n over the inward neighbours in the order (i), (j), (k), (ij), (ik), (jk), (ijk).                    */
+  __global__ void boundary_corners (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+				    const double* __restrict__ anm1)
+  {
+    const int t = threadIdx.x;                         /* 8 corners x ncomp threads                        */
+    if (t >= 8 * f.ncomp) return;
+    const int c = t >> 3, q = t & 7;
+    const bool ihi = q & 1, jhi = q & 2, khi = q & 4;
+    if (!khi && f.rank != 0) return;
+    if ( khi && f.rank != f.size - 1) return;
+    const long N1 = f.N1, Pp = f.Pp;
+    const long cb = (long) c * f.np * Pp;
+    double*       ap = anp1 + cb;
+    const double* a  = an   + cb;
+    const double* am = anm1 + cb;
+    const long m  = (long) (khi ? f.np - 1 : 0) * Pp + (ihi ? f.N0 - 1 : 0) * N1 + (jhi ? f.N1 - 1 : 0);
+    const long si = ihi ? -N1 : N1, sj = jhi ? -1 : 1, sk = khi ? -Pp : Pp;
+    const long nb[7] = { m + si, m + sj, m + sk, m + si + sj, m + si + sk, m + sj + sk, m + si + sj + sk };
+    const double* h = f.hC;
+    double s = a[m] * h[16] + am[m] * h[8];
+    #pragma unroll
+    for (int n = 0; n < 7; n++)
+      {
+	s = s + ap[nb[n]] * h[1 + n];
+	s = s + a [nb[n]] * h[16];
+	s = s + am[nb[n]] * h[9 + n];
+      }
+    ap[m] = - s / h[0];
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Clear the deposit box of J (FdTd::currentReset, fdtd.cpp:23-32, restricted to the nodes that can be
+   * non-zero) and leave the box empty for the next deposit.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(256)
+  clear_current_box (const FieldDev f, double* __restrict__ jn, Box* __restrict__ jbox, unsigned int* __restrict__ done)
+  {
+    const Box b = *jbox;
+    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
+    if (ni > 0 && nj > 0 && nk > 0)
+      {
+	const long per = (long) ni * nj * nk, tot = per * f.ncomp;
+	for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+	  {
+	    const int c = (int) (t / per); long r = t - (long) c * per;
+	    const int k = b.lo[2] + (int) (r / ((long) ni * nj)); r -= (long) (k - b.lo[2]) * ni * nj;
+	    const int i = b.lo[0] + (int) (r / nj), j = b.lo[1] + (int) (r % nj);
+	    jn[fidx(f.Pp, f.np, f.N1, c, k, i, j)] = 0.0;
+	  }
+      }
+    /* the last block to finish empties the box                                                          */
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+	__threadfence();
+	const unsigned int prev = atomicAdd(done, 1u);
+	if (prev == gridDim.x - 1)
+	  {
+	    *done = 0u;
+	    jbox->lo[0] = jbox->lo[1] = jbox->lo[2] = 0x7fffffff;
+	    jbox->hi[0] = jbox->hi[1] = jbox->hi[2] = -1;
+	  }
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * E / B evaluation at one node (fdtd.cpp:818-845; fdtdSC.cpp:1110-1141), including the float roundings of
+   * FieldVector<float>::dv / mdv (fieldvector.h:86-108): E is rounded to float twice (three times with phi).
+   * ------------------------------------------------------------------------------------------------ */
+  struct EB { float e[3]; float b[3]; };
+
+  template <bool SC>
+  __device__ __forceinline__ EB eval_eb_node (const FieldDev& f, const double* __restrict__ anp1,
+					      const double* __restrict__ an, int i, int j, int k)
+  {
+    const long N1 = f.N1, Pp = f.Pp;
+    const long cs = (long) f.np * Pp;                    /* component stride                              */
+    const long m  = (long) k * Pp + (long) i * N1 + j;
+    const double mdt = - f.dt;
+    EB o;
+    #pragma unroll
+    for (int c = 0; c < 3; c++)
+      {
+	float e = (float) ( anp1[c * cs + m] / mdt );
+	e = (float) ( (double) e - an[c * cs + m] / mdt );
+	o.e[c] = e;
+      }
+    if (SC)
+      {
+	const double* fn = an + 3 * cs;
+	o.e[0] = (float) ( (double) o.e[0] - ( fn[m + N1] - fn[m - N1] ) / f.dx2 );
+	o.e[1] = (float) ( (double) o.e[1] - ( fn[m + 1 ] - fn[m - 1 ] ) / f.dy2 );
+	o.e[2] = (float) ( (double) o.e[2] - ( fn[m + Pp] - fn[m - Pp] ) / f.dz2 );
+      }
+    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs;
+    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
+    o.b[0] = (float) ( 0.5 * (
+	( az[m + 1 ] - az[m - 1 ] ) / f.dy2 -
+	( ay[m + Pp] - ay[m - Pp] ) / f.dz2 +
+	( pz[m + 1 ] - pz[m - 1 ] ) / f.dy2 -
+	( py[m + Pp] - py[m - Pp] ) / f.dz2 ) );
+    o.b[1] = (float) ( 0.5 * (
+	( ax[m + Pp] - ax[m - Pp] ) / f.dz2 -
+	( az[m + N1] - az[m - N1] ) / f.dx2 +
+	( px[m + Pp] - px[m - Pp] ) / f.dz2 -
+	( pz[m + N1] - pz[m - N1] ) / f.dx2 ) );
+    o.b[2] = (float) ( 0.5 * (
+	( ay[m + N1] - ay[m - N1] ) / f.dx2 -
+	( ax[m + 1 ] - ax[m - 1 ] ) / f.dy2 +
+	( py[m + N1] - py[m - N1] ) / f.dx2 -
+	( px[m + 1 ] - px[m - 1 ] ) / f.dy2 ) );
+    return o;
+  }
+
+  /* Evaluate E/B on every node of `box` (node indices, already clamped to 1..N-2 transversally).  On the
+   * global z ends plane 0 / np-1 take the values of plane 1 / np-2 (fdtd.cpp:754-773).                 */
+  template <bool SC>
+  __global__ void __launch_bounds__(256)
+  eval_eb_box (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
+	       float4* __restrict__ eb, const Box* __restrict__ boxp)
+  {
+    const Box b = *boxp;
+    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
+    if (ni <= 0 || nj <= 0 || nk <= 0) return;
+    const long tot = (long) ni * nj * nk;
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	long r = t;
+	const int k = b.lo[2] + (int) (r / ((long) ni * nj)); r -= (long) (k - b.lo[2]) * ni * nj;
+	const int i = b.lo[0] + (int) (r / nj), j = b.lo[1] + (int) (r % nj);
+	int ke = k;
+	if (k == 0)        { if (f.rank != 0)          continue; ke = 1; }
+	if (k == f.np - 1) { if (f.rank != f.size - 1) continue; ke = f.np - 2; }
+	const EB o = eval_eb_node<SC>(f, anp1, an, i, j, ke);
+	const long m = (long) k * f.P + (long) i * f.N1 + j;
+	eb[2 * m]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
+	eb[2 * m + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+      }
+  }
+}
+
+#endif
