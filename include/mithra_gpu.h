@@ -175,10 +175,20 @@ int mithra_gpu_download_fields (MithraGpu* h, double* anp1, double* an, double* 
 /* en_, bn_ as float[.][3]; nodes never evaluated in this step hold 0; mask (may be NULL) flags evaluated nodes. */
 int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsigned char* mask);
 
+/* Solver::initializeField, solver.cpp:828-839: an_, anm1_ = Seed::fields(node, time_ / timem1_) inside the total-field
+ * box; no-op without a seed. Call after mithra_gpu_set_time.                                          */
+int mithra_gpu_seed_initial (MithraGpu* h);
+
 /* chargeVectorn_ (solver.h:271). */
 int mithra_gpu_upload_particles   (MithraGpu* h, const double* aos11, size_t n);
 int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_t capacity, size_t* n);
 int mithra_gpu_num_particles      (MithraGpu* h, size_t* n);
+
+/* Particle-to-cell assignment computed on the device with the arithmetic of the push (solver.cpp:1440-1469:
+ * push_m[n] = gather cell (k-k0) N0 N1 + i N1 + j, or -1 when the particle gathers no mesh field) and of the
+ * deposit (fdtd.cpp:70-77: ijk6[n] = ip, jp, kp, im, jm, km).  Either pointer may be NULL.  Diagnostic: this
+ * is what the bit-exact index parity is checked on.                                                   */
+int mithra_gpu_particle_cells (MithraGpu* h, long* push_m, int* ijk6, size_t capacity);
 
 /* time_, timeBunch_, nTime_ (solver.h:265-275). */
 int mithra_gpu_set_time (MithraGpu* h, double time, double time_bunch, unsigned int n_time);

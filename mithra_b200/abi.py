@@ -76,8 +76,9 @@ class Counters(C.Structure):
 # every symbol include/mithra_gpu.h declares (checked by tests/test_abi.py without touching a GPU)
 SYMBOLS = (
     "mithra_gpu_last_error", "mithra_gpu_abi_version", "mithra_gpu_device_count", "mithra_gpu_create",
-    "mithra_gpu_destroy", "mithra_gpu_upload_fields", "mithra_gpu_download_fields", "mithra_gpu_download_eb",
+    "mithra_gpu_destroy", "mithra_gpu_seed_initial", "mithra_gpu_upload_fields", "mithra_gpu_download_fields", "mithra_gpu_download_eb",
     "mithra_gpu_upload_particles", "mithra_gpu_download_particles", "mithra_gpu_num_particles",
+    "mithra_gpu_particle_cells",
     "mithra_gpu_set_time", "mithra_gpu_get_time", "mithra_gpu_field_update", "mithra_gpu_bunch_update",
     "mithra_gpu_screen_profile", "mithra_gpu_power_sample", "mithra_gpu_field_shift", "mithra_gpu_current_reset",
     "mithra_gpu_current_update", "mithra_gpu_current_communicate", "mithra_gpu_advance_time", "mithra_gpu_step",
@@ -108,10 +109,11 @@ def load():
     lib.mithra_gpu_upload_particles.argtypes = [vp, dp, C.c_size_t]
     lib.mithra_gpu_download_particles.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mithra_gpu_num_particles.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.mithra_gpu_particle_cells.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_int), C.c_size_t]
     lib.mithra_gpu_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_uint]
     lib.mithra_gpu_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_uint)]
     for name in ("field_update", "bunch_update", "screen_profile", "power_sample", "field_shift", "current_reset",
-                 "current_update", "current_communicate", "advance_time", "synchronize"):
+                 "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial"):
         getattr(lib, "mithra_gpu_" + name).argtypes = [vp]
     lib.mithra_gpu_step.argtypes = [vp, C.c_int]
     lib.mithra_gpu_step_timed.argtypes = [vp, C.c_int, fp]
@@ -188,6 +190,23 @@ class GpuSolver:
         self._check(self.lib.mithra_gpu_download_particles(self.h, _dptr(out), n.value, C.byref(n)))
         return out
 
+    def num_particles(self):
+        n = C.c_size_t()
+        self._check(self.lib.mithra_gpu_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def push_cells(self):
+        n = self.num_particles()
+        out = np.empty(n, dtype=np.int64)
+        self._check(self.lib.mithra_gpu_particle_cells(self.h, out.ctypes.data_as(C.POINTER(C.c_long)), None, n))
+        return out
+
+    def deposit_cells(self):
+        n = self.num_particles()
+        out = np.empty((n, 6), dtype=np.int32)
+        self._check(self.lib.mithra_gpu_particle_cells(self.h, None, out.ctypes.data_as(C.POINTER(C.c_int)), n))
+        return out
+
     def set_time(self, time, time_bunch, n_time):
         self._check(self.lib.mithra_gpu_set_time(self.h, time, time_bunch, n_time))
 
@@ -223,6 +242,9 @@ class GpuSolver:
 
     def advanceTime(self):
         self._check(self.lib.mithra_gpu_advance_time(self.h))
+
+    def seedInitial(self):
+        self._check(self.lib.mithra_gpu_seed_initial(self.h))
 
     def step(self, nsteps=1):
         self._check(self.lib.mithra_gpu_step(self.h, nsteps))

@@ -468,6 +468,17 @@ extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsig
   return 0;
 }
 
+extern "C" int mithra_gpu_seed_initial (MithraGpu* h)
+{
+  USE(h);
+  if (!h->d_seed) return 0;
+  seed_initial_kernel<<<h->num_sms * 8, 128, 0, h->stream>>>(h->d_seed, h->fd, h->A[h->in], h->A[h->im1], h->time, h->timem1);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 static int refresh_particle_box (MithraGpu* h)
 {
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
@@ -507,6 +518,23 @@ extern "C" int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_
     if (np) CU(cudaMemcpy(soa.data() + (size_t) c * np, h->pstore + (size_t) c * h->pcap, np * sizeof(double), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < np; i++)
     for (int c = 0; c < 11; c++) aos11[i * 11 + c] = soa[(size_t) c * np + i];
+  return 0;
+}
+
+extern "C" int mithra_gpu_particle_cells (MithraGpu* h, long* push_m, int* ijk6, size_t capacity)
+{
+  USE(h);
+  if (capacity < h->pn) return fail("mithra_gpu_particle_cells: capacity %zu < %zu particles", capacity, h->pn);
+  if (h->pn == 0) return 0;
+  long* dm = 0; int* dd = 0;
+  if (push_m) CU(cudaMalloc(&dm, h->pn * sizeof(long)));
+  if (ijk6)   CU(cudaMalloc(&dd, h->pn * 6 * sizeof(int)));
+  particle_cells<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, dm, dd);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaStreamSynchronize(h->stream));
+  if (push_m) { CU(cudaMemcpy(push_m, dm, h->pn * sizeof(long), cudaMemcpyDeviceToHost)); cudaFree(dm); }
+  if (ijk6)   { CU(cudaMemcpy(ijk6, dd, h->pn * 6 * sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(dd); }
   return 0;
 }
 

@@ -71,6 +71,45 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
+   * Particle-to-cell assignment exactly as the push (solver.cpp:1440-1469) and the deposit (fdtd.cpp:70-77)
+   * compute it, written out for the bit-exactness check of the parity tests.
+   * push_m[t]  = gather cell m = (k-k0) P + i N1 + j (reference node numbering), -1 when the particle gathers
+   *              no mesh field in this sub-step;   dep[t][6] = ip, jp, kp, im, jm, km.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(256)
+  particle_cells (const BunchDev* __restrict__ bp, ParticlesDev P, long n, long* __restrict__ push_m, int* __restrict__ dep)
+  {
+    const BunchDev& b = *bp;
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
+    if (push_m)
+      {
+	long m = -1;
+	const double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;
+	if ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) && P.e[t] == 1.0 &&
+	     x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zp1 && z >= b.zp0 )
+	  {
+	    double d1;
+	    modf( ( x - b.xmin ) / b.dx, &d1 ); const int i = (int) d1;
+	    modf( ( y - b.ymin ) / b.dy, &d1 ); const int j = (int) d1;
+	    modf( ( z - b.zmin ) / b.dz, &d1 ); const int k = (int) d1;
+	    m = (long) ( k - b.k0 ) * b.P + (long) i * b.N1 + j;
+	  }
+	push_m[t] = m;
+      }
+    if (dep)
+      {
+	dep[6 * t + 0] = (int) floor( ( x - b.xmin ) / b.dx );
+	dep[6 * t + 1] = (int) floor( ( y - b.ymin ) / b.dy );
+	dep[6 * t + 2] = (int) floor( ( z - b.zmin ) / b.dz );
+	dep[6 * t + 3] = (int) floor( ( P.rm[0][t] - b.xmin ) / b.dx );
+	dep[6 * t + 4] = (int) floor( ( P.rm[1][t] - b.ymin ) / b.dy );
+	dep[6 * t + 5] = (int) floor( ( P.rm[2][t] - b.zmin ) / b.dz );
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Push: `nsub` consecutive sub-steps of Solver::bunchUpdate for every particle (solver.cpp:1437-1549).
    * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312).
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.

@@ -182,35 +182,7 @@ class Oracle:
         return np.ctypeslib.as_array(self.lib.oracle_screen_data(self.o, s), shape=(n, 6)).copy()
 
 
-# ------------------------------------------------------------------------------------------------------
-# ref_dump record files
-
-_DT = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.uint8}
-
-
-def read_records(fn):
-    out = {}
-    with open(fn, "rb") as f:
-        while True:
-            h = f.read(48)
-            if len(h) < 48:
-                break
-            name = h.split(b"\0")[0].decode()
-            t = int(np.frombuffer(f.read(4), np.int32)[0])
-            n = int(np.frombuffer(f.read(8), np.int64)[0])
-            out[name] = np.frombuffer(f.read(n * np.dtype(_DT[t]).itemsize), _DT[t]).copy()
-    return out
-
-
-def write_records(fn, rec):
-    code = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int32): 2, np.dtype(np.uint8): 3}
-    with open(fn, "wb") as f:
-        for name, a in rec.items():
-            a = np.ascontiguousarray(a)
-            f.write(name.encode().ljust(48, b"\0"))
-            f.write(np.int32(code[a.dtype]).tobytes())
-            f.write(np.int64(a.size).tobytes())
-            f.write(a.tobytes())
+from mithra_b200.meta import read_records, write_records, params_from_meta  # noqa: E402,F401
 
 
 def have_reference():
@@ -226,51 +198,3 @@ def run_ref_dump(job, prefix, nsteps, full_at=(), phases_at=None, cwd=None):
     subprocess.check_call(cmd, cwd=cwd, stdout=subprocess.DEVNULL)
 
 
-def params_from_meta(meta, max_particles=0):
-    """Build the C-ABI parameter block from a ref_dump meta record (the reference's own initialize() results)."""
-    g = lambda k: meta[k][0]
-    p = abi.Params()
-    p.abi_version = abi.ABI_VERSION
-    p.N0, p.N1, p.N2, p.np, p.k0 = int(g("N0")), int(g("N1")), int(g("N2")), int(g("np")), int(g("k0"))
-    p.rank, p.size = int(g("rank")), int(g("size"))
-    p.dx, p.dy, p.dz, p.dt = g("dx"), g("dy"), g("dz"), g("dt")
-    p.xmin, p.xmax, p.ymin, p.ymax, p.zmin, p.zmax = g("xmin"), g("xmax"), g("ymin"), g("ymax"), g("zmin"), g("zmax")
-    p.zp[0], p.zp[1] = meta["zp"]
-    p.Lz = g("Lz")
-    p.solver, p.space_charge, p.truncation_order = int(g("solver")), int(g("spaceCharge")), int(g("truncationOrder"))
-    for k in ("a", "bB", "cB", "dB", "eE", "fE", "gE", "hC"):
-        for i, v in enumerate(meta[k]):
-            getattr(p, k)[i] = v
-    p.alpha, p.beta_nsfd = g("alpha"), g("betaNSFD")
-    p.c0, p.gamma, p.beta, p.dt_shift = g("c0"), g("gamma"), g("beta"), g("dtShift")
-    p.dt_bunch, p.n_update_bunch = g("dtBunch"), int(round(g("nUpdateBunch")))
-    p.r1, p.r2, p.dtb = g("r1"), g("r2"), g("dtb")
-    p.n_undulators = int(g("nUndulators"))
-    for u in range(p.n_undulators):
-        s = meta["und%d.static" % u]
-        U = p.undulator[u]
-        U.k, U.lu, U.rb, U.length, U.dist, U.theta, U.type = s[0], s[1], s[2], s[3], s[4], s[5], int(s[6])
-        o = meta["und%d.optical" % u]
-        U.beam.seed_type = int(s[7])
-        for c in range(3):
-            U.beam.position[c], U.beam.direction[c], U.beam.polarization[c] = o[c], o[3 + c], o[6 + c]
-        U.beam.amplitude = o[9]
-        U.beam.radius[0], U.beam.radius[1], U.beam.l, U.beam.zR[0], U.beam.zR[1] = o[11], o[12], o[13], o[14], o[15]
-        sg = meta["und%d.signal" % u]
-        U.beam.signal.type, U.beam.signal.t0, U.beam.signal.s, U.beam.signal.f0 = int(sg[0]), sg[1], sg[2], sg[3]
-        U.beam.signal.nR, U.beam.signal.cep = int(sg[4]), sg[5]
-    if "power0.N" in meta:
-        w = p.power
-        w.enabled, w.N, w.Nl, w.Nf, w.pc = 1, int(g("power0.N")), int(g("power0.Nl")), int(g("power0.Nf")), g("power0.pc")
-        for i, v in enumerate(meta["power0.z"]):
-            w.z[i] = v
-        for i, v in enumerate(meta["power0.w"]):
-            w.w[i] = v
-    if "screen0.pos" in meta:
-        s = p.screens
-        s.enabled, s.N = 1, len(meta["screen0.pos"])
-        for i, v in enumerate(meta["screen0.pos"]):
-            s.pos[i] = v
-    p.max_particles = max_particles
-    p.device = -1
-    return p

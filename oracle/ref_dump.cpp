@@ -7,11 +7,14 @@
  * the solver state to disk at chosen points. No reference file is modified or copied; every Solver member
  * is public (solver.h:23-345), which is what makes this possible.
  *
- * usage: ref_dump <job-file> <out-prefix> <nsteps> [--full-at a,b,c] [--phases-at s] [--quiet]
+ * usage: ref_dump <job-file> <out-prefix> <nsteps> [--full-at a,b,c] [--phases-at s] [--quiet] [--bench W]
  *   <nsteps>          number of field steps of the second while loop to run (0 = only initialise)
  *   --full-at LIST    write <prefix>.full<step>.bin holding the state at the START of field step <step>
  *                     (step 0 = right after initialize()); step == nsteps is allowed (= final state)
  *   --phases-at s     additionally write <prefix>.phase<s>.bin with the intermediate arrays of step s
+ *   --bench W         CPU-baseline mode (any number of mini-MPI ranks, MINIMPI_NP): no state dumps; W untimed
+ *                     warm-up steps, then <nsteps> field steps timed between two MPI_Barriers; rank 0 prints one
+ *                     line "BENCH {json}" with the wall seconds, the global node count and the particle count
  *   always written:   <prefix>.meta.bin (scalars, coefficient tables) and <prefix>.power.bin (pG per step)
  *
  * Record format (little endian): repeated { char name[48]; int32 dtype (0=f64,1=f32,2=i32,3=u8);
@@ -19,6 +22,7 @@
  */
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -119,6 +123,21 @@ namespace
     w.f64("particles", p.empty() ? 0 : &p[0], (int64_t) p.size());
   }
 
+  /* Seed, Undulator and ExtField carry the same beam members (classes.h:208-262, 303-352, 383-427). */
+  template <class T>
+  void dumpBeam (Writer& w, const std::string& key, const T& b)
+  {
+    double o[18] = { (double) b.seedType_, b.position_[0], b.position_[1], b.position_[2], b.direction_[0], b.direction_[1], b.direction_[2],
+		     b.polarization_[0], b.polarization_[1], b.polarization_[2], b.amplitude_,
+		     b.radius_.size() > 0 ? b.radius_[0] : 0.0, b.radius_.size() > 1 ? b.radius_[1] : 0.0, b.l_,
+		     b.zR_.size() > 0 ? b.zR_[0] : 0.0, b.zR_.size() > 1 ? b.zR_[1] : 0.0,
+		     b.order_.size() > 0 ? (double) b.order_[0] : 0.0, b.order_.size() > 1 ? (double) b.order_[1] : 0.0 };
+    w.f64((key + "beam").c_str(), o, 18);
+    double g[8] = { (double) b.signal_.signalType_, b.signal_.t0_, b.signal_.s_, b.signal_.f0_, (double) b.signal_.nR_, b.signal_.cep_,
+		    b.signal_.sigmaInvG_.size() > 0 ? b.signal_.sigmaInvG_[0] : 0.0, b.signal_.sigmaInvG_.size() > 1 ? b.signal_.sigmaInvG_[1] : 0.0 };
+    w.f64((key + "sig").c_str(), g, 8);
+  }
+
   std::set<int> parseList (const char* a)
   {
     std::set<int> out; std::stringstream ss(a); std::string tok;
@@ -134,12 +153,13 @@ int main (int argc, char* argv[])
   if (argc < 4) { fprintf(stderr, "usage: ref_dump <job> <out-prefix> <nsteps> [--full-at a,b] [--phases-at s] [--quiet]\n"); return 2; }
   const std::string prefix = argv[2];
   const int nsteps = atoi(argv[3]);
-  std::set<int> fullAt; int phasesAt = -1; bool quiet = false;
+  std::set<int> fullAt; int phasesAt = -1; bool quiet = false; int benchWarm = -1;
   for (int a = 4; a < argc; a++)
     {
       if      (!strcmp(argv[a], "--full-at")   && a + 1 < argc) fullAt = parseList(argv[++a]);
       else if (!strcmp(argv[a], "--phases-at") && a + 1 < argc) phasesAt = atoi(argv[++a]);
       else if (!strcmp(argv[a], "--quiet")) quiet = true;
+      else if (!strcmp(argv[a], "--bench")     && a + 1 < argc) benchWarm = atoi(argv[++a]);
     }
 
   std::streambuf* coutBuf = std::cout.rdbuf();
@@ -164,6 +184,7 @@ int main (int argc, char* argv[])
   s.initialize();
 
   /* ---- meta ------------------------------------------------------------------------------------- */
+  if (s.rank_ == 0)
   {
     Writer w(prefix + ".meta.bin");
     w.i("N0", s.N0_); w.i("N1", s.N1_); w.i("N2", s.N2_); w.i("np", s.np_); w.i("k0", s.k0_);
@@ -184,6 +205,10 @@ int main (int argc, char* argv[])
     w.d("dv", s.uc_.dv); w.d("rc", s.uc_.rc);
     w.d("r1", s.ub_.r1); w.d("r2", s.ub_.r2); w.d("dtb", s.ub_.dtb);
     w.d("seedAmplitude", seed.amplitude_);
+    dumpBeam(w, "seed.", seed);
+    w.i("nExtFields", (int) extField.size());
+    for (size_t u = 0; u < extField.size(); u++)
+      { std::ostringstream k; k << "ext" << u << "."; dumpBeam(w, k.str(), extField[u]); }
     w.i("nUndulators", (int) undulator.size());
     for (size_t u = 0; u < undulator.size(); u++)
       {
@@ -198,6 +223,7 @@ int main (int argc, char* argv[])
 	w.f64((k.str() + "optical").c_str(), o, 16);
 	double g[6] = { (double) U.signal_.signalType_, U.signal_.t0_, U.signal_.s_, U.signal_.f0_, (double) U.signal_.nR_, U.signal_.cep_ };
 	w.f64((k.str() + "signal").c_str(), g, 6);
+	dumpBeam(w, k.str(), U);
       }
     w.i("nFEL", (int) FEL.size());
     for (size_t jf = 0; jf < FEL.size(); jf++)
@@ -231,8 +257,15 @@ int main (int argc, char* argv[])
     }
 
   /* ---- second loop of solve(): solver.cpp:1300-1414 --------------------------------------------- */
-  for (int step = 0; step < nsteps; step++)
+  const bool bench = benchWarm >= 0;
+  std::chrono::steady_clock::time_point tBegin;
+  long nPushes = 0;
+  if (bench && benchWarm == 0) { MPI_Barrier(MPI_COMM_WORLD); tBegin = std::chrono::steady_clock::now(); }
+  const int nLoop = bench ? nsteps + benchWarm : nsteps;
+  for (int step = 0; step < nLoop; step++)
     {
+      if (bench && benchWarm > 0 && step == benchWarm) { MPI_Barrier(MPI_COMM_WORLD); tBegin = std::chrono::steady_clock::now(); nPushes = 0; }
+      if (bench) nPushes += (long) s.chargeVectorn_.size() * (long) s.nUpdateBunch_;
       if (fullAt.count(step)) dumpFull(prefix, step, s, sc);
       Writer* ph = 0;
       if (step == phasesAt)
@@ -305,8 +338,25 @@ int main (int argc, char* argv[])
 
       s.timem1_ += mesh.timeStep_; s.time_ += mesh.timeStep_; s.timep1_ += mesh.timeStep_; ++s.nTime_;
     }
+  if (bench)
+    {
+      MPI_Barrier(MPI_COMM_WORLD);
+      const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - tBegin).count();
+      double mine[2] = { (double) nPushes, (double) s.chargeVectorn_.size() }, all[2] = { 0.0, 0.0 };
+      MPI_Reduce(mine, all, 2, MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+      if (s.rank_ == 0)
+	{
+	  if (quiet) std::cout.rdbuf(coutBuf);
+	  printf("BENCH {\"seconds\": %.6f, \"steps\": %d, \"warmup\": %d, \"ranks\": %d, \"N0\": %d, \"N1\": %d, \"N2\": %d, "
+		 "\"pushes\": %.0f, \"particles\": %.0f, \"sub_steps\": %d, \"space_charge\": %d}\n",
+		 sec, nsteps, benchWarm, s.size_, s.N0_, s.N1_, s.N2_, all[0], all[1], (int) s.nUpdateBunch_, sc ? 1 : 0);
+	  fflush(stdout);
+	  if (quiet) std::cout.rdbuf(sink.rdbuf());
+	}
+    }
   if (fullAt.count(nsteps)) dumpFull(prefix, nsteps, s, sc);
 
+  if (s.rank_ == 0)
   {
     Writer w(prefix + ".power.bin");
     w.i("nsteps", nsteps);

@@ -1,0 +1,106 @@
+"""The CPU oracle (oracle/mithra_oracle.c) against the golden fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the CUDA path is then checked against the oracle.
+
+Potentials, currents and cell indices must be bit-identical (same association order, -ffp-contract=off, same libm);
+so are particles, power and E/B, because oracle and reference run on the same host libm."""
+import numpy as np
+import pytest
+
+from oracle import binding
+from tests import helpers
+
+
+@pytest.fixture(scope="module", params=helpers.JOBS)
+def run(request):
+    """Run the oracle for the 100 field steps of the fixture once per job, keeping the checkpoints."""
+    job = request.param
+    p, meta, g = helpers.params_for(job)
+    o = binding.Oracle(p)
+    helpers.start_from_golden(o, g)
+    keep = {"job": job, "g": g, "p": p, "start": o.download_fields(("an", "anm1"))}
+    for step in range(100):
+        if step == 50:
+            keep["p50"] = o.download_particles()
+        if step == 99:
+            o.fieldUpdate()
+            names = ("anp1", "fnp1") if p.space_charge else ("anp1",)
+            keep["ph_np1"] = o.download_fields(names)
+            o.bunchUpdate()
+            keep["ph_particles"] = o.download_particles()
+            o.screenProfile()
+            o.powerSample()
+            keep["ph_eb"] = o.download_eb()
+            o.fieldShift()
+            o.currentReset()
+            o.currentUpdate()
+            keep["ph_j"] = o.download_fields(names)
+            o.advanceTime()
+        else:
+            helpers.solve_step(o)
+    names = ("anp1", "an", "anm1") + (("fnp1", "fn", "fnm1") if p.space_charge else ())
+    keep["end"] = o.download_fields(names)
+    keep["p100"] = o.download_particles()
+    keep["power"] = o.fetch_power()
+    keep["screens"] = [o.fetch_screen(s) for s in range(p.screens.N)] if p.screens.enabled else []
+    o.close()
+    return keep
+
+
+def _check_array(g, key, step, arr, ncomp):
+    a = arr.reshape(-1, ncomp)
+    np.testing.assert_array_equal(a[g["idx"]], g["%s_s%s" % (key, step)], err_msg="%s step %s samples" % (key, step))
+    np.testing.assert_array_equal(helpers.stats(a), g["%s_n%s" % (key, step)], err_msg="%s step %s sums" % (key, step))
+
+
+def test_initial_fields(run):
+    g = run["g"]
+    _check_array(g, "an", 0, run["start"]["an"], 3)
+    _check_array(g, "anm1", 0, run["start"]["anm1"], 3)
+
+
+def test_particles_mid_run(run):
+    np.testing.assert_array_equal(run["p50"], run["g"]["p50"])
+
+
+def test_final_potentials_and_current(run):
+    g, e = run["g"], run["end"]
+    _check_array(g, "an", 100, e["an"], 3)
+    _check_array(g, "anm1", 100, e["anm1"], 3)
+    _check_array(g, "jn", 100, e["anp1"], 3)
+    if run["p"].space_charge:
+        _check_array(g, "fn", 100, e["fn"], 1)
+        _check_array(g, "fnm1", 100, e["fnm1"], 1)
+        _check_array(g, "rho", 100, e["fnp1"], 1)
+
+
+def test_final_particles(run):
+    np.testing.assert_array_equal(run["p100"], run["g"]["p100"])
+
+
+def test_step99_phases(run):
+    g = run["g"]
+    _check_array(g, "ph99/anp1", "", run["ph_np1"]["anp1"], 3)
+    _check_array(g, "ph99/jn", "", run["ph_j"]["anp1"], 3)
+    if run["p"].space_charge:
+        _check_array(g, "ph99/fnp1", "", run["ph_np1"]["fnp1"], 1)
+        _check_array(g, "ph99/rho", "", run["ph_j"]["fnp1"], 1)
+    np.testing.assert_array_equal(run["ph_particles"], g["ph99/particles"])
+    en, bn, pic = run["ph_eb"]
+    assert int(pic.sum()) == int(g["ph99/pic_count"][0])
+    idx = g["ph99/pic_idx"]
+    assert pic[idx].all()
+    np.testing.assert_array_equal(en.reshape(-1, 3)[idx], g["ph99/en"])
+    np.testing.assert_array_equal(bn.reshape(-1, 3)[idx], g["ph99/bn"])
+
+
+def test_power_series(run):
+    np.testing.assert_array_equal(run["power"], run["g"]["power"])
+
+
+def test_screens(run):
+    g = run["g"]
+    for s, rec in enumerate(run["screens"]):
+        ref = g["screen%d" % s]
+        assert rec.shape == ref.shape
+        # the reference writes 15 significant digits (solver.cpp:2183-2187)
+        np.testing.assert_allclose(rec, ref, rtol=2e-15, atol=0)
