@@ -29,6 +29,21 @@ namespace mithra
   __device__ __forceinline__ V3 scale3 (double s, const V3& a) { return v3(s * a.x, s * a.y, s * a.z); }
   __device__ __forceinline__ V3 add3   (const V3& a, const V3& b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
+  /* cos() for the carrier phase 2 pi f0 (t - t0) + cep + phase, which reaches 1e7 rad for an ultraviolet seed.
+   * CUDA's cos switches to a Payne-Hanek slow path above 1.05e5 rad; a three-constant Cody-Waite reduction by
+   * 2 pi with explicit FMAs (exact products) reduces |x| < 1e9 to [-pi, pi] with an absolute error below 4e-16,
+   * i.e. the same correctly-reduced argument to the last bit or two, at a fraction of the cost.             */
+  __device__ __forceinline__ double cos_wide (double x)
+  {
+    const double ax = fabs(x);
+    if (ax < 1.0e5 || !(ax < 1.0e9)) return cos(x);
+    const double k = rint(x * 0.15915494309189535);
+    double r = __fma_rn(-k, 6.283185307179586232, x);
+    r = __fma_rn(-k, 2.4492935982947064e-16, r);
+    r = __fma_rn(-k, -5.9895396194366794e-33, r);
+    return cos(r);
+  }
+
   /* Signal::self, classes.cpp:534-575 */
   __device__ inline double signal_self (const MithraSignal& g, double t, double phase)
   {
@@ -38,28 +53,28 @@ namespace mithra
     switch (g.type)
       {
       case MITHRA_SIGNAL_NEUMANN:
-	return - cos( 2 * PI * g.f0 * d + g.cep + phase ) * 2.7724 * d / ( g.s * g.s ) * exp( -1.3863 * d * d / ( g.s * g.s ) );
+	return - cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * 2.7724 * d / ( g.s * g.s ) * exp( -1.3863 * d * d / ( g.s * g.s ) );
       case MITHRA_SIGNAL_GAUSSIAN:
-	{ const double u = d / g.s; return cos( 2 * PI * g.f0 * d + g.cep + phase ) * exp( -1.3863 * ( u * u ) ); }
+	{ const double u = d / g.s; return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * exp( -1.3863 * ( u * u ) ); }
       case MITHRA_SIGNAL_SECANT:
-	return cos( 2 * PI * g.f0 * d + g.cep + phase ) / cosh( d / g.s );
+	return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) / cosh( d / g.s );
       case MITHRA_SIGNAL_FLATTOP:
 	if (d <= - g.s / 2.0)
-	  { const double u = ( d + g.s / 2.0 ) * g.f0 / g.nR; return cos( 2 * PI * g.f0 * d + g.cep + phase ) * exp( - ( u * u ) ); }
+	  { const double u = ( d + g.s / 2.0 ) * g.f0 / g.nR; return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * exp( - ( u * u ) ); }
 	else if (d <= g.s / 2.0)
-	  return cos( 2 * PI * g.f0 * d + g.cep + phase );
+	  return cos_wide( 2 * PI * g.f0 * d + g.cep + phase );
 	else
-	  { const double u = ( d - g.s / 2.0 ) * g.f0 / g.nR; return cos( 2 * PI * g.f0 * d + g.cep + phase ) * exp( - ( u * u ) ); }
+	  { const double u = ( d - g.s / 2.0 ) * g.f0 / g.nR; return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * exp( - ( u * u ) ); }
       case MITHRA_SIGNAL_INVGAUSSIAN:
 	{
 	  const double u0 = d / g.sigma_inv_g[0], u1 = d / g.sigma_inv_g[1];
 	  const double env = pow( ( 1.0 + u0 * u0 ) * ( 1.0 + u1 * u1 ), 0.25 );
 	  if (d <= - g.s / 2.0)
-	    { const double u = ( d + g.s / 2.0 ) * g.f0 / g.nR; return cos( 2 * PI * g.f0 * d + g.cep + phase ) * env * exp( - ( u * u ) ); }
+	    { const double u = ( d + g.s / 2.0 ) * g.f0 / g.nR; return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * env * exp( - ( u * u ) ); }
 	  else if (d <= g.s / 2.0)
-	    return cos( 2 * PI * g.f0 * d + g.cep + phase ) * env;
+	    return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * env;
 	  else
-	    { const double u = ( d - g.s / 2.0 ) * g.f0 / g.nR; return cos( 2 * PI * g.f0 * d + g.cep + phase ) * env * exp( - ( u * u ) ); }
+	    { const double u = ( d - g.s / 2.0 ) * g.f0 / g.nR; return cos_wide( 2 * PI * g.f0 * d + g.cep + phase ) * env * exp( - ( u * u ) ); }
 	}
       }
     return 0.0;

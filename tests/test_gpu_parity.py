@@ -83,8 +83,11 @@ def test_phases_from_identical_state(job):
     # 3. E/B on every node the reference evaluated lazily: bit-identical floats
     en_g, bn_g, mask_g = gpu.download_eb()
     en_c, bn_c, pic = cpu.download_eb()
-    idx = np.flatnonzero(pic)
-    assert idx.size > 0 or job == "micro-optical"
+    # the reference also evaluates the two boundary planes of every slab inside fieldUpdate (fdtd.cpp:742-774); the GPU
+    # evaluates the padded particle box only (the power kernel evaluates its own plane), so look at what particles touched
+    kk = np.arange(pic.size) // (p.N0 * p.N1)
+    idx = np.flatnonzero((pic != 0) & (kk > 1) & (kk < p.np - 2))
+    assert idx.size > 0
     assert mask_g[idx].all(), "GPU did not evaluate E/B on a node the reference used"
     if p.seed_enabled:
         np.testing.assert_allclose(en_g.reshape(-1, 3)[idx], en_c.reshape(-1, 3)[idx], rtol=1e-5, atol=1e-30)
