@@ -198,25 +198,6 @@ def run_oracle_sample(p_full, steps):
 
 # ---------------------------------------------------------------------------------------------------------------
 
-def slab_params(p, rank, size):
-    """The reference's z-slab partition (Solver::initializeMesh, solver.cpp:619-641, 677-680)."""
-    if size == 1:
-        return p
-    import copy
-    q = copy.copy(p)
-    N2 = p.N2
-    if rank == 0:
-        q.np, q.k0 = N2 // size + 1, 0
-    elif rank == size - 1:
-        q.np, q.k0 = N2 - (size - 1) * (N2 // size) + 1, (size - 1) * (N2 // size) - 1
-    else:
-        q.np, q.k0 = N2 // size + 2, rank * (N2 // size) - 1
-    q.rank, q.size = rank, size
-    q.zp[0] = p.zmin + q.k0 * p.dz if rank else p.zmin
-    q.zp[1] = p.zmin + (q.k0 + q.np - 2) * p.dz if rank != size - 1 else p.zmax
-    return q
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,13 +259,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the time-march has no CPU path")
 
     if world > 1:
-        # weak scaling over z-slabs: every GPU gets a slab of the workload's full z-extent (mesh and bunch scaled per GPU)
+        # weak scaling over z-slabs: the mesh grows with the GPU count so that every GPU keeps the workload's z-extent
+        # (mesh and bunch scaled per GPU, BASELINE.json configs[4]); the partition is the reference's (solver.cpp:619-641)
         import copy
+        from mithra_b200 import slabs
         pg = copy.copy(p)
         pg.N2 = (p.N2 - 2) * world + 2
+        pg.np = pg.N2
         pg.zmax = pg.zmin + (pg.N2 - 1) * pg.dz
         pg.Lz = pg.zmax - pg.zmin
-        pl = slab_params(pg, rank, world)
+        pg.zp[0], pg.zp[1] = pg.zmin, pg.zmax
+        pl = slabs.slab_params(pg, rank, world)
     else:
         pl = p
     pl.device = local_rank
@@ -296,9 +281,7 @@ def main():
     solver = abi.GpuSolver(pl)
     if world > 1:
         solver.connect_neighbours(dist, rank, world)
-    z0 = pl.zmin + pl.k0 * pl.dz
-    z1 = z0 + (pl.np - 1) * pl.dz
-    bunch = synthetic_bunch(pl, npart_local, seed_offset=1 + rank * npart_local, zlo=max(z0, pl.zp[0]), zhi=min(z1, pl.zp[1]))
+    bunch = synthetic_bunch(pl, npart_local, seed_offset=1 + rank * npart_local, zlo=pl.zp[0], zhi=pl.zp[1])
     a_n = synthetic_potential(pl)
     a_nm1 = a_n * 0.999
     tb = undulator_time(pl)

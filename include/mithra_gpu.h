@@ -226,11 +226,22 @@ int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 #define MITHRA_GPU_NPHASES 8
 int mithra_gpu_step_profiled (MithraGpu* h, int nsteps, float ms[MITHRA_GPU_NPHASES]);
 
-/* --- z-slab exchange between the GPUs of one box (one process per GPU) -------------------------------- */
-/* Export an opaque blob (CUDA IPC handles of the ghost mailboxes) to hand to both z-neighbours ...     */
+/* --- z-slab exchange between the GPUs of one box (one handle per slab / GPU) --------------------------- */
+/* The slab partition is the reference's (Solver::initializeMesh, solver.cpp:619-641: np local planes from global
+ * plane k0, two planes shared with each neighbour, ownership interval zp) with rank / size = slab index / count.
+ * Export an opaque blob (addresses + CUDA IPC handles of the arrays the ring neighbours write into; call with
+ * blob == NULL to get its size) ...                                                                    */
 int mithra_gpu_ipc_export  (MithraGpu* h, void* blob, size_t capacity, size_t* nbytes);
-/* ... and connect with the blobs of rank-1 (NULL on rank 0) and rank+1 (NULL on the last rank).        */
+/* ... and connect with the blobs of the ring neighbours (rank-1) mod size and (rank+1) mod size -- the ring closes
+ * for the particles exactly like the reference's rankB_/rankF_ (solver.cpp:49-52), the potentials do not wrap.
+ * Handles of one process (even on one device) and handles of different processes connect the same way.     */
 int mithra_gpu_ipc_connect (MithraGpu* h, const void* blob_prev, const void* blob_next);
+/* Particle hand-over between slabs once per field step, after the deposit (replaces the per-sub-step ring exchange
+ * of solver.cpp:1544-1568, recycleParticles solver.cpp:493-503 and the purge of fdtd.cpp:214-224; a crossing
+ * particle deposits both half-segments first, i.e. the k-slab run reproduces the single-slab result).
+ * mithra_gpu_step calls both; a process driving several slabs issues every _begin before the first _end.  */
+int mithra_gpu_migrate_begin (MithraGpu* h);
+int mithra_gpu_migrate_end   (MithraGpu* h);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ SYMBOLS = (
     "mithra_gpu_current_update", "mithra_gpu_current_communicate", "mithra_gpu_advance_time", "mithra_gpu_step",
     "mithra_gpu_step_timed", "mithra_gpu_synchronize", "mithra_gpu_fetch_power", "mithra_gpu_fetch_screen",
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
+    "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end",
 )
 
 _lib = None
@@ -113,7 +114,8 @@ def load():
     lib.mithra_gpu_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_uint]
     lib.mithra_gpu_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_uint)]
     for name in ("field_update", "bunch_update", "screen_profile", "power_sample", "field_shift", "current_reset",
-                 "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial"):
+                 "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial",
+                 "migrate_begin", "migrate_end"):
         getattr(lib, "mithra_gpu_" + name).argtypes = [vp]
     lib.mithra_gpu_step.argtypes = [vp, C.c_int]
     lib.mithra_gpu_step_timed.argtypes = [vp, C.c_int, fp]
@@ -278,6 +280,30 @@ class GpuSolver:
         if n.value:
             self._check(self.lib.mithra_gpu_fetch_screen(self.h, s, _dptr(out), n.value, C.byref(n)))
         return out
+
+    # -- z-slabs ----------------------------------------------------------------------------------------
+    def migrateBegin(self):
+        self._check(self.lib.mithra_gpu_migrate_begin(self.h))
+
+    def migrateEnd(self):
+        self._check(self.lib.mithra_gpu_migrate_end(self.h))
+
+    def export_blob(self):
+        n = C.c_size_t()
+        self._check(self.lib.mithra_gpu_ipc_export(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self.lib.mithra_gpu_ipc_export(self.h, buf, n.value, C.byref(n)))
+        return buf.raw
+
+    def connect(self, blob_prev, blob_next):
+        self._check(self.lib.mithra_gpu_ipc_connect(self.h, C.c_char_p(blob_prev), C.c_char_p(blob_next)))
+
+    def connect_neighbours(self, dist, rank, world):
+        """One process per GPU: exchange the blobs through torch.distributed and connect the ring neighbours."""
+        blobs = [None] * world
+        dist.all_gather_object(blobs, self.export_blob())
+        self.connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+        dist.barrier()
 
     def counters(self):
         c = Counters()

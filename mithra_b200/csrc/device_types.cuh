@@ -10,6 +10,12 @@
  *   E, B       : one float4 pair per node (Ex,Ey,Ez,0 | Bx,By,Bz,0), node m = N0*N1*k + N1*i + j -- the
  *                reference's FieldVector<float> en_, bn_ (solver.h:244-245) interleaved for the 8-node gather.
  *   particles  : struct-of-arrays of doubles q, r[3], rm[3], gb[3], e (reference Charge, stdinclude.h:130-144).
+ *
+ * z-slabs (one handle per GPU): the ABI speaks the reference's slab numbering (np local planes from global plane
+ * k0, two planes shared with each neighbour, solver.cpp:619-641).  Internally every slab except the first keeps
+ * ONE MORE plane below (kshift = 1): a particle is advanced and deposited for a whole field step by the slab that
+ * owns it at the start of the step, and it can drift at most one cell below the slab in that time.  Internal plane
+ * l = reference plane + kshift; planes [0, kb) and, except on the last slab, plane np-1 are ghosts.
  */
 #ifndef MITHRA_DEVICE_TYPES_CUH_
 #define MITHRA_DEVICE_TYPES_CUH_
@@ -25,7 +31,10 @@ namespace mithra
   /* Field-side constants, passed to kernels by value.                                                 */
   struct FieldDev
   {
-    int    N0, N1, np, k0;
+    int    N0, N1, np, k0;        /* np, k0: INTERNAL plane count / global index of internal plane 0       */
+    int    kshift;                /* internal plane = reference local plane + kshift (0 on the first slab) */
+    int    kb;                    /* first plane this slab updates (1 on the first slab, else kshift + 1); the
+				     last one is np-2; plane np-1 is the z face (last slab) or a ghost      */
     int    P;                     /* N0*N1                                                              */
     long   Pp;                    /* padded plane stride (doubles)                                      */
     int    ncomp;                 /* 3, or 4 with space charge                                          */
@@ -53,10 +62,13 @@ namespace mithra
   {
     double xmin, xmax, ymin, ymax, zmin, zmax;
     double zp0, zp1, Lz;
+    int    size;                        /* number of slabs; with more than one the particle list of a slab IS its
+					   ownership (migration once per field step) and the z tests are global */
     double dx, dy, dz;
     double c0, gamma, beta, dt_shift;
     double r1, r2, dtb, dt_bunch, dt_field;
-    int    N0, N1, np, k0, P;
+    int    N0, N1, np, k0, P;          /* np, k0 internal (see FieldDev)                                */
+    int    kshift;
     long   Pp;
     int    ncomp;
     int    n_und;

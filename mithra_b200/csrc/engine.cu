@@ -146,25 +146,27 @@ struct PhaseTimer
 /* ---------------------------------------------------------------------------------------------------- */
 /* layout conversion kernels (host AoS <-> device component-planar)                                      */
 
+/* `nodes` nodes in the reference's slab numbering; the device arrays hold np planes of which the reference's
+ * plane 0 is plane kshift                                                                                 */
 __global__ void aos_to_planar (const double* __restrict__ src, double* __restrict__ dst, int ncomp_src, int c0, int nc,
-			       long nodes, int P, long Pp, int np)
+			       long nodes, int P, long Pp, int np, int kshift)
 {
   for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < nodes * nc; t += (long) gridDim.x * blockDim.x)
     {
       const long m = t / nc; const int c = (int) (t - m * nc);
       const long k = m / P, r = m - k * P;
-      dst[((long) (c0 + c) * np + k) * Pp + r] = src[m * ncomp_src + c];
+      dst[((long) (c0 + c) * np + k + kshift) * Pp + r] = src[m * ncomp_src + c];
     }
 }
 
 __global__ void planar_to_aos (const double* __restrict__ src, double* __restrict__ dst, int ncomp_dst, int c0, int nc,
-			       long nodes, int P, long Pp, int np)
+			       long nodes, int P, long Pp, int np, int kshift)
 {
   for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < nodes * nc; t += (long) gridDim.x * blockDim.x)
     {
       const long m = t / nc; const int c = (int) (t - m * nc);
       const long k = m / P, r = m - k * P;
-      dst[m * ncomp_dst + c] = src[((long) (c0 + c) * np + k) * Pp + r];
+      dst[m * ncomp_dst + c] = src[((long) (c0 + c) * np + k + kshift) * Pp + r];
     }
 }
 
@@ -198,7 +200,9 @@ __global__ void make_eb_box (const Box* __restrict__ pbox_in, Box* __restrict__ 
 static void fill_field_dev (const MithraGpuParams& p, FieldDev& f)
 {
   memset(&f, 0, sizeof(f));
-  f.N0 = p.N0; f.N1 = p.N1; f.np = p.np; f.k0 = p.k0;
+  f.kshift = (p.size > 1 && p.rank > 0) ? 1 : 0;
+  f.kb = f.kshift + 1;
+  f.N0 = p.N0; f.N1 = p.N1; f.np = p.np + f.kshift; f.k0 = p.k0 - f.kshift;
   f.P  = p.N0 * p.N1;
   f.Pp = ((long) f.P + 15) / 16 * 16;
   f.ncomp = p.space_charge ? 4 : 3;
@@ -221,7 +225,8 @@ static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDe
   b.dx = p.dx; b.dy = p.dy; b.dz = p.dz;
   b.c0 = p.c0; b.gamma = p.gamma; b.beta = p.beta; b.dt_shift = p.dt_shift;
   b.r1 = p.r1; b.r2 = p.r2; b.dtb = p.dtb; b.dt_bunch = p.dt_bunch; b.dt_field = p.dt;
-  b.N0 = p.N0; b.N1 = p.N1; b.np = p.np; b.k0 = p.k0; b.P = f.P; b.Pp = f.Pp; b.ncomp = f.ncomp;
+  b.N0 = p.N0; b.N1 = p.N1; b.np = f.np; b.k0 = f.k0; b.kshift = f.kshift; b.P = f.P; b.Pp = f.Pp; b.ncomp = f.ncomp;
+  b.size = p.size;
   b.n_und = p.n_undulators;
   b.und0_dist = p.n_undulators > 0 ? p.undulator[0].dist : 0.0;
   for (int u = 0; u < p.n_undulators; u++)
@@ -252,6 +257,9 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   if (params->n_undulators > MITHRA_MAX_UNDULATORS || params->n_ext_fields > MITHRA_MAX_EXTFIELDS) return fail("mithra_gpu_create: too many undulators / external fields");
   if (params->power.enabled && (params->power.N > MITHRA_MAX_POWER_PLANES || params->power.Nl > MITHRA_MAX_POWER_LAMBDAS || params->power.Nf < 1)) return fail("mithra_gpu_create: power sampling out of range");
   if (params->screens.enabled && params->screens.N > MITHRA_MAX_SCREENS) return fail("mithra_gpu_create: too many screens");
+
+  if (params->size < 1 || params->rank < 0 || params->rank >= params->size) return fail("mithra_gpu_create: rank %d of %d slabs", params->rank, params->size);
+  if (params->size > 1 && params->np < 6) return fail("mithra_gpu_create: a slab of %d planes is too thin to be split further", params->np);
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -310,7 +318,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       for (int k = 0; k < pp.N; k++)
 	{
 	  h->power_mine[k] = ( pp.z[k] < params->zp[1] && pp.z[k] >= params->zp[0] );
-	  double c; h->power_dzr[k] = modf( ( pp.z[k] - params->zmin ) / params->dz, &c ); h->power_k[k] = (int) c - params->k0;
+	  double c; h->power_dzr[k] = modf( ( pp.z[k] - params->zmin ) / params->dz, &c ); h->power_k[k] = (int) c - f.k0;
 	  if (h->power_mine[k]) nmine++;
 	}
       const size_t ring = (size_t) pp.N * pp.Nf * 4 * pw.npx;
@@ -349,7 +357,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       CU(cudaMalloc(&h->d_seed, sizeof(SeedDev))); CU(cudaMemcpy(h->d_seed, &sd, sizeof(SeedDev), cudaMemcpyHostToDevice));
     }
 
-  exchange_init(h->xch);
+  if (exchange_init(h->xch, f, h->pcap, h->stream)) { std::string e = h->xch.error; mithra_gpu_destroy(h); return fail("mithra_gpu_create: %s", e.c_str()); }
 
   h->time = 0.0; h->timem1 = - params->dt; h->timep1 = params->dt; h->time_bunch = 0.0; h->n_time = 0; h->n_time_bunch = 0;
   memset(&h->cnt, 0, sizeof(h->cnt));
@@ -382,11 +390,11 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
 static int upload_vec (MithraGpu* h, const double* src, double* dst, int ncomp_src, int c0, int nc)
 {
   const FieldDev& f = h->fd;
-  const long nodes = (long) f.np * f.P;
+  const long nodes = (long) h->prm.np * f.P;
   double* tmp = 0;
   CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_src * sizeof(double)));
   CU(cudaMemcpyAsync(tmp, src, (size_t) nodes * ncomp_src * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  aos_to_planar<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(tmp, dst, ncomp_src, c0, nc, nodes, f.P, f.Pp, f.np);
+  aos_to_planar<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(tmp, dst, ncomp_src, c0, nc, nodes, f.P, f.Pp, f.np, f.kshift);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaFree(tmp));
@@ -396,10 +404,10 @@ static int upload_vec (MithraGpu* h, const double* src, double* dst, int ncomp_s
 static int download_vec (MithraGpu* h, const double* src, double* dst, int ncomp_dst, int c0, int nc)
 {
   const FieldDev& f = h->fd;
-  const long nodes = (long) f.np * f.P;
+  const long nodes = (long) h->prm.np * f.P;
   double* tmp = 0;
   CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_dst * sizeof(double)));
-  planar_to_aos<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, tmp, ncomp_dst, c0, nc, nodes, f.P, f.Pp, f.np);
+  planar_to_aos<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, tmp, ncomp_dst, c0, nc, nodes, f.P, f.Pp, f.np, f.kshift);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(dst, tmp, (size_t) nodes * ncomp_dst * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -451,19 +459,24 @@ extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsig
 {
   USE(h);
   const FieldDev& f = h->fd;
-  const size_t nodes = (size_t) f.np * f.P;
-  std::vector<float4> tmp(nodes * 2);
+  const size_t nodes_int = (size_t) f.np * f.P;
+  const size_t nodes = (size_t) h->prm.np * f.P;                  /* reference slab numbering                     */
+  std::vector<float4> tmp(nodes_int * 2);
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpy(tmp.data(), h->eb, nodes * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(tmp.data(), h->eb, nodes_int * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
   Box b; CU(cudaMemcpy(&b, h->d_ebox, sizeof(Box), cudaMemcpyDeviceToHost));
   for (size_t m = 0; m < nodes; m++)
     {
-      const int k = (int) (m / f.P), r = (int) (m % f.P), i = r / f.N1, j = r % f.N1;
+      const int kr = (int) (m / f.P), r = (int) (m % f.P), i = r / f.N1, j = r % f.N1;
+      const int k = kr + f.kshift;
+      const size_t mi = (size_t) k * f.P + r;
       bool in = ( i >= b.lo[0] && i <= b.hi[0] && j >= b.lo[1] && j <= b.hi[1] && k >= b.lo[2] && k <= b.hi[2] );
-      if (in && f.size > 1 && ((k == 0 && f.rank != 0) || (k == f.np - 1 && f.rank != f.size - 1))) in = h->xch.connected;
+      /* ghost planes hold what the neighbour evaluated on the whole plane                                     */
+      if (f.size > 1 && ((k < f.kb && f.rank != 0) || (k == f.np - 1 && f.rank != f.size - 1)))
+	in = h->xch.connected && i >= 1 && i <= f.N0 - 2 && j >= 1 && j <= f.N1 - 2;
       if (mask) mask[m] = in ? 1 : 0;
-      if (en) { en[3 * m] = in ? tmp[2 * m].x : 0.f; en[3 * m + 1] = in ? tmp[2 * m].y : 0.f; en[3 * m + 2] = in ? tmp[2 * m].z : 0.f; }
-      if (bn) { bn[3 * m] = in ? tmp[2 * m + 1].x : 0.f; bn[3 * m + 1] = in ? tmp[2 * m + 1].y : 0.f; bn[3 * m + 2] = in ? tmp[2 * m + 1].z : 0.f; }
+      if (en) { en[3 * m] = in ? tmp[2 * mi].x : 0.f; en[3 * m + 1] = in ? tmp[2 * mi].y : 0.f; en[3 * m + 2] = in ? tmp[2 * mi].z : 0.f; }
+      if (bn) { bn[3 * m] = in ? tmp[2 * mi + 1].x : 0.f; bn[3 * m + 1] = in ? tmp[2 * mi + 1].y : 0.f; bn[3 * m + 2] = in ? tmp[2 * mi + 1].z : 0.f; }
     }
   return 0;
 }
@@ -483,7 +496,7 @@ static int refresh_particle_box (MithraGpu* h)
 {
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   if (h->pn > 0)
-    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->d_pbox);
+    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_bd, h->P, 0L, (long) h->pn, h->d_pbox);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 2;
   return 0;
@@ -562,7 +575,7 @@ static void launch_stencil (MithraGpu* h)
 {
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
-  dim3 grid((f.P + BX - 1) / BX, (f.np - 2 + KC - 1) / KC, f.ncomp);
+  dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);
   stencil_interior<NSFD, BX, KC><<<grid, BX, 0, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox);
 }
 
@@ -595,7 +608,11 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
 	h->cnt.kernel_launches += 2;
       }
     CU(cudaGetLastError());
-    if (h->xch.connected) { TRY(exchange_potentials(h->xch, f, ap, h->stream)); h->cnt.kernel_launches += 2; }
+    if (f.size > 1)
+      {
+	if (!h->xch.connected) return fail("mithra_gpu_field_update: slab %d of %d is not connected to its neighbours (mithra_gpu_ipc_connect)", f.rank, f.size);
+	if (exchange_potentials(h->xch, f, ap, h->ip1, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("A ghost exchange: %s", h->xch.error.c_str());
+      }
   }
   {
     PhaseTimer t(h, PH_EVAL);
@@ -606,10 +623,27 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
     else              eval_eb_box<false><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 2;
-    if (h->xch.connected) { TRY(exchange_eb(h->xch, f, h->eb, h->stream)); h->cnt.kernel_launches += 2; }
+    if (f.size > 1)
+      {
+	/* whole planes the neighbours gather from and sample power on: kb -> prev; np-3, np-2 -> next           */
+	if (h->xch.prev.chain)
+	  {
+	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo);
+	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo);
+	    h->cnt.kernel_launches += 1;
+	  }
+	if (h->xch.next.chain)
+	  {
+	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi);
+	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi);
+	    h->cnt.kernel_launches += 1;
+	  }
+	CU(cudaGetLastError());
+	if (exchange_eb(h->xch, f, h->eb, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("E/B ghost exchange: %s", h->xch.error.c_str());
+      }
   }
   h->anp1_is_current = false;
-  h->cnt.cell_updates += (unsigned long long) f.np * f.P;
+  h->cnt.cell_updates += (unsigned long long) (f.np - 1 - f.kb + (f.rank == 0 ? 1 : 0) + (f.rank == f.size - 1 ? 1 : 0)) * f.P;
   return 0;
 }
 
@@ -623,13 +657,8 @@ extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
       /* the particle box is rebuilt by the push (it is read by the next field update)                      */
       set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
       const int grid = (int) ((h->pn + 127) / 128);
-      if (!h->xch.connected)
-	{
-	  push_particles<<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
-	  h->cnt.kernel_launches += 2;
-	}
-      else
-	return fail("mithra_gpu_bunch_update: slab migration is not wired yet");
+      push_particles<<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
+      h->cnt.kernel_launches += 2;
       CU(cudaGetLastError());
     }
   for (int s = 0; s < nsub; s++) { h->time_bunch += h->prm.dt_bunch; ++h->n_time_bunch; }
@@ -674,9 +703,9 @@ extern "C" int mithra_gpu_power_sample (MithraGpu* h)
     {
       if (!h->power_mine[k]) continue;
       if (f.ncomp == 4)
-	power_dft<true ><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
+	power_dft<true ><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->eb, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
       else
-	power_dft<false><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
+	power_dft<false><<<h->power_blocks, MITHRA_POWER_PX * MITHRA_POWER_MS, 0, h->stream>>>(f, h->pw, np1, an, h->eb, h->d_fdt, h->d_ep, k, h->power_k[k], h->power_dzr[k], slot, h->d_partial);
       h->cnt.kernel_launches += 1;
     }
   const int nout = h->pw.N * h->pw.Nl;
@@ -721,7 +750,40 @@ extern "C" int mithra_gpu_current_update (MithraGpu* h)
 extern "C" int mithra_gpu_current_communicate (MithraGpu* h)
 {
   USE(h);
-  if (h->xch.connected) { TRY(exchange_current(h->xch, h->fd, h->J, h->d_jbox, h->stream)); h->cnt.kernel_launches += 2; }
+  if (h->fd.size > 1)
+    {
+      if (!h->xch.connected) return fail("mithra_gpu_current_communicate: slab is not connected to its neighbours");
+      if (exchange_current(h->xch, h->fd, h->J, h->d_jbox, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("J merge: %s", h->xch.error.c_str());
+    }
+  return 0;
+}
+
+/* Particle hand-over between slabs, once per field step after the deposit (solver.cpp:1544-1568, 493-503 and the
+ * purge of fdtd.cpp:214-224).  _begin enqueues the sends, _end receives (one host synchronisation) -- split so that
+ * one process driving several slabs can issue every _begin before the first _end.                          */
+extern "C" int mithra_gpu_migrate_begin (MithraGpu* h)
+{
+  USE(h);
+  if (h->fd.size <= 1) return 0;
+  if (!h->xch.connected) return fail("mithra_gpu_migrate_begin: slab is not connected to its neighbours");
+  if (migrate_begin(h->xch, h->d_bd, h->P, h->pn, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
+  return 0;
+}
+
+extern "C" int mithra_gpu_migrate_end (MithraGpu* h)
+{
+  USE(h);
+  if (h->fd.size <= 1) return 0;
+  const size_t before = h->pn;
+  if (migrate_end(h->xch, h->P, &h->pn, h->pcap, h->stream, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
+  /* arrivals sit near the slab faces: grow the box the next E/B evaluation covers                           */
+  const size_t kept = before - h->xch.h_counts[2];
+  if (h->pn > kept)
+    {
+      particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->d_bd, h->P, (long) kept, (long) h->pn, h->d_pbox);
+      CU(cudaGetLastError());
+      h->cnt.kernel_launches += 1;
+    }
   return 0;
 }
 
@@ -746,6 +808,8 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_current_reset(h));
       TRY(mithra_gpu_current_update(h));
       TRY(mithra_gpu_current_communicate(h));
+      TRY(mithra_gpu_migrate_begin(h));
+      TRY(mithra_gpu_migrate_end(h));
       TRY(mithra_gpu_advance_time(h));
     }
   return 0;
@@ -756,6 +820,11 @@ extern "C" int mithra_gpu_synchronize (MithraGpu* h)
   USE(h);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
+  if (h->xch.d_err)
+    {
+      int e = 0; CU(cudaMemcpy(&e, h->xch.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+      if (e) return fail("mithra_gpu_synchronize: timed out waiting for a neighbouring slab");
+    }
   return 0;
 }
 
@@ -839,11 +908,11 @@ extern "C" int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out)
 extern "C" int mithra_gpu_ipc_export (MithraGpu* h, void* blob, size_t capacity, size_t* nbytes)
 {
   USE(h);
-  return exchange_export(h->xch, h->fd, h->A, h->J, h->eb, blob, capacity, nbytes) ? fail("mithra_gpu_ipc_export: %s", exchange_error()) : 0;
+  return exchange_export(h->xch, h->fd, h->device, h->A, h->eb, blob, capacity, nbytes) ? fail("mithra_gpu_ipc_export: %s", h->xch.error.c_str()) : 0;
 }
 
 extern "C" int mithra_gpu_ipc_connect (MithraGpu* h, const void* blob_prev, const void* blob_next)
 {
   USE(h);
-  return exchange_connect(h->xch, h->fd, blob_prev, blob_next) ? fail("mithra_gpu_ipc_connect: %s", exchange_error()) : 0;
+  return exchange_connect(h->xch, h->fd, h->device, blob_prev, blob_next) ? fail("mithra_gpu_ipc_connect: %s", h->xch.error.c_str()) : 0;
 }

@@ -48,10 +48,10 @@ namespace mithra
    * evaluation of the next step.  The host pads it by the distance a particle can travel in one field step.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
-  particle_box (const BunchDev* __restrict__ bp, ParticlesDev P, long n, Box* __restrict__ box)
+  particle_box (const BunchDev* __restrict__ bp, ParticlesDev P, long start, long n, Box* __restrict__ box)
   {
     const BunchDev& b = *bp;
-    for (long base = (long) blockIdx.x * blockDim.x; base < n; base += (long) gridDim.x * blockDim.x)
+    for (long base = start + (long) blockIdx.x * blockDim.x; base < n; base += (long) gridDim.x * blockDim.x)
       {
 	const long t = base + threadIdx.x;
 	bool valid = false; int i = 0, j = 0, k = 0;
@@ -87,14 +87,15 @@ namespace mithra
       {
 	long m = -1;
 	const double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;
-	if ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) && P.e[t] == 1.0 &&
-	     x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zp1 && z >= b.zp0 )
+	const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
+	if ( ( b.size > 1 || ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) && P.e[t] == 1.0 &&
+	     x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < zhi && z >= zlo )
 	  {
 	    double d1;
 	    modf( ( x - b.xmin ) / b.dx, &d1 ); const int i = (int) d1;
 	    modf( ( y - b.ymin ) / b.dy, &d1 ); const int j = (int) d1;
 	    modf( ( z - b.zmin ) / b.dz, &d1 ); const int k = (int) d1;
-	    m = (long) ( k - b.k0 ) * b.P + (long) i * b.N1 + j;
+	    m = (long) ( k - b.k0 - b.kshift ) * b.P + (long) i * b.N1 + j;      /* reference slab numbering     */
 	  }
 	push_m[t] = m;
       }
@@ -133,12 +134,16 @@ namespace mithra
 	for (int s = 0; s < nsub; s++, tb += b.dt_bunch)
 	  {
 	    /* ownership with the periodic z wrap (solver.cpp:1440-1441)                                    */
-	    double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;
-	    if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) continue;
-
+	    if (b.size == 1)
+	      {
+		const double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;
+		if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) continue;
+	      }
+	    /* several slabs: the list of a slab is what it owns for this field step (migrate once per step), and
+	     * "inside the mesh" is the single-slab test of the whole mesh, [zmin, zmax)                          */
 	    const bool b1x = ( x < b.xmax - b.dx && x > b.xmin + b.dx );
 	    const bool b1y = ( y < b.ymax - b.dy && y > b.ymin + b.dy );
-	    const bool b1z = ( z < b.zp1 && z >= b.zp0 );
+	    const bool b1z = ( b.size == 1 ) ? ( z < b.zp1 && z >= b.zp0 ) : ( z < b.zmax && z >= b.zmin );
 
 	    V3 et = v3(0.0, 0.0, 0.0), bt = v3(0.0, 0.0, 0.0);
 
@@ -304,10 +309,11 @@ namespace mithra
 	const double rpx = P.r[0][t],  rpy = P.r[1][t],  rpz = P.r[2][t];
 	const double rmx = P.rm[0][t], rmy = P.rm[1][t], rmz = P.rm[2][t];
 
+	const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
 	const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
-			   rpz < b.zp1 && rpz >= b.zp0 );
+			   rpz < zhi && rpz >= zlo );
 	const bool bmf = ( rmx < b.xmax - b.dx && rmx > b.xmin + b.dx && rmy < b.ymax - b.dy && rmy > b.ymin + b.dy &&
-			   rmz < b.zp1 && rmz >= b.zp0 );
+			   rmz < zhi && rmz >= zlo );
 	if (bpf || bmf)
 	  {
 	    const double q = P.q[t];
@@ -363,8 +369,11 @@ namespace mithra
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const double xp = P.r[0][t], yp = P.r[1][t], zp = P.r[2][t];
-    const double zr = pmod( zp - b.zmin, b.Lz ) + b.zmin;
-    if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) return;
+    if (b.size == 1)
+      {
+	const double zr = pmod( zp - b.zmin, b.Lz ) + b.zmin;
+	if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) return;
+      }
     const double xm = P.rm[0][t], ym = P.rm[1][t], zm = P.rm[2][t];
     const double lzm = b.gamma * ( zm + b.beta * b.c0 * ( time_bunch - b.dt_field + b.dt_shift ) );
     const double lzp = b.gamma * ( zp + b.beta * b.c0 * ( time_bunch + b.dt_shift ) );
@@ -411,7 +420,7 @@ namespace mithra
   template <bool SC>
   __global__ void __launch_bounds__(MITHRA_POWER_PX * MITHRA_POWER_MS)
   power_dft (const FieldDev f, const PowerDev pw, const double* __restrict__ anp1, const double* __restrict__ an,
-	     double* __restrict__ fdt, const double2* __restrict__ ep, int plane, int kplane, double dzr, int slot,
+	     const float4* __restrict__ ebn, double* __restrict__ fdt, const double2* __restrict__ ep, int plane, int kplane, double dzr, int slot,
 	     double* __restrict__ partial)
   {
     __shared__ double red[4][2][MITHRA_POWER_MS][MITHRA_POWER_PX];
@@ -429,8 +438,20 @@ namespace mithra
 	int ka = kplane, kb = kplane + 1;
 	if (ka == 0 && f.rank == 0) ka = 1;
 	if (kb == f.np - 1 && f.rank == f.size - 1) kb = f.np - 2;
-	const EB A = eval_eb_node<SC>(f, anp1, an, i, j, ka);
-	const EB B = eval_eb_node<SC>(f, anp1, an, i, j, kb);
+	/* a plane this slab does not update is a ghost whose E/B came from the neighbour (full plane)     */
+	EB A, B;
+	if (ka < f.kb && f.rank != 0)
+	  {
+	    const float4 e = ebn[2 * ((long) ka * f.P + (long) i * f.N1 + j)], bb = ebn[2 * ((long) ka * f.P + (long) i * f.N1 + j) + 1];
+	    A.e[0] = e.x; A.e[1] = e.y; A.e[2] = e.z; A.b[0] = bb.x; A.b[1] = bb.y; A.b[2] = bb.z;
+	  }
+	else A = eval_eb_node<SC>(f, anp1, an, i, j, ka);
+	if (kb == f.np - 1 && f.rank != f.size - 1)
+	  {
+	    const float4 e = ebn[2 * ((long) kb * f.P + (long) i * f.N1 + j)], bb = ebn[2 * ((long) kb * f.P + (long) i * f.N1 + j) + 1];
+	    B.e[0] = e.x; B.e[1] = e.y; B.e[2] = e.z; B.b[0] = bb.x; B.b[1] = bb.y; B.b[2] = bb.z;
+	  }
+	else B = eval_eb_node<SC>(f, anp1, an, i, j, kb);
 	const double et0 = ( 1.0 - dzr ) * A.e[0] + dzr * B.e[0];
 	const double et1 = ( 1.0 - dzr ) * A.e[1] + dzr * B.e[1];
 	const double bt0 = ( 1.0 - dzr ) * A.b[0] + dzr * B.b[0];

@@ -39,7 +39,7 @@ namespace mithra
     if (i < 1 || i > f.N0 - 2 || j < 1 || j > f.N1 - 2) return;
 
     const int c  = blockIdx.z;
-    const int ks = 1 + blockIdx.y * KC;
+    const int ks = f.kb + blockIdx.y * KC;
     const int ke = min(ks + KC, f.np - 1);               /* exclusive                                    */
     if (ks >= ke) return;
 
@@ -121,8 +121,9 @@ namespace mithra
   boundary_faces (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
 		  const double* __restrict__ anm1)
   {
-    const long nx = (long) (f.N1 - 2) * (f.np - 2);       /* per x face                                  */
-    const long ny = (long) (f.N0 - 2) * (f.np - 2);
+    const int  nk = f.np - 1 - f.kb;                      /* planes kb .. np-2                           */
+    const long nx = (long) (f.N1 - 2) * nk;               /* per x face                                  */
+    const long ny = (long) (f.N0 - 2) * nk;
     const long nz = (long) (f.N0 - 2) * (f.N1 - 2);
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
     const long per = 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0);
@@ -142,7 +143,7 @@ namespace mithra
 	  {
 	    const bool hi = r >= nx; if (hi) r -= nx;
 	    /* j fastest so that a warp walks along a row                                              */
-	    const int k = 1 + (int) (r / (f.N1 - 2)), j = 1 + (int) (r % (f.N1 - 2));
+	    const int k = f.kb + (int) (r / (f.N1 - 2)), j = 1 + (int) (r % (f.N1 - 2));
 	    const int i = hi ? f.N0 - 1 : 0;
 	    face_update(ap, a, am, (long) k * Pp + i * N1 + j, hi ? -N1 : N1, 1, Pp, f.bB);
 	    continue;
@@ -151,7 +152,7 @@ namespace mithra
 	if (r < 2 * ny)
 	  {
 	    const bool hi = r >= ny; if (hi) r -= ny;
-	    const int k = 1 + (int) (r / (f.N0 - 2)), i = 1 + (int) (r % (f.N0 - 2));
+	    const int k = f.kb + (int) (r / (f.N0 - 2)), i = 1 + (int) (r % (f.N0 - 2));
 	    const int j = hi ? f.N1 - 1 : 0;
 	    face_update(ap, a, am, (long) k * Pp + i * N1 + j, hi ? -1 : 1, N1, Pp, f.cB);
 	    continue;
@@ -192,7 +193,7 @@ namespace mithra
 		  const double* __restrict__ anm1)
   {
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
-    const long nze = 4L * (f.np - 2);
+    const long nze = 4L * (f.np - 1 - f.kb);
     const int  nends = (zlo ? 1 : 0) + (zhi ? 1 : 0);
     const long nxe = 2L * nends * (f.N0 - 2);
     const long nye = 2L * nends * (f.N1 - 2);
@@ -211,7 +212,7 @@ namespace mithra
 
 	if (r < nze)
 	  {
-	    const int q = (int) (r & 3); const int k = 1 + (int) (r >> 2);
+	    const int q = (int) (r & 3); const int k = f.kb + (int) (r >> 2);
 	    const bool ihi = q & 1, jhi = q & 2;
 	    const long e = (long) k * Pp + (ihi ? f.N0 - 1 : 0) * N1 + (jhi ? f.N1 - 1 : 0);
 	    edge_update(ap, a, am, e, ihi ? -N1 : N1, jhi ? -1 : 1, Pp, f.eE);
@@ -375,7 +376,7 @@ namespace mithra
 	const int k = b.lo[2] + (int) (r / ((long) ni * nj)); r -= (long) (k - b.lo[2]) * ni * nj;
 	const int i = b.lo[0] + (int) (r / nj), j = b.lo[1] + (int) (r % nj);
 	int ke = k;
-	if (k == 0)        { if (f.rank != 0)          continue; ke = 1; }
+	if (k < f.kb)      { if (f.rank != 0)          continue; ke = 1; }          /* ghosts come from the neighbour */
 	if (k == f.np - 1) { if (f.rank != f.size - 1) continue; ke = f.np - 2; }
 	const EB o = eval_eb_node<SC>(f, anp1, an, i, j, ke);
 	const long m = (long) k * f.P + (long) i * f.N1 + j;

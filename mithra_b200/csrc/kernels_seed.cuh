@@ -40,7 +40,7 @@ namespace mithra
   __device__ __forceinline__ void seed_node (const SeedDev& s, const FieldDev& f, double* __restrict__ anp1, int i, int j, int k, double time)
   {
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
-    const int KI = zlo ? 2 : 1, KF = zhi ? f.np - 2 : f.np - 1;
+    const int KI = zlo ? 2 : f.kb, KF = zhi ? f.np - 2 : f.np - 1;
     const long cs = (long) f.np * f.Pp;
     const bool sx = on_shell(i, f.N0), sy = on_shell(j, f.N1);
     const bool sz = (zlo && (k == 1 || k == 2)) || (zhi && (k == f.np - 2 || k == f.np - 3));
@@ -75,11 +75,11 @@ namespace mithra
   __global__ void __launch_bounds__(128)
   seed_inject_scan (const SeedDev* __restrict__ sp, const FieldDev f, double* __restrict__ anp1, double time)
   {
-    const long nin = (long) (f.N0 - 2) * (f.N1 - 2) * (f.np - 2);
+    const long nin = (long) (f.N0 - 2) * (f.N1 - 2) * (f.np - 1 - f.kb);
     for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < nin; t += (long) gridDim.x * blockDim.x)
       {
 	long r = t;
-	const int k = 1 + (int) (r / ((long) (f.N0 - 2) * (f.N1 - 2))); r -= (long) (k - 1) * (f.N0 - 2) * (f.N1 - 2);
+	const int k = f.kb + (int) (r / ((long) (f.N0 - 2) * (f.N1 - 2))); r -= (long) (k - f.kb) * (f.N0 - 2) * (f.N1 - 2);
 	const int i = 1 + (int) (r / (f.N1 - 2)), j = 1 + (int) (r % (f.N1 - 2));
 	seed_node(*sp, f, anp1, i, j, k, time);
       }
@@ -94,8 +94,9 @@ namespace mithra
   seed_inject_shell (const SeedDev* __restrict__ sp, const FieldDev f, double* __restrict__ anp1, double time)
   {
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
-    const long nX = 4L * (f.N1 - 2) * (f.np - 2);
-    const long nY = 4L * (f.N0 - 6) * (f.np - 2);
+    const int  nk = f.np - 1 - f.kb;
+    const long nX = 4L * (f.N1 - 2) * nk;
+    const long nY = 4L * (f.N0 - 6) * nk;
     const int  nzs = (zlo ? 2 : 0) + (zhi ? 2 : 0);
     const long nZ = (long) nzs * (f.N0 - 6) * (f.N1 - 6);
     const long tot = nX + nY + nZ;
@@ -104,15 +105,15 @@ namespace mithra
 	long r = t; int i, j, k;
 	if (r < nX)
 	  {
-	    const int q = (int) (r / ((long) (f.N1 - 2) * (f.np - 2))); r -= (long) q * (f.N1 - 2) * (f.np - 2);
-	    k = 1 + (int) (r / (f.N1 - 2)); j = 1 + (int) (r % (f.N1 - 2));
+	    const int q = (int) (r / ((long) (f.N1 - 2) * nk)); r -= (long) q * (f.N1 - 2) * nk;
+	    k = f.kb + (int) (r / (f.N1 - 2)); j = 1 + (int) (r % (f.N1 - 2));
 	    i = (q == 0) ? 1 : (q == 1) ? 2 : (q == 2) ? f.N0 - 3 : f.N0 - 2;
 	  }
 	else if (r < nX + nY)
 	  {
 	    r -= nX;
-	    const int q = (int) (r / ((long) (f.N0 - 6) * (f.np - 2))); r -= (long) q * (f.N0 - 6) * (f.np - 2);
-	    k = 1 + (int) (r / (f.N0 - 6)); i = 3 + (int) (r % (f.N0 - 6));
+	    const int q = (int) (r / ((long) (f.N0 - 6) * nk)); r -= (long) q * (f.N0 - 6) * nk;
+	    k = f.kb + (int) (r / (f.N0 - 6)); i = 3 + (int) (r % (f.N0 - 6));
 	    j = (q == 0) ? 1 : (q == 1) ? 2 : (q == 2) ? f.N1 - 3 : f.N1 - 2;
 	  }
 	else
