@@ -98,6 +98,8 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("%s is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
                            "There is no CPU fallback." % LIB_PATH)
+    # see preload_kernels() in engine.cu; harmless if CUDA is already initialised
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     lib = C.CDLL(LIB_PATH)
     dp, fp, vp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p
     lib.mithra_gpu_last_error.restype = C.c_char_p

@@ -249,6 +249,29 @@ static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDe
   for (int u = 0; u < p.n_ext_fields; u++) b.ext[u] = p.ext_field[u];
 }
 
+/* CUDA loads kernels lazily, and loading one while another kernel spins on a neighbour's flag can block the
+ * launching host thread until the spinning kernel ends -- a deadlock when the awaited neighbour is driven by the same
+ * thread.  Touching every kernel once at creation forces the loads up front.                               */
+template <class K> static inline cudaError_t preload (K kernel) { cudaFuncAttributes a; return cudaFuncGetAttributes(&a, (const void*) kernel); }
+
+static int preload_kernels ()
+{
+  cudaError_t e = cudaSuccess;
+  #define PL(k) do { cudaError_t r_ = preload(k); if (r_ != cudaSuccess) e = r_; } while (0)
+  PL(aos_to_planar); PL(planar_to_aos); PL(set_box); PL(make_eb_box);
+  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>));
+  PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
+  PL(eval_eb_box<true>); PL(eval_eb_box<false>);
+  PL(particle_box); PL(particle_cells); PL(push_particles); PL(deposit_current<true>); PL(deposit_current<false>);
+  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish);
+  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_initial_kernel);
+  PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
+  PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
+  #undef PL
+  if (e != cudaSuccess) return fail("preloading the kernels failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out)
 {
   if (!params || !out) return fail("mithra_gpu_create: null argument");
@@ -273,6 +296,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device));
   if (prop.major < 10) { delete h; return fail("mithra_gpu_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); }
   h->num_sms = prop.multiProcessorCount;
+  if (preload_kernels()) { delete h; return 1; }
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->pev[0])); CU(cudaEventCreate(&h->pev[1]));
   h->profiling = false; memset(h->pms, 0, sizeof(h->pms));
@@ -823,7 +847,7 @@ extern "C" int mithra_gpu_synchronize (MithraGpu* h)
   if (h->xch.d_err)
     {
       int e = 0; CU(cudaMemcpy(&e, h->xch.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-      if (e) return fail("mithra_gpu_synchronize: timed out waiting for a neighbouring slab");
+      if (e) return fail("mithra_gpu_synchronize: timed out waiting for a neighbouring slab (flag %d, sequence %d)", (e & 0xff) - 1, e >> 8);
     }
   return 0;
 }

@@ -179,14 +179,15 @@ namespace mithra
     __threadfence_system();
   }
 
-  __global__ void wait_flag (const unsigned long long* flag, unsigned long long seq, int* err)
+  /* err receives (first failure only) the flag index + 1 in the low byte and the awaited sequence above it  */
+  __global__ void wait_flag (const unsigned long long* flag, unsigned long long seq, int* err, int id)
   {
     unsigned long long t0, t1;
     asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*((volatile const unsigned long long*) flag) < seq)
       {
 	asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-	if (t1 - t0 > MITHRA_WAIT_TIMEOUT_NS) { *err = 1; break; }
+	if (t1 - t0 > MITHRA_WAIT_TIMEOUT_NS) { atomicCAS(err, 0, (int) (( seq << 8 ) | (unsigned) ( id + 1 ))); break; }
 	__nanosleep(200);
       }
     __threadfence_system();
@@ -415,8 +416,8 @@ namespace mithra
 	signal_flag<<<1, 1, 0, s>>>(&hdr(x.next.arena)->flag[XF_A_PREV], x.seqA);
 	*launches += 2;
       }
-    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_PREV], x.seqA, x.d_err); *launches += 1; }
-    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_NEXT], x.seqA, x.d_err); *launches += 1; }
+    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_PREV], x.seqA, x.d_err, XF_A_PREV); *launches += 1; }
+    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_NEXT], x.seqA, x.d_err, XF_A_NEXT); *launches += 1; }
     XCU(cudaGetLastError());
     return 0;
   }
@@ -438,8 +439,8 @@ namespace mithra
 	signal_flag<<<1, 1, 0, s>>>(&hdr(x.next.arena)->flag[XF_EB_PREV], x.seqEB);
 	*launches += 2;
       }
-    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_PREV], x.seqEB, x.d_err); *launches += 1; }
-    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_NEXT], x.seqEB, x.d_err); *launches += 1; }
+    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_PREV], x.seqEB, x.d_err, XF_EB_PREV); *launches += 1; }
+    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_NEXT], x.seqEB, x.d_err, XF_EB_NEXT); *launches += 1; }
     XCU(cudaGetLastError());
     return 0;
   }
@@ -466,7 +467,7 @@ namespace mithra
       }
     if (x.prev.chain)
       {
-	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_PREV], x.seqJ, x.d_err);
+	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_PREV], x.seqJ, x.d_err, XF_J_PREV);
 	/* the sender's plane np-1 is my plane kb                                                          */
 	add_jmail<<<sms, 256, 0, s>>>(jn, (const double*) (x.arena + x.L.jmail_prev), &hdr(x.arena)->jbox_from_prev, jbox,
 					f.ncomp, f.Pp, f.N1, f.np, x.prev.np - 1, f.kb, 1);
@@ -474,7 +475,7 @@ namespace mithra
       }
     if (x.next.chain)
       {
-	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_NEXT], x.seqJ, x.d_err);
+	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_NEXT], x.seqJ, x.d_err, XF_J_NEXT);
 	/* the sender's planes kb-2, kb-1 are my planes np-3, np-2                                         */
 	add_jmail<<<sms, 256, 0, s>>>(jn, (const double*) (x.arena + x.L.jmail_next), &hdr(x.arena)->jbox_from_next, jbox,
 					f.ncomp, f.Pp, f.N1, f.np, x.next.kb - 2, f.np - 3, 2);
@@ -508,14 +509,20 @@ namespace mithra
    * multi-slab field step), close the holes and append the arrivals.  Updates pn.                          */
   static inline int migrate_end (Exchange& x, ParticlesDev P, size_t* pn, size_t pcap, cudaStream_t s, unsigned long long* launches)
   {
-    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_PREV], x.seqP, x.d_err);
-    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_NEXT], x.seqP, x.d_err);
+    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_PREV], x.seqP, x.d_err, XF_P_PREV);
+    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_NEXT], x.seqP, x.d_err, XF_P_NEXT);
     *launches += 2;
     XCU(cudaMemcpyAsync(x.h_counts + 0, x.d_cursor, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     XCU(cudaMemcpyAsync(x.h_counts + 4, hdr(x.arena)->in_count, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     XCU(cudaMemcpyAsync(x.h_counts + 6, x.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     XCU(cudaStreamSynchronize(s));
-    if (x.h_counts[6]) { x.error = "timed out waiting for a neighbouring slab"; return 1; }
+    if (x.h_counts[6])
+      {
+	static const char* what[8] = { "A from prev", "A from next", "E/B from prev", "E/B from next", "J from prev", "J from next", "particles from prev", "particles from next" };
+	const int id = (int) (x.h_counts[6] & 0xff) - 1;
+	x.error = std::string("timed out waiting for a neighbouring slab (") + (id >= 0 && id < 8 ? what[id] : "?") + ", sequence " + std::to_string(x.h_counts[6] >> 8) + ")";
+	return 1;
+      }
     const unsigned int out_prev = x.h_counts[0], out_next = x.h_counts[1], nl = x.h_counts[2];
     const unsigned int in_prev = x.h_counts[4], in_next = x.h_counts[5];
     if (out_prev > x.L.inbox_cap || out_next > x.L.inbox_cap || in_prev > x.L.inbox_cap || in_next > x.L.inbox_cap)
