@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MITHRA_GPU_ABI_VERSION      1
+#define MITHRA_GPU_ABI_VERSION      2
 #define MITHRA_MAX_UNDULATORS       16
 #define MITHRA_MAX_EXTFIELDS        8
 #define MITHRA_MAX_POWER_PLANES     256
@@ -143,6 +143,8 @@ typedef struct MithraGpuParams
   size_t max_particles;           /* capacity of the particle arrays                                 */
   size_t max_screen_records;      /* capacity of the per-screen record buffers                       */
   int    device;                  /* CUDA device ordinal, -1 = current                               */
+  int    sort_interval;           /* field steps between two counting sorts of the bunch by cell: > 0 as given,
+				     < 0 never, 0 = library default (16 for bunches of >= 4096 particles)     */
 } MithraGpuParams;
 
 typedef struct MithraGpu MithraGpu;
@@ -183,6 +185,11 @@ int mithra_gpu_seed_initial (MithraGpu* h);
 int mithra_gpu_upload_particles   (MithraGpu* h, const double* aos11, size_t n);
 int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_t capacity, size_t* n);
 int mithra_gpu_num_particles      (MithraGpu* h, size_t* n);
+
+/* Re-order the bunch by mesh cell now (mithra_gpu_bunch_update does it every sort_interval steps).  The reference
+ * keeps a std::list in insertion order (solver.h:271); here the order in memory is free and every particle keeps
+ * its upload index, in which downloads, screen records and mithra_gpu_particle_cells are returned.        */
+int mithra_gpu_sort_particles     (MithraGpu* h);
 
 /* Particle-to-cell assignment computed on the device with the arithmetic of the push (solver.cpp:1440-1469:
  * push_m[n] = gather cell (k-k0) N0 N1 + i N1 + j, or -1 when the particle gathers no mesh field) and of the

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_UNDULATORS, MAX_EXTFIELDS = 16, 8
 MAX_POWER_PLANES, MAX_POWER_LAMBDAS, MAX_SCREENS = 256, 64, 64
 NPHASES = 8
@@ -65,6 +65,7 @@ class Params(C.Structure):
         ("seed_enabled", C.c_int), ("seed", Beam),
         ("power", Power), ("screens", Screens),
         ("max_particles", C.c_size_t), ("max_screen_records", C.c_size_t), ("device", C.c_int),
+        ("sort_interval", C.c_int),
     ]
 
 
@@ -78,7 +79,7 @@ SYMBOLS = (
     "mithra_gpu_last_error", "mithra_gpu_abi_version", "mithra_gpu_device_count", "mithra_gpu_create",
     "mithra_gpu_destroy", "mithra_gpu_seed_initial", "mithra_gpu_upload_fields", "mithra_gpu_download_fields", "mithra_gpu_download_eb",
     "mithra_gpu_upload_particles", "mithra_gpu_download_particles", "mithra_gpu_num_particles",
-    "mithra_gpu_particle_cells",
+    "mithra_gpu_particle_cells", "mithra_gpu_sort_particles",
     "mithra_gpu_set_time", "mithra_gpu_get_time", "mithra_gpu_field_update", "mithra_gpu_bunch_update",
     "mithra_gpu_screen_profile", "mithra_gpu_power_sample", "mithra_gpu_field_shift", "mithra_gpu_current_reset",
     "mithra_gpu_current_update", "mithra_gpu_current_communicate", "mithra_gpu_advance_time", "mithra_gpu_step",
@@ -116,7 +117,7 @@ def load():
     lib.mithra_gpu_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_uint]
     lib.mithra_gpu_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_uint)]
     for name in ("field_update", "bunch_update", "screen_profile", "power_sample", "field_shift", "current_reset",
-                 "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial",
+                 "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial", "sort_particles",
                  "migrate_begin", "migrate_end"):
         getattr(lib, "mithra_gpu_" + name).argtypes = [vp]
     lib.mithra_gpu_step.argtypes = [vp, C.c_int]
@@ -246,6 +247,9 @@ class GpuSolver:
 
     def advanceTime(self):
         self._check(self.lib.mithra_gpu_advance_time(self.h))
+
+    def sortParticles(self):
+        self._check(self.lib.mithra_gpu_sort_particles(self.h))
 
     def seedInitial(self):
         self._check(self.lib.mithra_gpu_seed_initial(self.h))

@@ -9,7 +9,9 @@
  *                by the stencil and cleared afterwards.
  *   E, B       : one float4 pair per node (Ex,Ey,Ez,0 | Bx,By,Bz,0), node m = N0*N1*k + N1*i + j -- the
  *                reference's FieldVector<float> en_, bn_ (solver.h:244-245) interleaved for the 8-node gather.
- *   particles  : struct-of-arrays of doubles q, r[3], rm[3], gb[3], e (reference Charge, stdinclude.h:130-144).
+ *   particles  : struct-of-arrays of doubles q, r[3], rm[3], gb[3], e (reference Charge, stdinclude.h:130-144) plus
+ *                the upload index id; two copies, the counting sort by cell (kernels_sort.cuh) moves the bunch
+ *                from one to the other.
  *
  * z-slabs (one handle per GPU): the ABI speaks the reference's slab numbering (np local planes from global plane
  * k0, two planes shared with each neighbour, solver.cpp:619-641).  Internally every slab except the first keeps
@@ -86,6 +88,8 @@ namespace mithra
     double* rm[3];
     double* gb[3];
     double* e;
+    unsigned int* id;                   /* index the particle had when it was uploaded (arrivals from a neighbouring
+					   slab get fresh ones): the reference's list order, kept across the sorts */
   };
 
   __host__ __device__ inline long fidx (const long Pp, const int np, const int N1, int c, int k, int i, int j)

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -21,6 +22,7 @@
 #include "device_types.cuh"
 #include "kernels_field.cuh"
 #include "kernels_bunch.cuh"
+#include "kernels_sort.cuh"
 #include "kernels_seed.cuh"
 #include "exchange.cuh"
 
@@ -69,10 +71,22 @@ struct MithraGpu
 
   /* particles */
   BunchDev*       d_bd;
-  ParticlesDev    P;
-  double*         pstore;                 /* one allocation of 11 * capacity doubles                      */
+  ParticlesDev    P, Palt;                /* the bunch and the copy the counting sort moves it into        */
+  double*         pstore[2];              /* 11 * capacity doubles each                                    */
+  unsigned int*   idstore[2];
   size_t          pcap, pn;
+  unsigned int    next_id;                /* upload index given to the next arrival from a neighbouring slab */
+  bool            ids_dense;              /* the ids are a permutation of 0 .. pn-1 (no migration yet)     */
   unsigned int*   d_noutside;
+
+  /* counting sort by cell (kernels_sort.cuh) */
+  long            sort_cap;               /* histogram bins                                                */
+  unsigned int*   d_hist;
+  unsigned int*   d_sums;
+  unsigned int*   d_key;
+  unsigned int*   d_rank;
+  int             sort_interval;          /* MithraGpuParams.sort_interval                                 */
+  int             steps_since_sort;
 
   /* power */
   PowerDev        pw;
@@ -96,6 +110,7 @@ struct MithraGpu
 
   /* seed */
   SeedDev*        d_seed;
+  double*         d_seed_tab;             /* per-plane table of a seed along +z (kernels_seed.cuh), else 0  */
 
   /* slab exchange */
   Exchange        xch;
@@ -168,6 +183,34 @@ __global__ void planar_to_aos (const double* __restrict__ src, double* __restric
       const long k = m / P, r = m - k * P;
       dst[m * ncomp_dst + c] = src[((long) (c0 + c) * np + k + kshift) * Pp + r];
     }
+}
+
+/* particles: host array-of-structures double[n][11] <-> device struct-of-arrays.  Row of particle t in the AoS:
+ * t on upload (which also numbers the particles), order[t] (or P.id[t] when order == 0) on download, i.e. the
+ * reference's list order whatever the counting sort did to the device order.                               */
+__global__ void __launch_bounds__(256) aos_to_particles (const double* __restrict__ aos, ParticlesDev P, long n)
+{
+  const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* o = aos + t * 11;
+  P.q[t] = o[0];
+  P.r[0][t] = o[1];  P.r[1][t] = o[2];  P.r[2][t] = o[3];
+  P.rm[0][t] = o[4]; P.rm[1][t] = o[5]; P.rm[2][t] = o[6];
+  P.gb[0][t] = o[7]; P.gb[1][t] = o[8]; P.gb[2][t] = o[9];
+  P.e[t] = o[10];
+  P.id[t] = (unsigned int) t;
+}
+
+__global__ void __launch_bounds__(256) particles_to_aos (ParticlesDev P, long n, const unsigned int* __restrict__ order, double* __restrict__ aos)
+{
+  const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double* o = aos + (long) (order ? order[t] : P.id[t]) * 11;
+  o[0] = P.q[t];
+  o[1] = P.r[0][t];  o[2] = P.r[1][t];  o[3] = P.r[2][t];
+  o[4] = P.rm[0][t]; o[5] = P.rm[1][t]; o[6] = P.rm[2][t];
+  o[7] = P.gb[0][t]; o[8] = P.gb[1][t]; o[9] = P.gb[2][t];
+  o[10] = P.e[t];
 }
 
 __global__ void set_box (Box* b, int l0, int l1, int l2, int h0, int h1, int h2)
@@ -258,13 +301,14 @@ static int preload_kernels ()
 {
   cudaError_t e = cudaSuccess;
   #define PL(k) do { cudaError_t r_ = preload(k); if (r_ != cudaSuccess) e = r_; } while (0)
-  PL(aos_to_planar); PL(planar_to_aos); PL(set_box); PL(make_eb_box);
+  PL(aos_to_planar); PL(planar_to_aos); PL(aos_to_particles); PL(particles_to_aos); PL(set_box); PL(make_eb_box);
+  PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
   PL(particle_box); PL(particle_cells); PL(push_particles); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish);
-  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_initial_kernel);
+  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
   #undef PL
@@ -321,12 +365,24 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
 
   CU(cudaMalloc(&h->d_bd, sizeof(BunchDev))); CU(cudaMemcpyAsync(h->d_bd, &h->bd, sizeof(BunchDev), cudaMemcpyHostToDevice, h->stream));
   h->pcap = params->max_particles ? params->max_particles : (size_t) 1 << 20;
-  h->pn = 0;
-  CU(cudaMalloc(&h->pstore, h->pcap * 11 * sizeof(double)));
-  {
-    double* s = h->pstore; const size_t c = h->pcap;
-    h->P.q = s; for (int a = 0; a < 3; a++) { h->P.r[a] = s + (1 + a) * c; h->P.rm[a] = s + (4 + a) * c; h->P.gb[a] = s + (7 + a) * c; } h->P.e = s + 10 * c;
-  }
+  h->pn = 0; h->next_id = 0; h->ids_dense = true;
+  for (int w = 0; w < 2; w++)
+    {
+      CU(cudaMalloc(&h->pstore[w], h->pcap * 11 * sizeof(double)));
+      CU(cudaMalloc(&h->idstore[w], h->pcap * sizeof(unsigned int)));
+      ParticlesDev& Q = w ? h->Palt : h->P;
+      double* s = h->pstore[w]; const size_t c = h->pcap;
+      Q.q = s; for (int a = 0; a < 3; a++) { Q.r[a] = s + (1 + a) * c; Q.rm[a] = s + (4 + a) * c; Q.gb[a] = s + (7 + a) * c; } Q.e = s + 10 * c;
+      Q.id = h->idstore[w];
+    }
+  /* counting sort: one bin per cell of the particle box, as many as the slab has cells (at most 2^27)      */
+  h->sort_cap = std::min<long>((long) f.np * f.P, 1L << 27);
+  h->sort_interval = params->sort_interval;
+  h->steps_since_sort = 0;
+  CU(cudaMalloc(&h->d_hist, (size_t) h->sort_cap * sizeof(unsigned int)));
+  CU(cudaMalloc(&h->d_sums, (size_t) (h->sort_cap / MITHRA_SCAN_CHUNK + 2) * sizeof(unsigned int)));
+  CU(cudaMalloc(&h->d_key,  h->pcap * sizeof(unsigned int)));
+  CU(cudaMalloc(&h->d_rank, h->pcap * sizeof(unsigned int)));
   CU(cudaMalloc(&h->d_noutside, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_noutside, 0, sizeof(unsigned int), h->stream));
 
   /* power sampling, radiation.cpp:18-121 */
@@ -372,13 +428,21 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     }
 
   /* seed */
-  h->d_seed = 0;
+  h->d_seed = 0; h->d_seed_tab = 0;
   if (params->seed_enabled)
     {
       SeedDev sd; memset(&sd, 0, sizeof(sd));
       sd.beam = params->seed; sd.c0 = params->c0; sd.gamma = params->gamma; sd.beta = params->beta; sd.dt_shift = params->dt_shift;
       sd.xmin = params->xmin; sd.ymin = params->ymin; sd.zmin = params->zmin; sd.dx = params->dx; sd.dy = params->dy; sd.dz = params->dz;
+      sd.k0 = f.k0;
+      const double* D = params->seed.direction; const double* Q = params->seed.polarization;
+      sd.yv[0] = D[1] * Q[2] - D[2] * Q[1]; sd.yv[1] = D[2] * Q[0] - D[0] * Q[2]; sd.yv[2] = D[0] * Q[1] - D[1] * Q[0];   /* fieldvector.h cross() */
+      const int st = params->seed.seed_type;
+      sd.along_z = ( D[0] == 0.0 && D[1] == 0.0 && D[2] == 1.0 &&
+		     ( st == MITHRA_BEAM_PLANEWAVE || st == MITHRA_BEAM_PLANEWAVETRUNCATED || st == MITHRA_BEAM_GAUSSIAN || st == MITHRA_BEAM_SUPERGAUSSIAN ) ) ? 1 : 0;
+      if (getenv("MITHRA_SEED_GENERIC")) sd.along_z = 0;
       CU(cudaMalloc(&h->d_seed, sizeof(SeedDev))); CU(cudaMemcpy(h->d_seed, &sd, sizeof(SeedDev), cudaMemcpyHostToDevice));
+      if (sd.along_z) CU(cudaMalloc(&h->d_seed_tab, (size_t) f.np * MITHRA_SEED_TAB * sizeof(double)));
     }
 
   if (exchange_init(h->xch, f, h->pcap, h->stream)) { std::string e = h->xch.error; mithra_gpu_destroy(h); return fail("mithra_gpu_create: %s", e.c_str()); }
@@ -398,9 +462,11 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   exchange_destroy(h->xch);
   for (int l = 0; l < 3; l++) cudaFree(h->A[l]);
   cudaFree(h->J); cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
-  cudaFree(h->eb); cudaFree(h->d_bd); cudaFree(h->pstore); cudaFree(h->d_noutside);
+  cudaFree(h->eb); cudaFree(h->d_bd); cudaFree(h->d_noutside);
+  for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
+  cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
   cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
-  cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed);
+  cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -526,19 +592,39 @@ static int refresh_particle_box (MithraGpu* h)
   return 0;
 }
 
+/* The copy the sort is not using at the moment doubles as the staging buffer of the AoS transfers.           */
 extern "C" int mithra_gpu_upload_particles (MithraGpu* h, const double* aos11, size_t n)
 {
   USE(h);
   if (n > h->pcap) return fail("mithra_gpu_upload_particles: %zu particles exceed the capacity %zu (MithraGpuParams.max_particles)", n, h->pcap);
-  std::vector<double> soa(11 * n);
-  for (size_t i = 0; i < n; i++)
-    for (int c = 0; c < 11; c++) soa[(size_t) c * n + i] = aos11[i * 11 + c];
-  CU(cudaStreamSynchronize(h->stream));
-  for (int c = 0; c < 11; c++)
-    if (n) CU(cudaMemcpy(h->pstore + (size_t) c * h->pcap, soa.data() + (size_t) c * n, n * sizeof(double), cudaMemcpyHostToDevice));
-  h->pn = n;
+  if (n)
+    {
+      double* stage = h->Palt.q;
+      CU(cudaMemcpyAsync(stage, aos11, n * 11 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      aos_to_particles<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(stage, h->P, (long) n);
+      CU(cudaGetLastError());
+      h->cnt.kernel_launches += 1;
+    }
+  h->pn = n; h->next_id = (unsigned int) n; h->ids_dense = true;
+  h->steps_since_sort = 1 << 30;                        /* sort before the next push (if sorting is on)             */
   TRY(refresh_particle_box(h));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+/* rank of every particle in the order of the upload indices, for bunches that lost or received particles     */
+static int id_ranks (MithraGpu* h, unsigned int** d_order)
+{
+  *d_order = 0;
+  if (h->ids_dense || h->pn == 0) return 0;
+  const size_t n = h->pn;
+  std::vector<unsigned int> ids(n), order(n), rank(n);
+  CU(cudaMemcpy(ids.data(), h->P.id, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) order[i] = (unsigned int) i;
+  std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) { return ids[a] < ids[b]; });
+  for (size_t i = 0; i < n; i++) rank[order[i]] = (unsigned int) i;
+  CU(cudaMalloc(d_order, n * sizeof(unsigned int)));
+  CU(cudaMemcpy(*d_order, rank.data(), n * sizeof(unsigned int), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -550,11 +636,16 @@ extern "C" int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_
   if (!aos11) return 0;
   if (capacity < h->pn) return fail("mithra_gpu_download_particles: capacity %zu < %zu particles", capacity, h->pn);
   const size_t np = h->pn;
-  std::vector<double> soa(11 * np);
-  for (int c = 0; c < 11; c++)
-    if (np) CU(cudaMemcpy(soa.data() + (size_t) c * np, h->pstore + (size_t) c * h->pcap, np * sizeof(double), cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < np; i++)
-    for (int c = 0; c < 11; c++) aos11[i * 11 + c] = soa[(size_t) c * np + i];
+  if (np == 0) return 0;
+  unsigned int* d_order = 0;
+  TRY(id_ranks(h, &d_order));
+  double* stage = h->Palt.q;
+  particles_to_aos<<<(int) ((np + 255) / 256), 256, 0, h->stream>>>(h->P, (long) np, d_order, stage);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaMemcpyAsync(aos11, stage, np * 11 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (d_order) cudaFree(d_order);
   return 0;
 }
 
@@ -563,15 +654,30 @@ extern "C" int mithra_gpu_particle_cells (MithraGpu* h, long* push_m, int* ijk6,
   USE(h);
   if (capacity < h->pn) return fail("mithra_gpu_particle_cells: capacity %zu < %zu particles", capacity, h->pn);
   if (h->pn == 0) return 0;
+  const size_t n = h->pn;
   long* dm = 0; int* dd = 0;
-  if (push_m) CU(cudaMalloc(&dm, h->pn * sizeof(long)));
-  if (ijk6)   CU(cudaMalloc(&dd, h->pn * 6 * sizeof(int)));
-  particle_cells<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, dm, dd);
+  if (push_m) CU(cudaMalloc(&dm, n * sizeof(long)));
+  if (ijk6)   CU(cudaMalloc(&dd, n * 6 * sizeof(int)));
+  particle_cells<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) n, dm, dd);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   CU(cudaStreamSynchronize(h->stream));
-  if (push_m) { CU(cudaMemcpy(push_m, dm, h->pn * sizeof(long), cudaMemcpyDeviceToHost)); cudaFree(dm); }
-  if (ijk6)   { CU(cudaMemcpy(ijk6, dd, h->pn * 6 * sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(dd); }
+  /* device order -> order of the upload indices                                                              */
+  std::vector<unsigned int> ids(n), order(n);
+  CU(cudaMemcpy(ids.data(), h->P.id, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) order[i] = (unsigned int) i;
+  if (!h->ids_dense) std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) { return ids[a] < ids[b]; });
+  else for (size_t i = 0; i < n; i++) order[ids[i]] = (unsigned int) i;
+  if (push_m)
+    {
+      std::vector<long> t(n); CU(cudaMemcpy(t.data(), dm, n * sizeof(long), cudaMemcpyDeviceToHost)); cudaFree(dm);
+      for (size_t i = 0; i < n; i++) push_m[i] = t[order[i]];
+    }
+  if (ijk6)
+    {
+      std::vector<int> t(n * 6); CU(cudaMemcpy(t.data(), dd, n * 6 * sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(dd);
+      for (size_t i = 0; i < n; i++) memcpy(ijk6 + 6 * i, t.data() + 6 * (size_t) order[i], 6 * sizeof(int));
+    }
   return 0;
 }
 
@@ -618,8 +724,8 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
     PhaseTimer t(h, PH_BOUNDARY);
     if (h->d_seed)
       {
-	TRY(seed_inject(h->d_seed, f, ap, h->time, h->stream, h->num_sms));
-	h->cnt.kernel_launches += 1;
+	TRY(seed_inject(h->d_seed, h->d_seed_tab, f, ap, h->time, h->stream, h->num_sms));
+	h->cnt.kernel_launches += h->d_seed_tab ? 2 : 1;
       }
     const long nface = (2L * (f.N1 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.N1 - 2)) * f.ncomp;
     boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am);
@@ -671,11 +777,39 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
   return 0;
 }
 
+/* Counting sort of the bunch by cell (kernels_sort.cuh); the particle box of the last push / upload bounds the keys. */
+extern "C" int mithra_gpu_sort_particles (MithraGpu* h)
+{
+  USE(h);
+  h->steps_since_sort = 0;
+  if (h->pn < 2) return 0;
+  const long n = (long) h->pn, cap = h->sort_cap;
+  const int pgrid = (int) ((n + 255) / 256);
+  const int cgrid = (int) ((cap + MITHRA_SCAN_CHUNK - 1) / MITHRA_SCAN_CHUNK);
+  sort_zero<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist);
+  sort_count<<<pgrid, 256, 0, h->stream>>>(h->d_bd, h->P, n, h->d_pbox, cap, h->d_hist, h->d_key, h->d_rank);
+  scan_chunk_sums<<<cgrid, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist, h->d_sums);
+  scan_sums<<<1, 1024, 0, h->stream>>>(h->d_pbox, cap, h->d_sums);
+  scan_chunks<<<cgrid, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist, h->d_sums);
+  sort_permute<<<pgrid, 256, 0, h->stream>>>(h->P, h->Palt, n, h->d_pbox, cap, h->d_hist, h->d_key, h->d_rank);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 6;
+  std::swap(h->P, h->Palt);
+  return 0;
+}
+
 extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
 {
   USE(h);
   PhaseTimer t(h, PH_PUSH);
   const int nsub = h->prm.n_update_bunch;
+  {
+    /* MithraGpuParams.sort_interval: > 0 field steps between two sorts, < 0 never, 0 = every 16 steps for bunches
+     * large enough for the order to matter                                                                   */
+    const int every = h->sort_interval > 0 ? h->sort_interval : (h->sort_interval == 0 && h->pn >= 4096 ? 16 : 0);
+    if (every > 0 && h->steps_since_sort >= every) TRY(mithra_gpu_sort_particles(h));
+    if (h->steps_since_sort < (1 << 30)) ++h->steps_since_sort;
+  }
   if (h->pn > 0)
     {
       /* the particle box is rebuilt by the push (it is read by the next field update)                      */
@@ -799,9 +933,10 @@ extern "C" int mithra_gpu_migrate_end (MithraGpu* h)
   USE(h);
   if (h->fd.size <= 1) return 0;
   const size_t before = h->pn;
-  if (migrate_end(h->xch, h->P, &h->pn, h->pcap, h->stream, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
+  if (migrate_end(h->xch, h->P, &h->pn, h->pcap, &h->next_id, h->stream, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
   /* arrivals sit near the slab faces: grow the box the next E/B evaluation covers                           */
   const size_t kept = before - h->xch.h_counts[2];
+  if (h->xch.h_counts[2] || h->pn != kept) h->ids_dense = false;
   if (h->pn > kept)
     {
       particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->d_bd, h->P, (long) kept, (long) h->pn, h->d_pbox);

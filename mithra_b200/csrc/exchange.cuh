@@ -256,15 +256,15 @@ namespace mithra
     for (int t = threadIdx.x; t < cnt; t += blockDim.x)
       {
 	const int d = holes[t], s = movers[t];
-	P.q[d] = P.q[s]; P.e[d] = P.e[s];
+	P.q[d] = P.q[s]; P.e[d] = P.e[s]; P.id[d] = P.id[s];
 	#pragma unroll
 	for (int a = 0; a < 3; a++) { P.r[a][d] = P.r[a][s]; P.rm[a][d] = P.rm[a][s]; P.gb[a][d] = P.gb[a][s]; }
       }
   }
 
-  /* Append the arrivals of one inbox at [n, n + cnt).                                                     */
+  /* Append the arrivals of one inbox at [n, n + cnt); they get the fresh upload indices id0, id0 + 1, ...     */
   __global__ void __launch_bounds__(256)
-  unpack_inbox (ParticlesDev P, long n, const double* __restrict__ inbox, int cnt)
+  unpack_inbox (ParticlesDev P, long n, const double* __restrict__ inbox, int cnt, unsigned int id0)
   {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -275,6 +275,7 @@ namespace mithra
     P.rm[0][d] = o[4]; P.rm[1][d] = o[5]; P.rm[2][d] = o[6];
     P.gb[0][d] = o[7]; P.gb[1][d] = o[8]; P.gb[2][d] = o[9];
     P.e[d] = o[10];
+    P.id[d] = id0 + (unsigned int) t;
   }
 
   /* ---------------------------------------------------------------------------------------------------- */
@@ -507,7 +508,7 @@ namespace mithra
 
   /* Migration, second half: wait for both inboxes, read the four counters (the one host synchronisation of a
    * multi-slab field step), close the holes and append the arrivals.  Updates pn.                          */
-  static inline int migrate_end (Exchange& x, ParticlesDev P, size_t* pn, size_t pcap, cudaStream_t s, unsigned long long* launches)
+  static inline int migrate_end (Exchange& x, ParticlesDev P, size_t* pn, size_t pcap, unsigned int* next_id, cudaStream_t s, unsigned long long* launches)
   {
     wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_PREV], x.seqP, x.d_err, XF_P_PREV);
     wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_NEXT], x.seqP, x.d_err, XF_P_NEXT);
@@ -537,13 +538,13 @@ namespace mithra
     if (n + in_prev + in_next > pcap) { x.error = "particle capacity exceeded by arrivals from the neighbouring slabs"; return 1; }
     if (in_prev > 0)
       {
-	unpack_inbox<<<(in_prev + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_prev), (int) in_prev);
-	n += in_prev; *launches += 1;
+	unpack_inbox<<<(in_prev + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_prev), (int) in_prev, *next_id);
+	n += in_prev; *next_id += in_prev; *launches += 1;
       }
     if (in_next > 0)
       {
-	unpack_inbox<<<(in_next + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_next), (int) in_next);
-	n += in_next; *launches += 1;
+	unpack_inbox<<<(in_next + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_next), (int) in_next, *next_id);
+	n += in_next; *next_id += in_next; *launches += 1;
       }
     XCU(cudaGetLastError());
     *pn = n;

@@ -20,6 +20,7 @@ namespace mithra
   /* pmod, stdinclude.cpp:88-93 */
   __device__ __forceinline__ double pmod (double a, double b)
   {
+    if (a >= 0.0 && a < b) return a;                   /* fmod(a, b) == a exactly: skip its division loop        */
     double x = fmod(a, b);
     x += ( x < 0.0 ) ? b : 0.0;
     return x;
@@ -262,12 +263,65 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
-   * ZigZag deposition of one particle (fdtd.cpp:47-184): relay point, two segments, each scattering the three
-   * current components to the 8 nodes of its cell (+ rho at the end point with space charge,
-   * fdtdSC.cpp:141-160).  FP64 atomics straight to L2 (RED.ADD.F64); the box of touched nodes is merged
-   * per warp.
+   * ZigZag deposition (fdtd.cpp:47-184): relay point, two segments, each scattering the three current components
+   * to the 8 nodes of its cell (+ rho at the end point with space charge, fdtdSC.cpp:141-160).
+   *
+   * A thread walks MITHRA_DEP_RUN particles that are consecutive in memory -- after the counting sort by cell these
+   * are particles of the same or of neighbouring cells -- and keeps the contributions to the 8 nodes of the cell
+   * it is currently in in registers: 4 distinct values per component (the reference gives the same J_x to both x
+   * nodes of a cell, fdtd.cpp:111-118, likewise y and z) and 8 charge weights.  Both segments of a particle that
+   * stays in its cell and all particles of a run that share the cell are summed there; only when the cell changes
+   * (and at the end of the run) the 24 (+8) sums go to L2 as FP64 reductions (RED.ADD.F64).  Measured on B200
+   * this is what bounds the kernel: the atomics' issue rate, not HBM.  The bounding box of the touched nodes is
+   * merged per warp for the stencil (which reads J only there) and the next clear.
    * ------------------------------------------------------------------------------------------------ */
-  __device__ __forceinline__ void scatter_segment (const BunchDev& b, double* __restrict__ jn, long m, double q,
+  #define MITHRA_DEP_RUN 4
+
+  template <bool SC>
+  struct DepositAcc
+  {
+    long   m;                         /* first node of the cell the sums belong to, -1 = none                 */
+    double jx[4], jy[4], jz[4];
+    double rho[SC ? 8 : 1];
+  };
+
+  template <bool SC>
+  __device__ __forceinline__ void deposit_flush (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a)
+  {
+    if (a.m < 0) return;
+    const long N1 = b.N1, Pp = b.Pp, cs = (long) b.np * b.Pp;
+    const long m = a.m;
+    const long o[8] = { m, m + N1, m + 1, m + N1 + 1, m + Pp, m + Pp + N1, m + Pp + 1, m + Pp + N1 + 1 };
+    double* J0 = jn; double* J1 = jn + cs; double* J2 = jn + 2 * cs;
+    atomicAdd(J0 + o[0], a.jx[0]); atomicAdd(J0 + o[1], a.jx[0]); atomicAdd(J0 + o[2], a.jx[1]); atomicAdd(J0 + o[3], a.jx[1]);
+    atomicAdd(J0 + o[4], a.jx[2]); atomicAdd(J0 + o[5], a.jx[2]); atomicAdd(J0 + o[6], a.jx[3]); atomicAdd(J0 + o[7], a.jx[3]);
+    atomicAdd(J1 + o[0], a.jy[0]); atomicAdd(J1 + o[2], a.jy[0]); atomicAdd(J1 + o[1], a.jy[1]); atomicAdd(J1 + o[3], a.jy[1]);
+    atomicAdd(J1 + o[4], a.jy[2]); atomicAdd(J1 + o[6], a.jy[2]); atomicAdd(J1 + o[5], a.jy[3]); atomicAdd(J1 + o[7], a.jy[3]);
+    atomicAdd(J2 + o[0], a.jz[0]); atomicAdd(J2 + o[4], a.jz[0]); atomicAdd(J2 + o[1], a.jz[1]); atomicAdd(J2 + o[5], a.jz[1]);
+    atomicAdd(J2 + o[2], a.jz[2]); atomicAdd(J2 + o[6], a.jz[2]); atomicAdd(J2 + o[3], a.jz[3]); atomicAdd(J2 + o[7], a.jz[3]);
+    if constexpr (SC)
+      {
+	double* R = jn + 3 * cs;
+	#pragma unroll
+	for (int q = 0; q < 8; q++) atomicAdd(R + o[q], a.rho[q]);
+      }
+    a.m = -1;
+  }
+
+  template <bool SC>
+  __device__ __forceinline__ void deposit_open (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a, long m)
+  {
+    if (a.m == m) return;
+    deposit_flush<SC>(b, jn, a);
+    a.m = m;
+    #pragma unroll
+    for (int q = 0; q < 4; q++) { a.jx[q] = 0.0; a.jy[q] = 0.0; a.jz[q] = 0.0; }
+    if constexpr (SC) { _Pragma("unroll") for (int q = 0; q < 8; q++) a.rho[q] = 0.0; }
+  }
+
+  /* one segment with midpoint (mx,my,mz) and flux q (jx,jy,jz), fdtd.cpp:92-131                               */
+  template <bool SC>
+  __device__ __forceinline__ void deposit_segment (const BunchDev& b, DepositAcc<SC>& a, double q,
 						   double mx, double my, double mz, double jx, double jy, double jz)
   {
     double c;
@@ -275,25 +329,10 @@ namespace mithra
     const double dyp = modf( ( my - b.ymin ) / b.dy, &c );
     const double dzp = modf( ( mz - b.zmin ) / b.dz, &c );
     const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
-    const long N1 = b.N1, Pp = b.Pp, cs = (long) b.np * b.Pp;
-    const long o[8] = { m, m + N1, m + 1, m + N1 + 1, m + Pp, m + Pp + N1, m + Pp + 1, m + Pp + N1 + 1 };
-    double* J0 = jn; double* J1 = jn + cs; double* J2 = jn + 2 * cs;
     const double h = q * 0.5;
-
-    atomicAdd(J0 + o[0], h * y1 * z1 * jx); atomicAdd(J0 + o[1], h * y1 * z1 * jx);
-    atomicAdd(J0 + o[2], h * y2 * z1 * jx); atomicAdd(J0 + o[3], h * y2 * z1 * jx);
-    atomicAdd(J0 + o[4], h * y1 * z2 * jx); atomicAdd(J0 + o[5], h * y1 * z2 * jx);
-    atomicAdd(J0 + o[6], h * y2 * z2 * jx); atomicAdd(J0 + o[7], h * y2 * z2 * jx);
-
-    atomicAdd(J1 + o[0], h * x1 * z1 * jy); atomicAdd(J1 + o[1], h * x2 * z1 * jy);
-    atomicAdd(J1 + o[2], h * x1 * z1 * jy); atomicAdd(J1 + o[3], h * x2 * z1 * jy);
-    atomicAdd(J1 + o[4], h * x1 * z2 * jy); atomicAdd(J1 + o[5], h * x2 * z2 * jy);
-    atomicAdd(J1 + o[6], h * x1 * z2 * jy); atomicAdd(J1 + o[7], h * x2 * z2 * jy);
-
-    atomicAdd(J2 + o[0], h * x1 * y1 * jz); atomicAdd(J2 + o[1], h * x2 * y1 * jz);
-    atomicAdd(J2 + o[2], h * x1 * y2 * jz); atomicAdd(J2 + o[3], h * x2 * y2 * jz);
-    atomicAdd(J2 + o[4], h * x1 * y1 * jz); atomicAdd(J2 + o[5], h * x2 * y1 * jz);
-    atomicAdd(J2 + o[6], h * x1 * y2 * jz); atomicAdd(J2 + o[7], h * x2 * y2 * jz);
+    a.jx[0] += h * y1 * z1 * jx; a.jx[1] += h * y2 * z1 * jx; a.jx[2] += h * y1 * z2 * jx; a.jx[3] += h * y2 * z2 * jx;
+    a.jy[0] += h * x1 * z1 * jy; a.jy[1] += h * x2 * z1 * jy; a.jy[2] += h * x1 * z2 * jy; a.jy[3] += h * x2 * z2 * jy;
+    a.jz[0] += h * x1 * y1 * jz; a.jz[1] += h * x2 * y1 * jz; a.jz[2] += h * x1 * y2 * jz; a.jz[3] += h * x2 * y2 * jz;
   }
 
   template <bool SC>
@@ -301,64 +340,62 @@ namespace mithra
   deposit_current (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox)
   {
     const BunchDev& b = *bp;
-    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false; int i0 = 0, i1 = 0, j0 = 0, j1 = 0, k0 = 0, k1 = 0;
+    const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * MITHRA_DEP_RUN;
+    bool valid = false; int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1, k0 = 0x7fffffff, k1 = -1;
+    DepositAcc<SC> acc; acc.m = -1;
+    const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
 
-    if (t < n)
+    for (int r = 0; r < MITHRA_DEP_RUN; r++)
       {
+	const long t = t0 + r;
+	if (t >= n) break;
 	const double rpx = P.r[0][t],  rpy = P.r[1][t],  rpz = P.r[2][t];
 	const double rmx = P.rm[0][t], rmy = P.rm[1][t], rmz = P.rm[2][t];
 
-	const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
 	const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
 			   rpz < zhi && rpz >= zlo );
 	const bool bmf = ( rmx < b.xmax - b.dx && rmx > b.xmin + b.dx && rmy < b.ymax - b.dy && rmy > b.ymin + b.dy &&
 			   rmz < zhi && rmz >= zlo );
-	if (bpf || bmf)
+	if (!bpf && !bmf) continue;
+
+	const double q = P.q[t];
+	const int ip = (int) floor( ( rpx - b.xmin ) / b.dx ), jp = (int) floor( ( rpy - b.ymin ) / b.dy ), kp = (int) floor( ( rpz - b.zmin ) / b.dz );
+	const int im = (int) floor( ( rmx - b.xmin ) / b.dx ), jm = (int) floor( ( rmy - b.ymin ) / b.dy ), km = (int) floor( ( rmz - b.zmin ) / b.dz );
+
+	/* relay point, fdtd.cpp:80-85 */
+	const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
+	const double ry = fmin( min(jm, jp) * b.dy + b.dy + b.ymin, fmax( max(jm, jp) * b.dy + b.ymin, 0.5 * ( rmy + rpy ) ) );
+	const double rz = fmin( min(km, kp) * b.dz + b.dz + b.zmin, fmax( max(km, kp) * b.dz + b.zmin, 0.5 * ( rmz + rpz ) ) );
+
+	valid = true;
+	if (bpf)
 	  {
-	    const double q = P.q[t];
-	    const int ip = (int) floor( ( rpx - b.xmin ) / b.dx ), jp = (int) floor( ( rpy - b.ymin ) / b.dy ), kp = (int) floor( ( rpz - b.zmin ) / b.dz );
-	    const int im = (int) floor( ( rmx - b.xmin ) / b.dx ), jm = (int) floor( ( rmy - b.ymin ) / b.dy ), km = (int) floor( ( rmz - b.zmin ) / b.dz );
-
-	    /* relay point, fdtd.cpp:80-85 */
-	    const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
-	    const double ry = fmin( min(jm, jp) * b.dy + b.dy + b.ymin, fmax( max(jm, jp) * b.dy + b.ymin, 0.5 * ( rmy + rpy ) ) );
-	    const double rz = fmin( min(km, kp) * b.dz + b.dz + b.zmin, fmax( max(km, kp) * b.dz + b.zmin, 0.5 * ( rmz + rpz ) ) );
-
-	    valid = true;
-	    i0 = 0x7fffffff; j0 = 0x7fffffff; k0 = 0x7fffffff; i1 = j1 = k1 = -1;
-	    if (bpf)
+	    deposit_open<SC>(b, jn, acc, (long) ( kp - b.k0 ) * b.Pp + (long) ip * b.N1 + jp);
+	    deposit_segment<SC>(b, acc, q, 0.5 * ( rpx + rx ), 0.5 * ( rpy + ry ), 0.5 * ( rpz + rz ), rpx - rx, rpy - ry, rpz - rz);
+	    if constexpr (SC)
 	      {
-		const long m = (long) ( kp - b.k0 ) * b.Pp + (long) ip * b.N1 + jp;
-		scatter_segment(b, jn, m, q, 0.5 * ( rpx + rx ), 0.5 * ( rpy + ry ), 0.5 * ( rpz + rz ), rpx - rx, rpy - ry, rpz - rz);
-		if (SC)
-		  {
-		    double c;
-		    const double dxp = modf( ( rpx - b.xmin ) / b.dx, &c ), dyp = modf( ( rpy - b.ymin ) / b.dy, &c ), dzp = modf( ( rpz - b.zmin ) / b.dz, &c );
-		    const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
-		    double* R = jn + 3 * (long) b.np * b.Pp + m;
-		    const long N1 = b.N1, Pp = b.Pp;
-		    atomicAdd(R,               q * x1 * y1 * z1); atomicAdd(R + N1,          q * x2 * y1 * z1);
-		    atomicAdd(R + 1,           q * x1 * y2 * z1); atomicAdd(R + N1 + 1,      q * x2 * y2 * z1);
-		    atomicAdd(R + Pp,          q * x1 * y1 * z2); atomicAdd(R + Pp + N1,     q * x2 * y1 * z2);
-		    atomicAdd(R + Pp + 1,      q * x1 * y2 * z2); atomicAdd(R + Pp + N1 + 1, q * x2 * y2 * z2);
-		  }
-		i0 = min(i0, ip); i1 = max(i1, ip + 1); j0 = min(j0, jp); j1 = max(j1, jp + 1); k0 = min(k0, kp - b.k0); k1 = max(k1, kp - b.k0 + 1);
+		double c;
+		const double dxp = modf( ( rpx - b.xmin ) / b.dx, &c ), dyp = modf( ( rpy - b.ymin ) / b.dy, &c ), dzp = modf( ( rpz - b.zmin ) / b.dz, &c );
+		const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
+		acc.rho[0] += q * x1 * y1 * z1; acc.rho[1] += q * x2 * y1 * z1; acc.rho[2] += q * x1 * y2 * z1; acc.rho[3] += q * x2 * y2 * z1;
+		acc.rho[4] += q * x1 * y1 * z2; acc.rho[5] += q * x2 * y1 * z2; acc.rho[6] += q * x1 * y2 * z2; acc.rho[7] += q * x2 * y2 * z2;
 	      }
-	    if (bmf)
-	      {
-		const long m = (long) ( km - b.k0 ) * b.Pp + (long) im * b.N1 + jm;
-		scatter_segment(b, jn, m, q, 0.5 * ( rmx + rx ), 0.5 * ( rmy + ry ), 0.5 * ( rmz + rz ), rx - rmx, ry - rmy, rz - rmz);
-		i0 = min(i0, im); i1 = max(i1, im + 1); j0 = min(j0, jm); j1 = max(j1, jm + 1); k0 = min(k0, km - b.k0); k1 = max(k1, km - b.k0 + 1);
-	      }
+	    i0 = min(i0, ip); i1 = max(i1, ip + 1); j0 = min(j0, jp); j1 = max(j1, jp + 1); k0 = min(k0, kp - b.k0); k1 = max(k1, kp - b.k0 + 1);
+	  }
+	if (bmf)
+	  {
+	    deposit_open<SC>(b, jn, acc, (long) ( km - b.k0 ) * b.Pp + (long) im * b.N1 + jm);
+	    deposit_segment<SC>(b, acc, q, 0.5 * ( rmx + rx ), 0.5 * ( rmy + ry ), 0.5 * ( rmz + rz ), rx - rmx, ry - rmy, rz - rmz);
+	    i0 = min(i0, im); i1 = max(i1, im + 1); j0 = min(j0, jm); j1 = max(j1, jm + 1); k0 = min(k0, km - b.k0); k1 = max(k1, km - b.k0 + 1);
 	  }
       }
+    deposit_flush<SC>(b, jn, acc);
     warp_box_merge(jbox, valid, i0, i1, j0, j1, k0, k1);
   }
 
   /* ------------------------------------------------------------------------------------------------
    * Screens (solver.cpp:2205-2257).  One thread per particle, loop over screens; a crossing appends a record
-   * { x, y, t, gbx, gby, gbz_lab, particle index, step } to the screen's buffer through an atomic cursor.
+   * { x, y, t, gbx, gby, gbz_lab, upload index of the particle, step } to the screen's buffer through an atomic cursor.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
   screen_cross (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double time_bunch, int nscreens,
@@ -394,7 +431,7 @@ namespace mithra
 	const double gx = P.gb[0][t], gy = P.gb[1][t], gz = P.gb[2][t];
 	r[3] = gx; r[4] = gy;
 	r[5] = b.gamma * ( gz + b.beta * sqrt( 1.0 + ( gx * gx + gy * gy + gz * gz ) ) );
-	r[6] = (double) t; r[7] = step_id;
+	r[6] = (double) P.id[t]; r[7] = step_id;
       }
   }
 

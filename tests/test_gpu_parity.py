@@ -142,6 +142,65 @@ def test_100_steps(job):
     assert helpers.rel_l2(pg, g["p100"]) < 1e-9
 
 
+@pytest.mark.parametrize("job", ["micro-sc", "micro-seeded", "micro-optical"])
+def test_bunch_sorted_by_cell_every_step(job):
+    """The counting sort by cell (kernels_sort.cuh) re-orders the bunch in device memory; results, the order of the
+    downloaded particles and of the screen records, and the cell assignment must not change."""
+    p, meta, g = helpers.params_for(job)
+    p.sort_interval = 1
+    gpu, cpu = abi.GpuSolver(p), binding.Oracle(p)
+    for s in (gpu, cpu):
+        helpers.start_from_golden(s, g)
+    gpu.step(100)
+    for _ in range(100):
+        helpers.solve_step(cpu)
+    names = _field_names(p)
+    a, b = gpu.download_fields(names), cpu.download_fields(names)
+    for k in names:
+        assert helpers.rel_l2(a[k], b[k]) < 1e-9, k
+    pg, pc = gpu.download_particles(), cpu.download_particles()
+    np.testing.assert_array_equal(pg[:, 0], pc[:, 0])
+    assert helpers.rel_l2(pg[:, 1:4], pc[:, 1:4]) < 1e-9
+    assert np.abs(pg[:, 1:4] - pc[:, 1:4]).max() < 1e-7 * np.abs(pc[:, 1:4]).max()      # row by row, not only in the norm
+    np.testing.assert_array_equal(gpu.deposit_cells(), cpu.deposit_cells())
+    np.testing.assert_array_equal(gpu.push_cells(), cpu.push_cells())
+    np.testing.assert_allclose(gpu.fetch_power(), cpu.fetch_power(), rtol=1e-8, atol=1e-12 * np.abs(cpu.fetch_power()).max() + 1e-300)
+    if p.screens.enabled:
+        for s in range(p.screens.N):
+            rg, rc = gpu.fetch_screen(s), cpu.fetch_screen(s)
+            assert rg.shape == rc.shape
+            np.testing.assert_allclose(rg, rc, rtol=1e-9, atol=1e-12)
+
+
+def test_explicit_sort_keeps_the_upload_order():
+    p, g, gpu, cpu = _pair("micro-nsfd")
+    before = gpu.download_particles()
+    gpu.sortParticles()
+    np.testing.assert_array_equal(gpu.download_particles(), before)
+    np.testing.assert_array_equal(gpu.deposit_cells(), cpu.deposit_cells())
+    rng = np.random.default_rng(3)
+    shuffled = before[rng.permutation(before.shape[0])]
+    gpu.upload_particles(shuffled)
+    gpu.sortParticles(); gpu.sortParticles()
+    np.testing.assert_array_equal(gpu.download_particles(), shuffled)
+
+
+def test_tabulated_seed_equals_full_evaluation(monkeypatch):
+    """A seed along +z is injected from the per-plane table (seed_plane_table); MITHRA_SEED_GENERIC=1 evaluates
+    Seed::fields in full at every shell node.  Same carrier phase bit for bit, envelope to rounding."""
+    p, meta, g = helpers.params_for("micro-seeded")
+    fast = abi.GpuSolver(p)
+    monkeypatch.setenv("MITHRA_SEED_GENERIC", "1")
+    full = abi.GpuSolver(p)
+    monkeypatch.delenv("MITHRA_SEED_GENERIC")
+    for s in (fast, full):
+        helpers.start_from_golden(s, g)
+        s.step(50)
+    a, b = fast.download_fields(("an",))["an"], full.download_fields(("an",))["an"]
+    assert np.abs(b).max() > 0
+    assert helpers.rel_l2(a, b) < 1e-13
+
+
 def test_step_entry_points_equal_fused_step():
     """mithra_gpu_step == the nine per-method entry points in the reference's order."""
     p, g, gpu, cpu = _pair("micro-nsfd")

@@ -17,7 +17,8 @@ PHASES = ("fieldUpdate", "bunchUpdate", "screenProfile", "powerSample", "fieldSh
           "currentCommunicate", "migrateBegin", "migrateEnd", "advanceTime")
 
 
-def make_slabs(p, g, size):
+def make_slabs(p, g, size, sort_interval=0):
+    p.sort_interval = sort_interval
     parts = [abi.GpuSolver(slabs.slab_params(p, r, size)) for r in range(size)]
     blobs = [s.export_blob() for s in parts]
     for r, s in enumerate(parts):
@@ -50,8 +51,8 @@ def match_particles(a, b):
     return d.max(), idx
 
 
-@pytest.mark.parametrize("job,size", [("micro-nsfd", 2), ("micro-nsfd", 3), ("micro-sc", 2), ("micro-seeded", 3), ("micro-fd", 4)])
-def test_slabs_reproduce_single_slab(job, size):
+@pytest.mark.parametrize("job,size,sort", [("micro-nsfd", 2, 0), ("micro-nsfd", 3, 3), ("micro-sc", 2, 1), ("micro-seeded", 3, 0), ("micro-fd", 4, 0)])
+def test_slabs_reproduce_single_slab(job, size, sort):
     p, meta, g = helpers.params_for(job)
     nsteps = 100
     cpu = binding.Oracle(p)
@@ -59,7 +60,7 @@ def test_slabs_reproduce_single_slab(job, size):
     for _ in range(nsteps):
         helpers.solve_step(cpu)
 
-    parts = make_slabs(p, g, size)
+    parts = make_slabs(p, g, size, sort)
     n0 = sum(s.num_particles() for s in parts)
     assert n0 == g["p0"].shape[0]
     step_all(parts, nsteps)
