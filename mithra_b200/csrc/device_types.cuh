@@ -59,7 +59,9 @@ namespace mithra
     MithraBeam beam;
   };
 
-  /* Bunch-side constants, kept in device memory (too large for the kernel-argument space).            */
+  /* Bunch-side constants.  Passed to the particle kernels BY VALUE as a __grid_constant__ parameter (about 6 KB;
+   * CUDA 12 allows 32 KB of kernel parameters): every field is then a constant-bank operand or a uniform register
+   * instead of a global load in front of the first use.                                                  */
   struct BunchDev
   {
     double xmin, xmax, ymin, ymax, zmin, zmax;

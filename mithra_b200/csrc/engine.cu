@@ -70,7 +70,6 @@ struct MithraGpu
   Box             h_ebox_last;
 
   /* particles */
-  BunchDev*       d_bd;
   ParticlesDev    P, Palt;                /* the bunch and the copy the counting sort moves it into        */
   double*         pstore[2];              /* 11 * capacity doubles each                                    */
   unsigned int*   idstore[2];
@@ -306,7 +305,7 @@ static int preload_kernels ()
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
-  PL(particle_box); PL(particle_cells); PL(push_particles); PL(deposit_current<true>); PL(deposit_current<false>);
+  PL(particle_box); PL(particle_cells); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
@@ -363,7 +362,6 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   const size_t nodes = (size_t) f.np * f.P;
   CU(cudaMalloc(&h->eb, nodes * 2 * sizeof(float4))); CU(cudaMemsetAsync(h->eb, 0, nodes * 2 * sizeof(float4), h->stream));
 
-  CU(cudaMalloc(&h->d_bd, sizeof(BunchDev))); CU(cudaMemcpyAsync(h->d_bd, &h->bd, sizeof(BunchDev), cudaMemcpyHostToDevice, h->stream));
   h->pcap = params->max_particles ? params->max_particles : (size_t) 1 << 20;
   h->pn = 0; h->next_id = 0; h->ids_dense = true;
   for (int w = 0; w < 2; w++)
@@ -462,7 +460,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   exchange_destroy(h->xch);
   for (int l = 0; l < 3; l++) cudaFree(h->A[l]);
   cudaFree(h->J); cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
-  cudaFree(h->eb); cudaFree(h->d_bd); cudaFree(h->d_noutside);
+  cudaFree(h->eb); cudaFree(h->d_noutside);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
   cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
@@ -586,7 +584,7 @@ static int refresh_particle_box (MithraGpu* h)
 {
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   if (h->pn > 0)
-    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->d_bd, h->P, 0L, (long) h->pn, h->d_pbox);
+    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->bd, h->P, 0L, (long) h->pn, h->d_pbox);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 2;
   return 0;
@@ -658,7 +656,7 @@ extern "C" int mithra_gpu_particle_cells (MithraGpu* h, long* push_m, int* ijk6,
   long* dm = 0; int* dd = 0;
   if (push_m) CU(cudaMalloc(&dm, n * sizeof(long)));
   if (ijk6)   CU(cudaMalloc(&dd, n * 6 * sizeof(int)));
-  particle_cells<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) n, dm, dd);
+  particle_cells<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(h->bd, h->P, (long) n, dm, dd);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   CU(cudaStreamSynchronize(h->stream));
@@ -787,7 +785,7 @@ extern "C" int mithra_gpu_sort_particles (MithraGpu* h)
   const int pgrid = (int) ((n + 255) / 256);
   const int cgrid = (int) ((cap + MITHRA_SCAN_CHUNK - 1) / MITHRA_SCAN_CHUNK);
   sort_zero<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist);
-  sort_count<<<pgrid, 256, 0, h->stream>>>(h->d_bd, h->P, n, h->d_pbox, cap, h->d_hist, h->d_key, h->d_rank);
+  sort_count<<<pgrid, 256, 0, h->stream>>>(h->bd, h->P, n, h->d_pbox, cap, h->d_hist, h->d_key, h->d_rank);
   scan_chunk_sums<<<cgrid, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist, h->d_sums);
   scan_sums<<<1, 1024, 0, h->stream>>>(h->d_pbox, cap, h->d_sums);
   scan_chunks<<<cgrid, 256, 0, h->stream>>>(h->d_pbox, cap, h->d_hist, h->d_sums);
@@ -815,7 +813,10 @@ extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
       /* the particle box is rebuilt by the push (it is read by the next field update)                      */
       set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
       const int grid = (int) ((h->pn + 127) / 128);
-      push_particles<<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
+      bool beams = h->bd.n_ext > 0;
+      for (int u = 0; u < h->bd.n_und; u++) if (h->bd.und[u].type != MITHRA_UNDULATOR_STATIC) beams = true;
+      if (beams) push_particles<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
+      else       push_particles<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
       h->cnt.kernel_launches += 2;
       CU(cudaGetLastError());
     }
@@ -829,7 +830,7 @@ extern "C" int mithra_gpu_screen_profile (MithraGpu* h)
   USE(h);
   if (!h->d_scr_pos || h->pn == 0) return 0;
   PhaseTimer t(h, PH_SCREEN);
-  screen_cross<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->time_bunch, h->prm.screens.N,
+  screen_cross<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->time_bunch, h->prm.screens.N,
 								     h->d_scr_pos, h->d_scr_rec, h->d_scr_cur, h->scr_cap, (double) h->n_time);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
@@ -898,8 +899,8 @@ extern "C" int mithra_gpu_current_update (MithraGpu* h)
   PhaseTimer t(h, PH_DEPOSIT);
   if (h->pn == 0) return 0;
   const int grid = (int) ((h->pn + 127) / 128);
-  if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->J, h->d_jbox);
-  else                  deposit_current<false><<<grid, 128, 0, h->stream>>>(h->d_bd, h->P, (long) h->pn, h->J, h->d_jbox);
+  if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox);
+  else                  deposit_current<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -924,7 +925,7 @@ extern "C" int mithra_gpu_migrate_begin (MithraGpu* h)
   USE(h);
   if (h->fd.size <= 1) return 0;
   if (!h->xch.connected) return fail("mithra_gpu_migrate_begin: slab is not connected to its neighbours");
-  if (migrate_begin(h->xch, h->d_bd, h->P, h->pn, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
+  if (migrate_begin(h->xch, h->bd, h->P, h->pn, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("particle migration: %s", h->xch.error.c_str());
   return 0;
 }
 
@@ -939,7 +940,7 @@ extern "C" int mithra_gpu_migrate_end (MithraGpu* h)
   if (h->xch.h_counts[2] || h->pn != kept) h->ids_dense = false;
   if (h->pn > kept)
     {
-      particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->d_bd, h->P, (long) kept, (long) h->pn, h->d_pbox);
+      particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->bd, h->P, (long) kept, (long) h->pn, h->d_pbox);
       CU(cudaGetLastError());
       h->cnt.kernel_launches += 1;
     }

@@ -200,10 +200,9 @@ namespace mithra
   /* Leavers of this field step (solver.cpp:1544-1548, evaluated once per field step from the start-of-step
    * position rm): wrapped start position + displacement below zp0 -> previous slab, at or above zp1 -> next.    */
   __global__ void __launch_bounds__(256)
-  migrate_pack (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double* __restrict__ out_prev, double* __restrict__ out_next,
+  migrate_pack (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ out_prev, double* __restrict__ out_next,
 		unsigned int* __restrict__ cursor, int* __restrict__ leave, unsigned int cap, unsigned int leave_cap)
   {
-    const BunchDev& b = *bp;
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const double z = P.r[2][t], zm = P.rm[2][t];
@@ -487,7 +486,7 @@ namespace mithra
   }
 
   /* Migration, first half: pack the leavers and put them into the ring neighbours' inboxes.               */
-  static inline int migrate_begin (Exchange& x, const BunchDev* d_bd, ParticlesDev P, size_t pn, cudaStream_t s, int sms, unsigned long long* launches)
+  static inline int migrate_begin (Exchange& x, const BunchDev& d_bd, ParticlesDev P, size_t pn, cudaStream_t s, int sms, unsigned long long* launches)
   {
     ++x.seqP;
     XCU(cudaMemsetAsync(x.d_cursor, 0, 4 * sizeof(unsigned int), s));

@@ -49,9 +49,8 @@ namespace mithra
    * evaluation of the next step.  The host pads it by the distance a particle can travel in one field step.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
-  particle_box (const BunchDev* __restrict__ bp, ParticlesDev P, long start, long n, Box* __restrict__ box)
+  particle_box (const __grid_constant__ BunchDev b, ParticlesDev P, long start, long n, Box* __restrict__ box)
   {
-    const BunchDev& b = *bp;
     for (long base = start + (long) blockIdx.x * blockDim.x; base < n; base += (long) gridDim.x * blockDim.x)
       {
 	const long t = base + threadIdx.x;
@@ -78,9 +77,8 @@ namespace mithra
    *              no mesh field in this sub-step;   dep[t][6] = ip, jp, kp, im, jm, km.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
-  particle_cells (const BunchDev* __restrict__ bp, ParticlesDev P, long n, long* __restrict__ push_m, int* __restrict__ dep)
+  particle_cells (const __grid_constant__ BunchDev b, ParticlesDev P, long n, long* __restrict__ push_m, int* __restrict__ dep)
   {
-    const BunchDev& b = *bp;
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
@@ -116,11 +114,11 @@ namespace mithra
    * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312).
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
    * ------------------------------------------------------------------------------------------------ */
+  template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
   __global__ void __launch_bounds__(128)
-  push_particles (const BunchDev* __restrict__ bp, ParticlesDev P, long n, const float4* __restrict__ eb,
+  push_particles (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const float4* __restrict__ eb,
 		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside)
   {
-    const BunchDev& b = *bp;
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     bool boxvalid = false; int bi = 0, bj = 0, bk = 0;
 
@@ -152,7 +150,7 @@ namespace mithra
 	    for (int u = 0; u < b.n_und; u++)
 	      {
 		const UndulatorDev& U = b.und[u];
-		if (U.type == MITHRA_UNDULATOR_STATIC)
+		if (!BEAMS || U.type == MITHRA_UNDULATOR_STATIC)
 		  {
 		    const double lz = b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) ) - U.rb;
 		    const double ly = x * U.ct + y * U.st;
@@ -176,7 +174,7 @@ namespace mithra
 	      }
 
 	    /* externalField, solver.cpp:1886-1947                                                          */
-	    if (b.n_ext > 0)
+	    if (BEAMS && b.n_ext > 0)
 	      {
 		const V3 rl = v3(x, y, b.gamma * ( z + b.beta * b.c0 * ( tb + b.dt_shift ) ));
 		const double t0 = b.gamma * ( tb + b.dt_shift + b.beta / b.c0 * z );
@@ -212,13 +210,23 @@ namespace mithra
 		      ( 1.0 - dxr ) *         dyr   * ( 1.0 - dzr ),         dxr   *         dyr   * ( 1.0 - dzr ),
 		      ( 1.0 - dxr ) * ( 1.0 - dyr ) *         dzr,           dxr   * ( 1.0 - dyr ) *         dzr,
 		      ( 1.0 - dxr ) *         dyr   *         dzr,           dxr   *         dyr   *         dzr };
-		    float4 fe[8], fb[8];
+		    /* two batches of four nodes (plane k, then k+1): half the registers in flight, same sum order   */
+		    double ex = et.x, ey = et.y, ez = et.z, bx = bt.x, by = bt.y, bz = bt.z;
 		    #pragma unroll
-		    for (int q = 0; q < 8; q++) { fe[q] = __ldg(&eb[2 * (m + off[q])]); fb[q] = __ldg(&eb[2 * (m + off[q]) + 1]); }
-		    #pragma unroll
-		    for (int q = 0; q < 8; q++) { et.x += w[q] * fe[q].x; et.y += w[q] * fe[q].y; et.z += w[q] * fe[q].z; }
-		    #pragma unroll
-		    for (int q = 0; q < 8; q++) { bt.x += w[q] * fb[q].x; bt.y += w[q] * fb[q].y; bt.z += w[q] * fb[q].z; }
+		    for (int hb = 0; hb < 8; hb += 4)
+		      {
+			float4 fe[4], fb[4];
+			#pragma unroll
+			for (int q = 0; q < 4; q++) { fe[q] = __ldg(&eb[2 * (m + off[hb + q])]); fb[q] = __ldg(&eb[2 * (m + off[hb + q]) + 1]); }
+			#pragma unroll
+			for (int q = 0; q < 4; q++)
+			  {
+			    ex += w[hb + q] * fe[q].x; ey += w[hb + q] * fe[q].y; ez += w[hb + q] * fe[q].z;
+			    bx += w[hb + q] * fb[q].x; by += w[hb + q] * fb[q].y; bz += w[hb + q] * fb[q].z;
+			  }
+		      }
+		    et.x = ex; et.y = ey; et.z = ez;
+		    bt.x = bx; bt.y = by; bt.z = bz;
 		  }
 		else if ( !b1x && !b1y && b1z )
 		  atomicAdd(n_outside, 1u);
@@ -337,9 +345,8 @@ namespace mithra
 
   template <bool SC>
   __global__ void __launch_bounds__(128)
-  deposit_current (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox)
+  deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox)
   {
-    const BunchDev& b = *bp;
     const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * MITHRA_DEP_RUN;
     bool valid = false; int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1, k0 = 0x7fffffff, k1 = -1;
     DepositAcc<SC> acc; acc.m = -1;
@@ -398,11 +405,10 @@ namespace mithra
    * { x, y, t, gbx, gby, gbz_lab, upload index of the particle, step } to the screen's buffer through an atomic cursor.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
-  screen_cross (const BunchDev* __restrict__ bp, ParticlesDev P, long n, double time_bunch, int nscreens,
+  screen_cross (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double time_bunch, int nscreens,
 		const double* __restrict__ pos, double* __restrict__ rec, unsigned int* __restrict__ cursor,
 		unsigned int capacity, double step_id)
   {
-    const BunchDev& b = *bp;
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const double xp = P.r[0][t], yp = P.r[1][t], zp = P.r[2][t];

@@ -50,10 +50,9 @@ namespace mithra
   }
 
   __global__ void __launch_bounds__(256)
-  sort_count (const BunchDev* __restrict__ bp, ParticlesDev P, long n, const Box* __restrict__ pbox, long cap,
+  sort_count (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const Box* __restrict__ pbox, long cap,
 	      unsigned int* __restrict__ hist, unsigned int* __restrict__ key, unsigned int* __restrict__ rank)
   {
-    const BunchDev& b = *bp;
     const SortBox s = sort_box(pbox, cap);
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
