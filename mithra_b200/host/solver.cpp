@@ -1,0 +1,877 @@
+/* solver.cpp -- Solver / FdTd / FdTdSC (see solver.h).
+ *
+ * Host side of the time-march: Solver::initialize() derives, in FP64 and in the reference's operation order, every
+ * scalar and table the device needs (cited per function), fills MithraGpuParams, splits the bunch over the z-slabs and
+ * hands both to the library; solve() then runs the reference's loop (solver.cpp:1212-1418) whose method calls are
+ * one-line forwards to the C ABI.  Power and screen files are written in the reference's byte format from the rows /
+ * records the library returns (radiation.cpp:76-86, 222-230; solver.cpp:2175-2187, 2229-2252).
+ */
+#include "solver.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <sys/time.h>
+
+namespace MITHRA
+{
+  /* ========================================================================================================== */
+  /* construction                                                                                                 */
+
+  Solver::Solver (Mesh& mesh, Bunch& bunch, Seed& seed, std::vector<Undulator>& undulator, std::vector<ExtField>& extField,
+		  std::vector<FreeElectronLaser>& FEL)
+    : mesh_(mesh), bunch_(bunch), seed_(seed), undulator_(undulator), extField_(extField), FEL_(FEL),
+      N0_(0), N1_(0), N2_(0), N1N0_(0), np_(0), k0_(0), rank_(0), size_(1),
+      xmin_(0), xmax_(0), ymin_(0), ymax_(0), zmin_(0), zmax_(0),
+      gamma_(1.0), beta_(0.0), dt_(0.0), timep1_(0.0), time_(0.0), timem1_(0.0), timeBunch_(0.0),
+      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), spaceChargeSolver_(false)
+  {
+    zp_[0] = zp_[1] = 0.0;
+    memset(&uf_, 0, sizeof(uf_)); memset(&uc_, 0, sizeof(uc_)); memset(&ub_, 0, sizeof(ub_));
+    /* light speed, vacuum permeability and permittivity in the job's units, solver.cpp:59-61                    */
+    c0_ = C0 / mesh_.lengthScale_ * mesh_.timeScale_;
+    m0_ = MU_ZERO / mesh_.lengthScale_;
+    e0_ = 1.0 / ( c0_ * c0_ * m0_ );
+  }
+
+  Solver::~Solver ()
+  {
+    for (MithraGpu* g : gpu_) mithra_gpu_destroy(g);
+  }
+
+  void Solver::check (int rc) const
+  {
+    if (rc == 0) return;
+    printmessage(__FILE__, __LINE__, std::string("libmithra_gpu: ") + mithra_gpu_last_error());
+    exit(1);
+  }
+
+  FdTd::FdTd (Mesh& mesh, Bunch& bunch, Seed& seed, std::vector<Undulator>& undulator, std::vector<ExtField>& extField,
+	      std::vector<FreeElectronLaser>& FEL) : Solver(mesh, bunch, seed, undulator, extField, FEL) {}
+
+  FdTdSC::FdTdSC (Mesh& mesh, Bunch& bunch, Seed& seed, std::vector<Undulator>& undulator, std::vector<ExtField>& extField,
+		  std::vector<FreeElectronLaser>& FEL) : FdTd(mesh, bunch, seed, undulator, extField, FEL) { spaceChargeSolver_ = true; }
+
+  /* ========================================================================================================== */
+  /* initialisation chain                                                                                         */
+
+  /* order of solver.cpp:547-595 */
+  void Solver::initialize ()
+  {
+    setSimulationParameters();
+    initializeBunch();
+    timeBunch_ = time_;
+    lorentzBoostMesh();
+    initializeMesh();
+    lorentzBoostBunch();
+    initializeField();
+    initializeBunchUpdate();
+    initializePowerSample();
+    initializeScreenProfile();
+    shiftBackInTime();
+  }
+
+  /* unit conversion of the beams, frame gamma, undulator sorting, bunching wavelength -- solver.cpp:68-214      */
+  void Solver::setSimulationParameters ()
+  {
+    auto toSolverUnits = [&] (Beam& b) {
+      b.c0_          = c0_;
+      b.signal_.t0_ /= c0_;
+      b.signal_.f0_ *= c0_;
+      b.signal_.s_  /= c0_;
+      b.l_           = c0_ / b.signal_.f0_;
+      b.zR_.assign(2, 0.0);
+      b.zR_[0]       = PI * b.radius_[0] * b.radius_[0] / b.l_;
+      b.zR_[1]       = PI * b.radius_[1] * b.radius_[1] / b.l_; };
+    toSolverUnits(seed_);
+    for (Undulator& u : undulator_) toSolverUnits(u);
+    for (ExtField&  e : extField_)  toSolverUnits(e);
+
+    /* the seed amplitude is that of the vector potential, the others are field amplitudes (solver.cpp:119-123)   */
+    seed_.amplitude_ = seed_.a0_ * EM * c0_ / EC;
+    for (Undulator& u : undulator_) u.amplitude_ = u.a0_ * EM * c0_ * 2 * PI * u.signal_.f0_ / EC;
+    for (ExtField&  e : extField_)  e.amplitude_ = e.a0_ * EM * c0_ * 2 * PI * e.signal_.f0_ / EC;
+
+    Double gamma = 0.0;
+    for (BunchInitialize& b : bunch_.bunchInit_)
+      {
+	if ( b.bunchType_ == "file" )  computeFileGamma(b);
+	if ( b.bunchType_ == "other" ) printmessage(__FILE__, __LINE__, "Bunch mean gamma and direction are given by an external program. ");
+	gamma += b.initialGamma_ / bunch_.bunchInit_.size();
+      }
+
+    /* range of the bunch's longitudinal gamma inside the undulators (solver.cpp:138-165)                         */
+    Double gmin = 1.0e100, gmax = -1.0e100, g = 0.0;
+    for (Undulator& u : undulator_)
+      {
+	const Double k = ( u.type_ == STATIC ) ? u.k_ : u.a0_;
+	g    = gamma / sqrt( 1.0 + k * k / 2.0 );
+	gmin = ( gmin < g ) ? gmin : g;
+	/* an optical pulse that is not flat-top leaves the electrons at their full gamma outside the pulse         */
+	if ( u.type_ != STATIC && u.signal_.signalType_ != FLATTOP ) g = gamma;
+	gmax = ( gmax > g ) ? gmax : g;
+      }
+    if ( mesh_.gamma_ == -1.0 ) gamma_ = ( undulator_.size() == 0 ) ? gamma : ( gmin + gmax ) / 2.0;
+    else                        gamma_ = mesh_.gamma_;
+
+    beta_ = sqrt( 1.0 - 1.0 / ( gamma_ * gamma_ ) );
+    for (Undulator& u : undulator_) if ( u.type_ == OPTICAL ) u.lu_ /= ( 1 + beta_ );
+
+    std::sort(undulator_.begin(), undulator_.end(), undulatorCompare);
+    for (std::vector<Undulator>::reverse_iterator u = undulator_.rbegin(); u != undulator_.rend(); u++) u->rb_ -= undulator_[0].rb_;
+
+    for (BunchInitialize& b : bunch_.bunchInit_)
+      {
+	b.initialBeta_ = sqrt( 1.0 - 1.0 / pow( b.initialGamma_ , 2 ) );
+	b.betaVector_.mv( b.initialBeta_, b.initialDirection_ );
+	b.lambda_ = ( undulator_.size() > 0 ) ? undulator_[0].lu_ / ( 2.0 * gamma_ * gamma_ ) * b.betaVector_[2] / beta_ : 0.0;
+	printmessage(__FILE__, __LINE__, "Modulation wavelength of the bunch outside the undulator is set to " + stringify(b.lambda_));
+      }
+    seed_.beta_  = beta_;
+    seed_.gamma_ = gamma_;
+  }
+
+  /* solver.cpp:508-539 */
+  void Solver::computeFileGamma (BunchInitialize& b)
+  {
+    Double ignore;
+    FieldVector gb (0.0);
+    b.initialGamma_ = 0.0;
+    b.initialDirection_ = FieldVector(0.0);
+    std::ifstream in ( b.fileName_.c_str() );
+    while (in.good())
+      {
+	in >> ignore; in >> ignore; in >> ignore;
+	in >> gb[0]; in >> gb[1]; in >> gb[2];
+	b.initialGamma_ += std::sqrt( 1 + gb.norm2() );
+	b.initialDirection_ += gb;
+      }
+    b.initialGamma_ /= b.numberOfParticles_;
+    b.initialDirection_ /= b.initialDirection_.norm();
+    printmessage(__FILE__, __LINE__, "Computed average gamma from file is " + stringify(b.initialGamma_));
+  }
+
+  /* solver.cpp:220-257 */
+  void Solver::lorentzBoostMesh ()
+  {
+    mesh_.meshLength_[2]     *= gamma_;
+    mesh_.meshResolution_[2] *= gamma_;
+    mesh_.meshCenter_[2]     *= gamma_;
+    mesh_.totalTime_         /= gamma_;
+    mesh_.timeShift_         /= gamma_;
+    std::vector<Double>& d = mesh_.meshResolution_;
+    if ( mesh_.solver_ == NSFD )
+      {
+	/* the transverse cells are enlarged until the NSFD stability margin holds, then dt = dz / c               */
+	const Double t = 1.0 / sqrt( pow( d[2] / d[0], 2.0 ) + pow( d[2] / d[1], 2.0 ) );
+	if ( t < 1.02 )
+	  {
+	    d[0] *= 1.02 / t;
+	    d[1] *= 1.02 / t;
+	    printmessage(__FILE__, __LINE__, "Transverse discretization is set to " + stringify(d[0]) + " x " + stringify(d[1]));
+	  }
+	mesh_.timeStep_ = d[2] / c0_;
+      }
+    else
+      mesh_.timeStep_ = 0.98 / ( c0_ * sqrt( 1.0 / pow(d[0], 2.0) + 1.0 / pow(d[1], 2.0) + 1.0 / pow(d[2], 2.0) ) );
+    printmessage(__FILE__, __LINE__, "Time step for the field update is set to " + stringify(mesh_.timeStep_ * gamma_));
+  }
+
+  /* node counts, slab extents (one slab per GPU), mesh borders -- solver.cpp:601-689                             */
+  void Solver::initializeMesh ()
+  {
+    N0_ = (int) ( mesh_.meshLength_[0] / mesh_.meshResolution_[0] ) + 2;
+    N1_ = (int) ( mesh_.meshLength_[1] / mesh_.meshResolution_[1] ) + 2;
+    N2_ = (int) ( mesh_.meshLength_[2] / mesh_.meshResolution_[2] ) + 2;
+    N1N0_ = N1_ * N0_;
+    mesh_.meshLength_[0] = ( N0_ - 1 ) * mesh_.meshResolution_[0];
+    mesh_.meshLength_[1] = ( N1_ - 1 ) * mesh_.meshResolution_[1];
+    mesh_.meshLength_[2] = ( N2_ - 1 ) * mesh_.meshResolution_[2];
+
+    xmin_ = mesh_.meshCenter_[0] - mesh_.meshLength_[0] / 2.0;
+    xmax_ = mesh_.meshCenter_[0] + mesh_.meshLength_[0] / 2.0;
+    ymin_ = mesh_.meshCenter_[1] - mesh_.meshLength_[1] / 2.0;
+    ymax_ = mesh_.meshCenter_[1] + mesh_.meshLength_[1] / 2.0;
+    zmin_ = mesh_.meshCenter_[2] - mesh_.meshLength_[2] / 2.0;
+    zmax_ = mesh_.meshCenter_[2] + mesh_.meshLength_[2] / 2.0;
+
+    if ( size_ > 1 && N2_ / size_ < 6 )
+      { printmessage(__FILE__, __LINE__, "The mesh has too few planes along z for " + stringify(size_) + " slabs."); exit(1); }
+    slabNp_.assign(size_, 0); slabK0_.assign(size_, 0); slabZp0_.assign(size_, 0.0); slabZp1_.assign(size_, 0.0);
+    for (int r = 0; r < size_; r++)
+      {
+	/* np_, k0_ of rank r (solver.cpp:619-641): two planes shared with each neighbour                          */
+	int np, k0;
+	if      ( size_ == 1 )      { np = N2_;                                          k0 = 0; }
+	else if ( r == 0 )          { np = N2_ / size_ + 1;                              k0 = 0; }
+	else if ( r == size_ - 1 )  { np = N2_ - ( size_ - 1 ) * ( N2_ / size_ ) + 1;    k0 = ( size_ - 1 ) * ( N2_ / size_ ) - 1; }
+	else                        { np = N2_ / size_ + 2;                              k0 = r * ( N2_ / size_ ) - 1; }
+	slabNp_[r] = np; slabK0_[r] = k0;
+	/* ownership interval: z of local plane 0 and of local plane np-2 (np-1 on the last slab), solver.cpp:677-680 */
+	slabZp0_[r] = zmin_ + ( 0 + k0 ) * mesh_.meshResolution_[2];
+	slabZp1_[r] = zmin_ + ( ( np - ( ( r == size_ - 1 ) ? 1 : 2 ) ) + k0 ) * mesh_.meshResolution_[2];
+      }
+    np_ = slabNp_[0]; k0_ = slabK0_[0];
+    /* the process as a whole owns [z(0), z(N2-1)), what a single rank of the reference owns                       */
+    zp_[0] = slabZp0_[0]; zp_[1] = slabZp1_[size_ - 1];
+
+    timep1_ =  mesh_.timeStep_;
+    time_   =  0.0;
+    timem1_ = -mesh_.timeStep_;
+  }
+
+  FieldVector Solver::rc (const long int& m)
+  {
+    const unsigned int k = m / N1N0_, i = ( m % N1N0_ ) / N1_, j = m - ( N1N0_ * k + N1_ * i );
+    FieldVector v;
+    v[0] = xmin_ + i          * mesh_.meshResolution_[0];
+    v[1] = ymin_ + j          * mesh_.meshResolution_[1];
+    v[2] = zmin_ + (k + k0_)  * mesh_.meshResolution_[2];
+    return v;
+  }
+
+  bool Solver::particleInProcessor (const Double& z)
+  {
+    const Double zr = pmod( z - zmin_ , mesh_.meshLength_[2] ) + zmin_;
+    return ( ( zr >= zp_[0] ) && ( zr < zp_[1] ) );
+  }
+
+  /* solver.cpp:1130-1178; the process generates the whole bunch (rank 0 of 1)                                    */
+  void Solver::initializeBunch ()
+  {
+    printmessage(__FILE__, __LINE__, "[[[ Initializing the bunch and prepare the charge vector ");
+    std::list<Charge> qv;
+    for (BunchInitialize& b : bunch_.bunchInit_)
+      {
+	qv.clear();
+	if ( b.position_.size() == 0 ) b.position_.push_back( FieldVector(0.0) );
+	for (unsigned int ia = 0; ia < b.position_.size(); ia++)
+	  {
+	    if      ( b.bunchType_ == "manual" )     bunch_.initializeManual   (b, qv, zp_, 0, 1, ia);
+	    else if ( b.bunchType_ == "ellipsoid" )  bunch_.initializeEllipsoid(b, qv, 0, 1, ia);
+	    else if ( b.bunchType_ == "3D-crystal" ) bunch_.initialize3DCrystal(b, qv, zp_, 0, 1, ia);
+	    else if ( b.bunchType_ == "file" )       bunch_.initializeFile     (b, qv, zp_, 0, 1, ia);
+	  }
+	if ( b.bunchType_ == "other" ) printmessage(__FILE__, __LINE__, "The charge vector has been filled in by an external program. ");
+	chargeVectorn_.splice(chargeVectorn_.end(), qv);
+      }
+    printmessage(__FILE__, __LINE__, "The bunch is initialized and the charge vector is prepared. ]]]");
+  }
+
+  /* bunch time step, boost of the particles, time origin dt_, ballistic back-projection -- solver.cpp:263-423     */
+  void Solver::lorentzBoostBunch ()
+  {
+    bunch_.timeStep_ /= gamma_;
+    if ( bunch_.timeStep_ == 0 ) bunch_.timeStep_ = mesh_.timeStep_;
+    else                         bunch_.timeStep_ = mesh_.timeStep_ / ceil( mesh_.timeStep_ / bunch_.timeStep_ );
+    nUpdateBunch_ = mesh_.timeStep_ / bunch_.timeStep_;
+    printmessage(__FILE__, __LINE__, "Time step for the bunch update is set to " + stringify(bunch_.timeStep_ * gamma_));
+
+    bunch_.rhythm_ /= gamma_; bunch_.bunchVTKRhythm_ /= gamma_; bunch_.bunchProfileRhythm_ /= gamma_;
+    for (Double& t : bunch_.bunchProfileTime_) t /= gamma_;
+
+    Double zmaxG = -1.0e100;
+    for (Charge& q : chargeVectorn_)
+      {
+	const Double g  = std::sqrt( 1.0 + q.gb.norm2() );
+	const Double bz = q.gb[2] / g;
+	q.rnp[2] *= gamma_;
+	q.gb[2]   = gamma_ * g * ( bz - beta_ );
+	zmaxG     = std::max( zmaxG , q.rnp[2] );
+      }
+
+    /* at bunch time zero the bunch head is undulator_[0].dist_ (lab frame) in front of the entrance              */
+    if ( undulator_.size() > 0 )
+      {
+	Undulator& u0 = undulator_[0];
+	const Double nl = ( u0.type_ == STATIC ) ? 2.0 : 5.0 * u0.signal_.nR_;
+	if      ( u0.dist_ == 0.0 )         u0.dist_ = nl * u0.lu_;
+	else if ( u0.dist_ < nl * u0.lu_ )  printmessage(__FILE__, __LINE__, "Warning: the undulator is set very close to the bunch, the results may be inaccurate.");
+	dt_ = - 1.0 / ( beta_ * u0.c0_ ) * ( zmaxG + u0.dist_ / gamma_ );
+	printmessage(__FILE__, __LINE__, "Initial distance from bunch head to undulator is " + stringify(u0.dist_));
+      }
+    seed_.dt_    = dt_;
+    bunch_.zu_   = zmaxG;
+    bunch_.beta_ = beta_;
+
+    /* the bunch properties are given at the start point: move the particles back along straight lines             */
+    for (Charge& q : chargeVectorn_)
+      {
+	const Double g = std::sqrt( 1.0 + q.gb.norm2() );
+	q.rnp[0] += q.gb[0] / g * ( q.rnp[2] - bunch_.zu_ ) * beta_;
+	q.rnp[1] += q.gb[1] / g * ( q.rnp[2] - bunch_.zu_ ) * beta_;
+	q.rnp[2] += q.gb[2] / g * ( q.rnp[2] - bunch_.zu_ ) * beta_;
+      }
+
+    if ( mesh_.optimizePosition_ && undulator_.size() > 0 )
+      {
+	Double zG = 0.0, bzG = 0.0;
+	for (Charge& q : chargeVectorn_) { zG += q.rnp[2]; bzG += q.gb[2] / std::sqrt( 1 + q.gb.norm2() ); }
+	const unsigned int NqG = chargeVectorn_.size();
+	zG /= NqG; bzG /= NqG;
+	const Double shift = bzG * ( zmaxG + undulator_[0].dist_ / gamma_ - zG ) / ( bzG + beta_ ) + zG;
+	zmaxG     -= shift;
+	bunch_.zu_ = zmaxG;
+	dt_        = - 1.0 / ( beta_ * undulator_[0].c0_ ) * ( zmaxG + undulator_[0].dist_ / gamma_ );
+	seed_.dt_  = dt_;
+	for (Charge& q : chargeVectorn_) q.rnp[2] -= shift;
+	printmessage(__FILE__, __LINE__, "The bunch center is shifted back by " + stringify(shift) + " .");
+      }
+
+    distributeParticles(chargeVectorn_);
+    Nc_ = chargeVectorn_.size();
+    printmessage(__FILE__, __LINE__, "The total number of macro-particles is equal to " + stringify(Nc_) + " .");
+
+    if ( mesh_.totalDist_ > 0.0 )
+      {
+	double Lu = 0.0;
+	for (Undulator& u : undulator_) Lu += u.lu_ * u.length_ / gamma_;
+	const double zEnd = mesh_.totalDist_ / gamma_;
+	double zMin = 1e100, bz = 0;
+	for (Charge& q : chargeVectorn_) { zMin = std::min(zMin, q.rnp[2]); bz += q.gb[2] / std::sqrt( 1 + q.gb.norm2() ); }
+	bz /= chargeVectorn_.size();
+	mesh_.totalTime_ = 1 / ( c0_ * ( bz + beta_ ) ) * ( zEnd - beta_ * c0_ * dt_ - zMin + bz / beta_ * Lu );
+	printmessage(__FILE__, __LINE__, "The total time to simulate has been set to " + stringify(mesh_.totalTime_ * gamma_) + " .");
+      }
+  }
+
+  /* A single rank of the reference keeps every particle whose wrapped z lies inside the mesh; one that does not is
+   * re-queued behind the others with rnm and e reset (solver.cpp:429-487).  The split over the slabs happens at
+   * upload time (attachGpu).                                                                                     */
+  void Solver::distributeParticles (std::list<Charge>& chargeVector)
+  {
+    std::list<Charge> moved;
+    for (std::list<Charge>::iterator it = chargeVector.begin(); it != chargeVector.end(); )
+      {
+	if ( particleInProcessor( it->rnp[2] ) ) { ++it; continue; }
+	Charge c; c.q = it->q; c.rnp = it->rnp; c.gb = it->gb;
+	moved.push_back(c);
+	it = chargeVector.erase(it);
+      }
+    for (Charge& c : moved) if ( particleInProcessor( c.rnp[2] ) ) chargeVector.push_back(c);
+  }
+
+  /* every coefficient of the field update, solver.cpp:695-824                                                    */
+  void Solver::initializeField ()
+  {
+    uc_.dx = mesh_.meshResolution_[0]; uc_.dy = mesh_.meshResolution_[1]; uc_.dz = mesh_.meshResolution_[2];
+    uc_.dv = - m0_ * EC / mesh_.timeStep_ / ( uc_.dx * uc_.dy * uc_.dz );
+    uc_.rc = - EC / e0_ /                   ( uc_.dx * uc_.dy * uc_.dz );
+
+    UpdateField& u = uf_;
+    u.dt = mesh_.timeStep_; u.dx = mesh_.meshResolution_[0]; u.dy = mesh_.meshResolution_[1]; u.dz = mesh_.meshResolution_[2];
+    u.dx2 = 2.0 * u.dx; u.dy2 = 2.0 * u.dy; u.dz2 = 2.0 * u.dz;
+    const Double c = c0_, dt = u.dt, dx = u.dx, dy = u.dy, dz = u.dz;
+
+    /* non-standard finite difference weights (doc MITHRA_FDTDPIC.tex:244-277)                                     */
+    const Double beta  = ( 1.0 + 0.02 / ( pow(dz/dx,2.0) + pow(dz/dy,2.0) ) ) / 4.0;
+    const Double alpha = 1.0 - 2.0 * beta;
+    u.alpha = alpha;
+    u.beta  = beta / alpha;
+    u.a[0] = 2.0 * ( 1.0 - alpha * pow(c*dt/dx,2) - alpha * pow(c*dt/dy,2) - pow(c*dt/dz,2) );
+    u.a[1] = pow(c*dt/dx,2.0);
+    u.a[2] = pow(c*dt/dy,2.0);
+    u.a[3] = pow(c*dt/dz,2.0) - 2.0 * ( beta * pow(c*dt/dx,2) + beta * pow(c*dt/dy,2) );
+    u.a[4] = pow(c*dt,2.0) * uc_.dv;
+    u.a[5] = pow(c*dt,2.0) * uc_.rc;
+
+    /* faces: first / second order absorbing condition at normal incidence (alpha1 = alpha2 = 0)                   */
+    const Double alpha1 = 0.0, alpha2 = 0.0;
+    const Double p = ( 1.0 + cos(alpha1) * cos(alpha2) ) / ( cos(alpha1) + cos(alpha2) );
+    const Double q = - 1.0 / ( cos(alpha1) + cos(alpha2) );
+    const Double o = mesh_.truncationOrder_ - 1.0;
+    auto face = [&] (Double* B, Double dn, Double dt1, Double dt2) {
+      const Double d = 1.0 / ( 2.0 * dt * dn ) + p / ( 2.0 * c * dt * dt );
+      B[0] = (   1.0 / ( 2.0 * dt * dn ) - p / ( 2.0 * c * dt * dt ) ) / d;
+      B[1] = ( - 1.0 / ( 2.0 * dt * dn ) - p / ( 2.0 * c * dt * dt ) ) / d;
+      B[2] = (   p / ( c * dt * dt ) + q * o * ( c / ( dt1 * dt1 ) + c / ( dt2 * dt2 ) ) ) / d;
+      B[3] = - q * o * ( c / ( 2.0 * dt1 * dt1 ) ) / d ;
+      B[4] = - q * o * ( c / ( 2.0 * dt2 * dt2 ) ) / d ; };
+    face(u.bB, dx, dy, dz);
+    face(u.cB, dy, dx, dz);
+    face(u.dB, dz, dx, dy);
+
+    /* edges along w between the faces normal to u and v: (da, db) = (d_v, d_u) in the reference's naming            */
+    auto edge = [&] (Double* E, Double da, Double db, Double dw) {
+      const Double d = ( 1.0 / da + 1.0 / db ) / ( 4.0 * dt ) + 3.0 / ( 8.0 * c * dt * dt );
+      E[0] = ( - ( 1.0 / da - 1.0 / db ) / ( 4.0 * dt ) - 3.0 / ( 8.0 * c * dt * dt ) ) / d;
+      E[1] = (   ( 1.0 / da - 1.0 / db ) / ( 4.0 * dt ) - 3.0 / ( 8.0 * c * dt * dt ) ) / d;
+      E[2] = (   ( 1.0 / da + 1.0 / db ) / ( 4.0 * dt ) - 3.0 / ( 8.0 * c * dt * dt ) ) / d;
+      E[3] = ( 3.0 / ( 4.0 * c * dt * dt ) - c / ( 4.0 * dw * dw ) ) / d;
+      E[4] = c / ( 8.0 * dw * dw ) / d; };
+    edge(u.eE, dy, dx, dz);
+    edge(u.fE, dz, dy, dx);
+    edge(u.gE, dx, dz, dy);
+
+    /* corners: signs of (1/dx, 1/dy, 1/dz) for hC[0..7]; hC[8+n] mirrors hC[n]                                    */
+    static const int sgn[8][3] = { {-1,-1,-1}, {1,-1,-1}, {-1,1,-1}, {-1,-1,1}, {1,1,-1}, {1,-1,1}, {-1,1,1}, {1,1,1} };
+    for (int n = 0; n < 8; n++)
+      {
+	const Double s = ( sgn[n][0] * 1.0 / dx + sgn[n][1] * 1.0 / dy + sgn[n][2] * 1.0 / dz );
+	u.hC[n]     =   s / ( 8.0 * dt ) - 1.0 / ( 4.0 * c * dt * dt );
+	u.hC[8 + n] = - s / ( 8.0 * dt ) - 1.0 / ( 4.0 * c * dt * dt );
+      }
+    u.hC[16] = 1.0 / ( 2.0 * c * dt * dt );
+    /* the seed's initial condition inside the total-field box (solver.cpp:828-839) is set on the device by
+     * mithra_gpu_seed_initial in attachGpu()                                                                      */
+  }
+
+  /* solver.cpp:1050-1059 */
+  void Solver::initializeBunchUpdate ()
+  {
+    ub_.dt  = mesh_.timeStep_;
+    ub_.dtb = c0_ * bunch_.timeStep_;
+    ub_.dx  = mesh_.meshResolution_[0]; ub_.dy = mesh_.meshResolution_[1]; ub_.dz = mesh_.meshResolution_[2];
+    ub_.r1  = - EC / ( EM * c0_ ) * bunch_.timeStep_ / 2.0;
+    ub_.r2  = - EC / EM * bunch_.timeStep_ / 2.0;
+    if ( bunch_.sampling_ || bunch_.bunchVTK_ || bunch_.bunchProfile_ )
+      printmessage(__FILE__, __LINE__, "Note: bunch-sampling / -visualization / -profile writers are outside this build's scope and are skipped.");
+  }
+
+  /* planes, wavelengths, window length and prefactor of the power sampling; opens the files -- radiation.cpp:18-121 */
+  void Solver::initializePowerSample ()
+  {
+    rp_.clear(); rp_.resize(FEL_.size());
+    for (unsigned int jf = 0; jf < FEL_.size(); jf++)
+      {
+	FreeElectronLaser::RadiationSampling& R = FEL_[jf].radiationPower_;
+	if (!R.sampling_) continue;
+	if ( undulator_.size() == 0 ) { printmessage(__FILE__, __LINE__, "Radiation power sampling needs an undulator."); exit(1); }
+	for (Double& z : R.z_) z *= gamma_;
+	R.lineBegin_ *= gamma_;
+	R.lineEnd_   *= gamma_;
+	Double dl = fabs( R.lineEnd_ - R.lineBegin_ ) / R.res_;
+	if ( R.samplingType_ == OVERLINE )
+	  for (Double l = 0.0; fabs(l) < fabs( R.lineEnd_ - R.lineBegin_ ); l += dl) R.z_.push_back( R.lineBegin_ + l );
+	rp_[jf].N = R.z_.size();
+	dl = ( R.lambdaMax_ - R.lambdaMin_ ) / R.lambdaRes_;
+	for (Double rw = R.lambdaMin_; rw < R.lambdaMax_; rw += dl) R.lambda_.push_back(rw);
+	rp_[jf].Nl = R.lambda_.size();
+	rp_[jf].Nf = 0;
+	rp_[jf].file.resize(rp_[jf].Nl);
+	rp_[jf].w.resize(rp_[jf].Nl);
+	for (unsigned int i = 0; i < rp_[jf].Nl; i++)
+	  {
+	    std::string name = "";
+	    if ( R.basename_.compare(0, 1, "/") != 0 ) name = R.directory_;
+	    name += R.basename_ + "-" + stringify(i) + ".txt";
+	    createDirectory(name, 0);
+	    rp_[jf].file[i] = new std::ofstream(name.c_str(), std::ios::trunc);
+	    rp_[jf].file[i]->setf(std::ios::scientific);
+	    rp_[jf].file[i]->precision(15);
+	    rp_[jf].file[i]->width(40);
+	    /* three radiation periods of this harmonic in the moving frame                                            */
+	    const Double dt = undulator_[0].lu_ / R.lambda_[i] / ( gamma_ * c0_ );
+	    rp_[jf].Nf   = ( unsigned( 3.0 * dt / mesh_.timeStep_ ) > rp_[jf].Nf ) ? unsigned( 3.0 * dt / mesh_.timeStep_ ) : rp_[jf].Nf;
+	    rp_[jf].w[i] = 2 * PI / dt;
+	  }
+	rp_[jf].pc = 2.0 * mesh_.meshResolution_[0] * mesh_.meshResolution_[1] / ( m0_ * rp_[jf].Nf * rp_[jf].Nf ) * pow(mesh_.lengthScale_,2) / pow(mesh_.timeScale_,3);
+	if ( powerGroup_ < 0 ) powerGroup_ = jf;
+	else printmessage(__FILE__, __LINE__, "Note: only the first radiation-power group is sampled by this build.");
+      }
+  }
+
+  /* solver.cpp:2145-2200 */
+  void Solver::initializeScreenProfile ()
+  {
+    scrp_.clear(); scrp_.resize(FEL_.size());
+    for (unsigned int jf = 0; jf < FEL_.size(); jf++)
+      {
+	FreeElectronLaser::ScreenProfile& S = FEL_[jf].screenProfile_;
+	if (!S.sampling_) continue;
+	if ( S.basename_.compare(0, 1, "/") != 0 ) S.basename_ = S.directory_ + S.basename_;
+	if ( S.rhythm_ > 0.0 && undulator_.size() > 0 )
+	  {
+	    /* screens every rhythm_ up to the end of the last module (the reference dereferences end() here, Q10)   */
+	    const Undulator& last = undulator_.back();
+	    for (Double z = 0.0; z < last.rb_ + last.length_ * last.lu_; z += S.rhythm_) S.pos_.push_back(z);
+	  }
+	if ( S.pos_.size() == 0 )
+	  { printmessage(__FILE__, __LINE__, "No position is set for the screen although the screen sampling is activated !!!"); exit(1); }
+	createDirectory(S.basename_, 0);
+	std::sort(S.pos_.begin(), S.pos_.end());
+	scrp_[jf].fileNames.resize(S.pos_.size());
+	scrp_[jf].files.resize(S.pos_.size());
+	for (unsigned int i = 0; i < S.pos_.size(); i++)
+	  {
+	    scrp_[jf].fileNames[i] = S.basename_ + "-p" + stringify(rank_) + "-screen" + stringify(i) + ".txt";
+	    scrp_[jf].files[i] = new std::ofstream(scrp_[jf].fileNames[i].c_str(), std::ios::trunc);
+	    scrp_[jf].files[i]->setf(std::ios::scientific);
+	    scrp_[jf].files[i]->precision(15);
+	    scrp_[jf].files[i]->width(40);
+	  }
+	if ( screenGroup_ < 0 ) screenGroup_ = jf;
+	else printmessage(__FILE__, __LINE__, "Note: only the first bunch-profile-lab-frame group is recorded by this build.");
+      }
+  }
+
+  /* solver.cpp:1184-1206 */
+  void Solver::shiftBackInTime ()
+  {
+    if ( mesh_.timeShift_ == 0.0 ) return;
+    timem1_ -= mesh_.timeShift_; time_ -= mesh_.timeShift_; timep1_ -= mesh_.timeShift_; timeBunch_ -= mesh_.timeShift_;
+    for (Charge& q : chargeVectorn_)
+      {
+	const Double t = c0_ * mesh_.timeShift_ / std::sqrt( 1.0 + q.gb.norm2() );
+	q.rnp.mmv( t , q.gb );
+      }
+    distributeParticles(chargeVectorn_);
+  }
+
+  /* ========================================================================================================== */
+  /* hand-over to the library                                                                                     */
+
+  static void fillBeam (MithraBeam& d, const Beam& b)
+  {
+    d.seed_type = (int) b.seedType_;
+    for (int c = 0; c < 3; c++) { d.position[c] = b.position_[c]; d.direction[c] = b.direction_[c]; d.polarization[c] = b.polarization_[c]; }
+    d.amplitude = b.amplitude_;
+    d.radius[0] = b.radius_[0]; d.radius[1] = b.radius_[1];
+    d.l = b.l_;
+    d.zR[0] = b.zR_[0]; d.zR[1] = b.zR_[1];
+    d.order[0] = b.order_[0]; d.order[1] = b.order_[1];
+    d.signal.type = (int) b.signal_.signalType_;
+    d.signal.t0 = b.signal_.t0_; d.signal.s = b.signal_.s_; d.signal.f0 = b.signal_.f0_; d.signal.cep = b.signal_.cep_;
+    d.signal.nR = (int) b.signal_.nR_;
+    d.signal.sigma_inv_g[0] = b.signal_.sigmaInvG_.size() > 0 ? b.signal_.sigmaInvG_[0] : 0.0;
+    d.signal.sigma_inv_g[1] = b.signal_.sigmaInvG_.size() > 1 ? b.signal_.sigmaInvG_[1] : 0.0;
+  }
+
+  void Solver::fillParams (MithraGpuParams& p, int slab) const
+  {
+    memset(&p, 0, sizeof(p));
+    p.abi_version = MITHRA_GPU_ABI_VERSION;
+    p.N0 = N0_; p.N1 = N1_; p.N2 = N2_; p.np = slabNp_[slab]; p.k0 = slabK0_[slab]; p.rank = slab; p.size = size_;
+    p.dx = mesh_.meshResolution_[0]; p.dy = mesh_.meshResolution_[1]; p.dz = mesh_.meshResolution_[2]; p.dt = mesh_.timeStep_;
+    p.xmin = xmin_; p.xmax = xmax_; p.ymin = ymin_; p.ymax = ymax_; p.zmin = zmin_; p.zmax = zmax_;
+    p.zp[0] = slabZp0_[slab]; p.zp[1] = slabZp1_[slab];
+    p.Lz = mesh_.meshLength_[2];
+    p.solver = (int) mesh_.solver_; p.space_charge = mesh_.spaceCharge_ ? 1 : 0; p.truncation_order = mesh_.truncationOrder_;
+    memcpy(p.a, uf_.a, sizeof(p.a)); p.alpha = uf_.alpha; p.beta_nsfd = uf_.beta;
+    memcpy(p.bB, uf_.bB, sizeof(p.bB)); memcpy(p.cB, uf_.cB, sizeof(p.cB)); memcpy(p.dB, uf_.dB, sizeof(p.dB));
+    memcpy(p.eE, uf_.eE, sizeof(p.eE)); memcpy(p.fE, uf_.fE, sizeof(p.fE)); memcpy(p.gE, uf_.gE, sizeof(p.gE));
+    memcpy(p.hC, uf_.hC, sizeof(p.hC));
+    p.c0 = c0_; p.gamma = gamma_; p.beta = beta_; p.dt_shift = dt_;
+    p.dt_bunch = bunch_.timeStep_;
+    p.n_update_bunch = 0;
+    for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) ++p.n_update_bunch;            /* trip count of the loop at solver.cpp:1316 */
+    p.r1 = ub_.r1; p.r2 = ub_.r2; p.dtb = ub_.dtb;
+
+    if ( undulator_.size() > MITHRA_MAX_UNDULATORS || extField_.size() > MITHRA_MAX_EXTFIELDS )
+      { printmessage(__FILE__, __LINE__, "Too many undulator modules / external fields for the GPU parameter block."); exit(1); }
+    p.n_undulators = undulator_.size();
+    for (size_t u = 0; u < undulator_.size(); u++)
+      {
+	const Undulator& U = undulator_[u];
+	MithraUndulator& D = p.undulator[u];
+	D.type = (int) U.type_; D.k = U.k_; D.lu = U.lu_; D.rb = U.rb_; D.theta = U.theta_; D.length = U.length_; D.dist = U.dist_;
+	fillBeam(D.beam, U);
+      }
+    p.n_ext_fields = extField_.size();
+    for (size_t u = 0; u < extField_.size(); u++) fillBeam(p.ext_field[u], extField_[u]);
+    p.seed_enabled = ( fabs(seed_.amplitude_) > 1.0e-50 ) ? 1 : 0;             /* fdtd.cpp:307 */
+    fillBeam(p.seed, seed_);
+
+    if ( powerGroup_ >= 0 )
+      {
+	const FreeElectronLaser::RadiationSampling& R = FEL_[powerGroup_].radiationPower_;
+	const SampleRadiationPower& S = rp_[powerGroup_];
+	if ( S.N > MITHRA_MAX_POWER_PLANES || S.Nl > MITHRA_MAX_POWER_LAMBDAS )
+	  { printmessage(__FILE__, __LINE__, "Too many power planes / frequencies for the GPU parameter block."); exit(1); }
+	p.power.enabled = 1; p.power.N = S.N; p.power.Nl = S.Nl; p.power.Nf = S.Nf; p.power.pc = S.pc;
+	for (unsigned i = 0; i < S.N; i++)  p.power.z[i] = R.z_[i];
+	for (unsigned i = 0; i < S.Nl; i++) p.power.w[i] = S.w[i];
+      }
+    if ( screenGroup_ >= 0 )
+      {
+	const std::vector<Double>& pos = FEL_[screenGroup_].screenProfile_.pos_;
+	if ( pos.size() > MITHRA_MAX_SCREENS ) { printmessage(__FILE__, __LINE__, "Too many screens for the GPU parameter block."); exit(1); }
+	p.screens.enabled = 1; p.screens.N = pos.size();
+	for (size_t i = 0; i < pos.size(); i++) p.screens.pos[i] = pos[i];
+      }
+    p.device = -1;
+  }
+
+  void Solver::attachGpu ()
+  {
+    const int ndev = mithra_gpu_device_count();
+    if ( ndev < 1 ) { printmessage(__FILE__, __LINE__, "No CUDA device: the time-march of this build runs on sm_100 GPUs only."); exit(1); }
+
+    /* the bunch of every slab: the particles it owns, in list order (solver.cpp:1440-1441)                         */
+    std::vector<std::vector<double>> rows(size_);
+    for (const Charge& q : chargeVectorn_)
+      {
+	const Double zr = pmod( q.rnp[2] - zmin_ , mesh_.meshLength_[2] ) + zmin_;
+	int owner = -1;
+	for (int r = 0; r < size_; r++) if ( zr >= slabZp0_[r] && zr < slabZp1_[r] ) owner = r;
+	if ( owner < 0 ) continue;
+	std::vector<double>& v = rows[owner];
+	v.push_back(q.q);
+	for (int d = 0; d < 3; d++) v.push_back(q.rnp[d]);
+	for (int d = 0; d < 3; d++) v.push_back(q.rnm[d]);
+	for (int d = 0; d < 3; d++) v.push_back(q.gb[d]);
+	v.push_back(q.e);
+      }
+
+    gpu_.assign(size_, (MithraGpu*) 0);
+    for (int r = 0; r < size_; r++)
+      {
+	MithraGpuParams p; fillParams(p, r);
+	p.device = r % ndev;
+	const size_t n = rows[r].size() / 11;
+	/* room for the particles that migrate in: the whole bunch fits on any slab                                   */
+	p.max_particles = ( size_ == 1 ) ? n + 1024 : chargeVectorn_.size() + 1024;
+	p.max_screen_records = std::max<size_t>(chargeVectorn_.size(), 4096);
+	check(mithra_gpu_create(&p, &gpu_[r]));
+      }
+    if ( size_ > 1 )
+      {
+	std::vector<std::vector<char>> blob(size_);
+	for (int r = 0; r < size_; r++)
+	  {
+	    size_t nb = 0; check(mithra_gpu_ipc_export(gpu_[r], 0, 0, &nb));
+	    blob[r].resize(nb); check(mithra_gpu_ipc_export(gpu_[r], blob[r].data(), nb, &nb));
+	  }
+	for (int r = 0; r < size_; r++)
+	  check(mithra_gpu_ipc_connect(gpu_[r], blob[(r + size_ - 1) % size_].data(), blob[(r + 1) % size_].data()));
+      }
+    for (int r = 0; r < size_; r++)
+      {
+	check(mithra_gpu_set_time(gpu_[r], time_, timeBunch_, nTime_));
+	check(mithra_gpu_upload_particles(gpu_[r], rows[r].data(), rows[r].size() / 11));
+	check(mithra_gpu_seed_initial(gpu_[r]));
+      }
+  }
+
+  /* ========================================================================================================== */
+  /* the time march                                                                                               */
+
+  void FdTd::fieldUpdate ()        { for (MithraGpu* g : gpu_) check(mithra_gpu_field_update(g)); }          /* fdtd.cpp:231-800  */
+  void FdTd::fieldShift ()         { for (MithraGpu* g : gpu_) check(mithra_gpu_field_shift(g)); }           /* fdtd.cpp:806-812  */
+  void FdTd::currentReset ()       { for (MithraGpu* g : gpu_) check(mithra_gpu_current_reset(g)); }         /* fdtd.cpp:23-32    */
+  void FdTd::currentUpdate ()      { for (MithraGpu* g : gpu_) check(mithra_gpu_current_update(g)); }        /* fdtd.cpp:38-185   */
+  void FdTd::currentCommunicate ()                                                                           /* fdtd.cpp:191-225  */
+  {
+    for (MithraGpu* g : gpu_) check(mithra_gpu_current_communicate(g));
+    /* particle hand-over between the slabs (solver.cpp:1544-1568, 493-503), once per field step after the deposit  */
+    for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_begin(g));
+    for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_end(g));
+  }
+
+  /* rnm = rnp and the nUpdateBunch_ sub-steps of Solver::bunchUpdate in one launch per slab, solver.cpp:1311-1321 */
+  void Solver::bunchUpdate ()
+  {
+    for (MithraGpu* g : gpu_) check(mithra_gpu_bunch_update(g));
+    for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) { timeBunch_ += bunch_.timeStep_; ++nTimeBunch_; }
+  }
+
+  void Solver::screenProfile () { if ( screenGroup_ >= 0 ) for (MithraGpu* g : gpu_) check(mithra_gpu_screen_profile(g)); }
+
+  void Solver::powerSample ()
+  {
+    if ( powerGroup_ < 0 ) return;
+    for (MithraGpu* g : gpu_) check(mithra_gpu_power_sample(g));
+    powerTimes_.push_back(timeBunch_);
+  }
+
+  /* write what the library has collected since the last call: power lines (radiation.cpp:222-230), screen records
+   * (solver.cpp:2229-2252)                                                                                        */
+  void Solver::flushOutputs ()
+  {
+    if ( powerGroup_ >= 0 && !powerTimes_.empty() )
+      {
+	const SampleRadiationPower& S = rp_[powerGroup_];
+	const std::vector<Double>& z = FEL_[powerGroup_].radiationPower_.z_;
+	const size_t w = (size_t) S.N * S.Nl, nrows = powerTimes_.size();
+	std::vector<double> sum(nrows * w, 0.0), part(nrows * w);
+	for (MithraGpu* g : gpu_)
+	  {
+	    size_t got = 0;
+	    check(mithra_gpu_fetch_power(g, part.data(), nrows, &got));
+	    if ( got != nrows ) { printmessage(__FILE__, __LINE__, "power rows out of step with the host loop"); exit(1); }
+	    /* every plane is sampled by exactly one slab, the others return zeros (the MPI_Allreduce of :218)         */
+	    for (size_t i = 0; i < nrows * w; i++) sum[i] += part[i];
+	  }
+	for (size_t r = 0; r < nrows; r++)
+	  for (unsigned l = 0; l < S.Nl; l++)
+	    {
+	      std::ofstream& f = *S.file[l];
+	      for (unsigned k = 0; k < S.N; ++k)
+		f << gamma_ * ( z[k] + beta_ * c0_ * ( powerTimes_[r] + dt_ ) ) << "\t" << sum[r * w + k * S.Nl + l] << "\t";
+	      f << std::endl;
+	    }
+	powerTimes_.clear();
+      }
+    if ( screenGroup_ >= 0 )
+      {
+	const size_t ns = FEL_[screenGroup_].screenProfile_.pos_.size();
+	std::vector<double> rec;
+	for (size_t s = 0; s < ns; s++)
+	  for (MithraGpu* g : gpu_)
+	    {
+	      size_t n = 0;
+	      check(mithra_gpu_fetch_screen(g, (int) s, 0, 0, &n));
+	      if ( n == 0 ) continue;
+	      rec.resize(n * 6);
+	      check(mithra_gpu_fetch_screen(g, (int) s, rec.data(), n, &n));
+	      std::ofstream& f = *scrp_[screenGroup_].files[s];
+	      for (size_t i = 0; i < n; i++)
+		f << rec[6 * i] << "\t" << rec[6 * i + 1] << "\t" << rec[6 * i + 2] << "\t" << rec[6 * i + 3] << "\t" << rec[6 * i + 4] << "\t" << rec[6 * i + 5] << std::endl;
+	    }
+      }
+  }
+
+  void Solver::finalize ()
+  {
+    for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
+    flushOutputs();
+    for (SampleRadiationPower& S : rp_) for (std::ofstream* f : S.file) if (f) f->close();
+    for (SampleScreenProfile& S : scrp_) for (std::ofstream* f : S.files) if (f) f->close();
+  }
+
+  /* solver.cpp:1212-1418 */
+  void Solver::solve ()
+  {
+    initialize();
+    attachGpu();
+
+    timeval t0, t1;
+    gettimeofday(&t0, NULL);
+    const unsigned int flushEvery = 512;
+    long steps = 0;
+    auto advance = [&] () {
+      for (MithraGpu* g : gpu_) check(mithra_gpu_advance_time(g));
+      timem1_ += mesh_.timeStep_; time_ += mesh_.timeStep_; timep1_ += mesh_.timeStep_; ++nTime_; ++steps;
+      if ( nTime_ % flushEvery == 0 ) flushOutputs(); };
+
+    /* particles only, up to the time origin (initial-time-back-shift), solver.cpp:1232-1291                        */
+    while ( time_ < 0.0 && ( maxSteps_ < 0 || steps < maxSteps_ ) )
+      {
+	bunchUpdate();
+	screenProfile();
+	for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_begin(g));
+	for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_end(g));
+	advance();
+      }
+
+    gettimeofday(&t0, NULL);
+    const unsigned int nStart = nTime_;
+    while ( time_ < mesh_.totalTime_ && ( maxSteps_ < 0 || steps < maxSteps_ ) )
+      {
+	fieldUpdate();
+	bunchUpdate();
+	recycleParticles();
+	screenProfile();
+	powerSample();
+	fieldShift();
+	currentReset();
+	currentUpdate();
+	currentCommunicate();
+	advance();
+
+	if ( int( time_ / mesh_.totalTime_ * 1000.0 ) != int( timem1_ / mesh_.totalTime_ * 1000.0 ) )
+	  {
+	    for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
+	    gettimeofday(&t1, NULL);
+	    const Double dT = ( t1.tv_usec - t0.tv_usec ) / 1.0e6 + ( t1.tv_sec - t0.tv_sec );
+	    printmessage(__FILE__, __LINE__, " Percentage of the total simulation completed (%)      = " + stringify( time_ / mesh_.totalTime_ * 100.0 ));
+	    printmessage(__FILE__, __LINE__, " Average calculation time for each time step (s) = " + stringify( dT / (double) ( nTime_ - nStart ) ));
+	    printmessage(__FILE__, __LINE__, " Estimated remaining time (min)                  = " + stringify( ( mesh_.totalTime_ / time_ - 1 ) * dT / 60 ));
+	  }
+      }
+    finalize();
+  }
+
+  /* ========================================================================================================== */
+  /* record file with the results of initialize(), same names as oracle/ref_dump.cpp's meta record                 */
+
+  namespace
+  {
+    struct Writer
+    {
+      std::ofstream f;
+      Writer (const std::string& fn) : f(fn.c_str(), std::ios::binary | std::ios::trunc) {}
+      void raw (const char* name, int32_t type, const void* p, int64_t n, size_t item)
+      {
+	char key[48]; memset(key, 0, sizeof(key)); strncpy(key, name, 47);
+	f.write(key, 48); f.write((const char*) &type, 4); f.write((const char*) &n, 8); f.write((const char*) p, n * item);
+      }
+      void f64 (const std::string& name, const double* p, int64_t n) { raw(name.c_str(), 0, p, n, 8); }
+      void d (const std::string& name, double v) { f64(name, &v, 1); }
+      void i (const std::string& name, int v) { int32_t x = v; raw(name.c_str(), 2, &x, 1, 4); }
+    };
+
+    void dumpBeam (Writer& w, const std::string& key, const Beam& b)
+    {
+      const double o[18] = { (double) b.seedType_, b.position_[0], b.position_[1], b.position_[2], b.direction_[0], b.direction_[1], b.direction_[2],
+			     b.polarization_[0], b.polarization_[1], b.polarization_[2], b.amplitude_, b.radius_[0], b.radius_[1], b.l_, b.zR_[0], b.zR_[1],
+			     (double) b.order_[0], (double) b.order_[1] };
+      w.f64(key + "beam", o, 18);
+      const double g[8] = { (double) b.signal_.signalType_, b.signal_.t0_, b.signal_.s_, b.signal_.f0_, (double) b.signal_.nR_, b.signal_.cep_,
+			    b.signal_.sigmaInvG_.size() > 0 ? b.signal_.sigmaInvG_[0] : 0.0, b.signal_.sigmaInvG_.size() > 1 ? b.signal_.sigmaInvG_[1] : 0.0 };
+      w.f64(key + "sig", g, 8);
+    }
+  }
+
+  void Solver::dumpParams (const std::string& prefix)
+  {
+    Writer w(prefix + ".meta.bin");
+    w.i("N0", N0_); w.i("N1", N1_); w.i("N2", N2_); w.i("np", np_); w.i("k0", k0_); w.i("rank", 0); w.i("size", size_);
+    w.i("spaceCharge", mesh_.spaceCharge_ ? 1 : 0); w.i("solver", (int) mesh_.solver_); w.i("truncationOrder", mesh_.truncationOrder_);
+    w.d("dx", mesh_.meshResolution_[0]); w.d("dy", mesh_.meshResolution_[1]); w.d("dz", mesh_.meshResolution_[2]);
+    w.d("Lx", mesh_.meshLength_[0]); w.d("Ly", mesh_.meshLength_[1]); w.d("Lz", mesh_.meshLength_[2]);
+    w.d("dt", mesh_.timeStep_); w.d("dtBunch", bunch_.timeStep_); w.d("nUpdateBunch", nUpdateBunch_);
+    w.d("totalTime", mesh_.totalTime_); w.d("timeShift", mesh_.timeShift_);
+    w.d("xmin", xmin_); w.d("xmax", xmax_); w.d("ymin", ymin_); w.d("ymax", ymax_); w.d("zmin", zmin_); w.d("zmax", zmax_);
+    const double zp[2] = { slabZp0_[0], slabZp1_[0] }; w.f64("zp", zp, 2);
+    w.d("gamma", gamma_); w.d("beta", beta_); w.d("dtShift", dt_); w.d("c0", c0_); w.d("m0", m0_); w.d("e0", e0_);
+    w.f64("a", uf_.a, 6); w.d("alpha", uf_.alpha); w.d("betaNSFD", uf_.beta);
+    w.f64("bB", uf_.bB, 5); w.f64("cB", uf_.cB, 5); w.f64("dB", uf_.dB, 5); w.f64("eE", uf_.eE, 5); w.f64("fE", uf_.fE, 5); w.f64("gE", uf_.gE, 5);
+    w.f64("hC", uf_.hC, 17);
+    w.d("dv", uc_.dv); w.d("rc", uc_.rc); w.d("r1", ub_.r1); w.d("r2", ub_.r2); w.d("dtb", ub_.dtb);
+    w.d("seedAmplitude", seed_.amplitude_);
+    dumpBeam(w, "seed.", seed_);
+    w.i("nExtFields", (int) extField_.size());
+    for (size_t u = 0; u < extField_.size(); u++) dumpBeam(w, "ext" + stringify(u) + ".", extField_[u]);
+    w.i("nUndulators", (int) undulator_.size());
+    for (size_t u = 0; u < undulator_.size(); u++)
+      {
+	const Undulator& U = undulator_[u];
+	const double v[8] = { U.k_, U.lu_, U.rb_, (double) U.length_, U.dist_, U.theta_, (double) U.type_, (double) U.seedType_ };
+	w.f64("und" + stringify(u) + ".static", v, 8);
+	dumpBeam(w, "und" + stringify(u) + ".", U);
+      }
+    w.i("nFEL", (int) FEL_.size());
+    for (size_t jf = 0; jf < FEL_.size(); jf++)
+      {
+	if (!FEL_[jf].radiationPower_.sampling_) continue;
+	const std::string k = "power" + stringify(jf) + ".";
+	w.i(k + "N", rp_[jf].N); w.i(k + "Nl", rp_[jf].Nl); w.i(k + "Nf", rp_[jf].Nf); w.d(k + "pc", rp_[jf].pc);
+	w.f64(k + "z", FEL_[jf].radiationPower_.z_.data(), FEL_[jf].radiationPower_.z_.size());
+	w.f64(k + "w", rp_[jf].w.data(), rp_[jf].w.size());
+      }
+    for (size_t jf = 0; jf < FEL_.size(); jf++)
+      if (FEL_[jf].screenProfile_.sampling_)
+	w.f64("screen" + stringify(jf) + ".pos", FEL_[jf].screenProfile_.pos_.data(), FEL_[jf].screenProfile_.pos_.size());
+    w.d("time", time_); w.d("timem1", timem1_); w.d("timep1", timep1_); w.d("timeBunch", timeBunch_);
+    w.i("nTime", (int) nTime_); w.i("nTimeBunch", (int) nTimeBunch_);
+    std::vector<double> rows; rows.reserve(chargeVectorn_.size() * 11);
+    for (const Charge& q : chargeVectorn_)
+      {
+	rows.push_back(q.q);
+	for (int d = 0; d < 3; d++) rows.push_back(q.rnp[d]);
+	for (int d = 0; d < 3; d++) rows.push_back(q.rnm[d]);
+	for (int d = 0; d < 3; d++) rows.push_back(q.gb[d]);
+	rows.push_back(q.e);
+      }
+    w.f64("particles", rows.data(), rows.size());
+    /* the parameter block of every slab exactly as mithra_gpu_create receives it                                   */
+    for (int r = 0; r < size_; r++)
+      {
+	MithraGpuParams p; fillParams(p, r);
+	w.raw(("params" + stringify(r)).c_str(), 3, &p, sizeof(p), 1);
+      }
+  }
+}

@@ -1,0 +1,148 @@
+"""The C++ host (mithra_b200/host): job-file front end + Solver/FdTd/FdTdSC over the C ABI.
+
+CPU part: Solver::initialize() re-derived on the host must reproduce, BIT FOR BIT, every scalar, coefficient table and
+the whole initial bunch the unmodified reference's own initialize() produced for the same job file (the `meta/*` records
+and `p0` of tests/golden/*.npz, written by oracle/_ref/ref_dump), and the parser must reject what the reference rejects.
+GPU part: the executable runs a job end to end and writes the reference's power / screen text files."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from mithra_b200 import meta as mmeta
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "mithra_b200", "host", "mithra_b200")
+
+
+def _exe():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(EXE)])
+    return EXE
+
+
+def _job(name):
+    return os.path.join(ROOT, "tests", "jobs", name + ".job")
+
+
+@pytest.mark.parametrize("job", helpers.JOBS)
+def test_initialize_matches_reference_bit_for_bit(job, tmp_path):
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), _job(job), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    meta, g = helpers.load_golden(job)
+    skipped = 0
+    for k, v in meta.items():
+        if k.endswith(".optical") or k.endswith(".signal"):      # redundant views of und<i>.beam / .sig in ref_dump
+            skipped += 1
+            continue
+        assert k in rec, k
+        np.testing.assert_array_equal(np.asarray(rec[k]), np.asarray(v), err_msg=k)
+    assert len(meta) - skipped > 50
+    np.testing.assert_array_equal(rec["particles"].reshape(-1, 11), g["p0"])
+
+
+@pytest.mark.parametrize("job", helpers.JOBS)
+def test_parameter_block_equals_harness_block(job, tmp_path):
+    """MithraGpuParams as the host fills it == the block the parity tests build from the reference's meta record."""
+    import ctypes as C
+    from mithra_b200 import abi
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), _job(job), "--dump-params", pre], cwd=str(tmp_path))
+    raw = mmeta.read_records(pre + ".meta.bin")["params0"].tobytes()
+    assert len(raw) == C.sizeof(abi.Params)
+    got = abi.Params.from_buffer_copy(raw)
+    want, _, _ = helpers.params_for(job)
+    for name, _t in abi.Params._fields_:
+        if name in ("max_particles", "max_screen_records", "device", "sort_interval"):
+            continue
+        a, b = getattr(got, name), getattr(want, name)
+        if isinstance(a, (C.Structure, C.Array)):
+            if name == "undulator":
+                n = got.n_undulators
+                assert bytes(a)[: n * C.sizeof(abi.Undulator)] == bytes(b)[: n * C.sizeof(abi.Undulator)], name
+            elif name == "ext_field":
+                n = got.n_ext_fields
+                assert bytes(a)[: n * C.sizeof(abi.Beam)] == bytes(b)[: n * C.sizeof(abi.Beam)], name
+            else:
+                assert bytes(a) == bytes(b), name
+        else:
+            assert a == b, name
+
+
+def test_two_slab_partition_matches_reference_scheme(tmp_path):
+    from mithra_b200 import abi, slabs
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), _job("micro-nsfd"), "--gpus", "2", "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    whole, _, _ = helpers.params_for("micro-nsfd")
+    for r in range(2):
+        got = abi.Params.from_buffer_copy(rec["params%d" % r].tobytes())
+        want = slabs.slab_params(whole, r, 2)
+        assert (got.np, got.k0, got.rank, got.size) == (want.np, want.k0, r, 2)
+        assert (got.zp[0], got.zp[1]) == (want.zp[0], want.zp[1])
+
+
+def test_unknown_key_and_group_exit_like_the_reference(tmp_path):
+    text = open(_job("micro-nsfd")).read()
+    bad = tmp_path / "bad.job"
+    bad.write_text(text.replace("total-time", "total-tyme", 1))
+    r = subprocess.run([_exe(), str(bad), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode == 1 and "total-tyme is not defined in solver group." in r.stdout
+    bad.write_text("NONSENSE\n{\n}\n" + text)
+    r = subprocess.run([_exe(), str(bad), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode == 1 and "NONSENSE is not a defined group." in r.stdout
+    r = subprocess.run([_exe(), str(tmp_path / "missing.job")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unable to open file" in r.stdout
+
+
+def test_without_gpu_the_executable_fails_loudly(tmp_path):
+    from mithra_b200 import abi
+    if abi.load().mithra_gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([_exe(), _job("micro-nsfd"), "--steps", "2"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 1 and "No CUDA device" in r.stdout
+
+
+def _numbers(fn):
+    return np.array([float(t) for t in open(fn).read().split()])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("job,gpus", [("micro-nsfd", 1), ("micro-sc", 1), ("micro-seeded", 1), ("micro-optical", 1), ("micro-nsfd", 2), ("micro-seeded", 3)])
+def test_executable_writes_the_reference_output_files(job, gpus, tmp_path):
+    """100 field steps from the job file alone: power-<l>.txt (z_lab, P per plane) and the screen files against the
+    unmodified reference's own output for the same job (tests/golden)."""
+    meta, g = helpers.load_golden(job)
+    subprocess.check_output([_exe(), _job(job), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    p, _, _ = helpers.params_for(job)
+    want = g["power"]
+    files = sorted(f for f in os.listdir(tmp_path / "power-sampling") if f.endswith(".txt"))
+    assert len(files) == p.power.Nl
+    for l, fn in enumerate(files):
+        a = _numbers(tmp_path / "power-sampling" / fn).reshape(100, p.power.N, 2)
+        ref = want.reshape(100, p.power.N, p.power.Nl)[:, :, l]
+        np.testing.assert_allclose(a[:, :, 1], ref, rtol=1e-8, atol=1e-12 * np.abs(ref).max() + 1e-300)
+        # abscissa: lab-frame position of the plane, gamma (z + beta c0 (t_b + dt)), radiation.cpp:226
+        t0 = g["t0"]
+        tb = t0[1] + p.dt_bunch * p.n_update_bunch * np.arange(1, 101)
+        for k in range(p.power.N):
+            zl = p.gamma * (p.power.z[k] + p.beta * p.c0 * (tb + p.dt_shift))
+            np.testing.assert_allclose(a[:, k, 0], zl, rtol=1e-12)
+    if p.screens.enabled:
+        d = [x for x in os.listdir(tmp_path) if os.path.isdir(tmp_path / x) and x != "power-sampling"]
+        for s in range(p.screens.N):
+            key = "screen%d" % s
+            ref = g[key] if key in g.files else np.zeros((0, 6))
+            fn = [os.path.join(str(tmp_path), x, f) for x in d for f in os.listdir(tmp_path / x) if f.endswith("-p0-screen%d.txt" % s)]
+            assert len(fn) == 1
+            rec = _numbers(fn[0]).reshape(-1, 6)
+            assert rec.shape == ref.shape
+            if gpus == 1:
+                np.testing.assert_allclose(rec, ref, rtol=1e-9, atol=1e-12)
+            else:
+                o1, o2 = np.lexsort((rec[:, 0], rec[:, 2])), np.lexsort((ref[:, 0], ref[:, 2]))
+                np.testing.assert_allclose(rec[o1], ref[o2], rtol=1e-8, atol=1e-10)
