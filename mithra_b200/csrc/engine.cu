@@ -57,6 +57,7 @@ struct MithraGpu
   /* potentials */
   size_t          level_doubles;          /* ncomp * np * Pp                                              */
   double*         A[3];                   /* rotating: A[ip1], A[in], A[im1]                              */
+  void*           Abase[4];               /* the allocations behind A[0..2] and J                          */
   int             ip1, in, im1;
   bool            anp1_is_current;        /* reference view: anp1_ currently holds J (after fieldShift)    */
   double*         J;
@@ -247,6 +248,7 @@ static void fill_field_dev (const MithraGpuParams& p, FieldDev& f)
   f.N0 = p.N0; f.N1 = p.N1; f.np = p.np + f.kshift; f.k0 = p.k0 - f.kshift;
   f.P  = p.N0 * p.N1;
   f.Pp = ((long) f.P + 15) / 16 * 16;
+  if (const char* e = getenv("MITHRA_PLANE_PAD")) f.Pp += 16L * atoi(e);                 /* experiments */
   f.ncomp = p.space_charge ? 4 : 3;
   f.rank = p.rank; f.size = p.size;
   f.nsfd = (p.solver == MITHRA_SOLVER_NSFD) ? 1 : 0;
@@ -302,7 +304,7 @@ static int preload_kernels ()
   #define PL(k) do { cudaError_t r_ = preload(k); if (r_ != cudaSuccess) e = r_; } while (0)
   PL(aos_to_planar); PL(planar_to_aos); PL(aos_to_particles); PL(particles_to_aos); PL(set_box); PL(make_eb_box);
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
-  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>));
+  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8>)); PL((stencil_stream<false, 512, 8>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
   PL(particle_box); PL(particle_cells); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
@@ -349,8 +351,17 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   const FieldDev& f = h->fd;
 
   h->level_doubles = (size_t) f.ncomp * f.np * f.Pp;
-  for (int l = 0; l < 3; l++) { CU(cudaMalloc(&h->A[l], h->level_doubles * sizeof(double))); CU(cudaMemsetAsync(h->A[l], 0, h->level_doubles * sizeof(double), h->stream)); }
-  CU(cudaMalloc(&h->J, h->level_doubles * sizeof(double))); CU(cudaMemsetAsync(h->J, 0, h->level_doubles * sizeof(double), h->stream));
+  {
+    /* experiments: MITHRA_LEVEL_SKEW = bytes by which consecutive levels are shifted against each other               */
+    const size_t skew = getenv("MITHRA_LEVEL_SKEW") ? (size_t) atol(getenv("MITHRA_LEVEL_SKEW")) / 128 * 128 : 0;
+    for (int l = 0; l < 4; l++)
+      {
+	CU(cudaMalloc(&h->Abase[l], h->level_doubles * sizeof(double) + 4 * skew));
+	double* q = (double*) ((char*) h->Abase[l] + l * skew);
+	CU(cudaMemsetAsync(q, 0, h->level_doubles * sizeof(double), h->stream));
+	if (l < 3) h->A[l] = q; else h->J = q;
+      }
+  }
   h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
   CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
   CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
@@ -376,6 +387,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   /* counting sort: one bin per cell of the particle box, as many as the slab has cells (at most 2^27)      */
   h->sort_cap = std::min<long>((long) f.np * f.P, 1L << 27);
   h->sort_interval = params->sort_interval;
+  if (const char* e = getenv("MITHRA_SORT_INTERVAL")) h->sort_interval = atoi(e);      /* experiments: overrides the parameter block */
   h->steps_since_sort = 0;
   CU(cudaMalloc(&h->d_hist, (size_t) h->sort_cap * sizeof(unsigned int)));
   CU(cudaMalloc(&h->d_sums, (size_t) (h->sort_cap / MITHRA_SCAN_CHUNK + 2) * sizeof(unsigned int)));
@@ -458,8 +470,8 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   exchange_destroy(h->xch);
-  for (int l = 0; l < 3; l++) cudaFree(h->A[l]);
-  cudaFree(h->J); cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
+  for (int l = 0; l < 4; l++) cudaFree(h->Abase[l]);
+  cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
   cudaFree(h->eb); cudaFree(h->d_noutside);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
@@ -698,9 +710,31 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 /* ---------------------------------------------------------------------------------------------------- */
 /* the time march                                                                                        */
 
+/* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
+template <bool NSFD>
+static bool launch_stencil_stream (MithraGpu* h)
+{
+  const FieldDev& f = h->fd;
+  constexpr int T = 512, NB = 8;
+  static const int KC = getenv("MITHRA_STENCIL_KC") ? atoi(getenv("MITHRA_STENCIL_KC")) : 64;
+  if (getenv("MITHRA_STENCIL_PLAIN")) return false;
+  const size_t smem = stencil_stream_smem(T, f.N1, NB);
+  if (smem > 200 * 1024) return false;
+  static bool configured[2] = { false, false };
+  if (!configured[NSFD])
+    {
+      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+      configured[NSFD] = true;
+    }
+  dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
+  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC);
+  return true;
+}
+
 template <bool NSFD>
 static void launch_stencil (MithraGpu* h)
 {
+  if (launch_stencil_stream<NSFD>(h)) return;
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
   dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);

@@ -100,6 +100,172 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
+   * Interior stencil, bulk-async plane pipeline (the production path; stencil_interior above stays as the
+   * plain-load fallback for meshes whose rows do not fit the staging buffers).
+   *
+   * A CTA owns T consecutive in-plane positions p = i*N1 + j of one component -- a CONTIGUOUS piece of every
+   * z plane because rows are contiguous -- and marches KC planes in +z.  Plane k+1 of A^n (the T positions plus
+   * one row of halo on either side) and plane k of A^{n-1} are fetched by ONE elected thread with
+   * cp.async.bulk (1-D bulk copy through the TMA unit, completion on an mbarrier) into a ring of NB stages, NB-1
+   * planes ahead of the plane being computed, so HBM latency is covered by the ring and not by occupancy.  A thread
+   * keeps the 5-point cross of planes k-1, k in registers, takes the five values of plane k+1 from shared memory
+   * and streams A^{n+1} out with a coalesced store.  Arithmetic and association order are those of
+   * stencil_interior (bit-identical results).
+   *
+   * Alignment: bulk copies need 16-byte aligned addresses and sizes; Pp is a multiple of 16 doubles, T is even and
+   * the halo is rounded up to an even number of doubles (N1e), the extra element is never read.
+   * ------------------------------------------------------------------------------------------------ */
+  __device__ __forceinline__ unsigned smem_u32 (const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void mbar_init (unsigned long long* b, int count)
+  { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count)); }
+  __device__ __forceinline__ void mbar_expect_tx (unsigned long long* b, unsigned bytes)
+  { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
+  __device__ __forceinline__ void mbar_wait (unsigned long long* b, unsigned parity)
+  {
+    unsigned done;
+    do
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+		   : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    while (!done);
+  }
+  __device__ __forceinline__ void bulk_g2s (void* dst, const void* src, unsigned bytes, unsigned long long* b)
+  {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+  }
+
+  __device__ __forceinline__ void mbar_arrive (unsigned long long* b)
+  { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
+
+  /* shared memory of one CTA: 2 * NB mbarriers, then NB stages of (T + 2 N1e) doubles of A^n and T doubles of A^{n-1} */
+  static inline size_t stencil_stream_smem (int T, int N1, int NB)
+  { const int N1e = (N1 + 1) & ~1; return 256 + (size_t) NB * ( (size_t) T + 2 * N1e + T ) * sizeof(double); }
+
+  /* the 5-point cross of one plane around the thread's node                                                    */
+  struct Cross { double c, xp, xm, yp, ym; };
+
+  template <bool NSFD>
+  __device__ __forceinline__ double stencil_value (const Cross& m, const Cross& z, const Cross& p, double vm1, double src,
+						   double a0, double a1, double a2, double a3, double as, double alpha, double beta)
+  {
+    if (NSFD)
+      return a0 * z.c - vm1 + alpha * (
+	     a1 * ( z.xp + z.xm + beta * ( p.xp + m.xp + p.xm + m.xm ) ) +
+	     a2 * ( z.yp + z.ym + beta * ( p.yp + m.yp + p.ym + m.ym ) ) ) +
+	     a3 * ( p.c + m.c ) +
+	     as * src;
+    return a0 * z.c - vm1 +
+	   a1 * ( z.xp + z.xm ) +
+	   a2 * ( z.yp + z.ym ) +
+	   a3 * ( p.c + m.c ) +
+	   as * src;
+  }
+
+  /* T consumer threads (one in-plane position each) + one producer warp                                        */
+  template <bool NSFD, int T, int NB>
+  __global__ void __launch_bounds__(T + 32, 2)
+  stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC)
+  {
+    static_assert((NB & (NB - 1)) == 0 && NB >= 2 && NB <= 16, "stages: a power of two");
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* full  = reinterpret_cast<unsigned long long*>(smraw);
+    unsigned long long* empty = full + NB;
+    const int  N1 = f.N1, N1e = (N1 + 1) & ~1;
+    const int  W  = T + 2 * N1e;                          /* doubles of one A^n stage                       */
+    double* stA = reinterpret_cast<double*>(smraw + 256);
+    double* stM = stA + (size_t) NB * W;
+
+    const int  tid = threadIdx.x, c = blockIdx.z;
+    const long p0  = (long) blockIdx.x * T;
+    const int  ks  = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);      /* planes ks .. ke-1            */
+    if (ks >= ke) return;
+    const long Pp = f.Pp, cb = (long) c * f.np * Pp;
+    const int  nq = ke - ks + 2;                          /* planes ks-1 .. ke travel through the ring       */
+
+    if (tid == 0)
+      {
+	for (int s = 0; s < NB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], T / 32); }
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    __syncthreads();
+
+    if (tid >= T)
+      {
+	/* ---- producer warp: one lane feeds the ring ---------------------------------------------------- */
+	if (tid != T) return;
+	/* source range of an A^n stage, clipped to the plane; both ends are even                              */
+	const long lo = max(0L, p0 - N1e), hi = min(Pp, p0 + T + N1e);
+	const int  dstoff = (int) (lo - (p0 - N1e));
+	const unsigned bytesA = (unsigned) ((hi - lo) * sizeof(double));
+	const unsigned bytesM = (unsigned) ((min(Pp, p0 + T) - p0) * sizeof(double));
+	const double* srcA = an   + cb + (long) (ks - 1) * Pp + lo;
+	const double* srcM = anm1 + cb + (long) (ks - 1) * Pp + p0;
+	for (int q = 0; q < nq; q++, srcA += Pp, srcM += Pp)
+	  {
+	    const int s = q & (NB - 1);
+	    if (q >= NB) mbar_wait(&empty[s], (unsigned) (((q / NB) - 1) & 1));
+	    const bool needM = (q >= 1 && q < nq - 1);     /* A^{n-1} rides along for the planes that are updated */
+	    mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
+	    bulk_g2s(stA + (size_t) s * W + dstoff, srcA, bytesA, &full[s]);
+	    if (needM) bulk_g2s(stM + (size_t) s * T, srcM, bytesM, &full[s]);
+	  }
+	return;
+      }
+
+    /* ---- consumers -------------------------------------------------------------------------------------- */
+    const long p = p0 + tid;
+    const int  i = (int) (p / N1), j = (int) (p - (long) i * N1);
+    const bool interior = (p < f.P && i >= 1 && i <= f.N0 - 2 && j >= 1 && j <= f.N1 - 2);
+    const bool lane0 = (tid & 31) == 0;
+
+    const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
+    const double as = (c < 3) ? f.a[4] : f.a[5];
+    const double alpha = f.alpha, beta = f.beta;
+    const Box bx = *jbox;
+    const bool inxy = interior && (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+    const double* Jn = jn   + cb + p + (long) ks * Pp;
+    double*       Ap = anp1 + cb + p + (long) ks * Pp;
+    const double* myA = stA + N1e + tid;
+    const double* myM = stM + tid;
+
+    int q = 0;                                            /* ring position of the next plane to take          */
+    /* take plane q out of the ring: its cross, the A^{n-1} value that came with it; then hand the stage back     */
+    auto take = [&] (Cross& x, double& vm) {
+      const int s = q & (NB - 1);
+      mbar_wait(&full[s], (unsigned) ((q / NB) & 1));
+      const double* a = myA + (size_t) s * W;
+      x.c = a[0]; x.xp = a[N1]; x.xm = a[-N1]; x.yp = a[1]; x.ym = a[-1];
+      vm = myM[(size_t) s * T];
+      __syncwarp();
+      if (lane0) mbar_arrive(&empty[s]);
+      ++q; };
+
+    Cross P0, P1, P2;
+    double vm1, vnext, dummy;
+    take(P0, dummy);                                      /* plane ks-1                                       */
+    take(P1, vm1);                                        /* plane ks with A^{n-1}(ks)                        */
+
+    int k = ks;
+    /* one plane: Z is plane k, M plane k-1, the new plane k+1 lands in Pn                                         */
+    #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
+      {                                                                                                         \
+	double src = 0.0;                                                                                       \
+	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = __ldg(Jn);                                            \
+	take(Pn, vnext);                                                                                        \
+	if (interior) *Ap = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);          \
+	vm1 = vnext; Ap += Pp; Jn += Pp; ++k;                                                                   \
+      }
+    while (true)
+      {
+	MITHRA_STREAM_STEP(P0, P1, P2); if (k >= ke) break;
+	MITHRA_STREAM_STEP(P1, P2, P0); if (k >= ke) break;
+	MITHRA_STREAM_STEP(P2, P0, P1); if (k >= ke) break;
+      }
+    #undef MITHRA_STREAM_STEP
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Faces.  A+_s = B0 (A-_s + A+_n) + B1 A-_n + B2 (A_s + A_n)
    *              + B3 (A_{n+t1} + A_{n-t1} + A_{s+t1} + A_{s-t1}) + B4 (same along t2)
    * s = face node, n = s + dn its inward neighbour; x faces: (t1,t2) = (y,z), y faces: (x,z), z: (x,y).
