@@ -285,12 +285,36 @@ namespace mithra
   }
 
   /* Seed::fields, classes.cpp:740-855: seed vector potential at a mesh node (moving frame) at `time`.    */
-  __device__ inline V3 seed_fields (const MithraBeam& s, double c0, double gamma, double beta, double dt_shift,
-				    double px, double py, double pz, double time)
+  /* Seed::fields is always  a = (sum of ni equal terms u * polarization), a_z *= gamma  (classes.cpp:783-852): the
+   * scalar u carries all the space and time dependence.  seed_assemble rebuilds the vector with the reference's
+   * roundings: scale3(u, pol), added ni times from zero for the super-Gaussian beam (quirk Q8), then a_z * gamma. */
+  __device__ __forceinline__ int seed_terms (const MithraBeam& s)
+  { return (s.seed_type == MITHRA_BEAM_SUPERGAUSSIAN) ? ( 2 * s.order[0] + 1 ) * ( 2 * s.order[1] + 1 ) : 1; }
+
+  __device__ __forceinline__ double seed_assemble_comp (double u, double polc, int ni, bool supergaussian, bool zcomp, double gamma)
+  {
+    const double one = u * polc;
+    double a = one;
+    if (supergaussian) { a = 0.0; for (int n = 0; n < ni; n++) a = a + one; }
+    if (zcomp) a *= gamma;
+    return a;
+  }
+
+  __device__ __forceinline__ V3 seed_assemble (const MithraBeam& s, double gamma, double u)
+  {
+    const bool sg = (s.seed_type == MITHRA_BEAM_SUPERGAUSSIAN);
+    const int  ni = seed_terms(s);
+    return v3(seed_assemble_comp(u, s.polarization[0], ni, sg, false, gamma),
+	      seed_assemble_comp(u, s.polarization[1], ni, sg, false, gamma),
+	      seed_assemble_comp(u, s.polarization[2], ni, sg, true,  gamma));
+  }
+
+  /* the scalar u of Seed::fields at the point (px, py, pz) of the moving frame, any beam direction              */
+  __device__ inline double seed_scalar (const MithraBeam& s, double c0, double gamma, double beta, double dt_shift,
+					double px, double py, double pz, double time)
   {
     const double PI = MITHRA_PI;
     const V3 dir = v3a(s.direction), pol = v3a(s.polarization);
-    V3 a = v3(0.0, 0.0, 0.0);
     const V3 rl = v3(px, py, gamma * ( pz + beta * c0 * ( time + dt_shift ) ));
     double tl = gamma * ( time + dt_shift + beta / c0 * pz );
     const V3 rv = v3(rl.x - s.position[0], rl.y - s.position[1], rl.z - s.position[2]);
@@ -301,13 +325,13 @@ namespace mithra
 
     if (s.seed_type == MITHRA_BEAM_PLANEWAVE)
       {
-	if (!(fabs(ts) < 1.0e-6)) a = scale3(s.amplitude * ts, pol);
+	if (!(fabs(ts) < 1.0e-6)) return s.amplitude * ts;
       }
     else if (s.seed_type == MITHRA_BEAM_PLANEWAVETRUNCATED)
       {
 	const double x = dot3(rv, pol);
 	const double y = dot3(rv, cross3(dir, pol));
-	if (!(fabs(ts) < 1.0e-6 || fabs(x) > s.radius[0] || fabs(y) > s.radius[1])) a = scale3(s.amplitude * ts, pol);
+	if (!(fabs(ts) < 1.0e-6 || fabs(x) > s.radius[0] || fabs(y) > s.radius[1])) return s.amplitude * ts;
       }
     else if (s.seed_type == MITHRA_BEAM_GAUSSIAN || s.seed_type == MITHRA_BEAM_SUPERGAUSSIAN)
       {
@@ -320,19 +344,20 @@ namespace mithra
 	    const double wrp = sqrt( 1.0 + z * z / ( zRp * zRp ) );
 	    const double zRs = PI * s.radius[1] * s.radius[1] / l;
 	    const double wrs = sqrt( 1.0 + z * z / ( zRs * zRs ) );
-	    const int ni = (s.seed_type == MITHRA_BEAM_SUPERGAUSSIAN) ? ( 2 * s.order[0] + 1 ) * ( 2 * s.order[1] + 1 ) : 1;
-	    for (int n = 0; n < ni; n++)
-	      {
-		p  = 0.5 * ( atan( z / zRp ) + atan( z / zRs ) - PI ) - PI * z / l * ( sq( x / ( zRp * wrp ) ) + sq( y / ( zRs * wrs ) ) );
-		ts = signal_self(s.signal, tl, p);
-		const double t = exp( - sq( x / ( s.radius[0] * wrp ) ) - sq( y / ( s.radius[1] * wrs ) ) ) / sqrt( wrs * wrp ) * s.amplitude;
-		a = add3(a, scale3(t * ts, pol));
-	      }
+	    /* every one of the ni terms of the reference's loop evaluates to this same value                         */
+	    p  = 0.5 * ( atan( z / zRp ) + atan( z / zRs ) - PI ) - PI * z / l * ( sq( x / ( zRp * wrp ) ) + sq( y / ( zRs * wrs ) ) );
+	    ts = signal_self(s.signal, tl, p);
+	    const double t = exp( - sq( x / ( s.radius[0] * wrp ) ) - sq( y / ( s.radius[1] * wrs ) ) ) / sqrt( wrs * wrp ) * s.amplitude;
+	    return t * ts;
 	  }
       }
-    a.z *= gamma;
-    return a;
+    return 0.0;
   }
+
+  /* Seed::fields, classes.cpp:740-855 */
+  __device__ inline V3 seed_fields (const MithraBeam& s, double c0, double gamma, double beta, double dt_shift,
+				    double px, double py, double pz, double time)
+  { return seed_assemble(s, gamma, seed_scalar(s, c0, gamma, beta, dt_shift, px, py, pz, time)); }
 }
 
 #endif

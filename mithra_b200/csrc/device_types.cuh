@@ -48,6 +48,20 @@ namespace mithra
     double dt, dx2, dy2, dz2;     /* uf_.dt, 2dx, 2dy, 2dz (solver.cpp:714-722)                         */
   };
 
+  /* The rim of every plane -- rows i = 1, 2, N0-3, N0-2 and columns j = 1, 2, N1-3, N1-2 -- is where the TF/SF
+   * seed corrections of the x / y shells land and from where the x / y absorbing faces are updated; rim_update
+   * (kernels_field.cuh) owns those nodes and stencil_stream skips them.  seedu: the line table seed_lines writes
+   * (kernels_seed.cuh), each entry the scalar u of Seed::fields at a source node of the shells.                 */
+  struct RimDev
+  {
+    int    seed;                  /* apply the x / y shell corrections                                              */
+    const double* seedu;          /* [np][8][L]                                                                     */
+    int    L;                     /* entries per line (even, >= max(N0, N1))                                        */
+    int    KI, KF;                /* planes [KI, KF) carry x / y shell corrections (fdtd.cpp:310-311)               */
+    int    ni, supergaussian;     /* number of equal terms the seed vector is summed from (quirk Q8)                */
+    double pol[3], gamma;
+  };
+
   /* One static-undulator module with the per-module constants of Solver::undulatorField precomputed on
    * the host in the reference's operation order (solver.cpp:1805-1812).                               */
   struct UndulatorDev

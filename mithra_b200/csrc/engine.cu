@@ -111,6 +111,8 @@ struct MithraGpu
   /* seed */
   SeedDev*        d_seed;
   double*         d_seed_tab;             /* per-plane table of a seed along +z (kernels_seed.cuh), else 0  */
+  double*         d_seedu;                /* RimDev.seedu: seed scalar on the 8 shell source lines of every plane */
+  int             seed_L;
 
   /* slab exchange */
   Exchange        xch;
@@ -309,7 +311,7 @@ static int preload_kernels ()
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
   PL(particle_box); PL(particle_cells); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish);
-  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_initial_kernel); PL(seed_plane_table);
+  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
   #undef PL
@@ -438,7 +440,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     }
 
   /* seed */
-  h->d_seed = 0; h->d_seed_tab = 0;
+  h->d_seed = 0; h->d_seed_tab = 0; h->d_seedu = 0; h->seed_L = 0;
   if (params->seed_enabled)
     {
       SeedDev sd; memset(&sd, 0, sizeof(sd));
@@ -453,6 +455,9 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       if (getenv("MITHRA_SEED_GENERIC")) sd.along_z = 0;
       CU(cudaMalloc(&h->d_seed, sizeof(SeedDev))); CU(cudaMemcpy(h->d_seed, &sd, sizeof(SeedDev), cudaMemcpyHostToDevice));
       if (sd.along_z) CU(cudaMalloc(&h->d_seed_tab, (size_t) f.np * MITHRA_SEED_TAB * sizeof(double)));
+      h->seed_L = (std::max(f.N0, f.N1) + 1) & ~1;
+      CU(cudaMalloc(&h->d_seedu, (size_t) f.np * 8 * h->seed_L * sizeof(double)));
+      CU(cudaMemsetAsync(h->d_seedu, 0, (size_t) f.np * 8 * h->seed_L * sizeof(double), h->stream));
     }
 
   if (exchange_init(h->xch, f, h->pcap, h->stream)) { std::string e = h->xch.error; mithra_gpu_destroy(h); return fail("mithra_gpu_create: %s", e.c_str()); }
@@ -476,7 +481,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
   cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
-  cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab);
+  cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab); cudaFree(h->d_seedu);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -712,7 +717,7 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 
 /* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
 template <bool NSFD>
-static bool launch_stencil_stream (MithraGpu* h)
+static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
 {
   const FieldDev& f = h->fd;
   constexpr int T = 512, NB = 8;
@@ -727,14 +732,15 @@ static bool launch_stencil_stream (MithraGpu* h)
       configured[NSFD] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC);
+  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0);
   return true;
 }
 
+/* the plain-load interior kernel always covers every interior node (rim_update afterwards simply rewrites the rim) */
 template <bool NSFD>
-static void launch_stencil (MithraGpu* h)
+static void launch_stencil (MithraGpu* h, bool skiprim)
 {
-  if (launch_stencil_stream<NSFD>(h)) return;
+  if (launch_stencil_stream<NSFD>(h, skiprim)) return;
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
   dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);
@@ -746,22 +752,69 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
   USE(h);
   const FieldDev& f = h->fd;
   double* ap = h->A[h->ip1]; const double* a = h->A[h->in]; const double* am = h->A[h->im1];
+  const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
+
+  /* Rim path (N0, N1, np >= 8): rim_update owns the two outer node layers in x and y -- interior value, x / y shell
+   * seed terms (from the line table) and the x / y faces in one pass; what remains afterwards is the z shell, the z
+   * faces, the edges and the corners.  MITHRA_NO_FUSE keeps the reference's three passes apart (the parity tests
+   * compare the two bit for bit).                                                                              */
+  const bool rim = f.N0 >= 8 && f.N1 >= 8 && f.np >= 8 && !getenv("MITHRA_NO_FUSE");
+  RimDev rz; memset(&rz, 0, sizeof(rz));
+  if (rim && h->d_seed)
+    {
+      PhaseTimer t(h, PH_BOUNDARY);
+      rz.seed = 1; rz.seedu = h->d_seedu; rz.L = h->seed_L;
+      rz.KI = zlo ? 2 : f.kb; rz.KF = zhi ? f.np - 2 : f.np - 1;
+      const MithraBeam& B = h->prm.seed;
+      rz.supergaussian = (B.seed_type == MITHRA_BEAM_SUPERGAUSSIAN) ? 1 : 0;
+      rz.ni = rz.supergaussian ? ( 2 * B.order[0] + 1 ) * ( 2 * B.order[1] + 1 ) : 1;
+      rz.pol[0] = B.polarization[0]; rz.pol[1] = B.polarization[1]; rz.pol[2] = B.polarization[2]; rz.gamma = h->prm.gamma;
+      if (h->d_seed_tab) { seed_plane_table<<<(f.np + 127) / 128, 128, 0, h->stream>>>(h->d_seed, f.np, h->time, h->d_seed_tab); h->cnt.kernel_launches += 1; }
+      const long tot = (long) (4 * (f.N1 - 4) + 4 * (f.N0 - 4)) * (rz.KF - rz.KI);
+      seed_lines<<<grid_for(tot, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->d_seed, h->d_seed_tab, f, rz.KI, rz.KF, rz.L, h->d_seedu, h->time);
+      h->cnt.kernel_launches += 1;
+      CU(cudaGetLastError());
+    }
   {
     PhaseTimer t(h, PH_STENCIL);
-    if (f.nsfd) launch_stencil<true>(h); else launch_stencil<false>(h);
+    if (f.nsfd) launch_stencil<true>(h, rim); else launch_stencil<false>(h, rim);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 1;
   }
   {
     PhaseTimer t(h, PH_BOUNDARY);
-    if (h->d_seed)
+    if (rim)
       {
-	TRY(seed_inject(h->d_seed, h->d_seed_tab, f, ap, h->time, h->stream, h->num_sms));
-	h->cnt.kernel_launches += h->d_seed_tab ? 2 : 1;
+	constexpr int KC = 64;
+	const int per = 4 * (f.N1 - 2) + 4 * (f.N0 - 6);
+	dim3 grid((unsigned) ((per + 127) / 128), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
+	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);
+	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);
+	h->cnt.kernel_launches += 1;
+	if (h->d_seed && (zlo || zhi))
+	  {
+	    const long tot = 4L * (f.N0 - 4) * (f.N1 - 4);
+	    seed_inject_zshell<<<grid_for(tot, 128, h->num_sms * 4), 128, 0, h->stream>>>(h->d_seed, h->d_seed_tab, f, ap, h->time);
+	    h->cnt.kernel_launches += 1;
+	  }
+	if (zlo || zhi)
+	  {
+	    const long nface = 2L * (f.N0 - 2) * (f.N1 - 2) * f.ncomp;
+	    boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am, 1);
+	    h->cnt.kernel_launches += 1;
+	  }
       }
-    const long nface = (2L * (f.N1 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.N1 - 2)) * f.ncomp;
-    boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am);
-    h->cnt.kernel_launches += 1;
+    else
+      {
+	if (h->d_seed)
+	  {
+	    TRY(seed_inject(h->d_seed, h->d_seed_tab, f, ap, h->time, h->stream, h->num_sms));
+	    h->cnt.kernel_launches += h->d_seed_tab ? 2 : 1;
+	  }
+	const long nface = (2L * (f.N1 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.np - 2) + 2L * (f.N0 - 2) * (f.N1 - 2)) * f.ncomp;
+	boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am, 0);
+	h->cnt.kernel_launches += 1;
+      }
     if (f.order == 2)
       {
 	const long nedge = (4L * (f.np - 2) + 4L * (f.N0 - 2) + 4L * (f.N1 - 2)) * f.ncomp;

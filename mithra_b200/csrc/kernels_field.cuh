@@ -15,6 +15,7 @@
 #define MITHRA_KERNELS_FIELD_CUH_
 
 #include "device_types.cuh"
+#include "beams.cuh"
 
 namespace mithra
 {
@@ -123,10 +124,13 @@ namespace mithra
   __device__ __forceinline__ void mbar_wait (unsigned long long* b, unsigned parity)
   {
     unsigned done;
-    do
-      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-		   : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    while (!done);
+    while (true)
+      {
+	asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+		     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+	if (done) break;
+	__nanosleep(32);                                   /* a waiting warp must not eat the issue slots of the working ones */
+      }
   }
   __device__ __forceinline__ void bulk_g2s (void* dst, const void* src, unsigned bytes, unsigned long long* b)
   {
@@ -165,7 +169,7 @@ namespace mithra
   template <bool NSFD, int T, int NB>
   __global__ void __launch_bounds__(T + 32, 2)
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC)
+		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 2 && NB <= 16, "stages: a power of two");
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -216,7 +220,9 @@ namespace mithra
     /* ---- consumers -------------------------------------------------------------------------------------- */
     const long p = p0 + tid;
     const int  i = (int) (p / N1), j = (int) (p - (long) i * N1);
-    const bool interior = (p < f.P && i >= 1 && i <= f.N0 - 2 && j >= 1 && j <= f.N1 - 2);
+    /* skiprim: the two outermost interior node layers in x and y belong to rim_update                          */
+    const int  rim = skiprim ? 2 : 0;
+    const bool interior = (p < f.P && i >= 1 + rim && i <= f.N0 - 2 - rim && j >= 1 + rim && j <= f.N1 - 2 - rim);
     const bool lane0 = (tid & 31) == 0;
 
     const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
@@ -224,8 +230,7 @@ namespace mithra
     const double alpha = f.alpha, beta = f.beta;
     const Box bx = *jbox;
     const bool inxy = interior && (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
-    const double* Jn = jn   + cb + p + (long) ks * Pp;
-    double*       Ap = anp1 + cb + p + (long) ks * Pp;
+    long off = cb + p + (long) ks * Pp;                   /* the node in plane k, in A^{n+1} and J             */
     const double* myA = stA + N1e + tid;
     const double* myM = stM + tid;
 
@@ -251,10 +256,10 @@ namespace mithra
     #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
       {                                                                                                         \
 	double src = 0.0;                                                                                       \
-	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = __ldg(Jn);                                            \
+	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = __ldg(jn + off);                                      \
 	take(Pn, vnext);                                                                                        \
-	if (interior) *Ap = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);          \
-	vm1 = vnext; Ap += Pp; Jn += Pp; ++k;                                                                   \
+	if (interior) anp1[off] = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);    \
+	vm1 = vnext; off += Pp; ++k;                                                                            \
       }
     while (true)
       {
@@ -263,6 +268,130 @@ namespace mithra
 	MITHRA_STREAM_STEP(P2, P0, P1); if (k >= ke) break;
       }
     #undef MITHRA_STREAM_STEP
+  }
+
+  /* AdvanceField::advanceBoundary{F,S} (database.cpp:137-176) for the face node s from the thread of its inward
+   * neighbour n, same association order as face_update below:
+   *   apn = A+_n, ams = A-_s, amn = A-_n, as_ = A_s, an_ = A_n, then the four tangential neighbours along t1 in the
+   *   order (n+, n-, s+, s-) and likewise along z                                                               */
+  __device__ __forceinline__ double face_value (const double* B, double ams, double apn, double amn, double as_, double an_,
+						double n1p, double n1m, double s1p, double s1m,
+						double n2p, double n2m, double s2p, double s2m)
+  {
+    return B[0] * ( ams + apn ) +
+	   B[1] * amn +
+	   B[2] * ( as_ + an_ ) +
+	   B[3] * ( n1p + n1m + s1p + s1m ) +
+	   B[4] * ( n2p + n2m + s2p + s2m );
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Rim of every plane: rows i = 1, 2, N0-3, N0-2 and columns j = 1, 2, N1-3, N1-2 (N0, N1 >= 8).
+   *
+   * On these nodes fdtd.cpp does three things one after the other: the interior sweep (:270-303), the TF/SF seed
+   * terms of the x shell and then of the y shell (:307-351), and -- reading the finished A+ of the nodes i = 1, N0-2
+   * / j = 1, N1-2 -- the x / y absorbing faces (:377-520).  As three grid passes the last two are strided
+   * read-modify-writes of single nodes per row; here ONE thread owns a rim node, marches KC planes in +z with the
+   * 5-point crosses of the planes k-1, k, k+1 in registers (like stencil_interior), and does all of it in the
+   * reference's order per node: interior value, x-shell term, y-shell term, store, then the face node(s) behind it
+   * from values it already holds plus three loads.  stencil_stream skips the rim (skiprim).
+   * Thread enumeration: 4 rows x (N1-2) nodes, j fastest, then 4 columns x rows [3, N0-4], column fastest.
+   * Results are bit-identical to stencil + seed_inject + boundary_faces run one after the other.
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool NSFD>
+  __global__ void __launch_bounds__(128)
+  rim_update (const FieldDev f, const RimDev rz, double* __restrict__ anp1, const double* __restrict__ an,
+	      const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC)
+  {
+    const int N0 = f.N0, N1 = f.N1;
+    const int nr = N1 - 2, nrows = 4 * nr, per = nrows + 4 * (N0 - 6);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    int i, j;
+    if (t < nrows) { const int q = t / nr; j = 1 + t - q * nr; i = (q == 0) ? 1 : (q == 1) ? 2 : (q == 2) ? N0 - 3 : N0 - 2; }
+    else           { const int u = t - nrows, q = u & 3; i = 3 + (u >> 2); j = (q == 0) ? 1 : (q == 1) ? 2 : (q == 2) ? N1 - 3 : N1 - 2; }
+
+    const int c  = blockIdx.z;
+    const int ks = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);    /* planes ks .. ke-1                */
+    if (ks >= ke) return;
+    const long Pp = f.Pp;
+    const long nb = (long) c * f.np * Pp + (long) i * N1 + j;            /* the node in plane 0               */
+    const double* A  = an   + nb;
+    const double* Am = anm1 + nb;
+    double*       Ap = anp1 + nb;
+    const double* Jn = jn   + nb;
+
+    const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
+    const double as = (c < 3) ? f.a[4] : f.a[5];
+    const double alpha = f.alpha, beta = f.beta;
+    const Box bx = *jbox;
+    const bool inxy = (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+
+    /* faces behind this node: offset of the face node s from n, 0 = none                                      */
+    const int dsx = (i == 1) ? -N1 : (i == N0 - 2) ? N1 : 0;
+    const int dsy = (j == 1) ? -1  : (j == N1 - 2) ? 1  : 0;
+    /* seed terms (fdtd.cpp:312-350): A+(1) -= a S(2), A+(2) += a S(1), A+(N-2) -= a S(N-3), A+(N-3) += a S(N-2)   */
+    int sxl = -1, syl = -1;                               /* source line in RimDev.seedu                      */
+    if (rz.seed && c < 3)
+      {
+	if (j >= 2 && j <= N1 - 3) sxl = (i == 1) ? 1 : (i == 2) ? 0 : (i == N0 - 2) ? 2 : (i == N0 - 3) ? 3 : -1;
+	if (i >= 2 && i <= N0 - 3) syl = (j == 1) ? 5 : (j == 2) ? 4 : (j == N1 - 2) ? 6 : (j == N1 - 3) ? 7 : -1;
+      }
+    const bool sxminus = (i == 1 || i == N0 - 2), syminus = (j == 1 || j == N1 - 2);
+    const double polc = (c < 3) ? rz.pol[c] : 0.0;
+
+    auto cross_at = [&] (int k) { Cross x; const double* q = A + (long) k * Pp; x.c = q[0]; x.xp = q[N1]; x.xm = q[-N1]; x.yp = q[1]; x.ym = q[-1]; return x; };
+
+    /* every iteration depends on loads of the next plane that nobody has touched yet: ask L2 for them PD planes
+     * ahead (no registers are held by a prefetch), so that the loads themselves find the lines there           */
+    constexpr int PD = 6;
+    auto prefetch_plane = [&] (int k) {
+      if (k + 1 > f.np - 1) return;
+      const double* q = A + (long) (k + 1) * Pp;
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(q + N1));
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(q - N1));
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(Am + (long) k * Pp));
+      if (dsx != 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(Am + (long) k * Pp + dsx)); };
+    for (int k = ks; k < min(ks + PD, ke); k++) prefetch_plane(k);
+
+    Cross M = cross_at(ks - 1), Z = cross_at(ks);
+    for (int k = ks; k < ke; k++)
+      {
+	const long ko = (long) k * Pp;
+	if (k + PD < ke) prefetch_plane(k + PD);
+	const Cross Pn = cross_at(k + 1);
+	const double vm1 = Am[ko];
+	double src = 0.0;
+	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = Jn[ko];
+	/* loads of the fused work, issued with the rest                                                          */
+	const bool seedk = (k >= rz.KI && k < rz.KF);
+	double ux = 0.0, uy = 0.0, amsx = 0.0, amsy = 0.0, dxp = 0.0, dxm = 0.0, dyp = 0.0, dym = 0.0;
+	if (sxl >= 0 && seedk) ux = rz.seedu[((long) k * 8 + sxl) * rz.L + j];
+	if (syl >= 0 && seedk) uy = rz.seedu[((long) k * 8 + syl) * rz.L + i];
+	if (dsx != 0) { amsx = Am[ko + dsx]; dxp = A[ko + dsx + 1];  dxm = A[ko + dsx - 1];  }
+	if (dsy != 0) { amsy = Am[ko + dsy]; dyp = A[ko + dsy + N1]; dym = A[ko + dsy - N1]; }
+
+	double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);
+	if (sxl >= 0 && seedk)
+	  { const double S = seed_assemble_comp(ux, polc, rz.ni, rz.supergaussian, c == 2, rz.gamma); r = sxminus ? r - a1 * S : r + a1 * S; }
+	if (syl >= 0 && seedk)
+	  { const double S = seed_assemble_comp(uy, polc, rz.ni, rz.supergaussian, c == 2, rz.gamma); r = syminus ? r - a2 * S : r + a2 * S; }
+	Ap[ko] = r;
+	if (dsx != 0)
+	  {
+	    const bool lo = dsx < 0;
+	    Ap[ko + dsx] = face_value(f.bB, amsx, r, vm1, lo ? Z.xm : Z.xp, Z.c, Z.yp, Z.ym, dxp, dxm,
+				      Pn.c, M.c, lo ? Pn.xm : Pn.xp, lo ? M.xm : M.xp);
+	  }
+	if (dsy != 0)
+	  {
+	    const bool lo = dsy < 0;
+	    Ap[ko + dsy] = face_value(f.cB, amsy, r, vm1, lo ? Z.ym : Z.yp, Z.c, Z.xp, Z.xm, dyp, dym,
+				      Pn.c, M.c, lo ? Pn.ym : Pn.yp, lo ? M.ym : M.yp);
+	  }
+	M = Z; Z = Pn;
+      }
   }
 
   /* ------------------------------------------------------------------------------------------------
@@ -285,21 +414,22 @@ namespace mithra
   /* grid-stride over all face nodes of all components; faces are enumerated x-, x+, y-, y+, [z-], [z+].  */
   __global__ void __launch_bounds__(256)
   boundary_faces (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		  const double* __restrict__ anm1)
+		  const double* __restrict__ anm1, int zonly)
   {
     const int  nk = f.np - 1 - f.kb;                      /* planes kb .. np-2                           */
     const long nx = (long) (f.N1 - 2) * nk;               /* per x face                                  */
     const long ny = (long) (f.N0 - 2) * nk;
     const long nz = (long) (f.N0 - 2) * (f.N1 - 2);
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
-    const long per = 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0);
+    const long first = zonly ? 2 * nx + 2 * ny : 0;       /* zonly: rim_update has done the x and y faces    */
+    const long per = 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0) - first;
     const long tot = per * f.ncomp;
     const long N1 = f.N1, Pp = f.Pp;
 
     for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
       {
 	const int  c = (int) (t / per);
-	long       r = t - (long) c * per;
+	long       r = t - (long) c * per + first;
 	const long cb = (long) c * f.np * Pp;
 	double*       ap = anp1 + cb;
 	const double* a  = an   + cb;

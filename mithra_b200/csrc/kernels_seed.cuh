@@ -92,41 +92,32 @@ namespace mithra
     T[ST_AMP]  = 1.0 / sqrt( wrs * wrp ) * B.amplitude;
   }
 
-  /* Seed::fields at node (i, j) of the tabulated plane                                                         */
-  __device__ __forceinline__ V3 seed_from_table (const SeedDev& s, const double* __restrict__ T, int i, int j)
+  /* The scalar u of Seed::fields (beams.cuh seed_assemble) at node (i, j) of the tabulated plane                 */
+  __device__ __forceinline__ double seed_scalar_from_table (const SeedDev& s, const double* __restrict__ T, int i, int j)
   {
     const MithraBeam& B = s.beam;
-    V3 a = v3(0.0, 0.0, 0.0);
-    if (T[ST_ACTIVE] == 0.0) return a;
+    if (T[ST_ACTIVE] == 0.0) return 0.0;
+    if (B.seed_type == MITHRA_BEAM_PLANEWAVE) return B.amplitude * T[ST_TS0];
     const V3 pol = v3a(B.polarization);
-    if (B.seed_type == MITHRA_BEAM_PLANEWAVE) a = scale3(B.amplitude * T[ST_TS0], pol);
-    else
-      {
-	const V3 rv = v3(s.xmin + i * s.dx - B.position[0], s.ymin + j * s.dy - B.position[1], T[ST_RVZ]);
-	const double x = dot3(rv, pol), y = dot3(rv, v3a(s.yv));
-	if (B.seed_type == MITHRA_BEAM_PLANEWAVETRUNCATED)
-	  { if (!(fabs(x) > B.radius[0] || fabs(y) > B.radius[1])) a = scale3(B.amplitude * T[ST_TS0], pol); }
-	else
-	  {
-	    const double p  = T[ST_P0] - T[ST_CURV] * ( sq( x / T[ST_DXP] ) + sq( y / T[ST_DYS] ) );
-	    const double ts = cos_wide( T[ST_PHASE] + p ) * T[ST_ENV];
-	    const double t  = exp( - sq( x / T[ST_RXW] ) - sq( y / T[ST_RYW] ) ) * T[ST_AMP];
-	    const V3 one = scale3(t * ts, pol);
-	    const int ni = (B.seed_type == MITHRA_BEAM_SUPERGAUSSIAN) ? ( 2 * B.order[0] + 1 ) * ( 2 * B.order[1] + 1 ) : 1;
-	    for (int n = 0; n < ni; n++) a = add3(a, one);                /* reference quirk Q8: the same term ni times */
-	  }
-      }
-    a.z *= s.gamma;
-    return a;
+    const V3 rv = v3(s.xmin + i * s.dx - B.position[0], s.ymin + j * s.dy - B.position[1], T[ST_RVZ]);
+    const double x = dot3(rv, pol), y = dot3(rv, v3a(s.yv));
+    if (B.seed_type == MITHRA_BEAM_PLANEWAVETRUNCATED)
+      return (!(fabs(x) > B.radius[0] || fabs(y) > B.radius[1])) ? B.amplitude * T[ST_TS0] : 0.0;
+    const double p  = T[ST_P0] - T[ST_CURV] * ( sq( x / T[ST_DXP] ) + sq( y / T[ST_DYS] ) );
+    const double ts = cos_wide( T[ST_PHASE] + p ) * T[ST_ENV];
+    const double t  = exp( - sq( x / T[ST_RXW] ) - sq( y / T[ST_RYW] ) ) * T[ST_AMP];
+    return t * ts;
   }
 
-  /* tab == 0: evaluate Seed::fields in full at the node (any beam direction)                                    */
-  __device__ __forceinline__ V3 seed_at (const SeedDev& s, const double* __restrict__ tab, int i, int j, int kglob, double time)
+  /* tab == 0: evaluate Seed::fields in full at the node (any beam direction); node = Solver::rc, solver.cpp:2302-2315 */
+  __device__ __forceinline__ double seed_scalar_at (const SeedDev& s, const double* __restrict__ tab, int i, int j, int kglob, double time)
   {
-    if (tab) return seed_from_table(s, tab + (long) ( kglob - s.k0 ) * MITHRA_SEED_TAB, i, j);
-    /* Solver::rc, solver.cpp:2302-2315 */
-    return seed_fields(s.beam, s.c0, s.gamma, s.beta, s.dt_shift, s.xmin + i * s.dx, s.ymin + j * s.dy, s.zmin + kglob * s.dz, time);
+    if (tab) return seed_scalar_from_table(s, tab + (long) ( kglob - s.k0 ) * MITHRA_SEED_TAB, i, j);
+    return seed_scalar(s.beam, s.c0, s.gamma, s.beta, s.dt_shift, s.xmin + i * s.dx, s.ymin + j * s.dy, s.zmin + kglob * s.dz, time);
   }
+
+  __device__ __forceinline__ V3 seed_at (const SeedDev& s, const double* __restrict__ tab, int i, int j, int kglob, double time)
+  { return seed_assemble(s.beam, s.gamma, seed_scalar_at(s, tab, i, j, kglob, time)); }
 
   __device__ __forceinline__ void seed_apply (double* __restrict__ ap, long cs, long m, double coef, const V3& S, bool minus)
   {
@@ -224,6 +215,52 @@ namespace mithra
 	    if (zlo && q < 2) k = 1 + q; else k = f.np - 3 + (q - (zlo ? 2 : 0));
 	  }
 	seed_node(*sp, tab, f, anp1, i, j, k, time);
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Rim path (rim_update, kernels_field.cuh, applies the x / y shell corrections itself): the seed scalar on the
+   * eight source lines of every plane, RimDev.seedu[k][line][idx]: lines 0..3 = rows i = 1, 2, N0-3, N0-2 indexed
+   * by j, lines 4..7 = columns j = 1, 2, N1-3, N1-2 indexed by i.  Only the entries the shells read are evaluated
+   * (j in [2, N1-3] on the rows, i in [2, N0-3] on the columns, k in [KI, KF)); the rest is never read.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(128)
+  seed_lines (const SeedDev* __restrict__ sp, const double* __restrict__ tab, const FieldDev f, int KI, int KF, int L,
+	      double* __restrict__ seedu, double time)
+  {
+    const int  nr = f.N1 - 4, nc = f.N0 - 4;              /* entries per row line / per column line           */
+    const int  per = 4 * nr + 4 * nc;
+    const long tot = (long) per * (KF - KI);
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int k = KI + (int) (t / per); int r = (int) (t - (long) (k - KI) * per);
+	int line, idx, i, j;
+	if (r < 4 * nr) { line = r / nr; idx = 2 + r % nr; j = idx; i = (line == 0) ? 1 : (line == 1) ? 2 : (line == 2) ? f.N0 - 3 : f.N0 - 2; }
+	else { r -= 4 * nr; line = 4 + r / nc; idx = 2 + r % nc; i = idx; j = (line == 4) ? 1 : (line == 5) ? 2 : (line == 6) ? f.N1 - 3 : f.N1 - 2; }
+	seedu[((long) k * 8 + line) * L + idx] = seed_scalar_at(*sp, tab, i, j, k + f.k0, time);
+      }
+  }
+
+  /* z shell only (first / last slab): A+(k=1) -= a3 S(k=2), A+(k=2) += a3 S(k=1), likewise at np-2 / np-3, for
+   * i in [2, N0-3], j in [2, N1-3] (fdtd.cpp:353-373); runs after rim_update, i.e. after the x and y terms.      */
+  __global__ void __launch_bounds__(128)
+  seed_inject_zshell (const SeedDev* __restrict__ sp, const double* __restrict__ tab, const FieldDev f, double* __restrict__ anp1, double time)
+  {
+    const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
+    const int  nzs = (zlo ? 2 : 0) + (zhi ? 2 : 0);
+    const long per = (long) (f.N0 - 4) * (f.N1 - 4), tot = per * nzs;
+    const long cs = (long) f.np * f.Pp;
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int q = (int) (t / per); const long r = t - (long) q * per;
+	const int i = 2 + (int) (r / (f.N1 - 4)), j = 2 + (int) (r % (f.N1 - 4));
+	int k; if (zlo && q < 2) k = 1 + q; else k = f.np - 3 + (q - (zlo ? 2 : 0));
+	const long m = (long) k * f.Pp + (long) i * f.N1 + j;
+	const int kg = k + f.k0;
+	if (zlo && k == 1)        seed_apply(anp1, cs, m, f.a[3], seed_at(*sp, tab, i, j, kg + 1, time), true);
+	if (zlo && k == 2)        seed_apply(anp1, cs, m, f.a[3], seed_at(*sp, tab, i, j, kg - 1, time), false);
+	if (zhi && k == f.np - 2) seed_apply(anp1, cs, m, f.a[3], seed_at(*sp, tab, i, j, kg - 1, time), true);
+	if (zhi && k == f.np - 3) seed_apply(anp1, cs, m, f.a[3], seed_at(*sp, tab, i, j, kg + 1, time), false);
       }
   }
 

@@ -225,3 +225,62 @@ def test_empty_bunch_and_errors():
         p2, _, _ = helpers.params_for("micro-nsfd", max_particles=4)
         s = abi.GpuSolver(p2)
         s.upload_particles(np.zeros((8, 11)))
+
+
+def _resized(job, N0, N1, npl):
+    """The parameter block of a micro job on a larger mesh (same cell sizes and update coefficients)."""
+    p, meta, g = helpers.params_for(job, max_particles=1024)
+    p.N0, p.N1, p.N2, p.np = N0, N1, npl, npl
+    p.xmin, p.xmax = -0.5 * (N0 - 1) * p.dx, 0.5 * (N0 - 1) * p.dx
+    p.ymin, p.ymax = -0.5 * (N1 - 1) * p.dy, 0.5 * (N1 - 1) * p.dy
+    p.zmax = p.zmin + (npl - 1) * p.dz
+    p.zp[0], p.zp[1], p.Lz = p.zmin, p.zmax, p.zmax - p.zmin
+    p.power.enabled, p.screens.enabled = 0, 0
+    return p, g
+
+
+@pytest.mark.parametrize("job,shape", [("micro-seeded", (14, 14, 242)), ("micro-seeded", (37, 85, 70)), ("micro-seeded", (80, 41, 9)),
+                                       ("micro-seeded", (8, 200, 12)), ("micro-seeded", (31, 8, 75)), ("micro-sc", (29, 53, 66)),
+                                       ("micro-o1", (33, 101, 40)), ("micro-fd", (64, 9, 130)), ("micro-nsfd", (85, 85, 70))])
+def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
+    """The production path -- stencil_stream on the inner nodes + rim_update (interior value, x / y shell seed terms and
+    x / y faces of the two outer node layers in one pass) -- against the reference's three passes as separate kernels
+    (MITHRA_NO_FUSE) and against the plain-load stencil (MITHRA_STENCIL_PLAIN): bit-identical potentials, on meshes
+    whose 512-node tiles cut through rows and down to the smallest mesh the rim path takes (8 nodes across)."""
+    p, g = _resized(job, *shape)
+    rng = np.random.default_rng(11)
+    n = p.N0 * p.N1 * p.np
+    an, anm1, jn = (rng.standard_normal(n * 3) for _ in range(3))
+    jn[rng.random(n * 3) < 0.7] = 0.0
+    sc = {}
+    if p.space_charge:
+        sc = dict(fn=rng.standard_normal(n), fnm1=rng.standard_normal(n), rho=rng.standard_normal(n))
+    # particles only to put the deposit box (the nodes where J is read) somewhere inside the mesh
+    bunch = np.zeros((64, 11))
+    bunch[:, 0] = 1.0
+    bunch[:, 1] = rng.uniform(0.6 * p.xmin, 0.6 * p.xmax, 64)
+    bunch[:, 2] = rng.uniform(0.6 * p.ymin, 0.6 * p.ymax, 64)
+    bunch[:, 3] = rng.uniform(p.zmin + 2 * p.dz, p.zmax - 2 * p.dz, 64)
+    bunch[:, 4:7] = bunch[:, 1:4] + 0.3 * np.array([p.dx, p.dy, p.dz])
+    bunch[:, 10] = 1.0
+    names = ("anp1", "an", "anm1") + (("fnp1", "fn", "fnm1") if p.space_charge else ())
+    out = {}
+    for mode in ("fused", "MITHRA_NO_FUSE", "MITHRA_STENCIL_PLAIN"):
+        if mode != "fused":
+            monkeypatch.setenv(mode, "1")
+        s = abi.GpuSolver(p)
+        s.set_time(0.37, 0.37, 5)
+        s.upload_fields(an=an, anm1=anm1, jn=jn, **sc)
+        s.upload_particles(bunch)
+        s.currentReset(); s.currentUpdate()            # J = deposit of the bunch; the random jn only pre-fills it
+        for _ in range(3):
+            s.fieldUpdate(); s.fieldShift(); s.advanceTime()
+        s.fieldUpdate()
+        out[mode] = s.download_fields(names)
+        s.close()
+        if mode != "fused":
+            monkeypatch.delenv(mode)
+    assert np.abs(out["fused"]["anp1"]).max() > 0
+    for mode in ("MITHRA_NO_FUSE", "MITHRA_STENCIL_PLAIN"):
+        for k in names:
+            np.testing.assert_array_equal(out["fused"][k], out[mode][k], err_msg="%s %s" % (mode, k))
