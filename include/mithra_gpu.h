@@ -233,6 +233,11 @@ int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 #define MITHRA_GPU_NPHASES 8
 int mithra_gpu_step_profiled (MithraGpu* h, int nsteps, float ms[MITHRA_GPU_NPHASES]);
 
+/* Device self-test of the constant-divisor division the kernels use for cell indices and E/B (div_by,
+ * mithra_b200/csrc/device_types.cuh): divides the n host doubles x[] by d on the current device both ways and
+ * returns the number of results that differ bitwise from IEEE division (must be 0).  No reference counterpart. */
+int mithra_gpu_selftest_divide (const double* x, size_t n, double d, unsigned long long* mismatches);
+
 /* --- z-slab exchange between the GPUs of one box (one handle per slab / GPU) --------------------------- */
 /* The slab partition is the reference's (Solver::initializeMesh, solver.cpp:619-641: np local planes from global
  * plane k0, two planes shared with each neighbour, ownership interval zp) with rank / size = slab index / count.

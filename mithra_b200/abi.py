@@ -85,7 +85,7 @@ SYMBOLS = (
     "mithra_gpu_current_update", "mithra_gpu_current_communicate", "mithra_gpu_advance_time", "mithra_gpu_step",
     "mithra_gpu_step_timed", "mithra_gpu_synchronize", "mithra_gpu_fetch_power", "mithra_gpu_fetch_screen",
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
-    "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end",
+    "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
 )
 
 _lib = None
@@ -128,6 +128,7 @@ def load():
     lib.mithra_gpu_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.mithra_gpu_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mithra_gpu_ipc_connect.argtypes = [vp, vp, vp]
+    lib.mithra_gpu_selftest_divide.argtypes = [dp, C.c_size_t, C.c_double, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
 
@@ -315,3 +316,13 @@ class GpuSolver:
         c = Counters()
         self._check(self.lib.mithra_gpu_counters(self.h, C.byref(c)))
         return c
+
+
+def selftest_divide(x, d):
+    """Number of elements of x for which the device's constant-divisor division differs bitwise from x / d."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    bad = C.c_ulonglong(0)
+    if lib.mithra_gpu_selftest_divide(_dptr(x), x.size, float(d), C.byref(bad)):
+        raise RuntimeError(lib.mithra_gpu_last_error().decode())
+    return bad.value

@@ -46,6 +46,7 @@ namespace mithra
     double a[6], alpha, beta;
     double bB[5], cB[5], dB[5], eE[5], fE[5], gE[5], hC[17];
     double dt, dx2, dy2, dz2;     /* uf_.dt, 2dx, 2dy, 2dz (solver.cpp:714-722)                         */
+    double rmdt, rdx2, rdy2, rdz2; /* reciprocal_of(-dt), (2dx), (2dy), (2dz) for div_by                  */
   };
 
   /* The rim of every plane -- rows i = 1, 2, N0-3, N0-2 and columns j = 1, 2, N1-3, N1-2 -- is where the TF/SF
@@ -83,6 +84,7 @@ namespace mithra
     int    size;                        /* number of slabs; with more than one the particle list of a slab IS its
 					   ownership (migration once per field step) and the z tests are global */
     double dx, dy, dz;
+    double rdx, rdy, rdz, rr2;          /* reciprocal_of(dx), (dy), (dz), (r2) for div_by                */
     double c0, gamma, beta, dt_shift;
     double r1, r2, dtb, dt_bunch, dt_field;
     int    N0, N1, np, k0, P;          /* np, k0 internal (see FieldDev)                                */
@@ -107,6 +109,30 @@ namespace mithra
     unsigned int* id;                   /* index the particle had when it was uploaded (arrivals from a neighbouring
 					   slab get fresh ones): the reference's list order, kept across the sorts */
   };
+
+  /* Correctly rounded x / d for a divisor that is a run-time CONSTANT of the job (cell sizes, time step): with
+   * rd = RN(1/d) from the host, q = RN(x rd) is within one ulp of x/d, the residual r = x - q d is exact in an FMA,
+   * and RN(q + r rd) is the correctly rounded quotient (Markstein's theorem; checked against x/d over 4.5e8 random
+   * operands on the CPU and by mithra_gpu_selftest_divide on the device).  Three FP64 issue slots instead of the
+   * ~25 of the generic division routine; bit-identical to IEEE division, which the cell indices and the E/B floats
+   * need.  Operands whose residual could leave the normal range (and NaN / Inf / zero) take the true division;
+   * rd == 0 marks a divisor the host would not vouch for.                                                      */
+  inline double reciprocal_of (double d)
+  { const double a = d < 0 ? -d : d; return (a > 1.0e-100 && a < 1.0e100) ? 1.0 / d : 0.0; }
+
+  __device__ __noinline__ double div_true (double x, double d) { return x / d; }    /* out of line: see div_by */
+
+  __device__ __forceinline__ double div_by (double x, double d, double rd)
+  {
+    const double ax = fabs(x);
+    const double q = x * rd;
+    const double r = __fma_rn(-q, d, x);
+    double res = __fma_rn(r, rd, q);
+    if (!(ax > 1.0e-150 && ax < 1.0e150 && rd != 0.0))    /* rare: keep the straight-line path free of calls */
+      res = (ax == 0.0 && rd != 0.0) ? q : div_true(x, d); /* (+-0) rd has the sign of (+-0) / d; a real call, or
+							      the compiler runs the division's inline part speculatively */
+    return res;
+  }
 
   __host__ __device__ inline long fidx (const long Pp, const int np, const int N1, int c, int k, int i, int j)
   { return ((long) c * np + k) * Pp + (long) i * N1 + j; }

@@ -260,6 +260,7 @@ static void fill_field_dev (const MithraGpuParams& p, FieldDev& f)
   memcpy(f.eE, p.eE, sizeof(f.eE)); memcpy(f.fE, p.fE, sizeof(f.fE)); memcpy(f.gE, p.gE, sizeof(f.gE));
   memcpy(f.hC, p.hC, sizeof(f.hC));
   f.dt = p.dt; f.dx2 = 2.0 * p.dx; f.dy2 = 2.0 * p.dy; f.dz2 = 2.0 * p.dz;
+  f.rmdt = reciprocal_of(- f.dt); f.rdx2 = reciprocal_of(f.dx2); f.rdy2 = reciprocal_of(f.dy2); f.rdz2 = reciprocal_of(f.dz2);
 }
 
 static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDev& b)
@@ -269,6 +270,7 @@ static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDe
   b.xmin = p.xmin; b.xmax = p.xmax; b.ymin = p.ymin; b.ymax = p.ymax; b.zmin = p.zmin; b.zmax = p.zmax;
   b.zp0 = p.zp[0]; b.zp1 = p.zp[1]; b.Lz = p.Lz;
   b.dx = p.dx; b.dy = p.dy; b.dz = p.dz;
+  b.rdx = reciprocal_of(b.dx); b.rdy = reciprocal_of(b.dy); b.rdz = reciprocal_of(b.dz); b.rr2 = reciprocal_of(p.r2);
   b.c0 = p.c0; b.gamma = p.gamma; b.beta = p.beta; b.dt_shift = p.dt_shift;
   b.r1 = p.r1; b.r2 = p.r2; b.dtb = p.dtb; b.dt_bunch = p.dt_bunch; b.dt_field = p.dt;
   b.N0 = p.N0; b.N1 = p.N1; b.np = f.np; b.k0 = f.k0; b.kshift = f.kshift; b.P = f.P; b.Pp = f.Pp; b.ncomp = f.ncomp;
@@ -974,7 +976,7 @@ extern "C" int mithra_gpu_current_reset (MithraGpu* h)
 {
   USE(h);
   PhaseTimer t(h, PH_CLEAR);
-  clear_current_box<<<h->num_sms * 2, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done);
+  clear_current_box<<<h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -985,9 +987,10 @@ extern "C" int mithra_gpu_current_update (MithraGpu* h)
   USE(h);
   PhaseTimer t(h, PH_DEPOSIT);
   if (h->pn == 0) return 0;
-  const int grid = (int) ((h->pn + 127) / 128);
-  if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox);
-  else                  deposit_current<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox);
+  static const int run = getenv("MITHRA_DEP_RUN") ? std::max(1, atoi(getenv("MITHRA_DEP_RUN"))) : MITHRA_DEP_RUN;
+  const int grid = (int) ((h->pn + (size_t) 128 * run - 1) / ((size_t) 128 * run));
+  if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox, run);
+  else                  deposit_current<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox, run);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -1142,6 +1145,28 @@ extern "C" int mithra_gpu_fetch_screen (MithraGpu* h, int screen, double* rec6, 
   for (size_t i = 0; i < fresh; i++) memcpy(rec6 + i * 6, raw.data() + order[i] * 8, 6 * sizeof(double));
   h->scr_fetched[screen] = cur;
   if (n) *n = fresh;
+  return 0;
+}
+
+__global__ void selftest_divide_kernel (const double* __restrict__ x, long n, double d, double rd, unsigned long long* __restrict__ bad)
+{
+  for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long) gridDim.x * blockDim.x)
+    {
+      const double a = div_by(x[t], d, rd), b = x[t] / d;
+      if (__double_as_longlong(a) != __double_as_longlong(b) && !(a != a && b != b)) atomicAdd(bad, 1ULL);
+    }
+}
+
+extern "C" int mithra_gpu_selftest_divide (const double* x, size_t n, double d, unsigned long long* mismatches)
+{
+  if (!x || !mismatches) return fail("mithra_gpu_selftest_divide: null argument");
+  double* dx = 0; unsigned long long* dbad = 0;
+  CU(cudaMalloc(&dx, n * sizeof(double))); CU(cudaMalloc(&dbad, sizeof(unsigned long long)));
+  CU(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice)); CU(cudaMemset(dbad, 0, sizeof(unsigned long long)));
+  selftest_divide_kernel<<<1024, 256>>>(dx, (long) n, d, reciprocal_of(d), dbad);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(mismatches, dbad, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dbad);
   return 0;
 }
 

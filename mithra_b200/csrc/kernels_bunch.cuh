@@ -60,9 +60,9 @@ namespace mithra
 	    const double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
 	    if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
 	      {
-		i = (int) floor( ( x - b.xmin ) / b.dx );
-		j = (int) floor( ( y - b.ymin ) / b.dy );
-		k = (int) floor( ( z - b.zmin ) / b.dz ) - b.k0;
+		i = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
+		j = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
+		k = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
 		valid = true;
 	      }
 	  }
@@ -91,21 +91,21 @@ namespace mithra
 	     x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < zhi && z >= zlo )
 	  {
 	    double d1;
-	    modf( ( x - b.xmin ) / b.dx, &d1 ); const int i = (int) d1;
-	    modf( ( y - b.ymin ) / b.dy, &d1 ); const int j = (int) d1;
-	    modf( ( z - b.zmin ) / b.dz, &d1 ); const int k = (int) d1;
+	    modf( div_by( x - b.xmin, b.dx, b.rdx ), &d1 ); const int i = (int) d1;
+	    modf( div_by( y - b.ymin, b.dy, b.rdy ), &d1 ); const int j = (int) d1;
+	    modf( div_by( z - b.zmin, b.dz, b.rdz ), &d1 ); const int k = (int) d1;
 	    m = (long) ( k - b.k0 - b.kshift ) * b.P + (long) i * b.N1 + j;      /* reference slab numbering     */
 	  }
 	push_m[t] = m;
       }
     if (dep)
       {
-	dep[6 * t + 0] = (int) floor( ( x - b.xmin ) / b.dx );
-	dep[6 * t + 1] = (int) floor( ( y - b.ymin ) / b.dy );
-	dep[6 * t + 2] = (int) floor( ( z - b.zmin ) / b.dz );
-	dep[6 * t + 3] = (int) floor( ( P.rm[0][t] - b.xmin ) / b.dx );
-	dep[6 * t + 4] = (int) floor( ( P.rm[1][t] - b.ymin ) / b.dy );
-	dep[6 * t + 5] = (int) floor( ( P.rm[2][t] - b.zmin ) / b.dz );
+	dep[6 * t + 0] = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
+	dep[6 * t + 1] = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
+	dep[6 * t + 2] = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) );
+	dep[6 * t + 3] = (int) floor( div_by( P.rm[0][t] - b.xmin, b.dx, b.rdx ) );
+	dep[6 * t + 4] = (int) floor( div_by( P.rm[1][t] - b.ymin, b.dy, b.rdy ) );
+	dep[6 * t + 5] = (int) floor( div_by( P.rm[2][t] - b.zmin, b.dz, b.rdz ) );
       }
   }
 
@@ -199,9 +199,9 @@ namespace mithra
 		if (b1x && b1y && b1z)
 		  {
 		    double d1;
-		    const double dxr = modf( ( x - b.xmin ) / b.dx, &d1 ); const int i = (int) d1;
-		    const double dyr = modf( ( y - b.ymin ) / b.dy, &d1 ); const int j = (int) d1;
-		    const double dzr = modf( ( z - b.zmin ) / b.dz, &d1 ); const int k = (int) d1;
+		    const double dxr = modf( div_by( x - b.xmin, b.dx, b.rdx ), &d1 ); const int i = (int) d1;
+		    const double dyr = modf( div_by( y - b.ymin, b.dy, b.rdy ), &d1 ); const int j = (int) d1;
+		    const double dzr = modf( div_by( z - b.zmin, b.dz, b.rdz ), &d1 ); const int k = (int) d1;
 		    const long m = (long) ( k - b.k0 ) * b.P + (long) i * b.N1 + j;
 		    const long N1 = b.N1, Pn = b.P;
 		    const long off[8] = { 0, N1, 1, N1 + 1, Pn, Pn + N1, Pn + 1, Pn + N1 + 1 };
@@ -246,7 +246,7 @@ namespace mithra
 	    const double f1 = b.r2 / d1;
 	    const double px = f1 * cx + mx, py = f1 * cy + my, pz = f1 * cz + mz;                      /* gb'   */
 	    cx = py * bt.z - pz * bt.y; cy = pz * bt.x - px * bt.z; cz = px * bt.y - py * bt.x;
-	    const double f2 = 2.0 / ( d1 / b.r2 + b.r2 / d1 * ( bt.x * bt.x + bt.y * bt.y + bt.z * bt.z ) );
+	    const double f2 = 2.0 / ( div_by( d1, b.r2, b.rr2 ) + b.r2 / d1 * ( bt.x * bt.x + bt.y * bt.y + bt.z * bt.z ) );
 	    const double lx = f2 * cx + mx, ly = f2 * cy + my, lzz = f2 * cz + mz;                     /* gb+   */
 	    gx = lx + b.r1 * et.x; gy = ly + b.r1 * et.y; gz = lzz + b.r1 * et.z;
 
@@ -261,9 +261,9 @@ namespace mithra
 
 	if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
 	  {
-	    bi = (int) floor( ( x - b.xmin ) / b.dx );
-	    bj = (int) floor( ( y - b.ymin ) / b.dy );
-	    bk = (int) floor( ( z - b.zmin ) / b.dz ) - b.k0;
+	    bi = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
+	    bj = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
+	    bk = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
 	    boxvalid = true;
 	  }
       }
@@ -283,7 +283,7 @@ namespace mithra
    * this is what bounds the kernel: the atomics' issue rate, not HBM.  The bounding box of the touched nodes is
    * merged per warp for the stencil (which reads J only there) and the next clear.
    * ------------------------------------------------------------------------------------------------ */
-  #define MITHRA_DEP_RUN 4
+  #define MITHRA_DEP_RUN 8
 
   template <bool SC>
   struct DepositAcc
@@ -333,9 +333,9 @@ namespace mithra
 						   double mx, double my, double mz, double jx, double jy, double jz)
   {
     double c;
-    const double dxp = modf( ( mx - b.xmin ) / b.dx, &c );
-    const double dyp = modf( ( my - b.ymin ) / b.dy, &c );
-    const double dzp = modf( ( mz - b.zmin ) / b.dz, &c );
+    const double dxp = modf( div_by( mx - b.xmin, b.dx, b.rdx ), &c );
+    const double dyp = modf( div_by( my - b.ymin, b.dy, b.rdy ), &c );
+    const double dzp = modf( div_by( mz - b.zmin, b.dz, b.rdz ), &c );
     const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
     const double h = q * 0.5;
     a.jx[0] += h * y1 * z1 * jx; a.jx[1] += h * y2 * z1 * jx; a.jx[2] += h * y1 * z2 * jx; a.jx[3] += h * y2 * z2 * jx;
@@ -345,14 +345,14 @@ namespace mithra
 
   template <bool SC>
   __global__ void __launch_bounds__(128)
-  deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox)
+  deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox, int run)
   {
-    const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * MITHRA_DEP_RUN;
+    const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * run;
     bool valid = false; int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1, k0 = 0x7fffffff, k1 = -1;
     DepositAcc<SC> acc; acc.m = -1;
     const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
 
-    for (int r = 0; r < MITHRA_DEP_RUN; r++)
+    for (int r = 0; r < run; r++)
       {
 	const long t = t0 + r;
 	if (t >= n) break;
@@ -366,8 +366,8 @@ namespace mithra
 	if (!bpf && !bmf) continue;
 
 	const double q = P.q[t];
-	const int ip = (int) floor( ( rpx - b.xmin ) / b.dx ), jp = (int) floor( ( rpy - b.ymin ) / b.dy ), kp = (int) floor( ( rpz - b.zmin ) / b.dz );
-	const int im = (int) floor( ( rmx - b.xmin ) / b.dx ), jm = (int) floor( ( rmy - b.ymin ) / b.dy ), km = (int) floor( ( rmz - b.zmin ) / b.dz );
+	const int ip = (int) floor( div_by( rpx - b.xmin, b.dx, b.rdx ) ), jp = (int) floor( div_by( rpy - b.ymin, b.dy, b.rdy ) ), kp = (int) floor( div_by( rpz - b.zmin, b.dz, b.rdz ) );
+	const int im = (int) floor( div_by( rmx - b.xmin, b.dx, b.rdx ) ), jm = (int) floor( div_by( rmy - b.ymin, b.dy, b.rdy ) ), km = (int) floor( div_by( rmz - b.zmin, b.dz, b.rdz ) );
 
 	/* relay point, fdtd.cpp:80-85 */
 	const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
@@ -382,7 +382,7 @@ namespace mithra
 	    if constexpr (SC)
 	      {
 		double c;
-		const double dxp = modf( ( rpx - b.xmin ) / b.dx, &c ), dyp = modf( ( rpy - b.ymin ) / b.dy, &c ), dzp = modf( ( rpz - b.zmin ) / b.dz, &c );
+		const double dxp = modf( div_by( rpx - b.xmin, b.dx, b.rdx ), &c ), dyp = modf( div_by( rpy - b.ymin, b.dy, b.rdy ), &c ), dzp = modf( div_by( rpz - b.zmin, b.dz, b.rdz ), &c );
 		const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
 		acc.rho[0] += q * x1 * y1 * z1; acc.rho[1] += q * x2 * y1 * z1; acc.rho[2] += q * x1 * y2 * z1; acc.rho[3] += q * x2 * y2 * z1;
 		acc.rho[4] += q * x1 * y1 * z2; acc.rho[5] += q * x2 * y1 * z2; acc.rho[6] += q * x1 * y2 * z2; acc.rho[7] += q * x2 * y2 * z2;

@@ -582,13 +582,16 @@ namespace mithra
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
     if (ni > 0 && nj > 0 && nk > 0)
       {
-	const long per = (long) ni * nj * nk, tot = per * f.ncomp;
-	for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+	/* one warp per row of the box (nj contiguous nodes): full sectors whatever the width of the box          */
+	const long rows = (long) ni * nk * f.ncomp;
+	const int  lane = threadIdx.x & 31;
+	const long wstride = ((long) gridDim.x * blockDim.x) >> 5;
+	for (long w = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < rows; w += wstride)
 	  {
-	    const int c = (int) (t / per); long r = t - (long) c * per;
-	    const int k = b.lo[2] + (int) (r / ((long) ni * nj)); r -= (long) (k - b.lo[2]) * ni * nj;
-	    const int i = b.lo[0] + (int) (r / nj), j = b.lo[1] + (int) (r % nj);
-	    jn[fidx(f.Pp, f.np, f.N1, c, k, i, j)] = 0.0;
+	    const int c = (int) (w / ((long) ni * nk)); long r = w - (long) c * ni * nk;
+	    const int k = b.lo[2] + (int) (r / ni), i = b.lo[0] + (int) (r % ni);
+	    double* row = jn + fidx(f.Pp, f.np, f.N1, c, k, i, b.lo[1]);
+	    for (int j = lane; j < nj; j += 32) row[j] = 0.0;
 	  }
       }
     /* the last block to finish empties the box                                                          */
@@ -621,37 +624,36 @@ namespace mithra
     const long m  = (long) k * Pp + (long) i * N1 + j;
     const double mdt = - f.dt;
     EB o;
-    #pragma unroll
-    for (int c = 0; c < 3; c++)
-      {
-	float e = (float) ( anp1[c * cs + m] / mdt );
-	e = (float) ( (double) e - an[c * cs + m] / mdt );
-	o.e[c] = e;
-      }
+    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs;
+    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
+    /* all the loads first, in straight-line code: the divisions below contain (rare) branches the compiler will
+     * not move loads across, and the kernel lives on having every load of a node in flight at once              */
+    const double p0 = px[m], p1 = py[m], p2 = pz[m], q0 = ax[m], q1 = ay[m], q2 = az[m];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (SC)
       {
 	const double* fn = an + 3 * cs;
-	o.e[0] = (float) ( (double) o.e[0] - ( fn[m + N1] - fn[m - N1] ) / f.dx2 );
-	o.e[1] = (float) ( (double) o.e[1] - ( fn[m + 1 ] - fn[m - 1 ] ) / f.dy2 );
-	o.e[2] = (float) ( (double) o.e[2] - ( fn[m + Pp] - fn[m - Pp] ) / f.dz2 );
+	g0 = fn[m + N1] - fn[m - N1]; g1 = fn[m + 1] - fn[m - 1]; g2 = fn[m + Pp] - fn[m - Pp];
       }
-    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs;
-    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
-    o.b[0] = (float) ( 0.5 * (
-	( az[m + 1 ] - az[m - 1 ] ) / f.dy2 -
-	( ay[m + Pp] - ay[m - Pp] ) / f.dz2 +
-	( pz[m + 1 ] - pz[m - 1 ] ) / f.dy2 -
-	( py[m + Pp] - py[m - Pp] ) / f.dz2 ) );
-    o.b[1] = (float) ( 0.5 * (
-	( ax[m + Pp] - ax[m - Pp] ) / f.dz2 -
-	( az[m + N1] - az[m - N1] ) / f.dx2 +
-	( px[m + Pp] - px[m - Pp] ) / f.dz2 -
-	( pz[m + N1] - pz[m - N1] ) / f.dx2 ) );
-    o.b[2] = (float) ( 0.5 * (
-	( ay[m + N1] - ay[m - N1] ) / f.dx2 -
-	( ax[m + 1 ] - ax[m - 1 ] ) / f.dy2 +
-	( py[m + N1] - py[m - N1] ) / f.dx2 -
-	( px[m + 1 ] - px[m - 1 ] ) / f.dy2 ) );
+    const double azy = az[m + 1 ] - az[m - 1 ], ayz = ay[m + Pp] - ay[m - Pp], pzy = pz[m + 1 ] - pz[m - 1 ], pyz = py[m + Pp] - py[m - Pp];
+    const double axz = ax[m + Pp] - ax[m - Pp], azx = az[m + N1] - az[m - N1], pxz = px[m + Pp] - px[m - Pp], pzx = pz[m + N1] - pz[m - N1];
+    const double ayx = ay[m + N1] - ay[m - N1], axy = ax[m + 1 ] - ax[m - 1 ], pyx = py[m + N1] - py[m - N1], pxy = px[m + 1 ] - px[m - 1 ];
+
+    {
+      float e;
+      e = (float) div_by( p0, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q0, mdt, f.rmdt ) ); o.e[0] = e;
+      e = (float) div_by( p1, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q1, mdt, f.rmdt ) ); o.e[1] = e;
+      e = (float) div_by( p2, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q2, mdt, f.rmdt ) ); o.e[2] = e;
+    }
+    if (SC)
+      {
+	o.e[0] = (float) ( (double) o.e[0] - div_by( g0, f.dx2, f.rdx2 ) );
+	o.e[1] = (float) ( (double) o.e[1] - div_by( g1, f.dy2, f.rdy2 ) );
+	o.e[2] = (float) ( (double) o.e[2] - div_by( g2, f.dz2, f.rdz2 ) );
+      }
+    o.b[0] = (float) ( 0.5 * ( div_by( azy, f.dy2, f.rdy2 ) - div_by( ayz, f.dz2, f.rdz2 ) + div_by( pzy, f.dy2, f.rdy2 ) - div_by( pyz, f.dz2, f.rdz2 ) ) );
+    o.b[1] = (float) ( 0.5 * ( div_by( axz, f.dz2, f.rdz2 ) - div_by( azx, f.dx2, f.rdx2 ) + div_by( pxz, f.dz2, f.rdz2 ) - div_by( pzx, f.dx2, f.rdx2 ) ) );
+    o.b[2] = (float) ( 0.5 * ( div_by( ayx, f.dx2, f.rdx2 ) - div_by( axy, f.dy2, f.rdy2 ) + div_by( pyx, f.dx2, f.rdx2 ) - div_by( pxy, f.dy2, f.rdy2 ) ) );
     return o;
   }
 
@@ -665,19 +667,24 @@ namespace mithra
     const Box b = *boxp;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
     if (ni <= 0 || nj <= 0 || nk <= 0) return;
-    const long tot = (long) ni * nj * nk;
-    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+    /* one warp per row of the box (lanes along j: neighbouring lanes share their y neighbours in L1 and the two
+     * float4 stores of a warp are contiguous); 32-bit index arithmetic, once per row                            */
+    const int rows = ni * nk;
+    const int lane = threadIdx.x & 31;
+    const int wstride = (int) (((long) gridDim.x * blockDim.x) >> 5);
+    for (int w = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < rows; w += wstride)
       {
-	long r = t;
-	const int k = b.lo[2] + (int) (r / ((long) ni * nj)); r -= (long) (k - b.lo[2]) * ni * nj;
-	const int i = b.lo[0] + (int) (r / nj), j = b.lo[1] + (int) (r % nj);
+	const int k = b.lo[2] + w / ni, i = b.lo[0] + w % ni;
 	int ke = k;
 	if (k < f.kb)      { if (f.rank != 0)          continue; ke = 1; }          /* ghosts come from the neighbour */
 	if (k == f.np - 1) { if (f.rank != f.size - 1) continue; ke = f.np - 2; }
-	const EB o = eval_eb_node<SC>(f, anp1, an, i, j, ke);
-	const long m = (long) k * f.P + (long) i * f.N1 + j;
-	eb[2 * m]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
-	eb[2 * m + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+	for (int j = b.lo[1] + lane; j <= b.hi[1]; j += 32)
+	  {
+	    const EB o = eval_eb_node<SC>(f, anp1, an, i, j, ke);
+	    const long m = (long) k * f.P + (long) i * f.N1 + j;
+	    eb[2 * m]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
+	    eb[2 * m + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+	  }
       }
   }
 }

@@ -284,3 +284,17 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
     for mode in ("MITHRA_NO_FUSE", "MITHRA_STENCIL_PLAIN"):
         for k in names:
             np.testing.assert_array_equal(out["fused"][k], out[mode][k], err_msg="%s %s" % (mode, k))
+
+
+@pytest.mark.parametrize("d", [60.0, 9.19059968, -0.01532827, 30.0, 4.59529984, -4.49297199e+08, 3.0, 1.9999999999999998,
+                               1.0000000000000002, 1e-3, 6.02e23, 1.7e-19, 1e-200])
+def test_constant_divisor_division_is_ieee(d):
+    """div_by (reciprocal + two FMAs, device_types.cuh) against the true division on the device, bit for bit: random
+    mantissas over 600 binades, the special values, and operands in the ranges that must take the fallback."""
+    rng = np.random.default_rng(5)
+    n = 4_000_000
+    x = rng.standard_normal(n) * np.exp2(rng.integers(-300, 300, n).astype(np.float64))
+    x[:16] = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+              1e-160, -1e-160, 1e160, 1.0, -1.0, 1e-149, 1e151]
+    x[16:1000] = rng.standard_normal(984) * 1e-305
+    assert abi.selftest_divide(x, d) == 0
