@@ -115,38 +115,74 @@ def undulator_time(p, periods=20.0):
 # clocks
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML every 2 ms (nvidia-smi every 100 ms if NVML is absent)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self._t = index, [], [], set(), threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        try:
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                                "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                if r and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace(".", "").isdigit():
+                    self.mx.append(float(r[1]))
+                for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+                    if len(r) > i and r[i].lower().startswith("active"):
+                        self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.1)
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
-            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -326,15 +362,30 @@ def main():
     # per-phase device times (CUDA events around each kernel group on the library's stream), same state
     nprof = min(K, 10)
     phases = solver.step_profiled(nprof)
+    # The dominant kernel is stencil_stream: one launch advances the nodes that are not on the rim (the two outer interior
+    # layers in x and y belong to rim_update, timed under "boundary"), (N0-6)(N1-6) nodes of each of the np-2 updated planes.
     stencil_ms = phases["stencil"] / nprof
-    algo_bytes = BYTES_PER_CELL[sc] * nodes_local
+    rim = pl.N0 >= 8 and pl.N1 >= 8 and pl.np >= 8
+    planes = pl.np - 2                                      # rank 0 updates its planes 1 .. np-2
+    stencil_nodes = ((pl.N0 - 6) * (pl.N1 - 6) if rim else (pl.N0 - 2) * (pl.N1 - 2)) * planes
+    algo_bytes = BYTES_PER_CELL[sc] * stencil_nodes
     achieved = algo_bytes / (stencil_ms * 1e-3) / 1e9
     push_ms = phases["push"] / nprof
-    roofline = {"bound": "hbm", "kernel": "stencil_interior", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": None,
-                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": stencil_ms,
+    field_ms = (phases["stencil"] + phases["boundary"]) / nprof
+    traffic = None
+    tfn = os.path.join(ROOT, "profiles", "traffic.json")            # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tfn) and world == 1 and args.workload == "fel-seeded":
+        traffic = json.load(open(tfn)).get("stencil_stream", {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "stencil_stream", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": traffic,
+                "algorithmic_bytes_per_launch": algo_bytes, "units_per_launch": stencil_nodes, "launch_ms": stencil_ms,
+                "note": "algorithmic bytes = 96 B (128 B with phi) per node the launch advances (SURVEY 8d: read A^n, A^n-1, J, write A^n+1); "
+                        "the kernel reads J only inside the deposit box, so its DRAM traffic is below the algorithmic figure",
                 "share_of_step": stencil_ms / max(1e-9, sum(phases.values()) / nprof),
                 "phases_ms_per_step": {k: v / nprof for k, v in phases.items()},
+                "field_update": {"what": "whole fieldUpdate (seed table, stencil_stream, rim_update, z shell / faces, edges, corners) over all nodes",
+                                 "ms": field_ms, "achieved": BYTES_PER_CELL[sc] * nodes_local / (field_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                 "frac": BYTES_PER_CELL[sc] * nodes_local / (field_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "push": {"achieved": BYTES_PER_PUSH * npart_local * pl.n_update_bunch / (push_ms * 1e-3) / 1e9 if push_ms > 0 else None,
                          "unit": "GB/s", "bytes_per_push": BYTES_PER_PUSH}}
 
@@ -347,6 +398,9 @@ def main():
             t = torch.empty(arr.size, dtype=torch.float64, pin_memory=True)
             t.numpy()[:] = arr
             pin[name] = t.numpy()
+        # results land in pinned host memory too
+        pin["out_a"] = torch.empty(a_n.size, dtype=torch.float64, pin_memory=True).numpy()
+        pin["out_p"] = torch.empty(int(pl.max_particles) * 11, dtype=torch.float64, pin_memory=True).numpy()
         solver.close()
         solver = abi.GpuSolver(pl)
         if world > 1:
@@ -364,8 +418,8 @@ def main():
             solver.step(1)
             row = solver.fetch_power()
             d2h += row.nbytes
-        out_p = solver.download_particles()
-        out_a = solver.download_fields(("an",))["an"]
+        out_p = solver.download_particles(out=pin["out_p"])
+        out_a = solver.download_fields(("an",), out={"an": pin["out_a"]})["an"]
         barrier()
         e2e_sec = time.perf_counter() - t0
         h2d = pin["an"].nbytes + pin["anm1"].nbytes + pin["bunch"].nbytes

@@ -168,11 +168,14 @@ class GpuSolver:
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (an, anm1, jn, fn, fnm1, rho)]
         self._check(self.lib.mithra_gpu_upload_fields(self.h, *[_dptr(a) for a in arrs]))
 
-    def download_fields(self, which=("anp1", "an", "anm1")):
+    def download_fields(self, which=("anp1", "an", "anm1"), out=None):
+        """`out`: optional dict name -> preallocated float64 array (e.g. pinned host memory) to receive the level."""
         names = ("anp1", "an", "anm1", "fnp1", "fn", "fnm1")
-        out = {}
+        given, out = out or {}, {}
         for n in which:
-            out[n] = np.empty(self.nodes * (3 if n.startswith("a") else 1), dtype=np.float64)
+            size = self.nodes * (3 if n.startswith("a") else 1)
+            out[n] = given[n] if n in given else np.empty(size, dtype=np.float64)
+            assert out[n].dtype == np.float64 and out[n].size == size and out[n].flags["C_CONTIGUOUS"]
         self._check(self.lib.mithra_gpu_download_fields(self.h, *[_dptr(out.get(n)) for n in names]))
         return out
 
@@ -189,10 +192,15 @@ class GpuSolver:
         a = np.ascontiguousarray(aos11, dtype=np.float64).reshape(-1, 11)
         self._check(self.lib.mithra_gpu_upload_particles(self.h, _dptr(a), a.shape[0]))
 
-    def download_particles(self):
+    def download_particles(self, out=None):
+        """`out`: optional preallocated float64 array of at least n x 11 (e.g. pinned host memory)."""
         n = C.c_size_t()
         self._check(self.lib.mithra_gpu_num_particles(self.h, C.byref(n)))
-        out = np.empty((n.value, 11), dtype=np.float64)
+        if out is None:
+            out = np.empty((n.value, 11), dtype=np.float64)
+        else:
+            assert out.dtype == np.float64 and out.size >= n.value * 11 and out.flags["C_CONTIGUOUS"]
+            out = out.reshape(-1)[:n.value * 11].reshape(n.value, 11)
         self._check(self.lib.mithra_gpu_download_particles(self.h, _dptr(out), n.value, C.byref(n)))
         return out
 

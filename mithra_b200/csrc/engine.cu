@@ -61,6 +61,9 @@ struct MithraGpu
   int             ip1, in, im1;
   bool            anp1_is_current;        /* reference view: anp1_ currently holds J (after fieldShift)    */
   double*         J;
+  double*         d_stage;                /* AoS staging of the field transfers (field_stage)              */
+  size_t          stage_bytes;
+  bool            stream_configured[2];   /* stencil_stream<NSFD>: dynamic shared memory limit raised on this device */
   Box*            d_jbox;
   unsigned int*   d_done;
 
@@ -367,6 +370,8 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       }
   }
   h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
+  h->stream_configured[0] = h->stream_configured[1] = false;
+  h->d_stage = 0; h->stage_bytes = 0;
   CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
   CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
   set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
@@ -478,6 +483,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaStreamSynchronize(h->stream);
   exchange_destroy(h->xch);
   for (int l = 0; l < 4; l++) cudaFree(h->Abase[l]);
+  cudaFree(h->d_stage);
   cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
   cudaFree(h->eb); cudaFree(h->d_noutside);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
@@ -494,17 +500,31 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
 /* ---------------------------------------------------------------------------------------------------- */
 /* state transfer                                                                                        */
 
+/* Staging buffer of the AoS <-> planar field transfers (the ABI speaks the reference's [node][xyz] layout): one level
+ * of potentials, allocated at the first transfer and kept -- cudaMalloc / cudaFree of 1.4 GB around every copy cost more
+ * than the copy.                                                                                              */
+static int field_stage (MithraGpu* h, size_t bytes, double** out)
+{
+  if (h->stage_bytes < bytes)
+    {
+      if (h->d_stage) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->d_stage)); h->d_stage = 0; h->stage_bytes = 0; }
+      CU(cudaMalloc(&h->d_stage, bytes));
+      h->stage_bytes = bytes;
+    }
+  *out = h->d_stage;
+  return 0;
+}
+
 static int upload_vec (MithraGpu* h, const double* src, double* dst, int ncomp_src, int c0, int nc)
 {
   const FieldDev& f = h->fd;
   const long nodes = (long) h->prm.np * f.P;
   double* tmp = 0;
-  CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_src * sizeof(double)));
+  TRY(field_stage(h, (size_t) nodes * ncomp_src * sizeof(double), &tmp));
   CU(cudaMemcpyAsync(tmp, src, (size_t) nodes * ncomp_src * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   aos_to_planar<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(tmp, dst, ncomp_src, c0, nc, nodes, f.P, f.Pp, f.np, f.kshift);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaFree(tmp));
   return 0;
 }
 
@@ -513,12 +533,11 @@ static int download_vec (MithraGpu* h, const double* src, double* dst, int ncomp
   const FieldDev& f = h->fd;
   const long nodes = (long) h->prm.np * f.P;
   double* tmp = 0;
-  CU(cudaMalloc(&tmp, (size_t) nodes * ncomp_dst * sizeof(double)));
+  TRY(field_stage(h, (size_t) nodes * ncomp_dst * sizeof(double), &tmp));
   planar_to_aos<<<grid_for(nodes * nc, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, tmp, ncomp_dst, c0, nc, nodes, f.P, f.Pp, f.np, f.kshift);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(dst, tmp, (size_t) nodes * ncomp_dst * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaFree(tmp));
   return 0;
 }
 
@@ -727,11 +746,11 @@ static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
   if (getenv("MITHRA_STENCIL_PLAIN")) return false;
   const size_t smem = stencil_stream_smem(T, f.N1, NB);
   if (smem > 200 * 1024) return false;
-  static bool configured[2] = { false, false };
-  if (!configured[NSFD])
+  /* the attribute belongs to the device: one process may drive several (one handle per slab)                */
+  if (!h->stream_configured[NSFD])
     {
       if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
-      configured[NSFD] = true;
+      h->stream_configured[NSFD] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
   stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0);

@@ -270,6 +270,10 @@ namespace mithra
     #undef MITHRA_STREAM_STEP
   }
 
+  #ifndef MITHRA_RIM_MINBLOCKS
+  #define MITHRA_RIM_MINBLOCKS 1
+  #endif
+
   /* AdvanceField::advanceBoundary{F,S} (database.cpp:137-176) for the face node s from the thread of its inward
    * neighbour n, same association order as face_update below:
    *   apn = A+_n, ams = A-_s, amn = A-_n, as_ = A_s, an_ = A_n, then the four tangential neighbours along t1 in the
@@ -299,7 +303,7 @@ namespace mithra
    * Results are bit-identical to stencil + seed_inject + boundary_faces run one after the other.
    * ------------------------------------------------------------------------------------------------ */
   template <bool NSFD>
-  __global__ void __launch_bounds__(128)
+  __global__ void __launch_bounds__(128, MITHRA_RIM_MINBLOCKS)
   rim_update (const FieldDev f, const RimDev rz, double* __restrict__ anp1, const double* __restrict__ an,
 	      const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC)
   {
@@ -342,24 +346,10 @@ namespace mithra
 
     auto cross_at = [&] (int k) { Cross x; const double* q = A + (long) k * Pp; x.c = q[0]; x.xp = q[N1]; x.xm = q[-N1]; x.yp = q[1]; x.ym = q[-1]; return x; };
 
-    /* every iteration depends on loads of the next plane that nobody has touched yet: ask L2 for them PD planes
-     * ahead (no registers are held by a prefetch), so that the loads themselves find the lines there           */
-    constexpr int PD = 6;
-    auto prefetch_plane = [&] (int k) {
-      if (k + 1 > f.np - 1) return;
-      const double* q = A + (long) (k + 1) * Pp;
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(q + N1));
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(q - N1));
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(Am + (long) k * Pp));
-      if (dsx != 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(Am + (long) k * Pp + dsx)); };
-    for (int k = ks; k < min(ks + PD, ke); k++) prefetch_plane(k);
-
     Cross M = cross_at(ks - 1), Z = cross_at(ks);
     for (int k = ks; k < ke; k++)
       {
 	const long ko = (long) k * Pp;
-	if (k + PD < ke) prefetch_plane(k + PD);
 	const Cross Pn = cross_at(k + 1);
 	const double vm1 = Am[ko];
 	double src = 0.0;
