@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MITHRA_GPU_ABI_VERSION      2
+#define MITHRA_GPU_ABI_VERSION      3
 #define MITHRA_MAX_UNDULATORS       16
 #define MITHRA_MAX_EXTFIELDS        8
 #define MITHRA_MAX_POWER_PLANES     256
@@ -87,6 +87,17 @@ typedef struct MithraPower
 } MithraPower;
 
 /* Screens (solver.cpp:2145-2257). */
+/* power-visualization group (FreeElectronLaser::vtkPower_, Solver::initializePowerVisualize radiation.cpp:238-318):
+ * one plane, one harmonic, the radiated power PER PIXEL of the plane                                  */
+typedef struct MithraPowerMap
+{
+  int    enabled;
+  int    Nf;                                    /* DFT window length                                 */
+  double z;                                     /* boosted plane position                            */
+  double w;                                     /* angular frequency 2 pi / dt_lambda                */
+  double pc;                                    /* power prefactor                                   */
+} MithraPowerMap;
+
 typedef struct MithraScreens
 {
   int    enabled;
@@ -145,6 +156,7 @@ typedef struct MithraGpuParams
   int    device;                  /* CUDA device ordinal, -1 = current                               */
   int    sort_interval;           /* field steps between two counting sorts of the bunch by cell: > 0 as given,
 				     < 0 never, 0 = library default (16 for bunches of >= 4096 particles)     */
+  MithraPowerMap power_map;       /* power-visualization (radiation.cpp:238-450)                      */
 } MithraGpuParams;
 
 typedef struct MithraGpu MithraGpu;
@@ -206,6 +218,7 @@ int mithra_gpu_field_update        (MithraGpu* h);   /* FdTd::fieldUpdate  fdtd.
 int mithra_gpu_bunch_update        (MithraGpu* h);   /* rnm = rnp + nUpdateBunch x Solver::bunchUpdate, solver.cpp:1311-1325 */
 int mithra_gpu_screen_profile      (MithraGpu* h);   /* Solver::screenProfile solver.cpp:2205-2257        */
 int mithra_gpu_power_sample        (MithraGpu* h);   /* Solver::powerSample  radiation.cpp:127-232        */
+int mithra_gpu_power_visualize     (MithraGpu* h);   /* Solver::powerVisualize radiation.cpp:324-391 (the map; the .vts writer is the host's) */
 int mithra_gpu_field_shift         (MithraGpu* h);   /* FdTd::fieldShift     fdtd.cpp:806-812             */
 int mithra_gpu_current_reset       (MithraGpu* h);   /* FdTd::currentReset   fdtd.cpp:23-32               */
 int mithra_gpu_current_update      (MithraGpu* h);   /* FdTd::currentUpdate  fdtd.cpp:38-185              */
@@ -225,6 +238,10 @@ int mithra_gpu_fetch_power (MithraGpu* h, double* rows, size_t capacity_rows, si
 /* Screen crossings: records of 6 doubles { x, y, t, gbx, gby, gbz_lab } (solver.cpp:2229-2252) since the
  * last fetch, in particle order within a step.                                                        */
 int mithra_gpu_fetch_screen (MithraGpu* h, int screen, double* rec6, size_t capacity, size_t* n);
+
+/* Power map of the last mithra_gpu_power_visualize call: pL[i*N1 + j] (radiation.cpp:388), N0*N1 doubles, zero
+ * outside 1 <= i <= N0-2, 1 <= j <= N1-2.  *mine = 1 when the plane lies in this slab (else pL is not written). */
+int mithra_gpu_fetch_power_map (MithraGpu* h, double* pL, size_t capacity, int* mine);
 
 int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 

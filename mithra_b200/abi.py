@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_UNDULATORS, MAX_EXTFIELDS = 16, 8
 MAX_POWER_PLANES, MAX_POWER_LAMBDAS, MAX_SCREENS = 256, 64, 64
 NPHASES = 8
@@ -40,6 +40,10 @@ class Power(C.Structure):
                 ("w", C.c_double * MAX_POWER_LAMBDAS), ("Nf", C.c_int), ("pc", C.c_double)]
 
 
+class PowerMap(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("Nf", C.c_int), ("z", C.c_double), ("w", C.c_double), ("pc", C.c_double)]
+
+
 class Screens(C.Structure):
     _fields_ = [("enabled", C.c_int), ("N", C.c_int), ("pos", C.c_double * MAX_SCREENS)]
 
@@ -66,6 +70,7 @@ class Params(C.Structure):
         ("power", Power), ("screens", Screens),
         ("max_particles", C.c_size_t), ("max_screen_records", C.c_size_t), ("device", C.c_int),
         ("sort_interval", C.c_int),
+        ("power_map", PowerMap),
     ]
 
 
@@ -86,6 +91,7 @@ SYMBOLS = (
     "mithra_gpu_step_timed", "mithra_gpu_synchronize", "mithra_gpu_fetch_power", "mithra_gpu_fetch_screen",
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
     "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
+    "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map",
 )
 
 _lib = None
@@ -118,7 +124,7 @@ def load():
     lib.mithra_gpu_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_uint)]
     for name in ("field_update", "bunch_update", "screen_profile", "power_sample", "field_shift", "current_reset",
                  "current_update", "current_communicate", "advance_time", "synchronize", "seed_initial", "sort_particles",
-                 "migrate_begin", "migrate_end"):
+                 "migrate_begin", "migrate_end", "power_visualize"):
         getattr(lib, "mithra_gpu_" + name).argtypes = [vp]
     lib.mithra_gpu_step.argtypes = [vp, C.c_int]
     lib.mithra_gpu_step_timed.argtypes = [vp, C.c_int, fp]
@@ -128,6 +134,7 @@ def load():
     lib.mithra_gpu_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.mithra_gpu_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mithra_gpu_ipc_connect.argtypes = [vp, vp, vp]
+    lib.mithra_gpu_fetch_power_map.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int)]
     lib.mithra_gpu_selftest_divide.argtypes = [dp, C.c_size_t, C.c_double, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
@@ -241,6 +248,16 @@ class GpuSolver:
 
     def powerSample(self):
         self._check(self.lib.mithra_gpu_power_sample(self.h))
+
+    def powerVisualize(self):
+        self._check(self.lib.mithra_gpu_power_visualize(self.h))
+
+    def fetch_power_map(self):
+        """pL[i*N1 + j] of the last powerVisualize call, or None when the plane lies in another slab."""
+        out = np.zeros(self.params.N0 * self.params.N1)
+        mine = C.c_int(0)
+        self._check(self.lib.mithra_gpu_fetch_power_map(self.h, _dptr(out), out.size, C.byref(mine)))
+        return out if mine.value else None
 
     def fieldShift(self):
         self._check(self.lib.mithra_gpu_field_shift(self.h))

@@ -104,6 +104,15 @@ struct MithraGpu
   double          power_dzr[MITHRA_MAX_POWER_PLANES];
   bool            power_mine[MITHRA_MAX_POWER_PLANES];
 
+  /* power map (power-visualization) */
+  PowerDev        pm;
+  double*         d_pm_fdt;               /* [Nf][4][P]                                                   */
+  double2*        d_pm_ep;                /* [Nf]                                                         */
+  double*         d_pm_pL;                /* [P]                                                          */
+  int             pm_k;
+  double          pm_dzr;
+  bool            pm_mine;
+
   /* screens */
   double*         d_scr_pos;
   double*         d_scr_rec;
@@ -315,7 +324,7 @@ static int preload_kernels ()
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
   PL(particle_box); PL(particle_cells); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
-  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish);
+  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
@@ -434,6 +443,29 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       CU(cudaMalloc(&h->d_rows, h->rows_cap * pp.N * pp.Nl * sizeof(double)));
     }
 
+  /* power map, radiation.cpp:238-318 */
+  memset(&h->pm, 0, sizeof(h->pm));
+  h->d_pm_fdt = 0; h->d_pm_ep = 0; h->d_pm_pL = 0; h->pm_mine = false; h->pm_k = 0; h->pm_dzr = 0.0;
+  if (params->power_map.enabled)
+    {
+      const MithraPowerMap& pp = params->power_map;
+      if (pp.Nf < 1) { mithra_gpu_destroy(h); return fail("mithra_gpu_create: power map window Nf = %d", pp.Nf); }
+      PowerDev& pm = h->pm;
+      pm.N = 1; pm.Nl = 1; pm.Nf = pp.Nf; pm.ni = f.N0 - 2; pm.nj = f.N1 - 2; pm.npx = f.P;
+      pm.pc = pp.pc; pm.gamma = params->gamma; pm.beta = params->beta; pm.c0 = params->c0;
+      h->pm_mine = ( pp.z < params->zp[1] && pp.z >= params->zp[0] );
+      double c; h->pm_dzr = modf( ( pp.z - params->zmin ) / params->dz, &c ); h->pm_k = (int) c - f.k0;
+      if (h->pm_mine)
+	{
+	  const size_t ring = (size_t) pp.Nf * 4 * f.P;
+	  CU(cudaMalloc(&h->d_pm_fdt, ring * sizeof(double))); CU(cudaMemsetAsync(h->d_pm_fdt, 0, ring * sizeof(double), h->stream));
+	  std::vector<double2> ep((size_t) pp.Nf);
+	  for (int m = 0; m < pp.Nf; m++) { ep[m].x = cos( pp.w * m * params->dt ); ep[m].y = sin( pp.w * m * params->dt ); }
+	  CU(cudaMalloc(&h->d_pm_ep, ep.size() * sizeof(double2))); CU(cudaMemcpy(h->d_pm_ep, ep.data(), ep.size() * sizeof(double2), cudaMemcpyHostToDevice));
+	  CU(cudaMalloc(&h->d_pm_pL, (size_t) f.P * sizeof(double))); CU(cudaMemsetAsync(h->d_pm_pL, 0, (size_t) f.P * sizeof(double), h->stream));
+	}
+    }
+
   /* screens */
   h->d_scr_pos = 0; h->d_scr_rec = 0; h->d_scr_cur = 0; h->scr_cap = 0;
   if (params->screens.enabled && params->screens.N > 0)
@@ -488,6 +520,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaFree(h->eb); cudaFree(h->d_noutside);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
+  cudaFree(h->d_pm_fdt); cudaFree(h->d_pm_ep); cudaFree(h->d_pm_pL);
   cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
   cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab); cudaFree(h->d_seedu);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
@@ -983,6 +1016,33 @@ extern "C" int mithra_gpu_power_sample (MithraGpu* h)
   return 0;
 }
 
+extern "C" int mithra_gpu_power_visualize (MithraGpu* h)
+{
+  USE(h);
+  if (!h->prm.power_map.enabled || !h->pm_mine) return 0;
+  PhaseTimer t(h, PH_POWER);
+  const FieldDev& f = h->fd;
+  const int slot = (int) (h->n_time % (unsigned int) h->pm.Nf);
+  const int npx = (f.N0 - 2) * (f.N1 - 2);
+  const int k = h->pm_k;                                 /* internal plane index (FieldDev.k0 is internal)          */
+  if (f.ncomp == 4) power_map<true ><<<(npx + 127) / 128, 128, 0, h->stream>>>(f, h->pm, h->A[h->ip1], h->A[h->in], h->eb, h->d_pm_fdt, h->d_pm_ep, k, h->pm_dzr, slot, h->d_pm_pL);
+  else              power_map<false><<<(npx + 127) / 128, 128, 0, h->stream>>>(f, h->pm, h->A[h->ip1], h->A[h->in], h->eb, h->d_pm_fdt, h->d_pm_ep, k, h->pm_dzr, slot, h->d_pm_pL);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  return 0;
+}
+
+extern "C" int mithra_gpu_fetch_power_map (MithraGpu* h, double* pL, size_t capacity, int* mine)
+{
+  USE(h);
+  if (mine) *mine = (h->prm.power_map.enabled && h->pm_mine) ? 1 : 0;
+  if (!h->prm.power_map.enabled || !h->pm_mine || !pL) return 0;
+  if (capacity < (size_t) h->fd.P) return fail("mithra_gpu_fetch_power_map: capacity %zu < %d pixels", capacity, h->fd.P);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(pL, h->d_pm_pL, (size_t) h->fd.P * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int mithra_gpu_field_shift (MithraGpu* h)
 {
   USE(h);
@@ -1073,6 +1133,7 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_bunch_update(h));
       TRY(mithra_gpu_screen_profile(h));
       TRY(mithra_gpu_power_sample(h));
+      TRY(mithra_gpu_power_visualize(h));
       TRY(mithra_gpu_field_shift(h));
       TRY(mithra_gpu_current_reset(h));
       TRY(mithra_gpu_current_update(h));

@@ -554,6 +554,71 @@ namespace mithra
       }
   }
 
+  /* ------------------------------------------------------------------------------------------------
+   * Power map (Solver::powerVisualize, radiation.cpp:324-391): the same lab-frame fields and length-Nf DFT as the
+   * power sampling, but kept per pixel for 1 <= i <= N0-2, 1 <= j <= N1-2 and one harmonic.  One thread per pixel
+   * sums the window in the reference's order m = 0 .. Nf-1, so the map is bit-identical to the reference's for
+   * identical E/B.  ring layout: fdt[slot][4][P] (pixel fastest), twiddles ep[m] = exp(+i w m dt).
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool SC>
+  __global__ void __launch_bounds__(128)
+  power_map (const FieldDev f, const PowerDev pw, const double* __restrict__ anp1, const double* __restrict__ an,
+	     const float4* __restrict__ ebn, double* __restrict__ fdt, const double2* __restrict__ ep, int kplane, double dzr, int slot,
+	     double* __restrict__ pL)
+  {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ni = f.N0 - 2, nj = f.N1 - 2;
+    if (t >= ni * nj) return;
+    const int i = 1 + t / nj, j = 1 + t % nj;
+    const int px = i * f.N1 + j;
+    int ka = kplane, kb = kplane + 1;
+    if (ka == 0 && f.rank == 0) ka = 1;
+    if (kb == f.np - 1 && f.rank == f.size - 1) kb = f.np - 2;
+    EB A, B;
+    if (ka < f.kb && f.rank != 0)
+      {
+	const float4 e = ebn[2 * ((long) ka * f.P + px)], bb = ebn[2 * ((long) ka * f.P + px) + 1];
+	A.e[0] = e.x; A.e[1] = e.y; A.e[2] = e.z; A.b[0] = bb.x; A.b[1] = bb.y; A.b[2] = bb.z;
+      }
+    else A = eval_eb_node<SC>(f, anp1, an, i, j, ka);
+    if (kb == f.np - 1 && f.rank != f.size - 1)
+      {
+	const float4 e = ebn[2 * ((long) kb * f.P + px)], bb = ebn[2 * ((long) kb * f.P + px) + 1];
+	B.e[0] = e.x; B.e[1] = e.y; B.e[2] = e.z; B.b[0] = bb.x; B.b[1] = bb.y; B.b[2] = bb.z;
+      }
+    else B = eval_eb_node<SC>(f, anp1, an, i, j, kb);
+    const double et0 = ( 1.0 - dzr ) * A.e[0] + dzr * B.e[0];
+    const double et1 = ( 1.0 - dzr ) * A.e[1] + dzr * B.e[1];
+    const double bt0 = ( 1.0 - dzr ) * A.b[0] + dzr * B.b[0];
+    const double bt1 = ( 1.0 - dzr ) * A.b[1] + dzr * B.b[1];
+    double cur[4];
+    cur[0] = pw.gamma * ( et0 + pw.c0 * pw.beta * bt1 );
+    cur[1] = pw.gamma * ( et1 - pw.c0 * pw.beta * bt0 );
+    cur[2] = pw.gamma * ( bt0 - pw.beta / pw.c0 * et1 );
+    cur[3] = pw.gamma * ( bt1 + pw.beta / pw.c0 * et0 );
+    const size_t P = (size_t) f.P;
+    #pragma unroll
+    for (int q = 0; q < 4; q++) fdt[( (size_t) slot * 4 + q ) * P + px] = cur[q];
+
+    double e1r = 0.0, e1i = 0.0, b1r = 0.0, b1i = 0.0, e2r = 0.0, e2i = 0.0, b2r = 0.0, b2i = 0.0;
+    for (int m = 0; m < pw.Nf; m++)
+      {
+	const double2 w = ep[m];
+	double v[4];
+	if (m == slot) { v[0] = cur[0]; v[1] = cur[1]; v[2] = cur[2]; v[3] = cur[3]; }
+	else
+	  {
+	    #pragma unroll
+	    for (int q = 0; q < 4; q++) v[q] = fdt[( (size_t) m * 4 + q ) * P + px];
+	  }
+	e1r += v[0] * w.x; e1i += v[0] * w.y;
+	b1r += v[3] * w.x; b1i += v[3] * ( - w.y );
+	e2r += v[1] * w.x; e2i += v[1] * w.y;
+	b2r += v[2] * w.x; b2i += v[2] * ( - w.y );
+      }
+    pL[px] = pw.pc * ( ( e1r * b1r - e1i * b1i ) - ( e2r * b2r - e2i * b2i ) );
+  }
+
   __global__ void power_finish (const PowerDev pw, const double* __restrict__ partial, int nblocks, double* __restrict__ row)
   {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

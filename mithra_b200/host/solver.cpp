@@ -26,7 +26,7 @@ namespace MITHRA
       N0_(0), N1_(0), N2_(0), N1N0_(0), np_(0), k0_(0), rank_(0), size_(1),
       xmin_(0), xmax_(0), ymin_(0), ymax_(0), zmin_(0), zmax_(0),
       gamma_(1.0), beta_(0.0), dt_(0.0), timep1_(0.0), time_(0.0), timem1_(0.0), timeBunch_(0.0),
-      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), spaceChargeSolver_(false)
+      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), spaceChargeSolver_(false)
   {
     zp_[0] = zp_[1] = 0.0;
     memset(&uf_, 0, sizeof(uf_)); memset(&uc_, 0, sizeof(uc_)); memset(&ub_, 0, sizeof(ub_));
@@ -69,6 +69,7 @@ namespace MITHRA
     initializeField();
     initializeBunchUpdate();
     initializePowerSample();
+    initializePowerVisualize();
     initializeScreenProfile();
     shiftBackInTime();
   }
@@ -473,6 +474,32 @@ namespace MITHRA
       }
   }
 
+  /* plane, window length and prefactor of the power-visualization group -- radiation.cpp:238-318                */
+  void Solver::initializePowerVisualize ()
+  {
+    for (unsigned int jf = 0; jf < FEL_.size(); jf++)
+      {
+	FreeElectronLaser::RadiationVisualization& V = FEL_[jf].vtkPower_;
+	if (!V.sampling_) continue;
+	if ( V.rhythm_ == 0 )
+	  { printmessage(__FILE__, __LINE__, "The power visualization rhythm of the field is zero although power visualization is activated !!!"); exit(1); }
+	if ( undulator_.size() == 0 ) { printmessage(__FILE__, __LINE__, "Radiation power visualization needs an undulator."); exit(1); }
+	V.rhythm_ /= gamma_;
+	V.z_      *= gamma_;
+	if ( V.basename_.compare(0, 1, "/") != 0 ) V.basename_ = V.directory_ + V.basename_;
+	createDirectory(V.basename_, 0);
+	rp_[jf].N = 1; rp_[jf].Nl = 1;
+	rp_[jf].w.resize(1);
+	/* three radiation periods of the harmonic in the moving frame                                               */
+	const Double dt = undulator_[0].lu_ / V.lambda_ / ( gamma_ * c0_ );
+	rp_[jf].Nf   = unsigned( 3.0 * dt / mesh_.timeStep_ );
+	rp_[jf].w[0] = 2 * PI / dt;
+	rp_[jf].pc   = 2.0 * mesh_.meshResolution_[0] * mesh_.meshResolution_[1] / ( m0_ * rp_[jf].Nf * rp_[jf].Nf ) * pow(mesh_.lengthScale_,2) / pow(mesh_.timeScale_,3);
+	if ( pmapGroup_ < 0 ) pmapGroup_ = jf;
+	else printmessage(__FILE__, __LINE__, "Note: only the first power-visualization group is evaluated by this build.");
+      }
+  }
+
   /* solver.cpp:2145-2200 */
   void Solver::initializeScreenProfile ()
   {
@@ -584,6 +611,12 @@ namespace MITHRA
 	for (unsigned i = 0; i < S.N; i++)  p.power.z[i] = R.z_[i];
 	for (unsigned i = 0; i < S.Nl; i++) p.power.w[i] = S.w[i];
       }
+    if ( pmapGroup_ >= 0 )
+      {
+	const SampleRadiationPower& S = rp_[pmapGroup_];
+	p.power_map.enabled = 1; p.power_map.Nf = S.Nf; p.power_map.z = FEL_[pmapGroup_].vtkPower_.z_;
+	p.power_map.w = S.w[0]; p.power_map.pc = S.pc;
+      }
     if ( screenGroup_ >= 0 )
       {
 	const std::vector<Double>& pos = FEL_[screenGroup_].screenProfile_.pos_;
@@ -676,6 +709,60 @@ namespace MITHRA
     powerTimes_.push_back(timeBunch_);
   }
 
+  /* Solver::powerVisualize, radiation.cpp:324-450: the library updates the per-pixel map every step; at the rhythm
+   * the slab that holds the plane hands it over and the .vts file is written in the reference's format (:393-447)  */
+  void Solver::powerVisualize ()
+  {
+    if ( pmapGroup_ < 0 ) return;
+    for (MithraGpu* g : gpu_) check(mithra_gpu_power_visualize(g));
+    const FreeElectronLaser::RadiationVisualization& V = FEL_[pmapGroup_].vtkPower_;
+    if ( !( fmod(time_, V.rhythm_) < mesh_.timeStep_ ) ) return;
+    std::vector<double> pL((size_t) N1N0_, 0.0);
+    bool have = false;
+    for (MithraGpu* g : gpu_)
+      {
+	int mine = 0;
+	check(mithra_gpu_fetch_power_map(g, pL.data(), pL.size(), &mine));
+	if ( mine ) { have = true; break; }
+      }
+    if ( !have ) return;
+    Double c;
+    const Double dzr = modf( ( V.z_ - zmin_ ) / mesh_.meshResolution_[2], &c );
+    const long int k = (long int) c;                            /* global plane index (k0_ of slab 0 is 0)           */
+    const std::string name = V.basename_ + "-" + stringify(nTime_) + ".vts";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    f << "<?xml version=\"1.0\"?>" << std::endl;
+    f << "<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << std::endl;
+    f << "<StructuredGrid WholeExtent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl;
+    f << "<Piece Extent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl;
+    f << "<Points>" << std::endl;
+    f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+    for (int j = 0; j < N1_; j++)
+      for (int i = 0; i < N0_; i++)
+	{
+	  const long int m = k * N1N0_ + i * N1_ + j;
+	  const FieldVector r1 = rc(m), r2 = rc(m + N1N0_);
+	  f << r1[0] * ( 1.0 - dzr ) + r2[0] * dzr << " " << r1[1] << " " << r1[2] << std::endl;
+	}
+    f << "</DataArray>" << std::endl;
+    f << "</Points>" << std::endl;
+    f << "<CellData>" << std::endl;
+    f << "</CellData>" << std::endl;
+    f << "<PointData Vectors = \"power\">" << std::endl;
+    f << "<DataArray type=\"Float64\" Name=\"power\" NumberOfComponents=\"" << 1 << "\" format=\"ascii\">" << std::endl;
+    for (int j = 0; j < N1_; j++)
+      for (int i = 0; i < N0_; i++)
+	f << pL[(size_t) i * N1_ + j] << std::endl;
+    f << "</DataArray>" << std::endl;
+    f << "</PointData>" << std::endl;
+    f << "</Piece>" << std::endl;
+    f << "</StructuredGrid>" << std::endl;
+    f << "</VTKFile>" << std::endl;
+    f.close();
+  }
+
   /* write what the library has collected since the last call: power lines (radiation.cpp:222-230), screen records
    * (solver.cpp:2229-2252)                                                                                        */
   void Solver::flushOutputs ()
@@ -765,6 +852,7 @@ namespace MITHRA
 	recycleParticles();
 	screenProfile();
 	powerSample();
+	powerVisualize();
 	fieldShift();
 	currentReset();
 	currentUpdate();
@@ -851,6 +939,13 @@ namespace MITHRA
 	w.i(k + "N", rp_[jf].N); w.i(k + "Nl", rp_[jf].Nl); w.i(k + "Nf", rp_[jf].Nf); w.d(k + "pc", rp_[jf].pc);
 	w.f64(k + "z", FEL_[jf].radiationPower_.z_.data(), FEL_[jf].radiationPower_.z_.size());
 	w.f64(k + "w", rp_[jf].w.data(), rp_[jf].w.size());
+      }
+    for (size_t jf = 0; jf < FEL_.size(); jf++)
+      {
+	if (!FEL_[jf].vtkPower_.sampling_) continue;
+	const std::string k = "pmap" + stringify(jf) + ".";
+	w.i(k + "Nf", rp_[jf].Nf); w.d(k + "pc", rp_[jf].pc); w.d(k + "z", FEL_[jf].vtkPower_.z_);
+	w.d(k + "w", rp_[jf].w.empty() ? 0.0 : rp_[jf].w[0]); w.d(k + "rhythm", FEL_[jf].vtkPower_.rhythm_);
       }
     for (size_t jf = 0; jf < FEL_.size(); jf++)
       if (FEL_[jf].screenProfile_.sampling_)

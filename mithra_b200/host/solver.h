@@ -60,6 +60,7 @@ namespace MITHRA
     void initializeBunchUpdate ();
     void initializeBunch ();
     void initializePowerSample ();
+    void initializePowerVisualize ();
     void initializeScreenProfile ();
     void shiftBackInTime ();
 
@@ -75,7 +76,7 @@ namespace MITHRA
     void bunchSample () {}
     void bunchVisualize () {}
     void bunchProfile () {}
-    void powerVisualize () {}
+    void powerVisualize ();
     void energySample () {}
 
     /* ---- the thirteen virtuals, solver.h:139-178 ------------------------------------------------------------ */
@@ -137,6 +138,7 @@ namespace MITHRA
   protected:
     long                maxSteps_;
     int                 powerGroup_, screenGroup_;     /* FEL_ entries the C ABI's single power / screen group mirror */
+    int                 pmapGroup_;                    /* ... and its single power-visualization group               */
     std::vector<Double> powerTimes_;                   /* timeBunch_ of the sampled steps not yet written             */
     bool                spaceChargeSolver_;
   };

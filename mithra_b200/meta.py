@@ -87,6 +87,11 @@ def params_from_meta(meta, max_particles=0):
             w.z[i] = v
         for i, v in enumerate(meta[key + "w"]):
             w.w[i] = v
+    mk = sorted(k for k in meta if k.startswith("pmap") and k.endswith(".Nf"))
+    if mk:
+        key = mk[0][:-2]
+        m = p.power_map
+        m.enabled, m.Nf, m.z, m.w, m.pc = 1, int(g(key + "Nf")), g(key + "z"), g(key + "w"), g(key + "pc")
     sk = sorted(k for k in meta if k.startswith("screen") and k.endswith(".pos"))
     if sk:
         s = p.screens

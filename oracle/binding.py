@@ -57,6 +57,9 @@ def load():
     lib.oracle_step.argtypes = [vp, C.c_int]
     lib.oracle_push_cells.argtypes = [vp, C.POINTER(C.c_long)]
     lib.oracle_deposit_cells.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.oracle_power_visualize.argtypes = [vp]
+    lib.oracle_power_map.argtypes = [vp]
+    lib.oracle_power_map.restype = dp
     lib.oracle_power_rows.argtypes = [vp]
     lib.oracle_power_rows.restype = C.c_size_t
     lib.oracle_power_data.argtypes = [vp]
@@ -134,6 +137,15 @@ class Oracle:
 
     def powerSample(self):
         self.lib.oracle_power_sample(self.o)
+
+    def powerVisualize(self):
+        self.lib.oracle_power_visualize(self.o)
+
+    def fetch_power_map(self):
+        ptr = self.lib.oracle_power_map(self.o)
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(self.params.N0 * self.params.N1,)).copy()
 
     def fieldShift(self):
         self.lib.oracle_field_shift(self.o)

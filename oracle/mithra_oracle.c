@@ -31,6 +31,10 @@ struct Oracle
   double *fdt;                /* [Nf][Nz*P][4] */
   double *ep_re, *ep_im;      /* [Nl][Nf] */
   double *rows; size_t nrows, rowcap;
+  /* power map (power-visualization) */
+  double *mfdt;               /* [Nf][P][4] */
+  double *mep_re, *mep_im;    /* [Nf] */
+  double *mpL;                /* [P] */
   /* screens */
   double *scr[MITHRA_MAX_SCREENS]; size_t scrn[MITHRA_MAX_SCREENS], scrcap[MITHRA_MAX_SCREENS];
 };
@@ -70,6 +74,20 @@ Oracle* oracle_create (const MithraGpuParams* p)
 	    o->ep_im[l * w->Nf + j] = sin( w->w[l] * j * p->dt );
 	  }
     }
+  if (p->power_map.enabled)
+    {
+      /* radiation.cpp:279-314 */
+      const MithraPowerMap* w = &p->power_map;
+      o->mfdt   = (double*) calloc((size_t) w->Nf * o->P * 4, sizeof(double));
+      o->mep_re = (double*) calloc((size_t) w->Nf, sizeof(double));
+      o->mep_im = (double*) calloc((size_t) w->Nf, sizeof(double));
+      o->mpL    = (double*) calloc((size_t) o->P, sizeof(double));
+      for (int j = 0; j < w->Nf; j++)
+	{
+	  o->mep_re[j] = cos( w->w * j * p->dt );
+	  o->mep_im[j] = sin( w->w * j * p->dt );
+	}
+    }
   return o;
 }
 
@@ -77,7 +95,7 @@ void oracle_destroy (Oracle* o)
 {
   if (!o) return;
   free(o->anp1); free(o->an); free(o->anm1); free(o->fnp1); free(o->fn); free(o->fnm1);
-  free(o->en); free(o->bn); free(o->pic); free(o->part); free(o->fdt); free(o->ep_re); free(o->ep_im); free(o->rows);
+  free(o->en); free(o->bn); free(o->pic); free(o->part); free(o->fdt); free(o->ep_re); free(o->ep_im); free(o->rows); free(o->mfdt); free(o->mep_re); free(o->mep_im); free(o->mpL);
   for (int s = 0; s < MITHRA_MAX_SCREENS; s++) free(o->scr[s]);
   free(o);
 }
@@ -880,6 +898,50 @@ void oracle_power_sample (Oracle* o)
   o->nrows++;
 }
 
+/* Per-pixel power map, Solver::powerVisualize radiation.cpp:324-391 (the .vts writer :393-447 is the host's)  */
+void oracle_power_visualize (Oracle* o)
+{
+  const MithraGpuParams* p = &o->p;
+  const MithraPowerMap* w = &p->power_map;
+  if (!w->enabled) return;
+  if ( !( w->z < p->zp[1] && w->z >= p->zp[0] ) ) return;                /* rp_.Nz == 1, radiation.cpp:271 */
+  const long N1 = p->N1, P = o->P;
+  double c;
+  const double dzr = modf( ( w->z - p->zmin ) / p->dz, &c );
+  const int kk = (int) c - p->k0;
+  const unsigned int slot = o->n_time % (unsigned int) w->Nf;
+  for (int i = 1; i < p->N0 - 1; i++)
+    for (int j = 1; j < p->N1 - 1; j++)
+      {
+	const long mi = kk * P + i * N1 + j;
+	const long ni = i * N1 + j;
+	if (!o->pic[mi])     oracle_field_evaluate(o, mi);
+	if (!o->pic[mi + P]) oracle_field_evaluate(o, mi + P);
+	const double et0 = ( 1.0 - dzr ) * o->en[3 * mi]     + dzr * o->en[3 * (mi + P)];
+	const double et1 = ( 1.0 - dzr ) * o->en[3 * mi + 1] + dzr * o->en[3 * (mi + P) + 1];
+	const double bt0 = ( 1.0 - dzr ) * o->bn[3 * mi]     + dzr * o->bn[3 * (mi + P)];
+	const double bt1 = ( 1.0 - dzr ) * o->bn[3 * mi + 1] + dzr * o->bn[3 * (mi + P) + 1];
+	double* f = o->mfdt + ( (size_t) slot * P + ni ) * 4;
+	f[0] = p->gamma * ( et0 + p->c0 * p->beta * bt1 );
+	f[1] = p->gamma * ( et1 - p->c0 * p->beta * bt0 );
+	f[2] = p->gamma * ( bt0 - p->beta / p->c0 * et1 );
+	f[3] = p->gamma * ( bt1 + p->beta / p->c0 * et0 );
+	double e1r = 0, e1i = 0, b1r = 0, b1i = 0, e2r = 0, e2i = 0, b2r = 0, b2i = 0;
+	for (int m = 0; m < w->Nf; m++)
+	  {
+	    const double* g = o->mfdt + ( (size_t) m * P + ni ) * 4;
+	    const double cr = o->mep_re[m], ci = o->mep_im[m];
+	    e1r += g[0] * cr; e1i += g[0] * ci;
+	    b1r += g[3] * cr; b1i += g[3] * ( - ci );
+	    e2r += g[1] * cr; e2i += g[1] * ci;
+	    b2r += g[2] * cr; b2i += g[2] * ( - ci );
+	  }
+	o->mpL[ni] = w->pc * ( ( e1r * b1r - e1i * b1i ) - ( e2r * b2r - e2i * b2i ) );
+      }
+}
+
+const double* oracle_power_map (Oracle* o) { return o->mpL; }
+
 size_t        oracle_power_rows (Oracle* o) { return o->nrows; }
 const double* oracle_power_data (Oracle* o) { return o->rows; }
 
@@ -933,6 +995,7 @@ void oracle_step (Oracle* o, int nsteps)
       oracle_bunch_update(o);
       oracle_screen_profile(o);
       oracle_power_sample(o);
+      oracle_power_visualize(o);
       oracle_field_shift(o);
       oracle_current_reset(o);
       oracle_current_update(o);

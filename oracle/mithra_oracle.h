@@ -59,6 +59,8 @@ void oracle_push_cells    (Oracle* o, long* m_out);
 void oracle_deposit_cells (Oracle* o, int* ijk6_out);
 
 /* outputs */
+void          oracle_power_visualize (Oracle* o);              /* Solver::powerVisualize radiation.cpp:324-391 */
+const double* oracle_power_map    (Oracle* o);                 /* pL[i*N1 + j], 0 when power_map is disabled  */
 size_t        oracle_power_rows   (Oracle* o);                 /* rows of N*Nl doubles recorded so far      */
 const double* oracle_power_data   (Oracle* o);
 size_t        oracle_screen_count (Oracle* o, int screen);

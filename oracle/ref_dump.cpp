@@ -237,6 +237,15 @@ int main (int argc, char* argv[])
       }
     for (size_t jf = 0; jf < FEL.size(); jf++)
       {
+	/* power-visualization group: Solver::initializePowerVisualize, radiation.cpp:238-318                      */
+	if (!FEL[jf].vtkPower_.sampling_) continue;
+	std::ostringstream k; k << "pmap" << jf << ".";
+	w.i((k.str() + "Nf").c_str(), (int) s.rp_[jf].Nf); w.d((k.str() + "pc").c_str(), s.rp_[jf].pc);
+	w.d((k.str() + "z").c_str(), FEL[jf].vtkPower_.z_); w.d((k.str() + "w").c_str(), s.rp_[jf].w.empty() ? 0.0 : s.rp_[jf].w[0]);
+	w.d((k.str() + "rhythm").c_str(), FEL[jf].vtkPower_.rhythm_);
+      }
+    for (size_t jf = 0; jf < FEL.size(); jf++)
+      {
 	if (!FEL[jf].screenProfile_.sampling_) continue;
 	std::ostringstream k; k << "screen" << jf << ".pos";
 	w.f64(k.str().c_str(), &FEL[jf].screenProfile_.pos_[0], (int64_t) FEL[jf].screenProfile_.pos_.size());
@@ -361,6 +370,13 @@ int main (int argc, char* argv[])
     Writer w(prefix + ".power.bin");
     w.i("nsteps", nsteps);
     w.f64("pG", powerSeries.empty() ? 0 : &powerSeries[0], (int64_t) powerSeries.size());
+    /* the per-pixel map of the last powerVisualize call (rp_[jf].pL, radiation.cpp:388)                         */
+    for (size_t jf = 0; jf < FEL.size(); jf++)
+      if (FEL[jf].vtkPower_.sampling_ && s.rp_[jf].Nz == 1 && !s.rp_[jf].pL.empty())
+	{
+	  std::ostringstream k; k << "pmap" << jf;
+	  w.f64(k.str().c_str(), &s.rp_[jf].pL[0], (int64_t) s.rp_[jf].pL.size());
+	}
   }
 
   s.finalize();

@@ -14,6 +14,7 @@ Every fixture <job>.npz holds, for one job:
                          nodes the reference evaluated (pic), J after the deposit -- same sampling
     power                pG per step (radiation.cpp:209-218), 100 rows
     screen<i>            the reference's screen text files parsed back to doubles (solver.cpp:2229-2252)
+    pmap, vts/<file>     power-visualization jobs: the per-pixel map after the last step and the .vts files as written
 The fixtures pin oracle/mithra_oracle.c (tests/test_oracle_golden.py) and, through it, the CUDA path.
 """
 import os
@@ -29,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import binding  # noqa: E402
 
-JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical")
+JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
 NSTEPS = 100
 NSAMPLE = 1024
 
@@ -83,8 +84,19 @@ def make(job):
         out["ph99/pic_count"] = np.array([int(ph["pic"].sum())])
         out["ph99/en"] = ph["en"].reshape(-1, 3)[pic]
         out["ph99/bn"] = ph["bn"].reshape(-1, 3)[pic]
-        pw = binding.read_records(prefix + ".power.bin")["pG"]
+        prec = binding.read_records(prefix + ".power.bin")
+        pw = prec["pG"]
         out["power"] = pw.reshape(NSTEPS, -1) if pw.size else np.zeros((0, 1))
+        # power-visualization: the per-pixel map after the last step (rp_.pL) and the reference's own .vts files
+        for k in prec:
+            if k.startswith("pmap"):
+                out["pmap"] = prec[k]
+        for d in sorted(os.listdir(work)):
+            dd = os.path.join(work, d)
+            if os.path.isdir(dd):
+                for fn in sorted(os.listdir(dd)):
+                    if fn.endswith(".vts"):
+                        out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
         scr_dir = os.path.join(work, "screens")
         if os.path.isdir(scr_dir):
             for fn in sorted(os.listdir(scr_dir)):

@@ -7,7 +7,7 @@ from oracle import binding
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical")
+JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
 
 
 def load_golden(job):
@@ -37,6 +37,7 @@ def solve_step(s):
     s.bunchUpdate()
     s.screenProfile()
     s.powerSample()
+    s.powerVisualize()
     s.fieldShift()
     s.currentReset()
     s.currentUpdate()

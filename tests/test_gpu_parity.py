@@ -137,6 +137,11 @@ def test_100_steps(job):
             rg, rc = gpu.fetch_screen(s), cpu.fetch_screen(s)
             assert rg.shape == rc.shape
             np.testing.assert_allclose(rg, rc, rtol=1e-9, atol=1e-12)
+    if p.power_map.enabled:
+        # Solver::powerVisualize: per-pixel map of the last step against the oracle and the reference's own
+        mg, mc = gpu.fetch_power_map(), cpu.fetch_power_map()
+        np.testing.assert_allclose(mg, mc, rtol=1e-7, atol=1e-10 * np.abs(mc).max())
+        np.testing.assert_allclose(mg, g["pmap"], rtol=1e-7, atol=1e-10 * np.abs(mc).max())
     # and against the reference's own golden output (power curve within 1 % is the contract; we are far inside)
     np.testing.assert_allclose(pw_g, g["power"], rtol=1e-8, atol=1e-12 * np.abs(g["power"]).max())
     assert helpers.rel_l2(pg, g["p100"]) < 1e-9

@@ -146,3 +146,33 @@ def test_executable_writes_the_reference_output_files(job, gpus, tmp_path):
             else:
                 o1, o2 = np.lexsort((rec[:, 0], rec[:, 2])), np.lexsort((ref[:, 0], ref[:, 2]))
                 np.testing.assert_allclose(rec[o1], ref[o2], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_writes_the_power_visualization_files(gpus, tmp_path):
+    """Solver::powerVisualize through the host executable: the .vts files of a power-visualization job (written at
+    steps 0, 40 and 80 of micro-pviz) against the unmodified reference's own files -- same file names, same XML lines,
+    same grid coordinates; the power values agree to the 5 digits the format prints."""
+    meta, g = helpers.load_golden("micro-pviz")
+    subprocess.check_output([_exe(), _job("micro-pviz"), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("vts/"))
+    assert want == ["pmap-0.vts", "pmap-40.vts", "pmap-80.vts"]
+    assert sorted(os.listdir(tmp_path / "power-map")) == want
+    for fn in want:
+        ref = bytes(g["vts/" + fn]).decode().splitlines()
+        got = open(tmp_path / "power-map" / fn).read().splitlines()
+        assert len(got) == len(ref)
+        num_r, num_g = [], []
+        for a, b in zip(got, ref):
+            if b.startswith("<"):
+                assert a == b
+            else:
+                num_g.append([float(x) for x in a.split()])
+                num_r.append([float(x) for x in b.split()])
+        flat_g = np.array([x for row in num_g for x in row])
+        flat_r = np.array([x for row in num_r for x in row])
+        assert flat_g.shape == flat_r.shape
+        np.testing.assert_allclose(flat_g, flat_r, rtol=2e-4, atol=1e-4 * np.abs(flat_r).max())
+        if fn != "pmap-0.vts":
+            assert np.abs(flat_r[-196:]).max() > 0

@@ -29,6 +29,7 @@ def run(request):
             keep["ph_particles"] = o.download_particles()
             o.screenProfile()
             o.powerSample()
+            o.powerVisualize()
             keep["ph_eb"] = o.download_eb()
             o.fieldShift()
             o.currentReset()
@@ -41,6 +42,7 @@ def run(request):
     keep["end"] = o.download_fields(names)
     keep["p100"] = o.download_particles()
     keep["power"] = o.fetch_power()
+    keep["pmap"] = o.fetch_power_map()
     keep["screens"] = [o.fetch_screen(s) for s in range(p.screens.N)] if p.screens.enabled else []
     o.close()
     return keep
@@ -95,6 +97,15 @@ def test_step99_phases(run):
 
 def test_power_series(run):
     np.testing.assert_array_equal(run["power"], run["g"]["power"])
+
+
+def test_power_map(run):
+    """Solver::powerVisualize: the per-pixel map after 100 steps, bit for bit (jobs with a power-visualization group)."""
+    if not run["p"].power_map.enabled:
+        assert "pmap" not in run["g"].files
+        return
+    assert np.abs(run["g"]["pmap"]).max() > 0
+    np.testing.assert_array_equal(run["pmap"], run["g"]["pmap"])
 
 
 def test_screens(run):
