@@ -53,6 +53,15 @@ struct MithraGpu
   int             device;
   int             num_sms;
   cudaStream_t    stream;
+  /* housekeeping that only has to be finished by the NEXT consumer runs beside the particle kernels on a second,
+   * low-priority stream when the loop is driven by mithra_gpu_step: the clear of the deposit box (needed by the
+   * deposit) and the seed line table of the next time level (needed by the next field update)                */
+  cudaStream_t    side;
+  cudaEvent_t     ev_main, ev_clear, ev_seed;
+  bool            overlap;                /* MITHRA_NO_OVERLAP unset                                       */
+  bool            clear_ahead;            /* the box has been cleared (or is being cleared) on `side`      */
+  bool            seed_ahead;             /* seed table + lines for seed_ahead_time are (being) computed   */
+  double          seed_ahead_time;
 
   /* potentials */
   size_t          level_doubles;          /* ncomp * np * Pp                                              */
@@ -358,7 +367,17 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   if (prop.major < 10) { delete h; return fail("mithra_gpu_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); }
   h->num_sms = prop.multiProcessorCount;
   if (preload_kernels()) { delete h; return 1; }
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_seed, cudaEventDisableTiming));
+    h->overlap = !getenv("MITHRA_NO_OVERLAP");
+    h->clear_ahead = false; h->seed_ahead = false; h->seed_ahead_time = 0.0;
+  }
   CU(cudaEventCreate(&h->pev[0])); CU(cudaEventCreate(&h->pev[1]));
   h->profiling = false; memset(h->pms, 0, sizeof(h->pms));
 
@@ -524,6 +543,10 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaFree(h->d_fdt); cudaFree(h->d_ep); cudaFree(h->d_partial); cudaFree(h->d_rows);
   cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab); cudaFree(h->d_seedu);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_clear) cudaEventDestroy(h->ev_clear);
+  if (h->ev_seed) cudaEventDestroy(h->ev_seed);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -801,6 +824,20 @@ static void launch_stencil (MithraGpu* h, bool skiprim)
   stencil_interior<NSFD, BX, KC><<<grid, BX, 0, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox);
 }
 
+/* per-plane seed table and the line table rim_update reads, for the time level `time`, on stream `st`           */
+static int launch_seed_lines (MithraGpu* h, double time, cudaStream_t st)
+{
+  const FieldDev& f = h->fd;
+  const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
+  const int KI = zlo ? 2 : f.kb, KF = zhi ? f.np - 2 : f.np - 1;
+  if (h->d_seed_tab) { seed_plane_table<<<(f.np + 127) / 128, 128, 0, st>>>(h->d_seed, f.np, time, h->d_seed_tab); h->cnt.kernel_launches += 1; }
+  const long tot = (long) (4 * (f.N1 - 4) + 4 * (f.N0 - 4)) * (KF - KI);
+  seed_lines<<<grid_for(tot, 128, h->num_sms * 16), 128, 0, st>>>(h->d_seed, h->d_seed_tab, f, KI, KF, h->seed_L, h->d_seedu, time);
+  h->cnt.kernel_launches += 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mithra_gpu_field_update (MithraGpu* h)
 {
   USE(h);
@@ -823,11 +860,14 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
       rz.supergaussian = (B.seed_type == MITHRA_BEAM_SUPERGAUSSIAN) ? 1 : 0;
       rz.ni = rz.supergaussian ? ( 2 * B.order[0] + 1 ) * ( 2 * B.order[1] + 1 ) : 1;
       rz.pol[0] = B.polarization[0]; rz.pol[1] = B.polarization[1]; rz.pol[2] = B.polarization[2]; rz.gamma = h->prm.gamma;
-      if (h->d_seed_tab) { seed_plane_table<<<(f.np + 127) / 128, 128, 0, h->stream>>>(h->d_seed, f.np, h->time, h->d_seed_tab); h->cnt.kernel_launches += 1; }
-      const long tot = (long) (4 * (f.N1 - 4) + 4 * (f.N0 - 4)) * (rz.KF - rz.KI);
-      seed_lines<<<grid_for(tot, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->d_seed, h->d_seed_tab, f, rz.KI, rz.KF, rz.L, h->d_seedu, h->time);
-      h->cnt.kernel_launches += 1;
-      CU(cudaGetLastError());
+      if (h->seed_ahead && h->seed_ahead_time == h->time)
+	CU(cudaStreamWaitEvent(h->stream, h->ev_seed, 0));        /* computed beside the last particle phase      */
+      else
+	{
+	  if (h->seed_ahead) CU(cudaStreamWaitEvent(h->stream, h->ev_seed, 0));      /* stale: let it finish first */
+	  TRY(launch_seed_lines(h, h->time, h->stream));
+	}
+      h->seed_ahead = false;
     }
   {
     PhaseTimer t(h, PH_STENCIL);
@@ -1055,9 +1095,39 @@ extern "C" int mithra_gpu_current_reset (MithraGpu* h)
 {
   USE(h);
   PhaseTimer t(h, PH_CLEAR);
+  if (h->clear_ahead)
+    {
+      /* mithra_gpu_step cleared the box beside the particle kernels: the deposit only has to wait for it          */
+      CU(cudaStreamWaitEvent(h->stream, h->ev_clear, 0));
+      h->clear_ahead = false;
+      return 0;
+    }
   clear_current_box<<<h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
+  return 0;
+}
+
+/* After the field update of a step driven by mithra_gpu_step: J has been consumed and nothing reads it or the seed
+ * tables before the next deposit / field update, so clear the box and prepare the next seed lines on the side stream. */
+static int housekeeping_ahead (MithraGpu* h)
+{
+  if (!h->overlap || h->profiling) return 0;
+  const FieldDev& f = h->fd;
+  CU(cudaEventRecord(h->ev_main, h->stream));
+  CU(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+  clear_current_box<<<h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaEventRecord(h->ev_clear, h->side));
+  h->clear_ahead = true;
+  if (h->d_seed && h->d_seedu && f.N0 >= 8 && f.N1 >= 8 && f.np >= 8 && !getenv("MITHRA_NO_FUSE"))
+    {
+      const double tnext = h->time + h->prm.dt;              /* exactly what mithra_gpu_advance_time will make of it */
+      TRY(launch_seed_lines(h, tnext, h->side));
+      CU(cudaEventRecord(h->ev_seed, h->side));
+      h->seed_ahead = true; h->seed_ahead_time = tnext;
+    }
   return 0;
 }
 
@@ -1130,6 +1200,7 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
   for (int s = 0; s < nsteps; s++)
     {
       TRY(mithra_gpu_field_update(h));
+      TRY(housekeeping_ahead(h));
       TRY(mithra_gpu_bunch_update(h));
       TRY(mithra_gpu_screen_profile(h));
       TRY(mithra_gpu_power_sample(h));
@@ -1142,6 +1213,9 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_migrate_end(h));
       TRY(mithra_gpu_advance_time(h));
     }
+  /* whatever was started ahead on the side stream belongs to this call: later work on the main stream (and the
+   * caller's timing events) come after it                                                                        */
+  if (h->seed_ahead) CU(cudaStreamWaitEvent(h->stream, h->ev_seed, 0));
   return 0;
 }
 
@@ -1149,6 +1223,7 @@ extern "C" int mithra_gpu_synchronize (MithraGpu* h)
 {
   USE(h);
   CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->side));
   CU(cudaGetLastError());
   if (h->xch.d_err)
     {
