@@ -243,6 +243,11 @@ int mithra_gpu_fetch_screen (MithraGpu* h, int screen, double* rec6, size_t capa
  * outside 1 <= i <= N0-2, 1 <= j <= N1-2.  *mine = 1 when the plane lies in this slab (else pL is not written). */
 int mithra_gpu_fetch_power_map (MithraGpu* h, double* pL, size_t capacity, int* mine);
 
+/* Solver::bunchSample (solver.cpp:1582-1608): the raw sums over the particles this slab owns, in the order
+ * q, q r[3], q r^2[3], q gb[3], q gb^2[3]; the division by q, the standard deviations and the text line
+ * (solver.cpp:1617-1640) stay with the host writer.                                                    */
+int mithra_gpu_bunch_moments (MithraGpu* h, double sums[13]);
+
 int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 
 /* Per-kernel timing of the last mithra_gpu_step_profiled call (device ms by CUDA events around each

@@ -91,7 +91,7 @@ SYMBOLS = (
     "mithra_gpu_step_timed", "mithra_gpu_synchronize", "mithra_gpu_fetch_power", "mithra_gpu_fetch_screen",
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
     "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
-    "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map",
+    "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map", "mithra_gpu_bunch_moments",
 )
 
 _lib = None
@@ -135,6 +135,7 @@ def load():
     lib.mithra_gpu_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mithra_gpu_ipc_connect.argtypes = [vp, vp, vp]
     lib.mithra_gpu_fetch_power_map.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int)]
+    lib.mithra_gpu_bunch_moments.argtypes = [vp, dp]
     lib.mithra_gpu_selftest_divide.argtypes = [dp, C.c_size_t, C.c_double, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
@@ -251,6 +252,12 @@ class GpuSolver:
 
     def powerVisualize(self):
         self._check(self.lib.mithra_gpu_power_visualize(self.h))
+
+    def bunch_moments(self):
+        """The 13 raw sums of Solver::bunchSample: q, q r[3], q r^2[3], q gb[3], q gb^2[3]."""
+        out = np.zeros(13)
+        self._check(self.lib.mithra_gpu_bunch_moments(self.h, _dptr(out)))
+        return out
 
     def fetch_power_map(self):
         """pL[i*N1 + j] of the last powerVisualize call, or None when the plane lies in another slab."""

@@ -332,7 +332,7 @@ static int preload_kernels ()
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8>)); PL((stencil_stream<false, 512, 8>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>);
-  PL(particle_box); PL(particle_cells); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
+  PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
@@ -738,6 +738,28 @@ extern "C" int mithra_gpu_download_particles (MithraGpu* h, double* aos11, size_
   CU(cudaMemcpyAsync(aos11, stage, np * 11 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   if (d_order) cudaFree(d_order);
+  return 0;
+}
+
+/* Solver::bunchSample's sums (solver.cpp:1582-1608) over the particles of this slab, reduced on the device           */
+extern "C" int mithra_gpu_bunch_moments (MithraGpu* h, double sums[13])
+{
+  USE(h);
+  if (!sums) return fail("mithra_gpu_bunch_moments: null argument");
+  for (int q = 0; q < MITHRA_MOMENTS; q++) sums[q] = 0.0;
+  if (h->pn == 0) return 0;
+  const int blocks = grid_for((long) h->pn, 256, h->num_sms * 4);
+  double* d_part = 0;
+  CU(cudaMalloc(&d_part, (size_t) blocks * MITHRA_MOMENTS * sizeof(double)));
+  bunch_moments<<<blocks, 256, 0, h->stream>>>(h->bd, h->P, (long) h->pn, d_part);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  std::vector<double> part((size_t) blocks * MITHRA_MOMENTS);
+  CU(cudaMemcpyAsync(part.data(), d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(d_part));
+  for (int bl = 0; bl < blocks; bl++)
+    for (int q = 0; q < MITHRA_MOMENTS; q++) sums[q] += part[(size_t) bl * MITHRA_MOMENTS + q];
   return 0;
 }
 

@@ -401,6 +401,54 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
+   * Moments of the bunch (Solver::bunchSample, solver.cpp:1582-1608): the 13 raw sums q, q r, q r^2, q gb, q gb^2
+   * over the particles this slab owns.  Block reduction in a fixed order (thread t sums particles t, t + stride, ...;
+   * shared-memory tree), one partial row per block; the host adds the rows in order -- deterministic.
+   * ------------------------------------------------------------------------------------------------ */
+  #define MITHRA_MOMENTS 13
+  __global__ void __launch_bounds__(256)
+  bunch_moments (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ partial)
+  {
+    __shared__ double red[MITHRA_MOMENTS][256];
+    double s[MITHRA_MOMENTS];
+    #pragma unroll
+    for (int q = 0; q < MITHRA_MOMENTS; q++) s[q] = 0.0;
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long) gridDim.x * blockDim.x)
+      {
+	const double z = P.r[2][t];
+	if (b.size == 1)
+	  {
+	    const double zr = pmod( z - b.zmin, b.Lz ) + b.zmin;            /* particleInProcessor, solver.cpp:2292-2298 */
+	    if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) continue;
+	  }
+	const double q = P.q[t];
+	const double r[3] = { P.r[0][t], P.r[1][t], z }, g[3] = { P.gb[0][t], P.gb[1][t], P.gb[2][t] };
+	s[0] += q;
+	#pragma unroll
+	for (int l = 0; l < 3; l++)
+	  {
+	    s[1 + l]  += q * r[l];
+	    s[4 + l]  += r[l] * r[l] * q;
+	    s[7 + l]  += q * g[l];
+	    s[10 + l] += g[l] * g[l] * q;
+	  }
+      }
+    #pragma unroll
+    for (int q = 0; q < MITHRA_MOMENTS; q++) red[q][threadIdx.x] = s[q];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1)
+      {
+	if (threadIdx.x < w)
+	  {
+	    #pragma unroll
+	    for (int q = 0; q < MITHRA_MOMENTS; q++) red[q][threadIdx.x] += red[q][threadIdx.x + w];
+	  }
+	__syncthreads();
+      }
+    if (threadIdx.x < MITHRA_MOMENTS) partial[(size_t) blockIdx.x * MITHRA_MOMENTS + threadIdx.x] = red[threadIdx.x][0];
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Screens (solver.cpp:2205-2257).  One thread per particle, loop over screens; a crossing appends a record
    * { x, y, t, gbx, gby, gbz_lab, upload index of the particle, step } to the screen's buffer through an atomic cursor.
    * ------------------------------------------------------------------------------------------------ */

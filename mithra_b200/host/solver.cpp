@@ -26,7 +26,7 @@ namespace MITHRA
       N0_(0), N1_(0), N2_(0), N1N0_(0), np_(0), k0_(0), rank_(0), size_(1),
       xmin_(0), xmax_(0), ymin_(0), ymax_(0), zmin_(0), zmax_(0),
       gamma_(1.0), beta_(0.0), dt_(0.0), timep1_(0.0), time_(0.0), timem1_(0.0), timeBunch_(0.0),
-      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), spaceChargeSolver_(false)
+      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), bunchSampleFile_(0), spaceChargeSolver_(false)
   {
     zp_[0] = zp_[1] = 0.0;
     memset(&uf_, 0, sizeof(uf_)); memset(&uc_, 0, sizeof(uc_)); memset(&ub_, 0, sizeof(ub_));
@@ -427,8 +427,24 @@ namespace MITHRA
     ub_.dx  = mesh_.meshResolution_[0]; ub_.dy = mesh_.meshResolution_[1]; ub_.dz = mesh_.meshResolution_[2];
     ub_.r1  = - EC / ( EM * c0_ ) * bunch_.timeStep_ / 2.0;
     ub_.r2  = - EC / EM * bunch_.timeStep_ / 2.0;
-    if ( bunch_.sampling_ || bunch_.bunchVTK_ || bunch_.bunchProfile_ )
-      printmessage(__FILE__, __LINE__, "Note: bunch-sampling / -visualization / -profile writers are outside this build's scope and are skipped.");
+    /* solver.cpp:1062-1124: files and checks of the bunch samplers                                                */
+    if ( bunch_.sampling_ )
+      {
+	std::string name = "";
+	if ( bunch_.basename_.compare(0, 1, "/") != 0 ) name = bunch_.directory_;
+	name += bunch_.basename_ + ".txt";
+	createDirectory(name, 0);
+	bunchSampleFile_ = new std::ofstream(name.c_str(), std::ios::trunc);
+	if ( bunch_.rhythm_ == 0 )
+	  { printmessage(__FILE__, __LINE__, "The sampling rhythm of the bunch is zero although sampling is activated !!!"); exit(1); }
+      }
+    if ( bunch_.bunchProfile_ )
+      {
+	if ( bunch_.bunchProfileBasename_.compare(0, 1, "/") != 0 ) bunch_.bunchProfileBasename_ = bunch_.bunchProfileDirectory_ + bunch_.bunchProfileBasename_;
+	createDirectory(bunch_.bunchProfileBasename_, 0);
+      }
+    if ( bunch_.bunchVTK_ )
+      printmessage(__FILE__, __LINE__, "Note: the bunch-visualization (.vtu) writer is outside this build's scope and is skipped.");
   }
 
   /* planes, wavelengths, window length and prefactor of the power sampling; opens the files -- radiation.cpp:18-121 */
@@ -700,6 +716,63 @@ namespace MITHRA
     for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) { timeBunch_ += bunch_.timeStep_; ++nTimeBunch_; }
   }
 
+  /* Solver::bunchSample, solver.cpp:1582-1641: the sums come from the device (one reduction per slab, added in slab
+   * order like the MPI_Reduce of :1611-1615), the line is written as the reference writes it                        */
+  void Solver::bunchSample ()
+  {
+    double T[13]; for (int q = 0; q < 13; q++) T[q] = 0.0;
+    for (MithraGpu* g : gpu_)
+      {
+	double s[13];
+	check(mithra_gpu_bunch_moments(g, s));
+	for (int q = 0; q < 13; q++) T[q] += s[q];
+      }
+    const Double qT = T[0];
+    Double rT[3], r2T[3], gbT[3], gb2T[3];
+    for (int l = 0; l < 3; l++) { rT[l] = T[1 + l] / qT; r2T[l] = T[4 + l] / qT; gbT[l] = T[7 + l] / qT; gb2T[l] = T[10 + l] / qT; }
+    std::ofstream& f = *bunchSampleFile_;
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    f << timeBunch_ << "\t";
+    f << rT[0]  << "\t" << rT[1]  << "\t" << rT[2]  << "\t";
+    f << gbT[0] << "\t" << gbT[1] << "\t" << gbT[2] << "\t";
+    f << sqrt( r2T[0]  - rT[0]  * rT[0]  ) << "\t";
+    f << sqrt( r2T[1]  - rT[1]  * rT[1]  ) << "\t";
+    f << sqrt( r2T[2]  - rT[2]  * rT[2]  ) << "\t";
+    f << sqrt( gb2T[0] - gbT[0] * gbT[0] ) << "\t";
+    f << sqrt( gb2T[1] - gbT[1] * gbT[1] ) << "\t";
+    f << sqrt( gb2T[2] - gbT[2] * gbT[2] ) << std::endl;
+  }
+
+  /* Solver::bunchProfile, solver.cpp:1763-1792: the particle list of every slab in the reference's order, one file
+   * (the reference writes one per rank; with one process there is one, "-p0-")                                       */
+  void Solver::bunchProfile ()
+  {
+    const std::string name = bunch_.bunchProfileBasename_ + "-p" + stringify(0) + "-" + stringify(nTime_) + ".txt";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f.setf(std::ios::scientific);
+    f.precision(15);
+    f.width(40);
+    f << time_ * gamma_ << std::endl;
+    std::vector<double> rows;
+    for (MithraGpu* g : gpu_)
+      {
+	size_t n = 0;
+	check(mithra_gpu_num_particles(g, &n));
+	if ( n == 0 ) continue;
+	rows.resize(n * 11);
+	check(mithra_gpu_download_particles(g, rows.data(), n, &n));
+	for (size_t i = 0; i < n; i++)
+	  {
+	    const double* q = &rows[11 * i];
+	    /* one slab: the reference's ownership test; several: the list of a slab is what it owns                     */
+	    if ( gpu_.size() == 1 && !particleInProcessor(q[3]) ) continue;
+	    f << q[0] << "\t" << q[1] << "\t" << q[2] << "\t" << q[3] << "\t" << q[7] << "\t" << q[8] << "\t" << q[9] << std::endl;
+	  }
+      }
+    f.close();
+  }
+
   void Solver::screenProfile () { if ( screenGroup_ >= 0 ) for (MithraGpu* g : gpu_) check(mithra_gpu_screen_profile(g)); }
 
   void Solver::powerSample ()
@@ -814,6 +887,7 @@ namespace MITHRA
   {
     for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
     flushOutputs();
+    if ( bunchSampleFile_ ) bunchSampleFile_->close();
     for (SampleRadiationPower& S : rp_) for (std::ofstream* f : S.file) if (f) f->close();
     for (SampleScreenProfile& S : scrp_) for (std::ofstream* f : S.files) if (f) f->close();
   }
@@ -850,6 +924,15 @@ namespace MITHRA
 	fieldUpdate();
 	bunchUpdate();
 	recycleParticles();
+	/* rhythm-gated bunch samplers, solver.cpp:1352-1371                                                           */
+	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
+	if ( bunch_.bunchProfile_ )
+	  {
+	    for (unsigned int i = 0; i < bunch_.bunchProfileTime_.size(); i++)
+	      if ( time_ - bunch_.bunchProfileTime_[i] < mesh_.timeStep_ && time_ > bunch_.bunchProfileTime_[i] ) bunchProfile();
+	    if ( fmod(time_ + mesh_.timeShift_, bunch_.bunchProfileRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) && ( bunch_.bunchProfileRhythm_ != 0.0 ) )
+	      bunchProfile();
+	  }
 	screenProfile();
 	powerSample();
 	powerVisualize();

@@ -73,9 +73,9 @@ namespace MITHRA
     void finalize ();
 
     /* rhythm-gated writers of the reference that are outside the hot path: accepted, not run */
-    void bunchSample () {}
+    void bunchSample ();
     void bunchVisualize () {}
-    void bunchProfile () {}
+    void bunchProfile ();
     void powerVisualize ();
     void energySample () {}
 
@@ -139,6 +139,7 @@ namespace MITHRA
     long                maxSteps_;
     int                 powerGroup_, screenGroup_;     /* FEL_ entries the C ABI's single power / screen group mirror */
     int                 pmapGroup_;                    /* ... and its single power-visualization group               */
+    std::ofstream*      bunchSampleFile_;              /* sb_.file, solver.cpp:1073                                  */
     std::vector<Double> powerTimes_;                   /* timeBunch_ of the sampled steps not yet written             */
     bool                spaceChargeSolver_;
   };

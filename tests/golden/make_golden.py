@@ -15,6 +15,7 @@ Every fixture <job>.npz holds, for one job:
     power                pG per step (radiation.cpp:209-218), 100 rows
     screen<i>            the reference's screen text files parsed back to doubles (solver.cpp:2229-2252)
     pmap, vts/<file>     power-visualization jobs: the per-pixel map after the last step and the .vts files as written
+    txt/<dir>/<file>     bunch-sampling / bunch-profile jobs: the reference's text files as written
 The fixtures pin oracle/mithra_oracle.c (tests/test_oracle_golden.py) and, through it, the CUDA path.
 """
 import os
@@ -31,6 +32,7 @@ sys.path.insert(0, ROOT)
 from oracle import binding  # noqa: E402
 
 JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
+EXTRA_JOBS = ("micro-bsample",)        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
 
@@ -97,6 +99,9 @@ def make(job):
                 for fn in sorted(os.listdir(dd)):
                     if fn.endswith(".vts"):
                         out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
+                    # bunch-sampling / bunch-profile text files exactly as the reference wrote them
+                    if d in ("bunch-sampling", "bunch-profile") and fn.endswith(".txt"):
+                        out["txt/%s/%s" % (d, fn)] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
         scr_dir = os.path.join(work, "screens")
         if os.path.isdir(scr_dir):
             for fn in sorted(os.listdir(scr_dir)):
@@ -114,5 +119,5 @@ def make(job):
 if __name__ == "__main__":
     if not binding.have_reference():
         sys.exit("oracle/_ref/ref_dump is missing: run `make -C oracle ref` where /root/reference exists")
-    for j in (sys.argv[1:] or JOBS):
+    for j in (sys.argv[1:] or JOBS + EXTRA_JOBS):
         make(j)

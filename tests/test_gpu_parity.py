@@ -303,3 +303,17 @@ def test_constant_divisor_division_is_ieee(d):
               1e-160, -1e-160, 1e160, 1.0, -1.0, 1e-149, 1e151]
     x[16:1000] = rng.standard_normal(984) * 1e-305
     assert abi.selftest_divide(x, d) == 0
+
+
+def test_bunch_moments_reduction():
+    """mithra_gpu_bunch_moments (Solver::bunchSample's sums, reduced on the device) against the same sums in numpy."""
+    p, g, gpu, cpu = _pair("micro-sc")
+    gpu.step(30)
+    q = gpu.download_particles()
+    w = q[:, 0]
+    want = np.concatenate(([w.sum()], (w[:, None] * q[:, 1:4]).sum(0), (q[:, 1:4] ** 2 * w[:, None]).sum(0),
+                           (w[:, None] * q[:, 7:10]).sum(0), (q[:, 7:10] ** 2 * w[:, None]).sum(0)))
+    got = gpu.bunch_moments()
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    # deterministic: the same reduction twice gives the same bits
+    np.testing.assert_array_equal(got, gpu.bunch_moments())

@@ -176,3 +176,33 @@ def test_executable_writes_the_power_visualization_files(gpus, tmp_path):
         np.testing.assert_allclose(flat_g, flat_r, rtol=2e-4, atol=1e-4 * np.abs(flat_r).max())
         if fn != "pmap-0.vts":
             assert np.abs(flat_r[-196:]).max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_writes_the_bunch_sampling_and_profile_files(gpus, tmp_path):
+    """Solver::bunchSample (moments reduced on the device) and Solver::bunchProfile through the host executable against
+    the unmodified reference's own text files for the same job: same files, same rows, numbers to the printed digits
+    (4 for the moments, 15 for the profile; positions carry the libm difference of the push, 1e-9)."""
+    meta, g = helpers.load_golden("micro-bsample")
+    subprocess.check_output([_exe(), _job("micro-bsample"), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("txt/"))
+    assert "bunch-sampling/bunch.txt" in want and len(want) >= 3
+    for rel in want:
+        ref = np.array([float(x) for x in bytes(g["txt/" + rel]).decode().split()])
+        path = tmp_path / rel
+        assert path.exists(), rel
+        got = np.array([float(x) for x in open(path).read().split()])
+        assert got.shape == ref.shape, rel
+        if rel.startswith("bunch-sampling"):
+            ref, got = ref.reshape(-1, 13), got.reshape(-1, 13)
+            np.testing.assert_allclose(got[:, 0], ref[:, 0], rtol=1e-4)
+            # means and standard deviations: 5 printed digits; the means of y, gb_x, gb_y are cancellation noise ~1e-9
+            scale = np.abs(ref).max(axis=0)
+            assert np.all(np.abs(got - ref) <= 2e-4 * np.abs(ref) + 1e-6 * scale + 1e-7)
+        else:
+            assert got[0] == pytest.approx(ref[0], rel=1e-14)
+            a, b = got[1:].reshape(-1, 7), ref[1:].reshape(-1, 7)
+            if gpus > 1:                                     # slab order: compare as sets (sort by charge-independent key)
+                a, b = a[np.lexsort((a[:, 1], a[:, 3]))], b[np.lexsort((b[:, 1], b[:, 3]))]
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-12)
