@@ -33,9 +33,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (meta fixture, sample job for the CPU baseline, sample fraction of z, description)
-    "fel-seeded": ("bench/fel-seeded.meta.npz", "jobs/fel-seeded-sample.job", 8,
-                   "FEL-SEEDED 85x85x8252 nodes, 4194304 macro-particles, 3 sub-pushes/step, NSFD, seed TF/SF, 1 power plane, 7 screens"),
+    # name: meta fixture (tools/make_bench_meta.py), sample job + z fraction for the CPU baseline, description, and the
+    # synthetic bunch (count per GPU, transverse sigma / truncation in length-scale units, momentum spread) of the job
+    "fel-seeded": dict(meta="bench/fel-seeded.meta.npz", sample="jobs/fel-seeded-sample.job", frac=8, particles=4194304,
+                       sigma_t=95.3, trunc_t=400.0, sigma_gb=0.0105,
+                       desc="FEL-SEEDED 85x85x8252 nodes, 4194304 macro-particles, 3 sub-pushes/step, NSFD, seed TF/SF, 1 power plane, 7 screens"),
+    # BASELINE.json configs[3]: the large-z X-ray FEL mesh on ONE GPU (46 GB resident); --gpus N stacks N of them
+    "fel-lcls": dict(meta="bench/fel-lcls.meta.npz", sample="jobs/fel-lcls-sample.job", frac=32, particles=8388608,
+                     sigma_t=30.0, trunc_t=180.0, sigma_gb=0.007,
+                     desc="FEL-LCLS 102x102x33335 nodes, 8388608 macro-particles, 1 sub-push/step, NSFD, 1 power plane"),
+    # BASELINE.json configs[4]: FdTdSC (A + phi) weak-scaling unit, 102 x 102 x 4096 cells and 1 Mi particles per GPU
+    "sc-weak": dict(meta="bench/sc-weak.meta.npz", sample="jobs/sc-weak-sample.job", frac=4, particles=1048576,
+                    sigma_t=30.0, trunc_t=180.0, sigma_gb=0.007,
+                    desc="fdtdSC weak-scaling unit 102x102x4098 nodes (A + phi), 1048576 macro-particles, 1 sub-push/step, NSFD, 1 power plane"),
 }
 
 BYTES_PER_CELL = {0: 96, 1: 128}      # read an, anm1, J + write anp1, 24 B each (+ 4 x 8 B with phi)
@@ -249,14 +259,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    meta_fn, sample_job, sample_frac, desc = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    meta_fn, sample_job, sample_frac, desc = wl["meta"], wl["sample"], wl["frac"], wl["desc"]
     pk, pk_kind = peaks()
     K, W = args.steps, max(args.warmup, 3)
 
     from mithra_b200 import meta as mmeta
     meta = dict(np.load(os.path.join(ROOT, meta_fn)))
     p = mmeta.params_from_meta(meta)
-    npart_total = args.particles or 4194304
+    npart_total = args.particles or wl["particles"]
     sc = int(p.space_charge)
 
     # ---------------------------------------------------------------- reference arm
@@ -317,7 +328,8 @@ def main():
     solver = abi.GpuSolver(pl)
     if world > 1:
         solver.connect_neighbours(dist, rank, world)
-    bunch = synthetic_bunch(pl, npart_local, seed_offset=1 + rank * npart_local, zlo=pl.zp[0], zhi=pl.zp[1])
+    bunch = synthetic_bunch(pl, npart_local, seed_offset=1 + rank * npart_local, zlo=pl.zp[0], zhi=pl.zp[1],
+                            sigma_t=wl["sigma_t"], trunc_t=wl["trunc_t"], sigma_gb=wl["sigma_gb"])
     a_n = synthetic_potential(pl)
     a_nm1 = a_n * 0.999
     tb = undulator_time(pl)
@@ -386,6 +398,13 @@ def main():
                 "field_update": {"what": "whole fieldUpdate (seed table, stencil_stream, rim_update, z shell / faces, edges, corners) over all nodes",
                                  "ms": field_ms, "achieved": BYTES_PER_CELL[sc] * nodes_local / (field_ms * 1e-3) / 1e9, "unit": "GB/s",
                                  "frac": BYTES_PER_CELL[sc] * nodes_local / (field_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                # the whole field step against the roofline: every algorithmic byte of SURVEY 8(d) (cell-updates, pushes,
+                # deposit reads) over the device time of one step -- the figure north_star's ">= 60 % of HBM roofline" is about
+                "time_march": {"what": "96/128 B x nodes + 112 B x pushes + 56 B x particles, per field step, over ms_per_step",
+                               "achieved": (BYTES_PER_CELL[sc] * nodes_local + BYTES_PER_PUSH * npart_local * pl.n_update_bunch + 56 * npart_local)
+                                           / (ms / K * 1e-3) / 1e9, "unit": "GB/s",
+                               "frac": (BYTES_PER_CELL[sc] * nodes_local + BYTES_PER_PUSH * npart_local * pl.n_update_bunch + 56 * npart_local)
+                                       / (ms / K * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "push": {"achieved": BYTES_PER_PUSH * npart_local * pl.n_update_bunch / (push_ms * 1e-3) / 1e9 if push_ms > 0 else None,
                          "unit": "GB/s", "bytes_per_push": BYTES_PER_PUSH}}
 
@@ -452,7 +471,7 @@ def main():
             "data": "synthetic",
             "pushes": {"value": pushes / sec, "unit": "particle-pushes/s"},
             "config": {"workload": desc, "parallelism": "z-slabs x%d" % world, "l2": "inputs larger than L2 (%.1f GB of potentials per GPU)" % (
-                4 * 24 * nodes_local / 1e9), "nodes_per_gpu": nodes_local, "particles_per_gpu": npart_local},
+                4 * (32 if sc else 24) * nodes_local / 1e9), "nodes_per_gpu": nodes_local, "particles_per_gpu": npart_local},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
         print(json.dumps(line))

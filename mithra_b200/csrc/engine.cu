@@ -57,7 +57,8 @@ struct MithraGpu
    * low-priority stream when the loop is driven by mithra_gpu_step: the clear of the deposit box (needed by the
    * deposit) and the seed line table of the next time level (needed by the next field update)                */
   cudaStream_t    side;
-  cudaEvent_t     ev_main, ev_clear, ev_seed;
+  cudaEvent_t     ev_main, ev_clear, ev_seed, ev_x;
+  Box*            d_nobox;                /* an always-empty box: a stencil launch that reads no source        */
   bool            overlap;                /* MITHRA_NO_OVERLAP unset                                       */
   bool            clear_ahead;            /* the box has been cleared (or is being cleared) on `side`      */
   bool            seed_ahead;             /* seed table + lines for seed_ahead_time are (being) computed   */
@@ -331,7 +332,7 @@ static int preload_kernels ()
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8>)); PL((stencil_stream<false, 512, 8>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
-  PL(eval_eb_box<true>); PL(eval_eb_box<false>);
+  PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL((eval_eb_march<true, 32>)); PL((eval_eb_march<false, 32>));
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
@@ -375,6 +376,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_seed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming));
     h->overlap = !getenv("MITHRA_NO_OVERLAP");
     h->clear_ahead = false; h->seed_ahead = false; h->seed_ahead_time = 0.0;
   }
@@ -405,6 +407,8 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_ebox, 0, 0, 0, -1, -1, -1);
+  CU(cudaMalloc(&h->d_nobox, sizeof(Box)));
+  set_box<<<1, 1, 0, h->stream>>>(h->d_nobox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
 
   const size_t nodes = (size_t) f.np * f.P;
@@ -421,8 +425,8 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       Q.q = s; for (int a = 0; a < 3; a++) { Q.r[a] = s + (1 + a) * c; Q.rm[a] = s + (4 + a) * c; Q.gb[a] = s + (7 + a) * c; } Q.e = s + 10 * c;
       Q.id = h->idstore[w];
     }
-  /* counting sort: one bin per cell of the particle box, as many as the slab has cells (at most 2^27)      */
-  h->sort_cap = std::min<long>((long) f.np * f.P, 1L << 27);
+  /* counting sort: one bin per cell of the particle box, as many as the slab has cells (at most 2^30)      */
+  h->sort_cap = std::min<long>((long) f.np * f.P, 1L << 30);
   h->sort_interval = params->sort_interval;
   if (const char* e = getenv("MITHRA_SORT_INTERVAL")) h->sort_interval = atoi(e);      /* experiments: overrides the parameter block */
   h->steps_since_sort = 0;
@@ -547,6 +551,8 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_clear) cudaEventDestroy(h->ev_clear);
   if (h->ev_seed) cudaEventDestroy(h->ev_seed);
+  if (h->ev_x) cudaEventDestroy(h->ev_x);
+  cudaFree(h->d_nobox);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -816,8 +822,10 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 
 /* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
 template <bool NSFD>
-static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
+static bool launch_stencil_stream (MithraGpu* h, bool skiprim, cudaStream_t st = 0, double* out = 0, const double* lvl_n = 0,
+				   const double* lvl_nm1 = 0, const Box* srcbox = 0)
 {
+  if (!st) { st = h->stream; out = h->A[h->ip1]; lvl_n = h->A[h->in]; lvl_nm1 = h->A[h->im1]; srcbox = h->d_jbox; }
   const FieldDev& f = h->fd;
   constexpr int T = 512, NB = 8;
   static const int KC = getenv("MITHRA_STENCIL_KC") ? atoi(getenv("MITHRA_STENCIL_KC")) : 64;
@@ -831,7 +839,7 @@ static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
       h->stream_configured[NSFD] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0);
+  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, st>>>(f, out, lvl_n, lvl_nm1, h->J, srcbox, KC, skiprim ? 1 : 0);
   return true;
 }
 
@@ -950,8 +958,25 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
     const double cdt = h->prm.c0 * h->prm.dt;
     const int padx = (int) ceil(cdt / h->prm.dx), pady = (int) ceil(cdt / h->prm.dy), padz = (int) ceil(cdt / h->prm.dz);
     make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
-    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
-    else              eval_eb_box<false><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+    if (getenv("MITHRA_EB_BOX"))
+      {
+	/* the node-at-a-time kernel over the whole box (the parity tests compare the two bit for bit)                  */
+	if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, 0);
+	else              eval_eb_box<false><<<h->num_sms * 4, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, 0);
+      }
+    else
+      {
+	constexpr int KC = 32;
+	if (f.ncomp == 4) eval_eb_march<true,  KC><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+	else              eval_eb_march<false, KC><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+	if (zlo || zhi)
+	  {
+	    /* planes 0 / np-1 of the global ends copy planes 1 / np-2 (fdtd.cpp:754-773)                               */
+	    if (f.ncomp == 4) eval_eb_box<true ><<<16, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, 1);
+	    else              eval_eb_box<false><<<16, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, 1);
+	    h->cnt.kernel_launches += 1;
+	  }
+      }
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 2;
     if (f.size > 1)
@@ -959,14 +984,14 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
 	/* whole planes the neighbours gather from and sample power on: kb -> prev; np-3, np-2 -> next           */
 	if (h->xch.prev.chain)
 	  {
-	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo);
-	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo);
+	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo, 0);
+	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_lo, 0);
 	    h->cnt.kernel_launches += 1;
 	  }
 	if (h->xch.next.chain)
 	  {
-	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi);
-	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi);
+	    if (f.ncomp == 4) eval_eb_box<true ><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi, 0);
+	    else              eval_eb_box<false><<<h->num_sms, 256, 0, h->stream>>>(f, ap, a, h->eb, h->xch.d_planes_hi, 0);
 	    h->cnt.kernel_launches += 1;
 	  }
 	CU(cudaGetLastError());
@@ -1223,6 +1248,15 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
     {
       TRY(mithra_gpu_field_update(h));
       TRY(housekeeping_ahead(h));
+      static const bool xov = getenv("MITHRA_X_OVERLAP") != 0;
+      if (xov && !h->profiling)
+	{
+	  /* experiment: what does a source-free stencil of the NEXT step cost when it runs beside the particle kernels?
+	   * (the level it writes is dead until the next field update rewrites every node of it)                           */
+	  if (h->fd.nsfd) launch_stencil_stream<true >(h, true, h->side, h->A[h->im1], h->A[h->ip1], h->A[h->in], h->d_nobox);
+	  else            launch_stencil_stream<false>(h, true, h->side, h->A[h->im1], h->A[h->ip1], h->A[h->in], h->d_nobox);
+	  CU(cudaEventRecord(h->ev_x, h->side));
+	}
       TRY(mithra_gpu_bunch_update(h));
       TRY(mithra_gpu_screen_profile(h));
       TRY(mithra_gpu_power_sample(h));
@@ -1234,6 +1268,7 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_migrate_begin(h));
       TRY(mithra_gpu_migrate_end(h));
       TRY(mithra_gpu_advance_time(h));
+      if (xov && !h->profiling) CU(cudaStreamWaitEvent(h->stream, h->ev_x, 0));
     }
   /* whatever was started ahead on the side stream belongs to this call: later work on the main stream (and the
    * caller's timing events) come after it                                                                        */

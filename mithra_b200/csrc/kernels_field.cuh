@@ -605,30 +605,17 @@ namespace mithra
    * ------------------------------------------------------------------------------------------------ */
   struct EB { float e[3]; float b[3]; };
 
+  /* the arithmetic of one node from the values already loaded: the node's own A+ (p*) and A (q*), the centred
+   * differences of phi (g*) and of the components of A (a**) and A+ (p**); every operation in the reference's order  */
   template <bool SC>
-  __device__ __forceinline__ EB eval_eb_node (const FieldDev& f, const double* __restrict__ anp1,
-					      const double* __restrict__ an, int i, int j, int k)
+  __device__ __forceinline__ EB eb_assemble (const FieldDev& f, double p0, double p1, double p2, double q0, double q1, double q2,
+					     double g0, double g1, double g2,
+					     double azy, double ayz, double pzy, double pyz,
+					     double axz, double azx, double pxz, double pzx,
+					     double ayx, double axy, double pyx, double pxy)
   {
-    const long N1 = f.N1, Pp = f.Pp;
-    const long cs = (long) f.np * Pp;                    /* component stride                              */
-    const long m  = (long) k * Pp + (long) i * N1 + j;
     const double mdt = - f.dt;
     EB o;
-    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs;
-    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
-    /* all the loads first, in straight-line code: the divisions below contain (rare) branches the compiler will
-     * not move loads across, and the kernel lives on having every load of a node in flight at once              */
-    const double p0 = px[m], p1 = py[m], p2 = pz[m], q0 = ax[m], q1 = ay[m], q2 = az[m];
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    if (SC)
-      {
-	const double* fn = an + 3 * cs;
-	g0 = fn[m + N1] - fn[m - N1]; g1 = fn[m + 1] - fn[m - 1]; g2 = fn[m + Pp] - fn[m - Pp];
-      }
-    const double azy = az[m + 1 ] - az[m - 1 ], ayz = ay[m + Pp] - ay[m - Pp], pzy = pz[m + 1 ] - pz[m - 1 ], pyz = py[m + Pp] - py[m - Pp];
-    const double axz = ax[m + Pp] - ax[m - Pp], azx = az[m + N1] - az[m - N1], pxz = px[m + Pp] - px[m - Pp], pzx = pz[m + N1] - pz[m - N1];
-    const double ayx = ay[m + N1] - ay[m - N1], axy = ax[m + 1 ] - ax[m - 1 ], pyx = py[m + N1] - py[m - N1], pxy = px[m + 1 ] - px[m - 1 ];
-
     {
       float e;
       e = (float) div_by( p0, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q0, mdt, f.rmdt ) ); o.e[0] = e;
@@ -647,24 +634,50 @@ namespace mithra
     return o;
   }
 
+  template <bool SC>
+  __device__ __forceinline__ EB eval_eb_node (const FieldDev& f, const double* __restrict__ anp1,
+					      const double* __restrict__ an, int i, int j, int k)
+  {
+    const long N1 = f.N1, Pp = f.Pp;
+    const long cs = (long) f.np * Pp;                    /* component stride                              */
+    const long m  = (long) k * Pp + (long) i * N1 + j;
+    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs;
+    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
+    /* all the loads first, in straight-line code: the divisions below contain (rare) branches the compiler will
+     * not move loads across, and the kernel lives on having every load of a node in flight at once              */
+    const double p0 = px[m], p1 = py[m], p2 = pz[m], q0 = ax[m], q1 = ay[m], q2 = az[m];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (SC)
+      {
+	const double* fn = an + 3 * cs;
+	g0 = fn[m + N1] - fn[m - N1]; g1 = fn[m + 1] - fn[m - 1]; g2 = fn[m + Pp] - fn[m - Pp];
+      }
+    const double azy = az[m + 1 ] - az[m - 1 ], ayz = ay[m + Pp] - ay[m - Pp], pzy = pz[m + 1 ] - pz[m - 1 ], pyz = py[m + Pp] - py[m - Pp];
+    const double axz = ax[m + Pp] - ax[m - Pp], azx = az[m + N1] - az[m - N1], pxz = px[m + Pp] - px[m - Pp], pzx = pz[m + N1] - pz[m - N1];
+    const double ayx = ay[m + N1] - ay[m - N1], axy = ax[m + 1 ] - ax[m - 1 ], pyx = py[m + N1] - py[m - N1], pxy = px[m + 1 ] - px[m - 1 ];
+    return eb_assemble<SC>(f, p0, p1, p2, q0, q1, q2, g0, g1, g2, azy, ayz, pzy, pyz, axz, azx, pxz, pzx, ayx, axy, pyx, pxy);
+  }
+
   /* Evaluate E/B on every node of `box` (node indices, already clamped to 1..N-2 transversally).  On the
    * global z ends plane 0 / np-1 take the values of plane 1 / np-2 (fdtd.cpp:754-773).                 */
   template <bool SC>
   __global__ void __launch_bounds__(256)
   eval_eb_box (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
-	       float4* __restrict__ eb, const Box* __restrict__ boxp)
+	       float4* __restrict__ eb, const Box* __restrict__ boxp, int ends_only)
   {
     const Box b = *boxp;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
     if (ni <= 0 || nj <= 0 || nk <= 0) return;
     /* one warp per row of the box (lanes along j: neighbouring lanes share their y neighbours in L1 and the two
      * float4 stores of a warp are contiguous); 32-bit index arithmetic, once per row                            */
-    const int rows = ni * nk;
+    /* ends_only: eval_eb_march has done the planes in between, what is left are the planes 0 and np-1 of the box  */
+    const int rows = ends_only ? ni * 2 : ni * nk;
     const int lane = threadIdx.x & 31;
     const int wstride = (int) (((long) gridDim.x * blockDim.x) >> 5);
     for (int w = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < rows; w += wstride)
       {
-	const int k = b.lo[2] + w / ni, i = b.lo[0] + w % ni;
+	const int k = ends_only ? ( (w / ni) ? f.np - 1 : 0 ) : b.lo[2] + w / ni, i = b.lo[0] + w % ni;
+	if (ends_only && (k < b.lo[2] || k > b.hi[2] || (k >= f.kb && k != f.np - 1))) continue;
 	int ke = k;
 	if (k < f.kb)      { if (f.rank != 0)          continue; ke = 1; }          /* ghosts come from the neighbour */
 	if (k == f.np - 1) { if (f.rank != f.size - 1) continue; ke = f.np - 2; }
@@ -674,6 +687,71 @@ namespace mithra
 	    const long m = (long) k * f.P + (long) i * f.N1 + j;
 	    eb[2 * m]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
 	    eb[2 * m + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+	  }
+      }
+  }
+  /* ------------------------------------------------------------------------------------------------
+   * E/B over the box, z-marching (the production path for the particle box; eval_eb_box above stays for the thin
+   * plane boxes of the slab exchange and for the two copied end planes).
+   *
+   * eval_eb_box fetches the 24 (30) potentials of a node afresh for every node, eight (ten) of them from the planes
+   * k-1 and k+1 that other CTAs own: fine for a bunch that fills a few dozen columns, but at FEL-LCLS scale the padded
+   * particle box is 2/3 of a 347 M-node mesh and the evaluation costs more than the stencil.  Here a thread owns one
+   * column (i, j) of the box and marches KC planes in +z: A_x, A_y (and phi) of the planes k-1, k, k+1 rotate through
+   * registers, so every potential is loaded from memory once per thread and its in-plane neighbours are the centre
+   * loads of the neighbouring threads of the same 32 x 8 tile (L1).  The arithmetic is eb_assemble, the same as
+   * eval_eb_node: bit-identical E/B (GPU test: march == box).
+   * Work items (z chunk, i tile, j tile) are strided over a grid of fixed size because the box lives on the device.
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool SC, int KC>
+  __global__ void __launch_bounds__(256)
+  eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
+		 float4* __restrict__ eb, const Box* __restrict__ boxp)
+  {
+    const Box b = *boxp;
+    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
+    const int kfirst = max(b.lo[2], f.kb), klast = min(b.hi[2], f.np - 2);
+    if (ni <= 0 || nj <= 0 || klast < kfirst) return;
+    const int njt = (nj + 31) >> 5, nit = (ni + 7) >> 3, nkc = (klast - kfirst + KC) / KC;
+    const long nwork = (long) njt * nit * nkc;
+    const int  tj = threadIdx.x & 31, ti = threadIdx.x >> 5;
+    const long N1 = f.N1, Pp = f.Pp, cs = (long) f.np * Pp;
+    const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs, * fn = an + 3 * cs;
+    const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
+
+    for (long w = blockIdx.x; w < nwork; w += gridDim.x)
+      {
+	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), kc = (int) (w / ((long) njt * nit));
+	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
+	if (j > b.hi[1] || i > b.hi[0]) continue;
+	const int ks = kfirst + kc * KC, ke = min(ks + KC, klast + 1);
+	long m = (long) ks * Pp + (long) i * N1 + j;              /* the node in the planar potentials            */
+	long e = (long) ks * f.P + (long) i * N1 + j;             /* ... and in the E/B array                      */
+
+	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z                                            */
+	double axm = ax[m - Pp], ax0 = ax[m], aym = ay[m - Pp], ay0 = ay[m];
+	double pxm = px[m - Pp], px0 = px[m], pym = py[m - Pp], py0 = py[m];
+	double fm = 0.0, f0 = 0.0;
+	if (SC) { fm = fn[m - Pp]; f0 = fn[m]; }
+
+	for (int k = ks; k < ke; k++, m += Pp, e += f.P)
+	  {
+	    const double axp = ax[m + Pp], ayp = ay[m + Pp], pxp = px[m + Pp], pyp = py[m + Pp];
+	    const double q2 = az[m], p2 = pz[m];
+	    double fp = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+	    if (SC) { fp = fn[m + Pp]; g0 = fn[m + N1] - fn[m - N1]; g1 = fn[m + 1] - fn[m - 1]; g2 = fp - fm; }
+	    const double azy = az[m + 1 ] - az[m - 1 ], pzy = pz[m + 1 ] - pz[m - 1 ];
+	    const double azx = az[m + N1] - az[m - N1], pzx = pz[m + N1] - pz[m - N1];
+	    const double ayx = ay[m + N1] - ay[m - N1], pyx = py[m + N1] - py[m - N1];
+	    const double axy = ax[m + 1 ] - ax[m - 1 ], pxy = px[m + 1 ] - px[m - 1 ];
+	    const EB o = eb_assemble<SC>(f, px0, py0, p2, ax0, ay0, q2, g0, g1, g2,
+					 azy, ayp - aym, pzy, pyp - pym,
+					 axp - axm, azx, pxp - pxm, pzx,
+					 ayx, axy, pyx, pxy);
+	    eb[2 * e]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
+	    eb[2 * e + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+	    axm = ax0; ax0 = axp; aym = ay0; ay0 = ayp; pxm = px0; px0 = pxp; pym = py0; py0 = pyp;
+	    if (SC) { fm = f0; f0 = fp; }
 	  }
       }
   }

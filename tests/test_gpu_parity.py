@@ -291,6 +291,46 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
             np.testing.assert_array_equal(out["fused"][k], out[mode][k], err_msg="%s %s" % (mode, k))
 
 
+@pytest.mark.parametrize("job,shape", [("micro-nsfd", (14, 14, 242)), ("micro-sc", (29, 53, 66)), ("micro-seeded", (85, 85, 70)),
+                                       ("micro-fd", (41, 100, 37)), ("micro-sc", (9, 9, 12))])
+def test_eb_march_equals_node_kernel(job, shape, monkeypatch):
+    """E/B over the particle box: the production z-marching kernel (eval_eb_march + the two copied end planes) against
+    the node-at-a-time kernel (MITHRA_EB_BOX), bit-identical floats on every node -- boxes wider than one 32 x 8 tile,
+    boxes that reach the first and the last plane, and a box that is the whole (tiny) mesh."""
+    p, g = _resized(job, *shape)
+    rng = np.random.default_rng(23)
+    n = p.N0 * p.N1 * p.np
+    an, anm1 = rng.standard_normal(n * 3), rng.standard_normal(n * 3)
+    sc = dict(fn=rng.standard_normal(n), fnm1=rng.standard_normal(n)) if p.space_charge else {}
+    nb = 256
+    bunch = np.zeros((nb, 11))
+    bunch[:, 0] = 1.0
+    bunch[:, 1] = rng.uniform(0.8 * p.xmin, 0.8 * p.xmax, nb)
+    bunch[:, 2] = rng.uniform(0.8 * p.ymin, 0.8 * p.ymax, nb)
+    bunch[:, 3] = rng.uniform(p.zmin + 1e-3 * p.dz, p.zmax - 1e-3 * p.dz, nb)      # first and last cell in z included
+    bunch[:, 4:7] = bunch[:, 1:4]
+    bunch[:, 10] = 1.0
+    out = {}
+    for mode in ("march", "MITHRA_EB_BOX"):
+        if mode != "march":
+            monkeypatch.setenv(mode, "1")
+        s = abi.GpuSolver(p)
+        s.set_time(0.37, 0.37, 5)
+        s.upload_fields(an=an, anm1=anm1, **sc)
+        s.upload_particles(bunch)
+        s.fieldUpdate()
+        out[mode] = s.download_eb()
+        s.close()
+        if mode != "march":
+            monkeypatch.delenv(mode)
+    e0, b0, m0 = out["march"]
+    e1, b1, m1 = out["MITHRA_EB_BOX"]
+    assert np.abs(e0).max() > 0 and np.abs(b0).max() > 0 and m0.sum() > 0
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_array_equal(e0.view(np.uint32), e1.view(np.uint32))
+    np.testing.assert_array_equal(b0.view(np.uint32), b1.view(np.uint32))
+
+
 @pytest.mark.parametrize("d", [60.0, 9.19059968, -0.01532827, 30.0, 4.59529984, -4.49297199e+08, 3.0, 1.9999999999999998,
                                1.0000000000000002, 1e-3, 6.02e23, 1.7e-19, 1e-200])
 def test_constant_divisor_division_is_ieee(d):
