@@ -57,8 +57,7 @@ struct MithraGpu
    * low-priority stream when the loop is driven by mithra_gpu_step: the clear of the deposit box (needed by the
    * deposit) and the seed line table of the next time level (needed by the next field update)                */
   cudaStream_t    side;
-  cudaEvent_t     ev_main, ev_clear, ev_seed, ev_x;
-  Box*            d_nobox;                /* an always-empty box: a stencil launch that reads no source        */
+  cudaEvent_t     ev_main, ev_clear, ev_seed;
   bool            overlap;                /* MITHRA_NO_OVERLAP unset                                       */
   bool            clear_ahead;            /* the box has been cleared (or is being cleared) on `side`      */
   bool            seed_ahead;             /* seed table + lines for seed_ahead_time are (being) computed   */
@@ -82,6 +81,10 @@ struct MithraGpu
   Box*            d_pbox;                 /* particle cell box (filled by push / particle_box)            */
   Box*            d_ebox;                 /* node box evaluated by eval_eb_box                            */
   Box             h_ebox_last;
+  bool            fuse_screens;           /* set by mithra_gpu_step around its push                         */
+  unsigned char*  d_emask_cells;          /* E/B pencil mask: cells that hold a particle (marked by push / particle_box) */
+  unsigned char*  d_emask_nodes;          /* ... spread to the nodes those particles can gather from (spread_eb_mask)      */
+  size_t          emask_bytes;
 
   /* particles */
   ParticlesDev    P, Palt;                /* the bunch and the copy the counting sort moves it into        */
@@ -332,7 +335,7 @@ static int preload_kernels ()
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8>)); PL((stencil_stream<false, 512, 8>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
-  PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL((eval_eb_march<true, 32>)); PL((eval_eb_march<false, 32>));
+  PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
@@ -376,7 +379,6 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_seed, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming));
     h->overlap = !getenv("MITHRA_NO_OVERLAP");
     h->clear_ahead = false; h->seed_ahead = false; h->seed_ahead_time = 0.0;
   }
@@ -407,10 +409,16 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_ebox, 0, 0, 0, -1, -1, -1);
-  CU(cudaMalloc(&h->d_nobox, sizeof(Box)));
-  set_box<<<1, 1, 0, h->stream>>>(h->d_nobox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+  h->fuse_screens = false;
   h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
 
+  h->d_emask_cells = 0; h->d_emask_nodes = 0;
+  h->emask_bytes = (size_t) ((f.np + (1 << MITHRA_EB_CHUNK_LOG2) - 1) >> MITHRA_EB_CHUNK_LOG2) * f.P;
+  if (!getenv("MITHRA_NO_EBMASK"))
+    {
+      CU(cudaMalloc(&h->d_emask_cells, h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
+      CU(cudaMalloc(&h->d_emask_nodes, h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_nodes, 0, h->emask_bytes, h->stream));
+    }
   const size_t nodes = (size_t) f.np * f.P;
   CU(cudaMalloc(&h->eb, nodes * 2 * sizeof(float4))); CU(cudaMemsetAsync(h->eb, 0, nodes * 2 * sizeof(float4), h->stream));
 
@@ -540,7 +548,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   for (int l = 0; l < 4; l++) cudaFree(h->Abase[l]);
   cudaFree(h->d_stage);
   cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
-  cudaFree(h->eb); cudaFree(h->d_noutside);
+  cudaFree(h->eb); cudaFree(h->d_noutside); cudaFree(h->d_emask_cells); cudaFree(h->d_emask_nodes);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
   cudaFree(h->d_pm_fdt); cudaFree(h->d_pm_ep); cudaFree(h->d_pm_pL);
@@ -551,8 +559,6 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_clear) cudaEventDestroy(h->ev_clear);
   if (h->ev_seed) cudaEventDestroy(h->ev_seed);
-  if (h->ev_x) cudaEventDestroy(h->ev_x);
-  cudaFree(h->d_nobox);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -653,12 +659,18 @@ extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsig
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(tmp.data(), h->eb, nodes_int * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
   Box b; CU(cudaMemcpy(&b, h->d_ebox, sizeof(Box), cudaMemcpyDeviceToHost));
+  std::vector<unsigned char> pencil;
+  const double cdt = h->prm.c0 * h->prm.dt;
+  if (h->d_emask_nodes && !getenv("MITHRA_EB_BOX") && (int) ceil(cdt / h->prm.dz) < 16)
+    { pencil.resize(h->emask_bytes); CU(cudaMemcpy(pencil.data(), h->d_emask_nodes, h->emask_bytes, cudaMemcpyDeviceToHost)); }
   for (size_t m = 0; m < nodes; m++)
     {
       const int kr = (int) (m / f.P), r = (int) (m % f.P), i = r / f.N1, j = r % f.N1;
       const int k = kr + f.kshift;
       const size_t mi = (size_t) k * f.P + r;
       bool in = ( i >= b.lo[0] && i <= b.hi[0] && j >= b.lo[1] && j <= b.hi[1] && k >= b.lo[2] && k <= b.hi[2] );
+      /* inside the box only the marked pencils are evaluated (the two copied end planes: the whole box)            */
+      if (in && !pencil.empty() && k >= f.kb && k <= f.np - 2) in = pencil[(size_t) (k >> MITHRA_EB_CHUNK_LOG2) * f.P + r] != 0;
       /* ghost planes hold what the neighbour evaluated on the whole plane                                     */
       if (f.size > 1 && ((k < f.kb && f.rank != 0) || (k == f.np - 1 && f.rank != f.size - 1)))
 	in = h->xch.connected && i >= 1 && i <= f.N0 - 2 && j >= 1 && j <= f.N1 - 2;
@@ -683,8 +695,9 @@ extern "C" int mithra_gpu_seed_initial (MithraGpu* h)
 static int refresh_particle_box (MithraGpu* h)
 {
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+  if (h->d_emask_cells) CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
   if (h->pn > 0)
-    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->bd, h->P, 0L, (long) h->pn, h->d_pbox);
+    particle_box<<<grid_for((long) h->pn, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->bd, h->P, 0L, (long) h->pn, h->d_pbox, h->d_emask_cells);
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 2;
   return 0;
@@ -822,10 +835,8 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 
 /* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
 template <bool NSFD>
-static bool launch_stencil_stream (MithraGpu* h, bool skiprim, cudaStream_t st = 0, double* out = 0, const double* lvl_n = 0,
-				   const double* lvl_nm1 = 0, const Box* srcbox = 0)
+static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
 {
-  if (!st) { st = h->stream; out = h->A[h->ip1]; lvl_n = h->A[h->in]; lvl_nm1 = h->A[h->im1]; srcbox = h->d_jbox; }
   const FieldDev& f = h->fd;
   constexpr int T = 512, NB = 8;
   static const int KC = getenv("MITHRA_STENCIL_KC") ? atoi(getenv("MITHRA_STENCIL_KC")) : 64;
@@ -839,7 +850,7 @@ static bool launch_stencil_stream (MithraGpu* h, bool skiprim, cudaStream_t st =
       h->stream_configured[NSFD] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, st>>>(f, out, lvl_n, lvl_nm1, h->J, srcbox, KC, skiprim ? 1 : 0);
+  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0);
   return true;
 }
 
@@ -966,9 +977,16 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
       }
     else
       {
-	constexpr int KC = 32;
-	if (f.ncomp == 4) eval_eb_march<true,  KC><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
-	else              eval_eb_march<false, KC><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox);
+	/* only the pencils a particle can gather from (make_eb_box's padding, per pencil instead of per box); the
+	 * mask needs less than one 32-plane chunk of motion per step in z                                          */
+	const unsigned char* mask = (h->d_emask_nodes && padz < 16) ? h->d_emask_nodes : 0;
+	if (mask)
+	  {
+	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, h->d_emask_nodes, h->d_ebox, padx, pady);
+	    h->cnt.kernel_launches += 1;
+	  }
+	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
+	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
 	if (zlo || zhi)
 	  {
 	    /* planes 0 / np-1 of the global ends copy planes 1 / np-2 (fdtd.cpp:754-773)                               */
@@ -1024,6 +1042,14 @@ extern "C" int mithra_gpu_sort_particles (MithraGpu* h)
   return 0;
 }
 
+static ScreensDev screens_dev (MithraGpu* h, double time_bunch)
+{
+  ScreensDev S;
+  S.n = h->prm.screens.N; S.pos = h->d_scr_pos; S.rec = h->d_scr_rec; S.cursor = h->d_scr_cur; S.capacity = h->scr_cap;
+  S.step_id = (double) h->n_time; S.time_bunch = time_bunch;
+  return S;
+}
+
 extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
 {
   USE(h);
@@ -1040,11 +1066,20 @@ extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
     {
       /* the particle box is rebuilt by the push (it is read by the next field update)                      */
       set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
+      if (h->d_emask_cells) CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
       const int grid = (int) ((h->pn + 127) / 128);
       bool beams = h->bd.n_ext > 0;
       for (int u = 0; u < h->bd.n_und; u++) if (h->bd.und[u].type != MITHRA_UNDULATOR_STATIC) beams = true;
-      if (beams) push_particles<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
-      else       push_particles<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside);
+      /* mithra_gpu_step lets the push test the screens on its way out (h->fuse_screens); the time is the one
+       * mithra_gpu_screen_profile would see: the sub-steps added one by one                                       */
+      ScreensDev scr; memset(&scr, 0, sizeof(scr));
+      if (h->fuse_screens && h->d_scr_pos)
+	{
+	  double ta = h->time_bunch; for (int s = 0; s < nsub; s++) ta += h->prm.dt_bunch;
+	  scr = screens_dev(h, ta);
+	}
+      if (beams) push_particles<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside, h->d_emask_cells, scr);
+      else       push_particles<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside, h->d_emask_cells, scr);
       h->cnt.kernel_launches += 2;
       CU(cudaGetLastError());
     }
@@ -1058,8 +1093,7 @@ extern "C" int mithra_gpu_screen_profile (MithraGpu* h)
   USE(h);
   if (!h->d_scr_pos || h->pn == 0) return 0;
   PhaseTimer t(h, PH_SCREEN);
-  screen_cross<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->time_bunch, h->prm.screens.N,
-								     h->d_scr_pos, h->d_scr_rec, h->d_scr_cur, h->scr_cap, (double) h->n_time);
+  screen_cross<<<(int) ((h->pn + 255) / 256), 256, 0, h->stream>>>(h->bd, h->P, (long) h->pn, screens_dev(h, h->time_bunch));
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -1226,7 +1260,7 @@ extern "C" int mithra_gpu_migrate_end (MithraGpu* h)
   if (h->xch.h_counts[2] || h->pn != kept) h->ids_dense = false;
   if (h->pn > kept)
     {
-      particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->bd, h->P, (long) kept, (long) h->pn, h->d_pbox);
+      particle_box<<<grid_for((long) (h->pn - kept), 256, h->num_sms), 256, 0, h->stream>>>(h->bd, h->P, (long) kept, (long) h->pn, h->d_pbox, h->d_emask_cells);
       CU(cudaGetLastError());
       h->cnt.kernel_launches += 1;
     }
@@ -1248,17 +1282,13 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
     {
       TRY(mithra_gpu_field_update(h));
       TRY(housekeeping_ahead(h));
-      static const bool xov = getenv("MITHRA_X_OVERLAP") != 0;
-      if (xov && !h->profiling)
-	{
-	  /* experiment: what does a source-free stencil of the NEXT step cost when it runs beside the particle kernels?
-	   * (the level it writes is dead until the next field update rewrites every node of it)                           */
-	  if (h->fd.nsfd) launch_stencil_stream<true >(h, true, h->side, h->A[h->im1], h->A[h->ip1], h->A[h->in], h->d_nobox);
-	  else            launch_stencil_stream<false>(h, true, h->side, h->A[h->im1], h->A[h->ip1], h->A[h->in], h->d_nobox);
-	  CU(cudaEventRecord(h->ev_x, h->side));
-	}
-      TRY(mithra_gpu_bunch_update(h));
-      TRY(mithra_gpu_screen_profile(h));
+      /* the screens ride on the push (one pass over the bunch less); phase profiling keeps the two kernels apart     */
+      h->fuse_screens = !h->profiling && !getenv("MITHRA_NO_FUSE");
+      const int rb = mithra_gpu_bunch_update(h);
+      const bool fused = h->fuse_screens;
+      h->fuse_screens = false;
+      if (rb) return rb;
+      if (!fused) TRY(mithra_gpu_screen_profile(h));
       TRY(mithra_gpu_power_sample(h));
       TRY(mithra_gpu_power_visualize(h));
       TRY(mithra_gpu_field_shift(h));
@@ -1268,7 +1298,6 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_migrate_begin(h));
       TRY(mithra_gpu_migrate_end(h));
       TRY(mithra_gpu_advance_time(h));
-      if (xov && !h->profiling) CU(cudaStreamWaitEvent(h->stream, h->ev_x, 0));
     }
   /* whatever was started ahead on the side stream belongs to this call: later work on the main stream (and the
    * caller's timing events) come after it                                                                        */

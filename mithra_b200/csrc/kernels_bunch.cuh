@@ -48,8 +48,15 @@ namespace mithra
    * Bounding box (cell indices) of the particles that will gather mesh fields, used to size the E/B
    * evaluation of the next step.  The host pads it by the distance a particle can travel in one field step.
    * ------------------------------------------------------------------------------------------------ */
+  /* the pencil (cell column x 32 planes) of a particle in the mask spread_eb_mask reads (kernels_field.cuh)       */
+  __device__ __forceinline__ void mark_eb_pencil (const BunchDev& b, unsigned char* __restrict__ emask, int i, int j, int k)
+  {
+    if (emask && k >= 0 && k < b.np) emask[((long) (k >> 5) * b.N0 + i) * b.N1 + j] = 1;
+  }
+
   __global__ void __launch_bounds__(256)
-  particle_box (const __grid_constant__ BunchDev b, ParticlesDev P, long start, long n, Box* __restrict__ box)
+  particle_box (const __grid_constant__ BunchDev b, ParticlesDev P, long start, long n, Box* __restrict__ box,
+		unsigned char* __restrict__ emask)
   {
     for (long base = start + (long) blockIdx.x * blockDim.x; base < n; base += (long) gridDim.x * blockDim.x)
       {
@@ -64,6 +71,7 @@ namespace mithra
 		j = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
 		k = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
 		valid = true;
+		mark_eb_pencil(b, emask, i, j, k);
 	      }
 	  }
 	warp_box_merge(box, valid, i, i, j, j, k, k);
@@ -110,14 +118,73 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
+   * Screens (solver.cpp:2205-2257).  One thread per particle, loop over screens; a crossing appends a record
+   * { x, y, t, gbx, gby, gbz_lab, upload index of the particle, step } to the screen's buffer through an atomic cursor.
+   * screen_records is the test for one particle with its positions at the start (m) and at the end (p) of the field
+   * step, called by the stand-alone kernel screen_cross and from the tail of push_particles (mithra_gpu_step).
+   * ------------------------------------------------------------------------------------------------ */
+  struct ScreensDev
+  {
+    int                    n;                  /* number of screens, 0 = none                                    */
+    const double*          pos;                /* lab-frame positions                                            */
+    double*                rec;                /* [screen][capacity][8]                                          */
+    unsigned int*          cursor;
+    unsigned int           capacity;
+    double                 step_id;
+    double                 time_bunch;         /* bunch time AFTER the field step's sub-steps                    */
+  };
+
+  __device__ __forceinline__ void screen_records (const BunchDev& b, const ScreensDev& S, double xm, double ym, double zm,
+						  double xp, double yp, double zp, double gx, double gy, double gz, unsigned int id)
+  {
+    if (b.size == 1)
+      {
+	const double zr = pmod( zp - b.zmin, b.Lz ) + b.zmin;
+	if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) return;
+      }
+    const double time_bunch = S.time_bunch;
+    const double lzm = b.gamma * ( zm + b.beta * b.c0 * ( time_bunch - b.dt_field + b.dt_shift ) );
+    const double lzp = b.gamma * ( zp + b.beta * b.c0 * ( time_bunch + b.dt_shift ) );
+    for (int s = 0; s < S.n; s++)
+      {
+	const double lzs = S.pos[s];
+	if (lzm >= lzs) continue;
+	if (lzp <  lzs) continue;
+	const unsigned int slot = atomicAdd(&S.cursor[s], 1u);
+	if (slot >= S.capacity) continue;
+	double* r = S.rec + ( (size_t) s * S.capacity + slot ) * 8;
+	const double fr = ( lzs - lzm ) / ( lzp - lzm );
+	r[0] = xm + fr * ( xp - xm );
+	r[1] = ym + fr * ( yp - ym );
+	const double tm = b.gamma * ( time_bunch + b.dt_shift - b.dt_field + b.beta / b.c0 * zm );
+	const double tp = b.gamma * ( time_bunch + b.dt_shift              + b.beta / b.c0 * zp );
+	r[2] = tm + fr * ( tp - tm );
+	r[3] = gx; r[4] = gy;
+	r[5] = b.gamma * ( gz + b.beta * sqrt( 1.0 + ( gx * gx + gy * gy + gz * gz ) ) );
+	r[6] = (double) id; r[7] = S.step_id;
+      }
+  }
+
+  __global__ void __launch_bounds__(256)
+  screen_cross (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const ScreensDev S)
+  {
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    screen_records(b, S, P.rm[0][t], P.rm[1][t], P.rm[2][t], P.r[0][t], P.r[1][t], P.r[2][t],
+		   P.gb[0][t], P.gb[1][t], P.gb[2][t], P.id[t]);
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Push: `nsub` consecutive sub-steps of Solver::bunchUpdate for every particle (solver.cpp:1437-1549).
-   * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312).
+   * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312); with scr.n > 0 the
+   * lab-frame screens are tested at the end (solver.cpp:2205-2257), which saves screen_cross's pass over the bunch.
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
    * ------------------------------------------------------------------------------------------------ */
   template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
   __global__ void __launch_bounds__(128)
   push_particles (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const float4* __restrict__ eb,
-		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside)
+		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside,
+		  unsigned char* __restrict__ emask, const ScreensDev scr)
   {
     const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
     bool boxvalid = false; int bi = 0, bj = 0, bk = 0;
@@ -259,12 +326,16 @@ namespace mithra
 	P.gb[0][t] = gx; P.gb[1][t] = gy; P.gb[2][t] = gz;
 	P.e[t] = e;
 
+	/* Solver::screenProfile on the way out (mithra_gpu_step): the start-of-step position is this thread's own store  */
+	if (scr.n > 0) screen_records(b, scr, P.rm[0][t], P.rm[1][t], P.rm[2][t], x, y, z, gx, gy, gz, P.id[t]);
+
 	if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
 	  {
 	    bi = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
 	    bj = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
 	    bk = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
 	    boxvalid = true;
+	    mark_eb_pencil(b, emask, bi, bj, bk);
 	  }
       }
     warp_box_merge(pbox, boxvalid, bi, bi, bj, bj, bk, bk);
@@ -446,47 +517,6 @@ namespace mithra
 	__syncthreads();
       }
     if (threadIdx.x < MITHRA_MOMENTS) partial[(size_t) blockIdx.x * MITHRA_MOMENTS + threadIdx.x] = red[threadIdx.x][0];
-  }
-
-  /* ------------------------------------------------------------------------------------------------
-   * Screens (solver.cpp:2205-2257).  One thread per particle, loop over screens; a crossing appends a record
-   * { x, y, t, gbx, gby, gbz_lab, upload index of the particle, step } to the screen's buffer through an atomic cursor.
-   * ------------------------------------------------------------------------------------------------ */
-  __global__ void __launch_bounds__(256)
-  screen_cross (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double time_bunch, int nscreens,
-		const double* __restrict__ pos, double* __restrict__ rec, unsigned int* __restrict__ cursor,
-		unsigned int capacity, double step_id)
-  {
-    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const double xp = P.r[0][t], yp = P.r[1][t], zp = P.r[2][t];
-    if (b.size == 1)
-      {
-	const double zr = pmod( zp - b.zmin, b.Lz ) + b.zmin;
-	if ( ! ( ( zr >= b.zp0 ) && ( zr < b.zp1 ) ) ) return;
-      }
-    const double xm = P.rm[0][t], ym = P.rm[1][t], zm = P.rm[2][t];
-    const double lzm = b.gamma * ( zm + b.beta * b.c0 * ( time_bunch - b.dt_field + b.dt_shift ) );
-    const double lzp = b.gamma * ( zp + b.beta * b.c0 * ( time_bunch + b.dt_shift ) );
-    for (int s = 0; s < nscreens; s++)
-      {
-	const double lzs = pos[s];
-	if (lzm >= lzs) continue;
-	if (lzp <  lzs) continue;
-	const unsigned int slot = atomicAdd(&cursor[s], 1u);
-	if (slot >= capacity) continue;
-	double* r = rec + ( (size_t) s * capacity + slot ) * 8;
-	const double fr = ( lzs - lzm ) / ( lzp - lzm );
-	r[0] = xm + fr * ( xp - xm );
-	r[1] = ym + fr * ( yp - ym );
-	const double tm = b.gamma * ( time_bunch + b.dt_shift - b.dt_field + b.beta / b.c0 * zm );
-	const double tp = b.gamma * ( time_bunch + b.dt_shift              + b.beta / b.c0 * zp );
-	r[2] = tm + fr * ( tp - tm );
-	const double gx = P.gb[0][t], gy = P.gb[1][t], gz = P.gb[2][t];
-	r[3] = gx; r[4] = gy;
-	r[5] = b.gamma * ( gz + b.beta * sqrt( 1.0 + ( gx * gx + gy * gy + gz * gz ) ) );
-	r[6] = (double) P.id[t]; r[7] = step_id;
-      }
   }
 
   /* ------------------------------------------------------------------------------------------------

@@ -697,22 +697,27 @@ namespace mithra
    * eval_eb_box fetches the 24 (30) potentials of a node afresh for every node, eight (ten) of them from the planes
    * k-1 and k+1 that other CTAs own: fine for a bunch that fills a few dozen columns, but at FEL-LCLS scale the padded
    * particle box is 2/3 of a 347 M-node mesh and the evaluation costs more than the stencil.  Here a thread owns one
-   * column (i, j) of the box and marches KC planes in +z: A_x, A_y (and phi) of the planes k-1, k, k+1 rotate through
+   * column (i, j) of the box and marches a chunk of 32 planes in +z: A_x, A_y (and phi) of the planes k-1, k, k+1 rotate through
    * registers, so every potential is loaded from memory once per thread and its in-plane neighbours are the centre
    * loads of the neighbouring threads of the same 32 x 8 tile (L1).  The arithmetic is eb_assemble, the same as
    * eval_eb_node: bit-identical E/B (GPU test: march == box).
-   * Work items (z chunk, i tile, j tile) are strided over a grid of fixed size because the box lives on the device.
+   * Work items (32-plane chunk, i tile, j tile) are strided over a grid of fixed size because the box lives on the
+   * device; pencils that the mask (spread_eb_mask below) leaves unmarked are skipped.
    * ------------------------------------------------------------------------------------------------ */
-  template <bool SC, int KC>
+  #define MITHRA_EB_CHUNK_LOG2 5                /* planes per pencil of the E/B mask = planes per work item of the march */
+
+  template <bool SC>
   __global__ void __launch_bounds__(256)
   eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
-		 float4* __restrict__ eb, const Box* __restrict__ boxp)
+		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask)
   {
+    constexpr int L = MITHRA_EB_CHUNK_LOG2;
     const Box b = *boxp;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
     const int kfirst = max(b.lo[2], f.kb), klast = min(b.hi[2], f.np - 2);
     if (ni <= 0 || nj <= 0 || klast < kfirst) return;
-    const int njt = (nj + 31) >> 5, nit = (ni + 7) >> 3, nkc = (klast - kfirst + KC) / KC;
+    const int cfirst = kfirst >> L;
+    const int njt = (nj + 31) >> 5, nit = (ni + 7) >> 3, nkc = (klast >> L) - cfirst + 1;
     const long nwork = (long) njt * nit * nkc;
     const int  tj = threadIdx.x & 31, ti = threadIdx.x >> 5;
     const long N1 = f.N1, Pp = f.Pp, cs = (long) f.np * Pp;
@@ -721,10 +726,11 @@ namespace mithra
 
     for (long w = blockIdx.x; w < nwork; w += gridDim.x)
       {
-	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), kc = (int) (w / ((long) njt * nit));
+	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), c = cfirst + (int) (w / ((long) njt * nit));
 	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
 	if (j > b.hi[1] || i > b.hi[0]) continue;
-	const int ks = kfirst + kc * KC, ke = min(ks + KC, klast + 1);
+	if (mask && !mask[((long) c * f.N0 + i) * N1 + j]) continue;       /* no particle can gather from this pencil */
+	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
 	long m = (long) ks * Pp + (long) i * N1 + j;              /* the node in the planar potentials            */
 	long e = (long) ks * f.P + (long) i * N1 + j;             /* ... and in the E/B array                      */
 
@@ -753,6 +759,36 @@ namespace mithra
 	    axm = ax0; ax0 = axp; aym = ay0; ay0 = ayp; pxm = px0; px0 = pxp; pym = py0; py0 = pyp;
 	    if (SC) { fm = f0; f0 = fp; }
 	  }
+      }
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Pencil mask of the E/B evaluation.  The padded particle box is a bounding box: for a bunch with Gaussian tails
+   * (FEL-LCLS: sigma 7.5 cells, truncation at 45) most of its columns hold no particle at all.  The push (and every
+   * other kernel that extends the particle box) marks the pencil -- cell column (i, j) x 32 planes -- of each particle
+   * in `cells`; here the marks are spread to the NODES a particle of that pencil can gather from during the next field
+   * step: the two nodes of its cell per axis plus the cells it can cross (padx, pady; less than one 32-plane chunk in
+   * z), which is exactly how make_eb_box pads the bounding box.  eval_eb_march skips the pencils left unmarked.
+   * ------------------------------------------------------------------------------------------------ */
+  __global__ void __launch_bounds__(256)
+  spread_eb_mask (const FieldDev f, const unsigned char* __restrict__ cells, unsigned char* __restrict__ nodes,
+		  const Box* __restrict__ eboxp, int padx, int pady)
+  {
+    constexpr int L = MITHRA_EB_CHUNK_LOG2;
+    const Box b = *eboxp;
+    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
+    if (ni <= 0 || nj <= 0 || b.hi[2] < b.lo[2]) return;
+    const int c0 = b.lo[2] >> L, nc = (b.hi[2] >> L) - c0 + 1, nch = (f.np + (1 << L) - 1) >> L;
+    const long tot = (long) nc * ni * nj;
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int j = b.lo[1] + (int) (t % nj), i = b.lo[0] + (int) ((t / nj) % ni), c = c0 + (int) (t / ((long) nj * ni));
+	unsigned int any = 0u;
+	for (int cc = max(0, c - 1); cc <= min(nch - 1, c + 1); cc++)
+	  for (int ii = max(0, i - 1 - padx); ii <= min(f.N0 - 1, i + padx); ii++)
+	    for (int jj = max(0, j - 1 - pady); jj <= min(f.N1 - 1, j + pady); jj++)
+	      any |= cells[((long) cc * f.N0 + ii) * f.N1 + jj];
+	nodes[((long) c * f.N0 + i) * f.N1 + j] = any ? 1 : 0;
       }
   }
 }

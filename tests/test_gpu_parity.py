@@ -294,24 +294,27 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
 @pytest.mark.parametrize("job,shape", [("micro-nsfd", (14, 14, 242)), ("micro-sc", (29, 53, 66)), ("micro-seeded", (85, 85, 70)),
                                        ("micro-fd", (41, 100, 37)), ("micro-sc", (9, 9, 12))])
 def test_eb_march_equals_node_kernel(job, shape, monkeypatch):
-    """E/B over the particle box: the production z-marching kernel (eval_eb_march + the two copied end planes) against
-    the node-at-a-time kernel (MITHRA_EB_BOX), bit-identical floats on every node -- boxes wider than one 32 x 8 tile,
+    """E/B over the particle box: the production z-marching kernel (eval_eb_march over the pencils the mask marks + the
+    two copied end planes) against the node-at-a-time kernel over the whole box (MITHRA_EB_BOX) and against the march
+    without the mask (MITHRA_NO_EBMASK): bit-identical floats on every evaluated node, the masked set lies inside the
+    box and covers the 8 nodes of every particle's cell and of the cells around it -- boxes wider than one 32 x 8 tile,
     boxes that reach the first and the last plane, and a box that is the whole (tiny) mesh."""
     p, g = _resized(job, *shape)
     rng = np.random.default_rng(23)
     n = p.N0 * p.N1 * p.np
     an, anm1 = rng.standard_normal(n * 3), rng.standard_normal(n * 3)
     sc = dict(fn=rng.standard_normal(n), fnm1=rng.standard_normal(n)) if p.space_charge else {}
-    nb = 256
+    nb = 24
     bunch = np.zeros((nb, 11))
     bunch[:, 0] = 1.0
     bunch[:, 1] = rng.uniform(0.8 * p.xmin, 0.8 * p.xmax, nb)
     bunch[:, 2] = rng.uniform(0.8 * p.ymin, 0.8 * p.ymax, nb)
-    bunch[:, 3] = rng.uniform(p.zmin + 1e-3 * p.dz, p.zmax - 1e-3 * p.dz, nb)      # first and last cell in z included
+    bunch[:, 3] = rng.uniform(p.zmin + 1e-3 * p.dz, p.zmax - 1e-3 * p.dz, nb)
+    bunch[0, 3], bunch[1, 3] = p.zmin + 1e-3 * p.dz, p.zmax - 1e-3 * p.dz          # first and last cell in z
     bunch[:, 4:7] = bunch[:, 1:4]
     bunch[:, 10] = 1.0
     out = {}
-    for mode in ("march", "MITHRA_EB_BOX"):
+    for mode in ("march", "MITHRA_EB_BOX", "MITHRA_NO_EBMASK"):
         if mode != "march":
             monkeypatch.setenv(mode, "1")
         s = abi.GpuSolver(p)
@@ -325,10 +328,33 @@ def test_eb_march_equals_node_kernel(job, shape, monkeypatch):
             monkeypatch.delenv(mode)
     e0, b0, m0 = out["march"]
     e1, b1, m1 = out["MITHRA_EB_BOX"]
+    e2, b2, m2 = out["MITHRA_NO_EBMASK"]
     assert np.abs(e0).max() > 0 and np.abs(b0).max() > 0 and m0.sum() > 0
-    np.testing.assert_array_equal(m0, m1)
-    np.testing.assert_array_equal(e0.view(np.uint32), e1.view(np.uint32))
-    np.testing.assert_array_equal(b0.view(np.uint32), b1.view(np.uint32))
+    # without the mask the march covers the box exactly like the node kernel
+    np.testing.assert_array_equal(m2, m1)
+    np.testing.assert_array_equal(e2.view(np.uint32), e1.view(np.uint32))
+    np.testing.assert_array_equal(b2.view(np.uint32), b1.view(np.uint32))
+    # with it: a subset of the box, same bits where evaluated
+    assert not np.any(m0 & ~m1.astype(bool))
+    w = np.repeat(m0.astype(bool), 3)
+    np.testing.assert_array_equal(e0.view(np.uint32)[w], e1.view(np.uint32)[w])
+    np.testing.assert_array_equal(b0.view(np.uint32)[w], b1.view(np.uint32)[w])
+    # every node a particle can gather from now or after moving one cell in any direction is evaluated
+    M = m0.reshape(p.np, p.N0, p.N1)
+    i = np.floor((bunch[:, 1] - p.xmin) / p.dx).astype(int)
+    j = np.floor((bunch[:, 2] - p.ymin) / p.dy).astype(int)
+    k = np.floor((bunch[:, 3] - p.zmin) / p.dz).astype(int)
+    for t in range(nb):
+        if not (1 <= i[t] <= p.N0 - 3 and 1 <= j[t] <= p.N1 - 3):
+            continue                                     # outside x/y (min + d, max - d): gathers nothing (solver.cpp:1444)
+        for dk in range(-1, 3):
+            for di in range(-1, 3):
+                for dj in range(-1, 3):
+                    kk, ii, jj = k[t] + dk, i[t] + di, j[t] + dj
+                    if 0 <= kk < p.np and 1 <= ii <= p.N0 - 2 and 1 <= jj <= p.N1 - 2:
+                        assert M[kk, ii, jj], (t, kk, ii, jj)
+    if min(shape) > 12:
+        assert m0.sum() < m1.sum()                       # the mask does skip something on a sparse bunch
 
 
 @pytest.mark.parametrize("d", [60.0, 9.19059968, -0.01532827, 30.0, 4.59529984, -4.49297199e+08, 3.0, 1.9999999999999998,
