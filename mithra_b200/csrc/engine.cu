@@ -920,8 +920,8 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
     PhaseTimer t(h, PH_BOUNDARY);
     if (rim)
       {
-	constexpr int KC = 64;
 	const int per = 4 * (f.N1 - 2) + 4 * (f.N0 - 6);
+	static const int KC = getenv("MITHRA_RIM_KC") ? std::max(1, atoi(getenv("MITHRA_RIM_KC"))) : 64;   /* planes per CTA (fitting the grid to whole waves changes nothing: measured) */
 	dim3 grid((unsigned) ((per + 127) / 128), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
 	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);
 	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);

@@ -165,6 +165,11 @@ namespace mithra
       }
   }
 
+  /* out of line for the push: a crossing is rare, and inlined the test costs the whole kernel 32 registers           */
+  __device__ __noinline__ void screen_records_call (const BunchDev& b, const ScreensDev& S, double xm, double ym, double zm,
+						    double xp, double yp, double zp, double gx, double gy, double gz, unsigned int id)
+  { screen_records(b, S, xm, ym, zm, xp, yp, zp, gx, gy, gz, id); }
+
   __global__ void __launch_bounds__(256)
   screen_cross (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const ScreensDev S)
   {
@@ -181,7 +186,7 @@ namespace mithra
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
    * ------------------------------------------------------------------------------------------------ */
   template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
-  __global__ void __launch_bounds__(128)
+  __global__ void __launch_bounds__(128, 5)          /* 5 CTAs per SM = at most 102 registers: the kernel lives on occupancy */
   push_particles (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const float4* __restrict__ eb,
 		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside,
 		  unsigned char* __restrict__ emask, const ScreensDev scr)
@@ -327,7 +332,16 @@ namespace mithra
 	P.e[t] = e;
 
 	/* Solver::screenProfile on the way out (mithra_gpu_step): the start-of-step position is this thread's own store  */
-	if (scr.n > 0) screen_records(b, scr, P.rm[0][t], P.rm[1][t], P.rm[2][t], x, y, z, gx, gy, gz, P.id[t]);
+	if (scr.n > 0)
+	  {
+	    /* nothing to do unless the step straddles a screen: the cheap part of the test stays inline              */
+	    const double zm0 = P.rm[2][t];
+	    const double lzm = b.gamma * ( zm0 + b.beta * b.c0 * ( scr.time_bunch - b.dt_field + b.dt_shift ) );
+	    const double lzp = b.gamma * ( z   + b.beta * b.c0 * ( scr.time_bunch + b.dt_shift ) );
+	    bool any = false;
+	    for (int s = 0; s < scr.n; s++) any = any || ( lzm < scr.pos[s] && lzp >= scr.pos[s] );
+	    if (any) screen_records_call(b, scr, P.rm[0][t], P.rm[1][t], zm0, x, y, z, gx, gy, gz, P.id[t]);
+	  }
 
 	if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
 	  {

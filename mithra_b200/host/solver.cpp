@@ -921,6 +921,32 @@ namespace MITHRA
     const unsigned int nStart = nTime_;
     while ( time_ < mesh_.totalTime_ && ( maxSteps_ < 0 || steps < maxSteps_ ) )
       {
+	/* A step without a rhythm-gated bunch output is exactly mithra_gpu_step: the same calls in the same order, with
+	 * the library free to run its housekeeping beside the particle kernels and to test the screens inside the push.
+	 * One process driving several slabs keeps the call-by-call loop (every slab must enqueue its sends before the
+	 * first one waits for its neighbours).                                                                          */
+	bool gated = false;
+	{
+	  const Double tb = time_ + mesh_.timeShift_;
+	  if ( bunch_.sampling_ && fmod(tb, bunch_.rhythm_) < mesh_.timeStep_ && tb > 0.0 ) gated = true;
+	  if ( bunch_.bunchProfile_ )
+	    {
+	      for (unsigned int i = 0; i < bunch_.bunchProfileTime_.size(); i++)
+		if ( time_ - bunch_.bunchProfileTime_[i] < mesh_.timeStep_ && time_ > bunch_.bunchProfileTime_[i] ) gated = true;
+	      if ( fmod(tb, bunch_.bunchProfileRhythm_) < mesh_.timeStep_ && tb > 0.0 && bunch_.bunchProfileRhythm_ != 0.0 ) gated = true;
+	    }
+	  if ( pmapGroup_ >= 0 ) gated = true;                  /* the power map is fetched from inside powerVisualize()    */
+	}
+	if ( gpu_.size() == 1 && !gated && !getenv("MITHRA_HOST_CALL_BY_CALL") )
+	  {
+	    check(mithra_gpu_step(gpu_[0], 1));
+	    for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) { timeBunch_ += bunch_.timeStep_; ++nTimeBunch_; }
+	    if ( powerGroup_ >= 0 ) powerTimes_.push_back(timeBunch_);
+	    timem1_ += mesh_.timeStep_; time_ += mesh_.timeStep_; timep1_ += mesh_.timeStep_; ++nTime_; ++steps;
+	    if ( nTime_ % flushEvery == 0 ) flushOutputs();
+	  }
+	else
+	  {
 	fieldUpdate();
 	bunchUpdate();
 	recycleParticles();
@@ -941,6 +967,7 @@ namespace MITHRA
 	currentUpdate();
 	currentCommunicate();
 	advance();
+	  }
 
 	if ( int( time_ / mesh_.totalTime_ * 1000.0 ) != int( timem1_ / mesh_.totalTime_ * 1000.0 ) )
 	  {
