@@ -102,6 +102,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("MITHRA_GPU_LIB"):                 # tuning experiments: another build of the same library
+        LIB_PATH = os.environ["MITHRA_GPU_LIB"]
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("%s is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
                            "There is no CPU fallback." % LIB_PATH)

@@ -247,8 +247,10 @@ namespace mithra
     double d1, bz;
     if (lz >= 0.0 && lz <= u.len)
       {
-	d1 = u.b0 * cosh( u.ku * ly ) * sin( u.ku * lz ) * gamma;
-	bz = u.b0 * sinh( u.ku * ly ) * cos( u.ku * lz );
+	double sn, cs;
+	sincos( u.ku * lz, &sn, &cs );                          /* one argument reduction for both (same values as sin, cos) */
+	d1 = u.b0 * cosh( u.ku * ly ) * sn * gamma;
+	bz = u.b0 * sinh( u.ku * ly ) * cs;
       }
     else if (lz < 0.0)
       {

@@ -186,7 +186,10 @@ namespace mithra
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
    * ------------------------------------------------------------------------------------------------ */
   template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
-  __global__ void __launch_bounds__(128, 5)          /* 5 CTAs per SM = at most 102 registers: the kernel lives on occupancy */
+  #ifndef MITHRA_PUSH_MINBLOCKS
+  #define MITHRA_PUSH_MINBLOCKS 5                      /* 5 CTAs per SM = at most 102 registers: the kernel lives on occupancy */
+  #endif
+  __global__ void __launch_bounds__(128, MITHRA_PUSH_MINBLOCKS)
   push_particles (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const float4* __restrict__ eb,
 		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside,
 		  unsigned char* __restrict__ emask, const ScreensDev scr)
@@ -429,7 +432,7 @@ namespace mithra
   }
 
   template <bool SC>
-  __global__ void __launch_bounds__(128)
+  __global__ void __launch_bounds__(128, SC ? 3 : 4)
   deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox, int run)
   {
     const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * run;
@@ -437,12 +440,21 @@ namespace mithra
     DepositAcc<SC> acc; acc.m = -1;
     const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
 
+    /* the particle of the NEXT iteration is loaded before the current one is worked on: a thread's particles are 64 bytes
+     * apart in every array, the loads miss L1 and nothing else hides their latency (the flush is fire-and-forget)       */
+    double nx = 0.0, ny = 0.0, nz = 0.0, nmx = 0.0, nmy = 0.0, nmz = 0.0, nq = 0.0;
+    if (t0 < n)
+      { nx = __ldg(P.r[0] + t0); ny = __ldg(P.r[1] + t0); nz = __ldg(P.r[2] + t0); nmx = __ldg(P.rm[0] + t0); nmy = __ldg(P.rm[1] + t0); nmz = __ldg(P.rm[2] + t0); nq = __ldg(P.q + t0); }
+
     for (int r = 0; r < run; r++)
       {
 	const long t = t0 + r;
 	if (t >= n) break;
-	const double rpx = P.r[0][t],  rpy = P.r[1][t],  rpz = P.r[2][t];
-	const double rmx = P.rm[0][t], rmy = P.rm[1][t], rmz = P.rm[2][t];
+	const double rpx = nx,  rpy = ny,  rpz = nz;
+	const double rmx = nmx, rmy = nmy, rmz = nmz;
+	const double q = nq;
+	if (r + 1 < run && t + 1 < n)
+	  { nx = __ldg(P.r[0] + t + 1); ny = __ldg(P.r[1] + t + 1); nz = __ldg(P.r[2] + t + 1); nmx = __ldg(P.rm[0] + t + 1); nmy = __ldg(P.rm[1] + t + 1); nmz = __ldg(P.rm[2] + t + 1); nq = __ldg(P.q + t + 1); }
 
 	const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
 			   rpz < zhi && rpz >= zlo );
@@ -450,7 +462,6 @@ namespace mithra
 			   rmz < zhi && rmz >= zlo );
 	if (!bpf && !bmf) continue;
 
-	const double q = P.q[t];
 	const int ip = (int) floor( div_by( rpx - b.xmin, b.dx, b.rdx ) ), jp = (int) floor( div_by( rpy - b.ymin, b.dy, b.rdy ) ), kp = (int) floor( div_by( rpz - b.zmin, b.dz, b.rdz ) );
 	const int im = (int) floor( div_by( rmx - b.xmin, b.dx, b.rdx ) ), jm = (int) floor( div_by( rmy - b.ymin, b.dy, b.rdy ) ), km = (int) floor( div_by( rmz - b.zmin, b.dz, b.rdz ) );
 

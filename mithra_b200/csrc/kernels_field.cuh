@@ -271,7 +271,7 @@ namespace mithra
   }
 
   #ifndef MITHRA_RIM_MINBLOCKS
-  #define MITHRA_RIM_MINBLOCKS 1
+  #define MITHRA_RIM_MINBLOCKS 6                        /* 80 registers: the kernel is pure load latency, 6 beats 5 and 8    */
   #endif
 
   /* AdvanceField::advanceBoundary{F,S} (database.cpp:137-176) for the face node s from the thread of its inward
@@ -706,8 +706,11 @@ namespace mithra
    * ------------------------------------------------------------------------------------------------ */
   #define MITHRA_EB_CHUNK_LOG2 5                /* planes per pencil of the E/B mask = planes per work item of the march */
 
+  #ifndef MITHRA_MARCH_MINBLOCKS
+  #define MITHRA_MARCH_MINBLOCKS 3                      /* 85 registers, 24 warps per SM: measured against 2 and 4           */
+  #endif
   template <bool SC>
-  __global__ void __launch_bounds__(256)
+  __global__ void __launch_bounds__(256, MITHRA_MARCH_MINBLOCKS)
   eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
 		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask)
   {
