@@ -82,6 +82,7 @@ struct MithraGpu
   Box*            d_ebox;                 /* node box evaluated by eval_eb_box                            */
   Box             h_ebox_last;
   bool            fuse_screens;           /* set by mithra_gpu_step around its push                         */
+  bool            ev_main_fresh;          /* ev_main was recorded inside the last field update (after J's last reader) */
   unsigned char*  d_emask_cells;          /* E/B pencil mask: cells that hold a particle (marked by push / particle_box) */
   unsigned char*  d_emask_nodes;          /* ... spread to the nodes those particles can gather from (spread_eb_mask)      */
   size_t          emask_bytes;
@@ -409,7 +410,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   set_box<<<1, 1, 0, h->stream>>>(h->d_ebox, 0, 0, 0, -1, -1, -1);
-  h->fuse_screens = false;
+  h->fuse_screens = false; h->ev_main_fresh = false;
   h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
 
   h->d_emask_cells = 0; h->d_emask_nodes = 0;
@@ -950,6 +951,9 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
 	boundary_faces<<<grid_for(nface, 256, h->num_sms * 8), 256, 0, h->stream>>>(f, ap, a, am, 0);
 	h->cnt.kernel_launches += 1;
       }
+    /* J, its box and the seed tables have had their last reader: housekeeping_ahead may clear / refill them from here
+     * on, beside the edges, the ghost exchange and the E/B evaluation                                              */
+    if (h->overlap && !h->profiling) { CU(cudaEventRecord(h->ev_main, h->stream)); h->ev_main_fresh = true; }
     if (f.order == 2)
       {
 	const long nedge = (4L * (f.np - 2) + 4L * (f.N0 - 2) + 4L * (f.N1 - 2)) * f.ncomp;
@@ -1195,7 +1199,8 @@ static int housekeeping_ahead (MithraGpu* h)
 {
   if (!h->overlap || h->profiling) return 0;
   const FieldDev& f = h->fd;
-  CU(cudaEventRecord(h->ev_main, h->stream));
+  if (!h->ev_main_fresh) CU(cudaEventRecord(h->ev_main, h->stream));
+  h->ev_main_fresh = false;
   CU(cudaStreamWaitEvent(h->side, h->ev_main, 0));
   clear_current_box<<<h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done);
   CU(cudaGetLastError());
@@ -1283,7 +1288,8 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_field_update(h));
       TRY(housekeeping_ahead(h));
       /* the screens ride on the push (one pass over the bunch less); phase profiling keeps the two kernels apart     */
-      h->fuse_screens = !h->profiling && !getenv("MITHRA_NO_FUSE");
+      static const bool nofuse = getenv("MITHRA_NO_FUSE") != 0;
+      h->fuse_screens = !h->profiling && !nofuse;
       const int rb = mithra_gpu_bunch_update(h);
       const bool fused = h->fuse_screens;
       h->fuse_screens = false;

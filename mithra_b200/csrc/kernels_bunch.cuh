@@ -180,15 +180,163 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
+   * ZigZag deposition (fdtd.cpp:47-184): relay point, two segments, each scattering the three current components
+   * to the 8 nodes of its cell (+ rho at the end point with space charge, fdtdSC.cpp:141-160).
+   *
+   * A thread walks MITHRA_DEP_RUN particles that are consecutive in memory -- after the counting sort by cell these
+   * are particles of the same or of neighbouring cells -- and keeps the contributions to the 8 nodes of the cell
+   * it is currently in in registers: 4 distinct values per component (the reference gives the same J_x to both x
+   * nodes of a cell, fdtd.cpp:111-118, likewise y and z) and 8 charge weights.  Both segments of a particle that
+   * stays in its cell and all particles of a run that share the cell are summed there; only when the cell changes
+   * (and at the end of the run) the 24 (+8) sums go to L2 as FP64 reductions (RED.ADD.F64).  Measured on B200
+   * this is what bounds the kernel: the atomics' issue rate, not HBM.  The bounding box of the touched nodes is
+   * merged per warp for the stencil (which reads J only there) and the next clear.
+   * ------------------------------------------------------------------------------------------------ */
+  #define MITHRA_DEP_RUN 8
+
+  template <bool SC>
+  struct DepositAcc
+  {
+    long   m;                         /* first node of the cell the sums belong to, -1 = none                 */
+    double jx[4], jy[4], jz[4];
+    double rho[SC ? 8 : 1];
+  };
+
+  template <bool SC>
+  __device__ __forceinline__ void deposit_flush (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a)
+  {
+    if (a.m < 0) return;
+    const long N1 = b.N1, Pp = b.Pp, cs = (long) b.np * b.Pp;
+    const long m = a.m;
+    const long o[8] = { m, m + N1, m + 1, m + N1 + 1, m + Pp, m + Pp + N1, m + Pp + 1, m + Pp + N1 + 1 };
+    double* J0 = jn; double* J1 = jn + cs; double* J2 = jn + 2 * cs;
+    atomicAdd(J0 + o[0], a.jx[0]); atomicAdd(J0 + o[1], a.jx[0]); atomicAdd(J0 + o[2], a.jx[1]); atomicAdd(J0 + o[3], a.jx[1]);
+    atomicAdd(J0 + o[4], a.jx[2]); atomicAdd(J0 + o[5], a.jx[2]); atomicAdd(J0 + o[6], a.jx[3]); atomicAdd(J0 + o[7], a.jx[3]);
+    atomicAdd(J1 + o[0], a.jy[0]); atomicAdd(J1 + o[2], a.jy[0]); atomicAdd(J1 + o[1], a.jy[1]); atomicAdd(J1 + o[3], a.jy[1]);
+    atomicAdd(J1 + o[4], a.jy[2]); atomicAdd(J1 + o[6], a.jy[2]); atomicAdd(J1 + o[5], a.jy[3]); atomicAdd(J1 + o[7], a.jy[3]);
+    atomicAdd(J2 + o[0], a.jz[0]); atomicAdd(J2 + o[4], a.jz[0]); atomicAdd(J2 + o[1], a.jz[1]); atomicAdd(J2 + o[5], a.jz[1]);
+    atomicAdd(J2 + o[2], a.jz[2]); atomicAdd(J2 + o[6], a.jz[2]); atomicAdd(J2 + o[3], a.jz[3]); atomicAdd(J2 + o[7], a.jz[3]);
+    if constexpr (SC)
+      {
+	double* R = jn + 3 * cs;
+	#pragma unroll
+	for (int q = 0; q < 8; q++) atomicAdd(R + o[q], a.rho[q]);
+      }
+    a.m = -1;
+  }
+
+  template <bool SC>
+  __device__ __forceinline__ void deposit_open (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a, long m)
+  {
+    if (a.m == m) return;
+    deposit_flush<SC>(b, jn, a);
+    a.m = m;
+    #pragma unroll
+    for (int q = 0; q < 4; q++) { a.jx[q] = 0.0; a.jy[q] = 0.0; a.jz[q] = 0.0; }
+    if constexpr (SC) { _Pragma("unroll") for (int q = 0; q < 8; q++) a.rho[q] = 0.0; }
+  }
+
+  /* one segment with midpoint (mx,my,mz) and flux q (jx,jy,jz), fdtd.cpp:92-131                               */
+  template <bool SC>
+  __device__ __forceinline__ void deposit_segment (const BunchDev& b, DepositAcc<SC>& a, double q,
+						   double mx, double my, double mz, double jx, double jy, double jz)
+  {
+    double c;
+    const double dxp = modf( div_by( mx - b.xmin, b.dx, b.rdx ), &c );
+    const double dyp = modf( div_by( my - b.ymin, b.dy, b.rdy ), &c );
+    const double dzp = modf( div_by( mz - b.zmin, b.dz, b.rdz ), &c );
+    const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
+    const double h = q * 0.5;
+    a.jx[0] += h * y1 * z1 * jx; a.jx[1] += h * y2 * z1 * jx; a.jx[2] += h * y1 * z2 * jx; a.jx[3] += h * y2 * z2 * jx;
+    a.jy[0] += h * x1 * z1 * jy; a.jy[1] += h * x2 * z1 * jy; a.jy[2] += h * x1 * z2 * jy; a.jy[3] += h * x2 * z2 * jy;
+    a.jz[0] += h * x1 * y1 * jz; a.jz[1] += h * x2 * y1 * jz; a.jz[2] += h * x1 * y2 * jz; a.jz[3] += h * x2 * y2 * jz;
+  }
+
+  /* one particle of FdTd::currentUpdate (fdtd.cpp:47-184): end point p, start point m, charge q; the sums go to the
+   * accumulator of the cell they belong to (flushed when the cell changes), `valid` and the node box are updated       */
+  template <bool SC>
+  __device__ __forceinline__ void deposit_particle (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& acc,
+						    double rpx, double rpy, double rpz, double rmx, double rmy, double rmz, double q,
+						    double zlo, double zhi, bool& valid, int& i0, int& i1, int& j0, int& j1, int& k0, int& k1)
+  {
+    const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
+    		   rpz < zhi && rpz >= zlo );
+    const bool bmf = ( rmx < b.xmax - b.dx && rmx > b.xmin + b.dx && rmy < b.ymax - b.dy && rmy > b.ymin + b.dy &&
+    		   rmz < zhi && rmz >= zlo );
+    if (!bpf && !bmf) return;
+
+    const int ip = (int) floor( div_by( rpx - b.xmin, b.dx, b.rdx ) ), jp = (int) floor( div_by( rpy - b.ymin, b.dy, b.rdy ) ), kp = (int) floor( div_by( rpz - b.zmin, b.dz, b.rdz ) );
+    const int im = (int) floor( div_by( rmx - b.xmin, b.dx, b.rdx ) ), jm = (int) floor( div_by( rmy - b.ymin, b.dy, b.rdy ) ), km = (int) floor( div_by( rmz - b.zmin, b.dz, b.rdz ) );
+
+    /* relay point, fdtd.cpp:80-85 */
+    const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
+    const double ry = fmin( min(jm, jp) * b.dy + b.dy + b.ymin, fmax( max(jm, jp) * b.dy + b.ymin, 0.5 * ( rmy + rpy ) ) );
+    const double rz = fmin( min(km, kp) * b.dz + b.dz + b.zmin, fmax( max(km, kp) * b.dz + b.zmin, 0.5 * ( rmz + rpz ) ) );
+
+    valid = true;
+    if (bpf)
+      {
+        deposit_open<SC>(b, jn, acc, (long) ( kp - b.k0 ) * b.Pp + (long) ip * b.N1 + jp);
+        deposit_segment<SC>(b, acc, q, 0.5 * ( rpx + rx ), 0.5 * ( rpy + ry ), 0.5 * ( rpz + rz ), rpx - rx, rpy - ry, rpz - rz);
+        if constexpr (SC)
+          {
+    	double c;
+    	const double dxp = modf( div_by( rpx - b.xmin, b.dx, b.rdx ), &c ), dyp = modf( div_by( rpy - b.ymin, b.dy, b.rdy ), &c ), dzp = modf( div_by( rpz - b.zmin, b.dz, b.rdz ), &c );
+    	const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
+    	acc.rho[0] += q * x1 * y1 * z1; acc.rho[1] += q * x2 * y1 * z1; acc.rho[2] += q * x1 * y2 * z1; acc.rho[3] += q * x2 * y2 * z1;
+    	acc.rho[4] += q * x1 * y1 * z2; acc.rho[5] += q * x2 * y1 * z2; acc.rho[6] += q * x1 * y2 * z2; acc.rho[7] += q * x2 * y2 * z2;
+          }
+        i0 = min(i0, ip); i1 = max(i1, ip + 1); j0 = min(j0, jp); j1 = max(j1, jp + 1); k0 = min(k0, kp - b.k0); k1 = max(k1, kp - b.k0 + 1);
+      }
+    if (bmf)
+      {
+        deposit_open<SC>(b, jn, acc, (long) ( km - b.k0 ) * b.Pp + (long) im * b.N1 + jm);
+        deposit_segment<SC>(b, acc, q, 0.5 * ( rmx + rx ), 0.5 * ( rmy + ry ), 0.5 * ( rmz + rz ), rx - rmx, ry - rmy, rz - rmz);
+        i0 = min(i0, im); i1 = max(i1, im + 1); j0 = min(j0, jm); j1 = max(j1, jm + 1); k0 = min(k0, km - b.k0); k1 = max(k1, km - b.k0 + 1);
+      }
+  }
+
+  template <bool SC>
+  __global__ void __launch_bounds__(128, SC ? 3 : 4)
+  deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox, int run)
+  {
+    const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * run;
+    bool valid = false; int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1, k0 = 0x7fffffff, k1 = -1;
+    DepositAcc<SC> acc; acc.m = -1;
+    const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
+
+    /* the particle of the NEXT iteration is loaded before the current one is worked on: a thread's particles are 64 bytes
+     * apart in every array, the loads miss L1 and nothing else hides their latency (the flush is fire-and-forget)       */
+    double nx = 0.0, ny = 0.0, nz = 0.0, nmx = 0.0, nmy = 0.0, nmz = 0.0, nq = 0.0;
+    if (t0 < n)
+      { nx = __ldg(P.r[0] + t0); ny = __ldg(P.r[1] + t0); nz = __ldg(P.r[2] + t0); nmx = __ldg(P.rm[0] + t0); nmy = __ldg(P.rm[1] + t0); nmz = __ldg(P.rm[2] + t0); nq = __ldg(P.q + t0); }
+
+    for (int r = 0; r < run; r++)
+      {
+	const long t = t0 + r;
+	if (t >= n) break;
+	const double rpx = nx,  rpy = ny,  rpz = nz;
+	const double rmx = nmx, rmy = nmy, rmz = nmz;
+	const double q = nq;
+	if (r + 1 < run && t + 1 < n)
+	  { nx = __ldg(P.r[0] + t + 1); ny = __ldg(P.r[1] + t + 1); nz = __ldg(P.r[2] + t + 1); nmx = __ldg(P.rm[0] + t + 1); nmy = __ldg(P.rm[1] + t + 1); nmz = __ldg(P.rm[2] + t + 1); nq = __ldg(P.q + t + 1); }
+
+	deposit_particle<SC>(b, jn, acc, rpx, rpy, rpz, rmx, rmy, rmz, q, zlo, zhi, valid, i0, i1, j0, j1, k0, k1);
+      }
+    deposit_flush<SC>(b, jn, acc);
+    warp_box_merge(jbox, valid, i0, i1, j0, j1, k0, k1);
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Push: `nsub` consecutive sub-steps of Solver::bunchUpdate for every particle (solver.cpp:1437-1549).
    * With first_of_step the start-of-step position is saved to rm first (solver.cpp:1311-1312); with scr.n > 0 the
    * lab-frame screens are tested at the end (solver.cpp:2205-2257), which saves screen_cross's pass over the bunch.
    * E,B of the mesh are gathered from the interleaved float4 pairs written by eval_eb_box.
    * ------------------------------------------------------------------------------------------------ */
-  template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
   #ifndef MITHRA_PUSH_MINBLOCKS
   #define MITHRA_PUSH_MINBLOCKS 5                      /* 5 CTAs per SM = at most 102 registers: the kernel lives on occupancy */
   #endif
+  template <bool BEAMS>                                /* false: static undulators only, no optical beam code in the kernel */
   __global__ void __launch_bounds__(128, MITHRA_PUSH_MINBLOCKS)
   push_particles (const __grid_constant__ BunchDev b, ParticlesDev P, long n, const float4* __restrict__ eb,
 		  double time_bunch, int nsub, int first_of_step, Box* __restrict__ pbox, unsigned int* __restrict__ n_outside,
@@ -356,144 +504,6 @@ namespace mithra
 	  }
       }
     warp_box_merge(pbox, boxvalid, bi, bi, bj, bj, bk, bk);
-  }
-
-  /* ------------------------------------------------------------------------------------------------
-   * ZigZag deposition (fdtd.cpp:47-184): relay point, two segments, each scattering the three current components
-   * to the 8 nodes of its cell (+ rho at the end point with space charge, fdtdSC.cpp:141-160).
-   *
-   * A thread walks MITHRA_DEP_RUN particles that are consecutive in memory -- after the counting sort by cell these
-   * are particles of the same or of neighbouring cells -- and keeps the contributions to the 8 nodes of the cell
-   * it is currently in in registers: 4 distinct values per component (the reference gives the same J_x to both x
-   * nodes of a cell, fdtd.cpp:111-118, likewise y and z) and 8 charge weights.  Both segments of a particle that
-   * stays in its cell and all particles of a run that share the cell are summed there; only when the cell changes
-   * (and at the end of the run) the 24 (+8) sums go to L2 as FP64 reductions (RED.ADD.F64).  Measured on B200
-   * this is what bounds the kernel: the atomics' issue rate, not HBM.  The bounding box of the touched nodes is
-   * merged per warp for the stencil (which reads J only there) and the next clear.
-   * ------------------------------------------------------------------------------------------------ */
-  #define MITHRA_DEP_RUN 8
-
-  template <bool SC>
-  struct DepositAcc
-  {
-    long   m;                         /* first node of the cell the sums belong to, -1 = none                 */
-    double jx[4], jy[4], jz[4];
-    double rho[SC ? 8 : 1];
-  };
-
-  template <bool SC>
-  __device__ __forceinline__ void deposit_flush (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a)
-  {
-    if (a.m < 0) return;
-    const long N1 = b.N1, Pp = b.Pp, cs = (long) b.np * b.Pp;
-    const long m = a.m;
-    const long o[8] = { m, m + N1, m + 1, m + N1 + 1, m + Pp, m + Pp + N1, m + Pp + 1, m + Pp + N1 + 1 };
-    double* J0 = jn; double* J1 = jn + cs; double* J2 = jn + 2 * cs;
-    atomicAdd(J0 + o[0], a.jx[0]); atomicAdd(J0 + o[1], a.jx[0]); atomicAdd(J0 + o[2], a.jx[1]); atomicAdd(J0 + o[3], a.jx[1]);
-    atomicAdd(J0 + o[4], a.jx[2]); atomicAdd(J0 + o[5], a.jx[2]); atomicAdd(J0 + o[6], a.jx[3]); atomicAdd(J0 + o[7], a.jx[3]);
-    atomicAdd(J1 + o[0], a.jy[0]); atomicAdd(J1 + o[2], a.jy[0]); atomicAdd(J1 + o[1], a.jy[1]); atomicAdd(J1 + o[3], a.jy[1]);
-    atomicAdd(J1 + o[4], a.jy[2]); atomicAdd(J1 + o[6], a.jy[2]); atomicAdd(J1 + o[5], a.jy[3]); atomicAdd(J1 + o[7], a.jy[3]);
-    atomicAdd(J2 + o[0], a.jz[0]); atomicAdd(J2 + o[4], a.jz[0]); atomicAdd(J2 + o[1], a.jz[1]); atomicAdd(J2 + o[5], a.jz[1]);
-    atomicAdd(J2 + o[2], a.jz[2]); atomicAdd(J2 + o[6], a.jz[2]); atomicAdd(J2 + o[3], a.jz[3]); atomicAdd(J2 + o[7], a.jz[3]);
-    if constexpr (SC)
-      {
-	double* R = jn + 3 * cs;
-	#pragma unroll
-	for (int q = 0; q < 8; q++) atomicAdd(R + o[q], a.rho[q]);
-      }
-    a.m = -1;
-  }
-
-  template <bool SC>
-  __device__ __forceinline__ void deposit_open (const BunchDev& b, double* __restrict__ jn, DepositAcc<SC>& a, long m)
-  {
-    if (a.m == m) return;
-    deposit_flush<SC>(b, jn, a);
-    a.m = m;
-    #pragma unroll
-    for (int q = 0; q < 4; q++) { a.jx[q] = 0.0; a.jy[q] = 0.0; a.jz[q] = 0.0; }
-    if constexpr (SC) { _Pragma("unroll") for (int q = 0; q < 8; q++) a.rho[q] = 0.0; }
-  }
-
-  /* one segment with midpoint (mx,my,mz) and flux q (jx,jy,jz), fdtd.cpp:92-131                               */
-  template <bool SC>
-  __device__ __forceinline__ void deposit_segment (const BunchDev& b, DepositAcc<SC>& a, double q,
-						   double mx, double my, double mz, double jx, double jy, double jz)
-  {
-    double c;
-    const double dxp = modf( div_by( mx - b.xmin, b.dx, b.rdx ), &c );
-    const double dyp = modf( div_by( my - b.ymin, b.dy, b.rdy ), &c );
-    const double dzp = modf( div_by( mz - b.zmin, b.dz, b.rdz ), &c );
-    const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
-    const double h = q * 0.5;
-    a.jx[0] += h * y1 * z1 * jx; a.jx[1] += h * y2 * z1 * jx; a.jx[2] += h * y1 * z2 * jx; a.jx[3] += h * y2 * z2 * jx;
-    a.jy[0] += h * x1 * z1 * jy; a.jy[1] += h * x2 * z1 * jy; a.jy[2] += h * x1 * z2 * jy; a.jy[3] += h * x2 * z2 * jy;
-    a.jz[0] += h * x1 * y1 * jz; a.jz[1] += h * x2 * y1 * jz; a.jz[2] += h * x1 * y2 * jz; a.jz[3] += h * x2 * y2 * jz;
-  }
-
-  template <bool SC>
-  __global__ void __launch_bounds__(128, SC ? 3 : 4)
-  deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox, int run)
-  {
-    const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * run;
-    bool valid = false; int i0 = 0x7fffffff, i1 = -1, j0 = 0x7fffffff, j1 = -1, k0 = 0x7fffffff, k1 = -1;
-    DepositAcc<SC> acc; acc.m = -1;
-    const double zlo = ( b.size == 1 ) ? b.zp0 : b.zmin, zhi = ( b.size == 1 ) ? b.zp1 : b.zmax;
-
-    /* the particle of the NEXT iteration is loaded before the current one is worked on: a thread's particles are 64 bytes
-     * apart in every array, the loads miss L1 and nothing else hides their latency (the flush is fire-and-forget)       */
-    double nx = 0.0, ny = 0.0, nz = 0.0, nmx = 0.0, nmy = 0.0, nmz = 0.0, nq = 0.0;
-    if (t0 < n)
-      { nx = __ldg(P.r[0] + t0); ny = __ldg(P.r[1] + t0); nz = __ldg(P.r[2] + t0); nmx = __ldg(P.rm[0] + t0); nmy = __ldg(P.rm[1] + t0); nmz = __ldg(P.rm[2] + t0); nq = __ldg(P.q + t0); }
-
-    for (int r = 0; r < run; r++)
-      {
-	const long t = t0 + r;
-	if (t >= n) break;
-	const double rpx = nx,  rpy = ny,  rpz = nz;
-	const double rmx = nmx, rmy = nmy, rmz = nmz;
-	const double q = nq;
-	if (r + 1 < run && t + 1 < n)
-	  { nx = __ldg(P.r[0] + t + 1); ny = __ldg(P.r[1] + t + 1); nz = __ldg(P.r[2] + t + 1); nmx = __ldg(P.rm[0] + t + 1); nmy = __ldg(P.rm[1] + t + 1); nmz = __ldg(P.rm[2] + t + 1); nq = __ldg(P.q + t + 1); }
-
-	const bool bpf = ( rpx < b.xmax - b.dx && rpx > b.xmin + b.dx && rpy < b.ymax - b.dy && rpy > b.ymin + b.dy &&
-			   rpz < zhi && rpz >= zlo );
-	const bool bmf = ( rmx < b.xmax - b.dx && rmx > b.xmin + b.dx && rmy < b.ymax - b.dy && rmy > b.ymin + b.dy &&
-			   rmz < zhi && rmz >= zlo );
-	if (!bpf && !bmf) continue;
-
-	const int ip = (int) floor( div_by( rpx - b.xmin, b.dx, b.rdx ) ), jp = (int) floor( div_by( rpy - b.ymin, b.dy, b.rdy ) ), kp = (int) floor( div_by( rpz - b.zmin, b.dz, b.rdz ) );
-	const int im = (int) floor( div_by( rmx - b.xmin, b.dx, b.rdx ) ), jm = (int) floor( div_by( rmy - b.ymin, b.dy, b.rdy ) ), km = (int) floor( div_by( rmz - b.zmin, b.dz, b.rdz ) );
-
-	/* relay point, fdtd.cpp:80-85 */
-	const double rx = fmin( min(im, ip) * b.dx + b.dx + b.xmin, fmax( max(im, ip) * b.dx + b.xmin, 0.5 * ( rmx + rpx ) ) );
-	const double ry = fmin( min(jm, jp) * b.dy + b.dy + b.ymin, fmax( max(jm, jp) * b.dy + b.ymin, 0.5 * ( rmy + rpy ) ) );
-	const double rz = fmin( min(km, kp) * b.dz + b.dz + b.zmin, fmax( max(km, kp) * b.dz + b.zmin, 0.5 * ( rmz + rpz ) ) );
-
-	valid = true;
-	if (bpf)
-	  {
-	    deposit_open<SC>(b, jn, acc, (long) ( kp - b.k0 ) * b.Pp + (long) ip * b.N1 + jp);
-	    deposit_segment<SC>(b, acc, q, 0.5 * ( rpx + rx ), 0.5 * ( rpy + ry ), 0.5 * ( rpz + rz ), rpx - rx, rpy - ry, rpz - rz);
-	    if constexpr (SC)
-	      {
-		double c;
-		const double dxp = modf( div_by( rpx - b.xmin, b.dx, b.rdx ), &c ), dyp = modf( div_by( rpy - b.ymin, b.dy, b.rdy ), &c ), dzp = modf( div_by( rpz - b.zmin, b.dz, b.rdz ), &c );
-		const double x1 = 1.0 - dxp, x2 = dxp, y1 = 1.0 - dyp, y2 = dyp, z1 = 1.0 - dzp, z2 = dzp;
-		acc.rho[0] += q * x1 * y1 * z1; acc.rho[1] += q * x2 * y1 * z1; acc.rho[2] += q * x1 * y2 * z1; acc.rho[3] += q * x2 * y2 * z1;
-		acc.rho[4] += q * x1 * y1 * z2; acc.rho[5] += q * x2 * y1 * z2; acc.rho[6] += q * x1 * y2 * z2; acc.rho[7] += q * x2 * y2 * z2;
-	      }
-	    i0 = min(i0, ip); i1 = max(i1, ip + 1); j0 = min(j0, jp); j1 = max(j1, jp + 1); k0 = min(k0, kp - b.k0); k1 = max(k1, kp - b.k0 + 1);
-	  }
-	if (bmf)
-	  {
-	    deposit_open<SC>(b, jn, acc, (long) ( km - b.k0 ) * b.Pp + (long) im * b.N1 + jm);
-	    deposit_segment<SC>(b, acc, q, 0.5 * ( rmx + rx ), 0.5 * ( rmy + ry ), 0.5 * ( rmz + rz ), rx - rmx, ry - rmy, rz - rmz);
-	    i0 = min(i0, im); i1 = max(i1, im + 1); j0 = min(j0, jm); j1 = max(j1, jm + 1); k0 = min(k0, km - b.k0); k1 = max(k1, km - b.k0 + 1);
-	  }
-      }
-    deposit_flush<SC>(b, jn, acc);
-    warp_box_merge(jbox, valid, i0, i1, j0, j1, k0, k1);
   }
 
   /* ------------------------------------------------------------------------------------------------
