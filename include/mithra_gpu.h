@@ -226,7 +226,9 @@ int mithra_gpu_current_communicate (MithraGpu* h);   /* FdTd::currentCommunicate
 int mithra_gpu_advance_time        (MithraGpu* h);   /* solver.cpp:1396-1399                              */
 
 /* The body of the second while loop of Solver::solve (solver.cpp:1300-1399), nsteps times, without host
- * synchronisation between steps.                                                                       */
+ * synchronisation between steps.  Same results as the calls above issued one by one; the library additionally
+ * clears J and prepares the next seed tables on a side stream as soon as the field update has read them, and
+ * tests the screens at the tail of the push instead of in a pass of its own.                            */
 int mithra_gpu_step (MithraGpu* h, int nsteps);
 /* Same, bracketed by CUDA events on the library's stream; *ms = elapsed device time.                  */
 int mithra_gpu_step_timed (MithraGpu* h, int nsteps, float* ms);
