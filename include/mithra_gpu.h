@@ -250,6 +250,15 @@ int mithra_gpu_fetch_power_map (MithraGpu* h, double* pL, size_t capacity, int* 
  * (solver.cpp:1617-1640) stay with the host writer.                                                    */
 int mithra_gpu_bunch_moments (MithraGpu* h, double sums[13]);
 
+/* FdTd::fieldSample / FdTdSC::fieldSample (fdtd.cpp:851-950, fdtdSC.cpp:1147-1250), to be called where solve() calls
+ * it (after the field update and the bunch update of the step, before the field shift: solver.cpp:1326-1328).
+ * pos3 = n sampling points (x, y, z) in the moving frame, i.e. seed_.samplingPosition_ after initializeSeedSampling
+ * (solver.cpp:862-866); out9[9 t ..] = et[3], bt[3], at[3]: E and B evaluated at the 8 nodes of the point's cell and
+ * A^n, interpolated with the reference's weights and summation order (sf_.et, sf_.bt, sf_.at); mine[t] = 1 when the
+ * point lies in this slab (solver.cpp:896), else the nine values are 0.  The lab-frame combinations, the unit factors
+ * Ce, Cb, Ca and the text line (fdtd.cpp:914-942) stay with the host writer.                                   */
+int mithra_gpu_field_sample (MithraGpu* h, const double* pos3, size_t n, double* out9, unsigned char* mine);
+
 int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 
 /* Per-kernel timing of the last mithra_gpu_step_profiled call (device ms by CUDA events around each

@@ -91,7 +91,7 @@ SYMBOLS = (
     "mithra_gpu_step_timed", "mithra_gpu_synchronize", "mithra_gpu_fetch_power", "mithra_gpu_fetch_screen",
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
     "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
-    "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map", "mithra_gpu_bunch_moments",
+    "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map", "mithra_gpu_bunch_moments", "mithra_gpu_field_sample",
 )
 
 _lib = None
@@ -139,6 +139,7 @@ def load():
     lib.mithra_gpu_ipc_connect.argtypes = [vp, vp, vp]
     lib.mithra_gpu_fetch_power_map.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int)]
     lib.mithra_gpu_bunch_moments.argtypes = [vp, dp]
+    lib.mithra_gpu_field_sample.argtypes = [vp, dp, C.c_size_t, dp, C.POINTER(C.c_ubyte)]
     lib.mithra_gpu_selftest_divide.argtypes = [dp, C.c_size_t, C.c_double, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
@@ -261,6 +262,14 @@ class GpuSolver:
         out = np.zeros(13)
         self._check(self.lib.mithra_gpu_bunch_moments(self.h, _dptr(out)))
         return out
+
+    def field_sample(self, pos):
+        """FdTd::fieldSample at the points pos[n][3] (moving frame): (et, bt, at per point as an (n, 9) array, mine[n])."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(pos), 9))
+        mine = np.zeros(len(pos), dtype=np.uint8)
+        self._check(self.lib.mithra_gpu_field_sample(self.h, _dptr(pos), len(pos), _dptr(out), mine.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return out, mine
 
     def fetch_power_map(self):
         """pL[i*N1 + j] of the last powerVisualize call, or None when the plane lies in another slab."""

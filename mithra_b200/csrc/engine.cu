@@ -338,7 +338,7 @@ static int preload_kernels ()
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
-  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>);
+  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>); PL(field_sample<true>); PL(field_sample<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
@@ -780,6 +780,27 @@ extern "C" int mithra_gpu_bunch_moments (MithraGpu* h, double sums[13])
   CU(cudaFree(d_part));
   for (int bl = 0; bl < blocks; bl++)
     for (int q = 0; q < MITHRA_MOMENTS; q++) sums[q] += part[(size_t) bl * MITHRA_MOMENTS + q];
+  return 0;
+}
+
+/* FdTd::fieldSample / FdTdSC::fieldSample (fdtd.cpp:851-950, fdtdSC.cpp:1147-1250): interpolated E, B, A^n at n points  */
+extern "C" int mithra_gpu_field_sample (MithraGpu* h, const double* pos3, size_t n, double* out9, unsigned char* mine)
+{
+  USE(h);
+  if (n == 0) return 0;
+  if (!pos3 || !out9 || !mine) return fail("mithra_gpu_field_sample: null argument");
+  double* d_pos = 0; double* d_out = 0; unsigned char* d_mine = 0;
+  CU(cudaMalloc(&d_pos, n * 3 * sizeof(double))); CU(cudaMalloc(&d_out, n * 9 * sizeof(double))); CU(cudaMalloc(&d_mine, n));
+  CU(cudaMemcpyAsync(d_pos, pos3, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int grid = (int) ((n + 63) / 64);
+  if (h->fd.ncomp == 4) field_sample<true ><<<grid, 64, 0, h->stream>>>(h->fd, h->bd, h->A[h->ip1], h->A[h->in], h->eb, d_pos, (int) n, d_out, d_mine);
+  else                  field_sample<false><<<grid, 64, 0, h->stream>>>(h->fd, h->bd, h->A[h->ip1], h->A[h->in], h->eb, d_pos, (int) n, d_out, d_mine);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaMemcpyAsync(out9, d_out, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(mine, d_mine, n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_pos); cudaFree(d_out); cudaFree(d_mine);
   return 0;
 }
 

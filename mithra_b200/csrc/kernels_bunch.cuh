@@ -732,6 +732,72 @@ namespace mithra
     pL[px] = pw.pc * ( ( e1r * b1r - e1i * b1i ) - ( e2r * b2r - e2i * b2i ) );
   }
 
+  /* ------------------------------------------------------------------------------------------------
+   * FdTd::fieldSample / FdTdSC::fieldSample (fdtd.cpp:851-950): E, B (floats evaluated at the 8 nodes of the cell like
+   * fieldEvaluate) and A^n interpolated to sampling points, one thread per point, weights and summation in the
+   * reference's order (m, m+N1, m+1, m+N1+1, then plane k+1).  out[9 t ..] = et[3], bt[3], at[3]; mine[t] = 1 when the
+   * point lies in this slab's [zp0, zp1) (solver.cpp:896).  Nodes on a ghost plane take the E/B the neighbour
+   * evaluated for the whole plane.  The lab-frame combinations and unit factors stay with the host writer.
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool SC>
+  __global__ void __launch_bounds__(64)
+  field_sample (const FieldDev f, const __grid_constant__ BunchDev b, const double* __restrict__ anp1, const double* __restrict__ an,
+		const float4* __restrict__ ebn, const double* __restrict__ pos, int n, double* __restrict__ out,
+		unsigned char* __restrict__ mine)
+  {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double x = pos[3 * t], y = pos[3 * t + 1], z = pos[3 * t + 2];
+    const bool own = ( z < b.zp1 && z >= b.zp0 );
+    mine[t] = own ? 1 : 0;
+    double* o = out + 9 * t;
+    #pragma unroll
+    for (int q = 0; q < 9; q++) o[q] = 0.0;
+    if (!own) return;
+    double c1;
+    const double dxr = modf( ( x - b.xmin ) / b.dx, &c1 ); const int i = (int) c1;
+    const double dyr = modf( ( y - b.ymin ) / b.dy, &c1 ); const int j = (int) c1;
+    const double dzr = modf( ( z - b.zmin ) / b.dz, &c1 ); const int k = (int) c1 - b.k0;
+    if (i < 1 || i > f.N0 - 3 || j < 1 || j > f.N1 - 3 || k < 0 || k > f.np - 2) { mine[t] = 0; return; }
+    const double w[8] = {
+      ( 1.0 - dxr ) * ( 1.0 - dyr ) * ( 1.0 - dzr ),         dxr   * ( 1.0 - dyr ) * ( 1.0 - dzr ),
+      ( 1.0 - dxr ) *         dyr   * ( 1.0 - dzr ),         dxr   *         dyr   * ( 1.0 - dzr ),
+      ( 1.0 - dxr ) * ( 1.0 - dyr ) *         dzr,           dxr   * ( 1.0 - dyr ) *         dzr,
+      ( 1.0 - dxr ) *         dyr   *         dzr,           dxr   *         dyr   *         dzr };
+    const int di[8] = { 0, 1, 0, 1, 0, 1, 0, 1 }, dj[8] = { 0, 0, 1, 1, 0, 0, 1, 1 }, dk[8] = { 0, 0, 0, 0, 1, 1, 1, 1 };
+    const long cs = (long) f.np * f.Pp;
+    double et[3] = { 0.0, 0.0, 0.0 }, bt[3] = { 0.0, 0.0, 0.0 }, at[3] = { 0.0, 0.0, 0.0 };
+    for (int q = 0; q < 8; q++)
+      {
+	const int ii = i + di[q], jj = j + dj[q]; int kk = k + dk[q];
+	EB v;
+	const bool ghost = ( kk < f.kb && f.rank != 0 ) || ( kk == f.np - 1 && f.rank != f.size - 1 );
+	if (ghost)
+	  {
+	    const long m = (long) kk * f.P + (long) ii * f.N1 + jj;
+	    const float4 e = ebn[2 * m], bb = ebn[2 * m + 1];
+	    v.e[0] = e.x; v.e[1] = e.y; v.e[2] = e.z; v.b[0] = bb.x; v.b[1] = bb.y; v.b[2] = bb.z;
+	  }
+	else
+	  {
+	    int ke = kk;
+	    if (ke == 0 && f.rank == 0) ke = 1;                               /* the copied end planes, fdtd.cpp:754-773 */
+	    if (ke == f.np - 1 && f.rank == f.size - 1) ke = f.np - 2;
+	    v = eval_eb_node<SC>(f, anp1, an, ii, jj, ke);
+	  }
+	const long ma = (long) kk * f.Pp + (long) ii * f.N1 + jj;
+	#pragma unroll
+	for (int c = 0; c < 3; c++)
+	  {
+	    /* FieldVector::mv for the first node, pmv for the others (fieldvector.h): product, then sum             */
+	    const double pe = w[q] * (double) v.e[c], pb = w[q] * (double) v.b[c], pa = w[q] * an[c * cs + ma];
+	    et[c] = q ? et[c] + pe : pe;  bt[c] = q ? bt[c] + pb : pb;  at[c] = q ? at[c] + pa : pa;
+	  }
+      }
+    #pragma unroll
+    for (int c = 0; c < 3; c++) { o[c] = et[c]; o[3 + c] = bt[c]; o[6 + c] = at[c]; }
+  }
+
   __global__ void power_finish (const PowerDev pw, const double* __restrict__ partial, int nblocks, double* __restrict__ row)
   {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -26,7 +26,7 @@ namespace MITHRA
       N0_(0), N1_(0), N2_(0), N1N0_(0), np_(0), k0_(0), rank_(0), size_(1),
       xmin_(0), xmax_(0), ymin_(0), ymax_(0), zmin_(0), zmax_(0),
       gamma_(1.0), beta_(0.0), dt_(0.0), timep1_(0.0), time_(0.0), timem1_(0.0), timeBunch_(0.0),
-      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), bunchSampleFile_(0), spaceChargeSolver_(false)
+      nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), bunchSampleFile_(0), fieldSampleFile_(0), sfCe_(0.0), sfCb_(0.0), sfCa_(0.0), spaceChargeSolver_(false)
   {
     zp_[0] = zp_[1] = 0.0;
     memset(&uf_, 0, sizeof(uf_)); memset(&uc_, 0, sizeof(uc_)); memset(&ub_, 0, sizeof(ub_));
@@ -67,6 +67,7 @@ namespace MITHRA
     initializeMesh();
     lorentzBoostBunch();
     initializeField();
+    if ( seed_.sampling_ ) initializeSeedSampling();
     initializeBunchUpdate();
     initializePowerSample();
     initializePowerVisualize();
@@ -417,6 +418,100 @@ namespace MITHRA
     u.hC[16] = 1.0 / ( 2.0 * c * dt * dt );
     /* the seed's initial condition inside the total-field box (solver.cpp:828-839) is set on the device by
      * mithra_gpu_seed_initial in attachGpu()                                                                      */
+  }
+
+  /* Solver::initializeSeedSampling, solver.cpp:848-931: boost of the rhythm and of the points, the points of an
+   * over-line request, the filter to the mesh, the output file (single-rank naming: <base>-0.txt holds every point,
+   * whatever the number of slabs) and the unit factors.                                                            */
+  void Solver::initializeSeedSampling ()
+  {
+    printmessage(__FILE__, __LINE__, " ::: Initializing the field sampling data");
+    if ( seed_.samplingRhythm_ == 0 )
+      { printmessage(__FILE__, __LINE__, "The sampling rhythm of the field is zero although sampling is activated !!!"); exit(1); }
+    seed_.samplingRhythm_ /= gamma_;
+    for (unsigned i = 0; i < seed_.samplingPosition_.size(); i++) seed_.samplingPosition_[i][2] *= gamma_;
+    seed_.samplingLineBegin_[2] *= gamma_;
+    seed_.samplingLineEnd_  [2] *= gamma_;
+    if ( seed_.samplingType_ == OVERLINE )
+      {
+	FieldVector l = seed_.samplingLineEnd_;
+	const Double n = seed_.samplingRes_;
+	for (int d = 0; d < 3; d++) { l[d] -= seed_.samplingLineBegin_[d]; l[d] /= n; }
+	for (unsigned i = 0; i < n; i++)
+	  {
+	    FieldVector position;
+	    position[0] = seed_.samplingLineBegin_[0] + i * l[0];
+	    position[1] = seed_.samplingLineBegin_[1] + i * l[1];
+	    position[2] = seed_.samplingLineBegin_[2] + i * l[2];
+	    seed_.samplingPosition_.push_back(position);
+	  }
+      }
+    /* the reference reads ub_.dx, dy, dz here before initializeBunchUpdate has set them (solver.cpp:891-893 against
+     * :1056): zero-initialised members, so the margin of the test is zero                                            */
+    std::vector<FieldVector> kept;
+    for (unsigned int n = 0; n < seed_.samplingPosition_.size(); ++n)
+      {
+	const FieldVector& q = seed_.samplingPosition_[n];
+	if ( q[0] < xmax_ - ub_.dx && q[0] > xmin_ + ub_.dx && q[1] < ymax_ - ub_.dy && q[1] > ymin_ + ub_.dy &&
+	     q[2] < zmax_ - ub_.dz && q[2] > zmin_ + ub_.dz )
+	  kept.push_back(q);                                       /* every slab of this process: zmin_ <= z < zmax_       */
+	else
+	  printmessage(__FILE__, __LINE__, "The sampling point does not reside in the grid. No data is saved.");
+      }
+    seed_.samplingPosition_ = kept;
+    if ( !kept.empty() )
+      {
+	std::string name = "";
+	if ( seed_.samplingBasename_.compare(0, 1, "/") != 0 ) name = seed_.samplingDirectory_;
+	name += seed_.samplingBasename_ + "-" + stringify(0) + ".txt";
+	createDirectory(name, 0);
+	fieldSampleFile_ = new std::ofstream(name.c_str(), std::ios::trunc);
+      }
+    sfCe_ = mesh_.lengthScale_ / pow( mesh_.timeScale_, 2 );
+    sfCb_ = 1.0 / ( mesh_.lengthScale_ * mesh_.timeScale_ );
+    sfCa_ = 1.0 / mesh_.timeScale_;
+    printmessage(__FILE__, __LINE__, " The field sampling data are initialized. :::");
+  }
+
+  /* FdTd::fieldSample, fdtd.cpp:851-950 (FdTdSC::fieldSample writes the same columns): one line per call -- the time,
+   * then per point its coordinates and the requested fields; the interpolated et, bt, at come from the slab that
+   * holds the point (mithra_gpu_field_sample), the lab-frame combinations are the reference's expressions.          */
+  void FdTd::fieldSample ()
+  {
+    const size_t N = seed_.samplingPosition_.size();
+    if ( N == 0 || !fieldSampleFile_ ) return;
+    std::vector<double> pos(3 * N), val(9 * N, 0.0), part(9 * N);
+    std::vector<unsigned char> mine(N), have(N, 0);
+    for (size_t n = 0; n < N; n++) for (int d = 0; d < 3; d++) pos[3 * n + d] = seed_.samplingPosition_[n][d];
+    for (MithraGpu* g : gpu_)
+      {
+	check(mithra_gpu_field_sample(g, pos.data(), N, part.data(), mine.data()));
+	for (size_t n = 0; n < N; n++)
+	  if ( mine[n] && !have[n] ) { have[n] = 1; for (int q = 0; q < 9; q++) val[9 * n + q] = part[9 * n + q]; }
+      }
+    std::ofstream& f = *fieldSampleFile_;
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    f << time_ * gamma_ << "\t";
+    for (size_t n = 0; n < N; n++)
+      {
+	const double* et = &val[9 * n]; const double* bt = et + 3; const double* at = et + 6;
+	f << pos[3 * n] << "\t" << pos[3 * n + 1] << "\t" << pos[3 * n + 2] << "\t";
+	for (unsigned int i = 0; i < seed_.samplingField_.size(); i++)
+	  {
+	    const FieldType t = seed_.samplingField_[i];
+	    if      ( t == Ex ) f << ( gamma_ * et[0] + c0_ * sqrt( pow(gamma_, 2) - 1 ) * bt[1] ) * sfCe_ << "\t";
+	    else if ( t == Ey ) f << ( gamma_ * et[1] - c0_ * sqrt( pow(gamma_, 2) - 1 ) * bt[0] ) * sfCe_ << "\t";
+	    else if ( t == Ez ) f << et[2] * sfCe_ << "\t";
+	    else if ( t == Bx ) f << ( gamma_ * bt[0] - sqrt( pow(gamma_, 2) - 1 ) / c0_ * et[1] ) * sfCb_ << "\t";
+	    else if ( t == By ) f << ( gamma_ * bt[1] + sqrt( pow(gamma_, 2) - 1 ) / c0_ * et[0] ) * sfCb_ << "\t";
+	    else if ( t == Bz ) f << bt[2] * sfCb_ << "\t";
+	    else if ( t == Ax ) f << at[0] * sfCa_ << "\t";
+	    else if ( t == Ay ) f << at[1] * sfCa_ << "\t";
+	    else if ( t == Az ) f << at[2] * sfCa_ << "\t";
+	  }
+      }
+    f << std::endl;
   }
 
   /* solver.cpp:1050-1059 */
@@ -888,6 +983,7 @@ namespace MITHRA
     for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
     flushOutputs();
     if ( bunchSampleFile_ ) bunchSampleFile_->close();
+    if ( fieldSampleFile_ ) fieldSampleFile_->close();
     for (SampleRadiationPower& S : rp_) for (std::ofstream* f : S.file) if (f) f->close();
     for (SampleScreenProfile& S : scrp_) for (std::ofstream* f : S.files) if (f) f->close();
   }
@@ -936,6 +1032,7 @@ namespace MITHRA
 	      if ( fmod(tb, bunch_.bunchProfileRhythm_) < mesh_.timeStep_ && tb > 0.0 && bunch_.bunchProfileRhythm_ != 0.0 ) gated = true;
 	    }
 	  if ( pmapGroup_ >= 0 ) gated = true;                  /* the power map is fetched from inside powerVisualize()    */
+	  if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) gated = true;
 	}
 	if ( gpu_.size() == 1 && !gated && !getenv("MITHRA_HOST_CALL_BY_CALL") )
 	  {
@@ -950,6 +1047,8 @@ namespace MITHRA
 	fieldUpdate();
 	bunchUpdate();
 	recycleParticles();
+	/* rhythm-gated field sampling, solver.cpp:1326-1328                                                           */
+	if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) fieldSample();
 	/* rhythm-gated bunch samplers, solver.cpp:1352-1371                                                           */
 	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
 	if ( bunch_.bunchProfile_ )

@@ -56,6 +56,7 @@ namespace MITHRA
     void distributeParticles (std::list<Charge>& chargeVector);
     void computeFileGamma (BunchInitialize& bunchInit);
     void initializeMesh ();
+    void initializeSeedSampling ();                            /* solver.cpp:848-931 */
     void initializeField ();
     void initializeBunchUpdate ();
     void initializeBunch ();
@@ -140,6 +141,8 @@ namespace MITHRA
     int                 powerGroup_, screenGroup_;     /* FEL_ entries the C ABI's single power / screen group mirror */
     int                 pmapGroup_;                    /* ... and its single power-visualization group               */
     std::ofstream*      bunchSampleFile_;              /* sb_.file, solver.cpp:1073                                  */
+    std::ofstream*      fieldSampleFile_;              /* sf_.file, solver.cpp:918                                   */
+    Double              sfCe_, sfCb_, sfCa_;           /* sf_.Ce, Cb, Ca, solver.cpp:922-924                         */
     std::vector<Double> powerTimes_;                   /* timeBunch_ of the sampled steps not yet written             */
     bool                spaceChargeSolver_;
   };
@@ -155,7 +158,7 @@ namespace MITHRA
     void fieldUpdate ();
     void fieldShift ();
     void fieldEvaluate (long int) {}               /* E, B are evaluated eagerly on the device (eval_eb_box)         */
-    void fieldSample () {}
+    void fieldSample ();                           /* fdtd.cpp:851-950: values from mithra_gpu_field_sample, the reference's line */
     void fieldVisualizeAllDomain (unsigned int) {}
     void fieldVisualizeInPlane (unsigned int) {}
     void fieldVisualizeInPlaneXNormal (unsigned int) {}

@@ -54,6 +54,7 @@ def load():
               "current_update", "advance_time", "seed_initial"):
         getattr(lib, "oracle_" + n).argtypes = [vp]
     lib.oracle_field_evaluate.argtypes = [vp, C.c_long]
+    lib.oracle_field_sample.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.oracle_step.argtypes = [vp, C.c_int]
     lib.oracle_push_cells.argtypes = [vp, C.POINTER(C.c_long)]
     lib.oracle_deposit_cells.argtypes = [vp, C.POINTER(C.c_int)]
@@ -140,6 +141,14 @@ class Oracle:
 
     def powerVisualize(self):
         self.lib.oracle_power_visualize(self.o)
+
+    def field_sample(self, pos):
+        """FdTd::fieldSample at the points pos[n][3] (moving frame): et, bt, at per point as an (n, 9) array."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(pos), 9))
+        for t in range(len(pos)):
+            self.lib.oracle_field_sample(self.o, pos[t].ctypes.data_as(C.POINTER(C.c_double)), out[t].ctypes.data_as(C.POINTER(C.c_double)))
+        return out
 
     def fetch_power_map(self):
         ptr = self.lib.oracle_power_map(self.o)

@@ -435,6 +435,38 @@ void oracle_field_evaluate (Oracle* o, long m)
   o->pic[m] = 1;
 }
 
+/* FdTd::fieldSample fdtd.cpp:851-913 (FdTdSC::fieldSample likewise): interpolated et, bt, at of one sampling point
+ * (moving-frame coordinates, already boosted and filtered like solver.cpp:862-905); out[9] = et[3], bt[3], at[3].       */
+void oracle_field_sample (Oracle* o, const double* pos, double* out)
+{
+  const MithraGpuParams* p = &o->p;
+  const long N1 = p->N1, P = o->P;
+  double c1;
+  const double dxr = modf( ( pos[0] - p->xmin ) / p->dx, &c1 ); const int i = (int) c1;
+  const double dyr = modf( ( pos[1] - p->ymin ) / p->dy, &c1 ); const int j = (int) c1;
+  const double dzr = modf( ( pos[2] - p->zmin ) / p->dz, &c1 ); const int k = (int) c1;
+  const long m = ( k - p->k0 ) * P + i * N1 + j;
+  const long node[8] = { m, m + N1, m + 1, m + N1 + 1, m + P, m + P + N1, m + P + 1, m + P + N1 + 1 };
+  const double w[8] = {
+    ( 1.0 - dxr ) * ( 1.0 - dyr ) * ( 1.0 - dzr ),         dxr   * ( 1.0 - dyr ) * ( 1.0 - dzr ),
+    ( 1.0 - dxr ) *         dyr   * ( 1.0 - dzr ),         dxr   *         dyr   * ( 1.0 - dzr ),
+    ( 1.0 - dxr ) * ( 1.0 - dyr ) *         dzr,           dxr   * ( 1.0 - dyr ) *         dzr,
+    ( 1.0 - dxr ) *         dyr   *         dzr,           dxr   *         dyr   *         dzr };
+  for (int q = 0; q < 8; q++) if (!o->pic[node[q]]) oracle_field_evaluate(o, node[q]);
+  for (int c = 0; c < 3; c++)
+    {
+      /* FieldVector::mv then pmv (fieldvector.h:62-77): w * v, then += w * v                                       */
+      double et = w[0] * o->en[3 * node[0] + c], bt = w[0] * o->bn[3 * node[0] + c], at = w[0] * o->an[3 * node[0] + c];
+      for (int q = 1; q < 8; q++)
+	{
+	  et += w[q] * o->en[3 * node[q] + c];
+	  bt += w[q] * o->bn[3 * node[q] + c];
+	  at += w[q] * o->an[3 * node[q] + c];
+	}
+      out[c] = et; out[3 + c] = bt; out[6 + c] = at;
+    }
+}
+
 /* FdTd::fieldUpdate fdtd.cpp:231-800 (single slab: no MPI exchange) */
 void oracle_field_update (Oracle* o)
 {

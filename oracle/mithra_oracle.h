@@ -44,6 +44,7 @@ double  oracle_time_bunch (Oracle* o);
 /* the reference methods of the time march */
 void oracle_field_update   (Oracle* o);          /* FdTd::fieldUpdate / FdTdSC::fieldUpdate                 */
 void oracle_field_evaluate (Oracle* o, long m);  /* FdTd::fieldEvaluate                                    */
+void oracle_field_sample (Oracle* o, const double* pos3, double* out9);   /* FdTd::fieldSample fdtd.cpp:851-913 (one point) */
 void oracle_bunch_update   (Oracle* o);          /* rnm = rnp, then nUpdateBunch x Solver::bunchUpdate     */
 void oracle_screen_profile (Oracle* o);          /* Solver::screenProfile                                  */
 void oracle_power_sample   (Oracle* o);          /* Solver::powerSample                                    */

@@ -357,6 +357,37 @@ def test_eb_march_equals_node_kernel(job, shape, monkeypatch):
         assert m0.sum() < m1.sum()                       # the mask does skip something on a sparse bunch
 
 
+@pytest.mark.parametrize("job", ["micro-nsfd", "micro-sc", "micro-fd", "micro-seeded"])
+def test_field_sample_matches_oracle(job):
+    """mithra_gpu_field_sample (FdTd::fieldSample, fdtd.cpp:851-913) against the oracle's restatement after a field update
+    from identical state: E/B at the 8 nodes are bit-identical floats and the interpolation runs in the reference's
+    order, so et, bt, at are bit-identical doubles (seeded job: the libm of the injected seed -- 1e-12 on A, a float ulp
+    on E and B); points anywhere
+    inside the mesh, in the first and in the last cell the reference admits."""
+    p, g, gpu, cpu = _pair(job)
+    for _ in range(40):
+        helpers.solve_step(cpu)
+    _sync_gpu_to_cpu(p, gpu, cpu)
+    gpu.fieldUpdate(); cpu.fieldUpdate()
+    rng = np.random.default_rng(3)
+    n = 200
+    pos = np.empty((n, 3))
+    pos[:, 0] = rng.uniform(p.xmin + 1.001 * p.dx, p.xmax - 1.001 * p.dx, n)
+    pos[:, 1] = rng.uniform(p.ymin + 1.001 * p.dy, p.ymax - 1.001 * p.dy, n)
+    pos[:, 2] = rng.uniform(p.zmin + 1.001 * p.dz, p.zmax - 1.001 * p.dz, n)
+    pos[0] = [p.xmin + 1.001 * p.dx, p.ymin + 1.001 * p.dy, p.zmin + 1.001 * p.dz]
+    pos[1] = [p.xmax - 1.001 * p.dx, p.ymax - 1.001 * p.dy, p.zmax - 1.001 * p.dz]
+    got, mine = gpu.field_sample(pos)
+    want = cpu.field_sample(pos)
+    assert mine.all() and np.abs(want).max() > 0
+    if p.seed_enabled:
+        # E/B are FLOATS of differences of potentials that carry the 1e-13 of the seed's libm: the last float bit may flip
+        assert np.all(np.abs(got - want) <= 1e-6 * np.abs(want).max(axis=0))
+        np.testing.assert_allclose(got[:, 6:], want[:, 6:], rtol=1e-9, atol=1e-12 * np.abs(want[:, 6:]).max())
+    else:
+        np.testing.assert_array_equal(got, want)
+
+
 @pytest.mark.parametrize("d", [60.0, 9.19059968, -0.01532827, 30.0, 4.59529984, -4.49297199e+08, 3.0, 1.9999999999999998,
                                1.0000000000000002, 1e-3, 6.02e23, 1.7e-19, 1e-200])
 def test_constant_divisor_division_is_ieee(d):

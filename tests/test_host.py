@@ -206,3 +206,23 @@ def test_executable_writes_the_bunch_sampling_and_profile_files(gpus, tmp_path):
             if gpus > 1:                                     # slab order: compare as sets (sort by charge-independent key)
                 a, b = a[np.lexsort((a[:, 1], a[:, 3]))], b[np.lexsort((b[:, 1], b[:, 3]))]
             np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("job,rel,gpus", [("micro-fsample", "field-sampling/field-0.txt", 1), ("micro-fsample", "field-sampling/field-0.txt", 2),
+                                          ("micro-fline", "field-sampling/line-0.txt", 1), ("micro-fline", "field-sampling/line-0.txt", 3)])
+def test_executable_writes_the_field_sampling_file(job, rel, gpus, tmp_path):
+    """FdTd::fieldSample through the host executable (points at-point and over-line, all nine field columns) against the
+    unmodified reference's own text file for the same job: same rows at the same rhythm, same point coordinates, field
+    values to the 5 digits the format prints (relative to the largest value of the column: E_x of a y-polarised seed is
+    cancellation noise).  With several slabs every point is served by the slab that holds it, in one file."""
+    meta, g = helpers.load_golden(job)
+    subprocess.check_output([_exe(), _job(job), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    ref = [[float(x) for x in ln.split()] for ln in bytes(g["txt/" + rel]).decode().splitlines()]
+    got = [[float(x) for x in ln.split()] for ln in open(tmp_path / rel).read().splitlines()]
+    assert len(got) == len(ref) and len(ref) >= 5
+    assert [len(r) for r in got] == [len(r) for r in ref]
+    R, G = np.array(ref), np.array(got)
+    scale = np.abs(R).max(axis=0)
+    assert np.all(np.abs(G - R) <= 2e-4 * np.abs(R) + 2e-4 * scale)
+    assert (scale[4:] > 0).sum() >= 3
