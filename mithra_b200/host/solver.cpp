@@ -539,7 +539,12 @@ namespace MITHRA
 	createDirectory(bunch_.bunchProfileBasename_, 0);
       }
     if ( bunch_.bunchVTK_ )
-      printmessage(__FILE__, __LINE__, "Note: the bunch-visualization (.vtu) writer is outside this build's scope and is skipped.");
+      {
+	if ( bunch_.bunchVTKBasename_.compare(0, 1, "/") != 0 ) bunch_.bunchVTKBasename_ = bunch_.bunchVTKDirectory_ + bunch_.bunchVTKBasename_;
+	createDirectory(bunch_.bunchVTKBasename_, 0);
+	if ( bunch_.bunchVTKRhythm_ == 0 )
+	  { printmessage(__FILE__, __LINE__, "The visualization rhythm of the bunch is zero although visualization is activated !!!"); exit(1); }
+      }
   }
 
   /* planes, wavelengths, window length and prefactor of the power sampling; opens the files -- radiation.cpp:18-121 */
@@ -868,6 +873,85 @@ namespace MITHRA
     f.close();
   }
 
+  /* Solver::bunchVisualize, solver.cpp:1647-1757: the particle cloud as one ASCII .vtu piece (single-rank naming,
+   * "-p0-") with (q, lab-frame gamma, gamma x 0.512 MeV) per particle, plus the .pvtu that lists it                  */
+  void Solver::bunchVisualize ()
+  {
+    std::vector<double> all;
+    for (MithraGpu* g : gpu_)
+      {
+	size_t n = 0;
+	check(mithra_gpu_num_particles(g, &n));
+	if ( n == 0 ) continue;
+	std::vector<double> rows(n * 11);
+	check(mithra_gpu_download_particles(g, rows.data(), n, &n));
+	for (size_t i = 0; i < n; i++)
+	  {
+	    if ( gpu_.size() == 1 && !particleInProcessor(rows[11 * i + 3]) ) continue;
+	    all.insert(all.end(), rows.begin() + 11 * i, rows.begin() + 11 * i + 11);
+	  }
+      }
+    const size_t N = all.size() / 11;
+    std::string name = bunch_.bunchVTKBasename_ + "-p" + stringify(0) + "-" + stringify(nTimeBunch_) + ".vtu";
+    {
+      std::ofstream f(name.c_str(), std::ios::trunc);
+      f.setf(std::ios::scientific);
+      f.precision(4);
+      f << "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">" << std::endl;
+      f << "<UnstructuredGrid>" << std::endl;
+      f << "<Piece NumberOfPoints=\"" << N + 1 << "\" NumberOfCells=\"" << 1 << "\">" << std::endl;
+      f << "<Points>" << std::endl;
+      f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+      for (size_t i = 0; i < N; i++) f << all[11 * i + 1] << " " << all[11 * i + 2] << " " << all[11 * i + 3] << std::endl;
+      f << xmin_ << " " << ymin_ << " " << zmin_ << std::endl;
+      f << "</DataArray>" << std::endl;
+      f << "</Points>" << std::endl;
+      f << "<Cells>" << std::endl;
+      f << "<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">" << std::endl;
+      for (size_t i = 0; i < N + 1; ++i) f << i << " ";
+      f << std::endl;
+      f << "</DataArray>" << std::endl;
+      f << "<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">" << std::endl;
+      f << N + 1 << std::endl;
+      f << "</DataArray>" << std::endl;
+      f << "<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">" << std::endl;
+      f << 2 << std::endl;
+      f << "</DataArray>" << std::endl;
+      f << "</Cells>" << std::endl;
+      f << "<PointData Vectors = \"charge\">" << std::endl;
+      f << "<DataArray type=\"Float64\" Name=\"charge\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+      for (size_t i = 0; i < N; i++)
+	{
+	  const double* q = &all[11 * i];
+	  const Double gamma = sqrt( 1.0 + ( q[7] * q[7] + q[8] * q[8] + q[9] * q[9] ) );
+	  const Double beta  = q[9] / gamma;
+	  f << q[0] << " " << gamma * gamma_ * ( 1.0 + beta_ * beta ) << " " << gamma * gamma_ * ( 1.0 + beta_ * beta ) * 0.512 << std::endl;
+	}
+      f << 0.0 << " " << 0.0 << " " << 0.0 << std::endl;
+      f << 0.0 << " " << 0.0 << " " << 0.0 << std::endl;
+      f << "</DataArray>" << std::endl;
+      f << "</PointData>" << std::endl;
+      f << "</Piece>" << std::endl;
+      f << "</UnstructuredGrid>" << std::endl;
+      f << "</VTKFile>" << std::endl;
+    }
+    name = bunch_.bunchVTKBasename_ + "-" + stringify(nTimeBunch_) + ".pvtu";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    const size_t found = bunch_.bunchVTKBasename_.find_last_of("/");
+    const std::string base = bunch_.bunchVTKBasename_.substr(found + 1);
+    f << "<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">" << std::endl;
+    f << "<PUnstructuredGrid> GhostLevel = \"0\"" << std::endl;
+    f << "<PPoints>" << std::endl;
+    f << "<PDataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\" />" << std::endl;
+    f << "</PPoints>" << std::endl;
+    f << "<PPointData>" << std::endl;
+    f << "<PDataArray type=\"Float64\" Name=\"charge\" NumberOfComponents=\"3\" format=\"ascii\" />" << std::endl;
+    f << "</PPointData>" << std::endl;
+    f << "<Piece  Source=\"" << base + "-p" + stringify(0) + "-" + stringify(nTimeBunch_) + ".vtu" << "\"/>" << std::endl;
+    f << "</PUnstructuredGrid>" << std::endl;
+    f << "</VTKFile>" << std::endl;
+  }
+
   void Solver::screenProfile () { if ( screenGroup_ >= 0 ) for (MithraGpu* g : gpu_) check(mithra_gpu_screen_profile(g)); }
 
   void Solver::powerSample ()
@@ -1025,6 +1109,7 @@ namespace MITHRA
 	{
 	  const Double tb = time_ + mesh_.timeShift_;
 	  if ( bunch_.sampling_ && fmod(tb, bunch_.rhythm_) < mesh_.timeStep_ && tb > 0.0 ) gated = true;
+	  if ( bunch_.bunchVTK_ && fmod(tb, bunch_.bunchVTKRhythm_) < mesh_.timeStep_ && tb > 0.0 ) gated = true;
 	  if ( bunch_.bunchProfile_ )
 	    {
 	      for (unsigned int i = 0; i < bunch_.bunchProfileTime_.size(); i++)
@@ -1051,6 +1136,7 @@ namespace MITHRA
 	if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) fieldSample();
 	/* rhythm-gated bunch samplers, solver.cpp:1352-1371                                                           */
 	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
+	if ( bunch_.bunchVTK_ && fmod(time_ + mesh_.timeShift_, bunch_.bunchVTKRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchVisualize();
 	if ( bunch_.bunchProfile_ )
 	  {
 	    for (unsigned int i = 0; i < bunch_.bunchProfileTime_.size(); i++)

@@ -75,7 +75,7 @@ namespace MITHRA
 
     /* rhythm-gated writers of the reference that are outside the hot path: accepted, not run */
     void bunchSample ();
-    void bunchVisualize () {}
+    void bunchVisualize ();                        /* solver.cpp:1647-1757: .vtu / .pvtu of the particle cloud          */
     void bunchProfile ();
     void powerVisualize ();
     void energySample () {}

@@ -15,6 +15,7 @@ Every fixture <job>.npz holds, for one job:
     power                pG per step (radiation.cpp:209-218), 100 rows
     screen<i>            the reference's screen text files parsed back to doubles (solver.cpp:2229-2252)
     pmap, vts/<file>     power-visualization jobs: the per-pixel map after the last step and the .vts files as written
+    vtu/<file>           bunch-visualization jobs: the reference's .vtu / .pvtu files as written
     txt/<dir>/<file>     bunch-sampling / bunch-profile / field-sampling jobs: the reference's text files as written
 The fixtures pin oracle/mithra_oracle.c (tests/test_oracle_golden.py) and, through it, the CUDA path.
 """
@@ -32,7 +33,7 @@ sys.path.insert(0, ROOT)
 from oracle import binding  # noqa: E402
 
 JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
-EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
+EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
 
@@ -97,6 +98,8 @@ def make(job):
             dd = os.path.join(work, d)
             if os.path.isdir(dd):
                 for fn in sorted(os.listdir(dd)):
+                    if fn.endswith(".vtu") or fn.endswith(".pvtu"):
+                        out["vtu/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
                     if fn.endswith(".vts"):
                         out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
                     # bunch-sampling / bunch-profile text files exactly as the reference wrote them

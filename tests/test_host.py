@@ -226,3 +226,39 @@ def test_executable_writes_the_field_sampling_file(job, rel, gpus, tmp_path):
     scale = np.abs(R).max(axis=0)
     assert np.all(np.abs(G - R) <= 2e-4 * np.abs(R) + 2e-4 * scale)
     assert (scale[4:] > 0).sum() >= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_writes_the_bunch_visualization_files(gpus, tmp_path):
+    """Solver::bunchVisualize through the host executable: the .vtu / .pvtu files of a bunch-visualization job against the
+    unmodified reference's own files -- same file names (numbered by nTimeBunch_), same XML lines, particle coordinates
+    and (q, gamma_lab, gamma_lab x 0.512) to the 5 digits the format prints."""
+    meta, g = helpers.load_golden("micro-bvtk")
+    subprocess.check_output([_exe(), _job("micro-bvtk"), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("vtu/"))
+    assert len(want) == 10
+    assert sorted(os.listdir(tmp_path / "bunch-visualization")) == want
+    for fn in want:
+        ref = bytes(g["vtu/" + fn]).decode().splitlines()
+        got = open(tmp_path / "bunch-visualization" / fn).read().splitlines()
+        assert len(got) == len(ref), fn
+        rows_g, rows_r = [], []
+        for a, b in zip(got, ref):
+            if b.startswith("<"):
+                assert a == b, fn
+            else:
+                ta, tb = a.split(), b.split()
+                assert len(ta) == len(tb), fn
+                if len(tb) == 3:
+                    rows_g.append([float(x) for x in ta]); rows_r.append([float(x) for x in tb])
+                else:
+                    assert ta == tb, fn                  # connectivity, offsets, types
+        if rows_r:
+            G, R = np.array(rows_g), np.array(rows_r)
+            if gpus > 1:                                 # slab order: compare the two halves (points, data) as sets
+                h = len(R) // 2
+                for sl in (slice(0, h), slice(h, None)):
+                    np.testing.assert_allclose(np.sort(G[sl], axis=0), np.sort(R[sl], axis=0), rtol=2e-4, atol=2e-4 * np.abs(R[sl]).max())
+            else:
+                np.testing.assert_allclose(G, R, rtol=2e-4, atol=2e-4 * np.abs(R).max())
