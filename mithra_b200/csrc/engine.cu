@@ -84,7 +84,14 @@ struct MithraGpu
   bool            fuse_screens;           /* set by mithra_gpu_step around its push                         */
   bool            ev_main_fresh;          /* ev_main was recorded inside the last field update (after J's last reader) */
   unsigned char*  d_emask_cells;          /* E/B pencil mask: cells that hold a particle (marked by push / particle_box) */
-  unsigned char*  d_emask_nodes;          /* ... spread to the nodes those particles can gather from (spread_eb_mask)      */
+  unsigned char*  d_emask_nodes[2];       /* ... spread to the nodes those particles can gather from (spread_eb_mask); two
+					     buffers: the one of the last field update also bounds the deposit that followed */
+  int             emask_cur;              /* buffer of the last spread                                              */
+  int             pushes_since_spread;    /* the mask bounds a deposit only after exactly one push                  */
+  bool            emask_fresh;            /* no particle upload since the last spread                               */
+  bool            jmask_valid;            /* J lies inside d_emask_nodes[jmask_buf] (plus the slab merge planes)       */
+  bool            j_empty;                /* J has been cleared and nothing deposited or uploaded since               */
+  int             jmask_buf;
   size_t          emask_bytes;
 
   /* particles */
@@ -413,12 +420,13 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   h->fuse_screens = false; h->ev_main_fresh = false;
   h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
 
-  h->d_emask_cells = 0; h->d_emask_nodes = 0;
+  h->d_emask_cells = 0; h->d_emask_nodes[0] = h->d_emask_nodes[1] = 0;
+  h->emask_cur = 0; h->pushes_since_spread = 0; h->emask_fresh = false; h->jmask_valid = false; h->jmask_buf = 0; h->j_empty = true;
   h->emask_bytes = (size_t) ((f.np + (1 << MITHRA_EB_CHUNK_LOG2) - 1) >> MITHRA_EB_CHUNK_LOG2) * f.P;
   if (!getenv("MITHRA_NO_EBMASK"))
     {
       CU(cudaMalloc(&h->d_emask_cells, h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
-      CU(cudaMalloc(&h->d_emask_nodes, h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_nodes, 0, h->emask_bytes, h->stream));
+      for (int w = 0; w < 2; w++) { CU(cudaMalloc(&h->d_emask_nodes[w], h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_nodes[w], 0, h->emask_bytes, h->stream)); }
     }
   const size_t nodes = (size_t) f.np * f.P;
   CU(cudaMalloc(&h->eb, nodes * 2 * sizeof(float4))); CU(cudaMemsetAsync(h->eb, 0, nodes * 2 * sizeof(float4), h->stream));
@@ -549,7 +557,7 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   for (int l = 0; l < 4; l++) cudaFree(h->Abase[l]);
   cudaFree(h->d_stage);
   cudaFree(h->d_jbox); cudaFree(h->d_pbox); cudaFree(h->d_ebox); cudaFree(h->d_done);
-  cudaFree(h->eb); cudaFree(h->d_noutside); cudaFree(h->d_emask_cells); cudaFree(h->d_emask_nodes);
+  cudaFree(h->eb); cudaFree(h->d_noutside); cudaFree(h->d_emask_cells); cudaFree(h->d_emask_nodes[0]); cudaFree(h->d_emask_nodes[1]);
   for (int w = 0; w < 2; w++) { cudaFree(h->pstore[w]); cudaFree(h->idstore[w]); }
   cudaFree(h->d_hist); cudaFree(h->d_sums); cudaFree(h->d_key); cudaFree(h->d_rank);
   cudaFree(h->d_pm_fdt); cudaFree(h->d_pm_ep); cudaFree(h->d_pm_pL);
@@ -625,7 +633,10 @@ extern "C" int mithra_gpu_upload_fields (MithraGpu* h, const double* an, const d
       if (rho)  TRY(upload_vec(h, rho,  h->J,         1, 3, 1));
     }
   if (jn || rho)
-    set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0, 0, 0, f.N0 - 1, f.N1 - 1, f.np - 1);
+    {
+      set_box<<<1, 1, 0, h->stream>>>(h->d_jbox, 0, 0, 0, f.N0 - 1, f.N1 - 1, f.np - 1);
+      h->jmask_valid = false; h->j_empty = false;          /* an arbitrary source: the box alone bounds it               */
+    }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   h->anp1_is_current = true;
@@ -662,8 +673,8 @@ extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsig
   Box b; CU(cudaMemcpy(&b, h->d_ebox, sizeof(Box), cudaMemcpyDeviceToHost));
   std::vector<unsigned char> pencil;
   const double cdt = h->prm.c0 * h->prm.dt;
-  if (h->d_emask_nodes && !getenv("MITHRA_EB_BOX") && (int) ceil(cdt / h->prm.dz) < 16)
-    { pencil.resize(h->emask_bytes); CU(cudaMemcpy(pencil.data(), h->d_emask_nodes, h->emask_bytes, cudaMemcpyDeviceToHost)); }
+  if (h->d_emask_nodes[0] && !getenv("MITHRA_EB_BOX") && (int) ceil(cdt / h->prm.dz) < 16)
+    { pencil.resize(h->emask_bytes); CU(cudaMemcpy(pencil.data(), h->d_emask_nodes[h->emask_cur], h->emask_bytes, cudaMemcpyDeviceToHost)); }
   for (size_t m = 0; m < nodes; m++)
     {
       const int kr = (int) (m / f.P), r = (int) (m % f.P), i = r / f.N1, j = r % f.N1;
@@ -695,6 +706,7 @@ extern "C" int mithra_gpu_seed_initial (MithraGpu* h)
 
 static int refresh_particle_box (MithraGpu* h)
 {
+  h->emask_fresh = false;                                /* new positions: the node mask of the last field update is not theirs */
   set_box<<<1, 1, 0, h->stream>>>(h->d_pbox, 0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1);
   if (h->d_emask_cells) CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
   if (h->pn > 0)
@@ -855,13 +867,20 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 /* ---------------------------------------------------------------------------------------------------- */
 /* the time march                                                                                        */
 
+/* the pencil mask that bounds the J of the last deposit (kernels_field.cuh SourceMask), or 0: the box alone            */
+static const unsigned char* source_mask (const MithraGpu* h)
+{
+  static const bool off = getenv("MITHRA_NO_JMASK") != 0;
+  return (h->jmask_valid && !off) ? h->d_emask_nodes[h->jmask_buf] : 0;
+}
+
 /* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
 template <bool NSFD>
 static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
 {
   const FieldDev& f = h->fd;
   constexpr int T = 512, NB = 8;
-  static const int KC = getenv("MITHRA_STENCIL_KC") ? atoi(getenv("MITHRA_STENCIL_KC")) : 64;
+  static const int KC = getenv("MITHRA_STENCIL_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_STENCIL_KC")))) : 64;   /* <= 64: source_planes */
   if (getenv("MITHRA_STENCIL_PLAIN")) return false;
   const size_t smem = stencil_stream_smem(T, f.N1, NB);
   if (smem > 200 * 1024) return false;
@@ -872,7 +891,7 @@ static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
       h->stream_configured[NSFD] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0);
+  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h));
   return true;
 }
 
@@ -884,7 +903,7 @@ static void launch_stencil (MithraGpu* h, bool skiprim)
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
   dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);
-  stencil_interior<NSFD, BX, KC><<<grid, BX, 0, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox);
+  stencil_interior<NSFD, BX, KC><<<grid, BX, 0, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, source_mask(h));
 }
 
 /* per-plane seed table and the line table rim_update reads, for the time level `time`, on stream `st`           */
@@ -943,10 +962,10 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
     if (rim)
       {
 	const int per = 4 * (f.N1 - 2) + 4 * (f.N0 - 6);
-	static const int KC = getenv("MITHRA_RIM_KC") ? std::max(1, atoi(getenv("MITHRA_RIM_KC"))) : 64;   /* planes per CTA (fitting the grid to whole waves changes nothing: measured) */
+	static const int KC = getenv("MITHRA_RIM_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_RIM_KC")))) : 64;   /* planes per CTA (fitting the grid to whole waves changes nothing: measured) */
 	dim3 grid((unsigned) ((per + 127) / 128), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);
-	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC);
+	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h));
+	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h));
 	h->cnt.kernel_launches += 1;
 	if (h->d_seed && (zlo || zhi))
 	  {
@@ -1004,12 +1023,18 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
       {
 	/* only the pencils a particle can gather from (make_eb_box's padding, per pencil instead of per box); the
 	 * mask needs less than one 32-plane chunk of motion per step in z                                          */
-	const unsigned char* mask = (h->d_emask_nodes && padz < 16) ? h->d_emask_nodes : 0;
-	if (mask)
+	const unsigned char* mask = 0;
+	if (h->d_emask_nodes[0] && padz < 16)
 	  {
-	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, h->d_emask_nodes, h->d_ebox, padx, pady);
+	    /* into the buffer the source mask of this step's stencil and clear is NOT (they may still be reading it)  */
+	    h->emask_cur ^= 1;
+	    unsigned char* nodes = h->d_emask_nodes[h->emask_cur];
+	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, nodes, h->d_ebox, padx, pady);
 	    h->cnt.kernel_launches += 1;
+	    mask = nodes;
+	    h->emask_fresh = true; h->pushes_since_spread = 0;
 	  }
+	else h->emask_fresh = false;
 	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
 	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
 	if (zlo || zhi)
@@ -1107,6 +1132,7 @@ extern "C" int mithra_gpu_bunch_update (MithraGpu* h)
       else       push_particles<false><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->eb, h->time_bunch, nsub, 1, h->d_pbox, h->d_noutside, h->d_emask_cells, scr);
       h->cnt.kernel_launches += 2;
       CU(cudaGetLastError());
+      ++h->pushes_since_spread;
     }
   for (int s = 0; s < nsub; s++) { h->time_bunch += h->prm.dt_bunch; ++h->n_time_bunch; }
   h->cnt.particle_pushes += (unsigned long long) h->pn * nsub;
@@ -1208,7 +1234,8 @@ extern "C" int mithra_gpu_current_reset (MithraGpu* h)
       h->clear_ahead = false;
       return 0;
     }
-  clear_current_box<<<h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done);
+  clear_current_box<<<h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done, source_mask(h));
+  h->jmask_valid = false; h->j_empty = true;             /* J is zero: whatever is put there next decides            */
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -1223,7 +1250,8 @@ static int housekeeping_ahead (MithraGpu* h)
   if (!h->ev_main_fresh) CU(cudaEventRecord(h->ev_main, h->stream));
   h->ev_main_fresh = false;
   CU(cudaStreamWaitEvent(h->side, h->ev_main, 0));
-  clear_current_box<<<h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done);
+  clear_current_box<<<h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done, source_mask(h));
+  h->jmask_valid = false; h->j_empty = true;
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   CU(cudaEventRecord(h->ev_clear, h->side));
@@ -1243,6 +1271,15 @@ extern "C" int mithra_gpu_current_update (MithraGpu* h)
   USE(h);
   PhaseTimer t(h, PH_DEPOSIT);
   if (h->pn == 0) return 0;
+  /* Does the node mask of this step's E/B evaluation bound what is deposited now?  It does when the particles are the
+   * ones it was spread from, moved by exactly one push (rm and r both within the padding of the cell at the start of
+   * the step), and J was empty or bounded by the same mask before.                                                  */
+  {
+    const bool bounded = h->d_emask_nodes[0] && h->emask_fresh && h->pushes_since_spread == 1;
+    if (h->j_empty) { h->jmask_valid = bounded; h->jmask_buf = h->emask_cur; }
+    else if (!(h->jmask_valid && bounded && h->jmask_buf == h->emask_cur)) h->jmask_valid = false;
+    h->j_empty = false;
+  }
   static const int run = getenv("MITHRA_DEP_RUN") ? std::max(1, atoi(getenv("MITHRA_DEP_RUN"))) : MITHRA_DEP_RUN;
   const int grid = (int) ((h->pn + (size_t) 128 * run - 1) / ((size_t) 128 * run));
   if (h->fd.ncomp == 4) deposit_current<true ><<<grid, 128, 0, h->stream>>>(h->bd, h->P, (long) h->pn, h->J, h->d_jbox, run);

@@ -20,6 +20,29 @@
 namespace mithra
 {
   /* ------------------------------------------------------------------------------------------------
+   * Pencil mask of the source term.  J is non-zero only where the deposit of the last step put it: inside the box
+   * `jbox`, and there only on the node pencils (node column x 32 planes, see spread_eb_mask) the particles could reach
+   * -- the mask the E/B evaluation of the same step was given, because both ends of a particle's path of this step lie
+   * within the padding around its cell at the start of the step.  On a slab with neighbours the planes kb, np-3 and
+   * np-2 also receive the neighbours' deposits (exchange.cuh exchange_current) and are always taken.  jmask = 0: box only.
+   * ------------------------------------------------------------------------------------------------ */
+  /* bit (k - ks) of the result: does the thread of node column (i, j), p = i N1 + j, read the source on plane k of its
+   * march ks .. ke-1 (at most 64 planes)?  Box, pencil mask and merge planes folded into one word before the march.    */
+  __device__ __forceinline__ unsigned long long source_planes (const FieldDev& f, const Box& bx, const unsigned char* __restrict__ mask,
+							       int i, int j, long p, int ks, int ke)
+  {
+    if (!(i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1])) return 0ull;
+    unsigned long long en = 0ull;
+    int chunk = -1; bool on = true;
+    for (int k = max(ks, bx.lo[2]); k < ke && k <= bx.hi[2]; k++)
+      {
+	if (mask && (k >> 5) != chunk) { chunk = k >> 5; on = mask[(long) chunk * f.P + p] != 0; }
+	if (on || ( f.size > 1 && ( k == f.kb || k >= f.np - 3 ) )) en |= 1ull << (k - ks);
+      }
+    return en;
+  }
+
+  /* ------------------------------------------------------------------------------------------------
    * Interior stencil, z-marching register pipeline.
    *
    * grid  = ( ceil(P / BX), ceil((np-2) / KC), ncomp ),  block = BX threads.
@@ -32,7 +55,8 @@ namespace mithra
   template <bool NSFD, int BX, int KC>
   __global__ void __launch_bounds__(BX)
   stencil_interior (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		    const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox)
+		    const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox,
+		    const unsigned char* __restrict__ jmask)
   {
     const int p = blockIdx.x * BX + threadIdx.x;
     if (p >= f.P) return;
@@ -58,7 +82,7 @@ namespace mithra
 
     /* is this column inside the deposit box at all?                                                     */
     const Box bx = *jbox;
-    const bool inxy = (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+    const unsigned long long srcon = source_planes(f, bx, jmask, i, j, p, ks, ke);
 
     /* planes k-1 (suffix m), k (suffix 0), k+1 (suffix p) of the 5-point cross                          */
     double cm, c0, cp, xpm, xp0, xpp, xmm, xm0, xmp, ypm, yp0, ypp, ymm, ym0, ymp;
@@ -77,7 +101,7 @@ namespace mithra
 	if (NSFD) { xpp = q[N1]; xmp = q[-N1]; ypp = q[1]; ymp = q[-1]; }
 	const double vm1 = Am[(long) k * Pp];
 	double src = 0.0;
-	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = Jn[(long) k * Pp];
+	if ((srcon >> (k - ks)) & 1ull) src = Jn[(long) k * Pp];
 
 	double r;
 	if (NSFD)
@@ -169,7 +193,8 @@ namespace mithra
   template <bool NSFD, int T, int NB>
   __global__ void __launch_bounds__(T + 32, 2)
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim)
+		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
+		  const unsigned char* __restrict__ jmask)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 2 && NB <= 16, "stages: a power of two");
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -229,7 +254,7 @@ namespace mithra
     const double as = (c < 3) ? f.a[4] : f.a[5];
     const double alpha = f.alpha, beta = f.beta;
     const Box bx = *jbox;
-    const bool inxy = interior && (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+    unsigned long long srcon = interior ? source_planes(f, bx, jmask, i, j, p, ks, ke) : 0ull;      /* bit 0 = the next plane */
     long off = cb + p + (long) ks * Pp;                   /* the node in plane k, in A^{n+1} and J             */
     const double* myA = stA + N1e + tid;
     const double* myM = stM + tid;
@@ -256,7 +281,8 @@ namespace mithra
     #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
       {                                                                                                         \
 	double src = 0.0;                                                                                       \
-	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = __ldg(jn + off);                                      \
+	if (srcon & 1ull) src = __ldg(jn + off);                                                                \
+	srcon >>= 1;                                                                                            \
 	take(Pn, vnext);                                                                                        \
 	if (interior) anp1[off] = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);    \
 	vm1 = vnext; off += Pp; ++k;                                                                            \
@@ -305,7 +331,8 @@ namespace mithra
   template <bool NSFD>
   __global__ void __launch_bounds__(128, MITHRA_RIM_MINBLOCKS)
   rim_update (const FieldDev f, const RimDev rz, double* __restrict__ anp1, const double* __restrict__ an,
-	      const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC)
+	      const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC,
+	      const unsigned char* __restrict__ jmask)
   {
     const int N0 = f.N0, N1 = f.N1;
     const int nr = N1 - 2, nrows = 4 * nr, per = nrows + 4 * (N0 - 6);
@@ -329,7 +356,7 @@ namespace mithra
     const double as = (c < 3) ? f.a[4] : f.a[5];
     const double alpha = f.alpha, beta = f.beta;
     const Box bx = *jbox;
-    const bool inxy = (i >= bx.lo[0] && i <= bx.hi[0] && j >= bx.lo[1] && j <= bx.hi[1]);
+    unsigned long long srcon = source_planes(f, bx, jmask, i, j, (long) i * N1 + j, ks, ke);
 
     /* faces behind this node: offset of the face node s from n, 0 = none                                      */
     const int dsx = (i == 1) ? -N1 : (i == N0 - 2) ? N1 : 0;
@@ -353,7 +380,8 @@ namespace mithra
 	const Cross Pn = cross_at(k + 1);
 	const double vm1 = Am[ko];
 	double src = 0.0;
-	if (inxy && k >= bx.lo[2] && k <= bx.hi[2]) src = Jn[ko];
+	if (srcon & 1ull) src = Jn[ko];
+	srcon >>= 1;
 	/* loads of the fused work, issued with the rest                                                          */
 	const bool seedk = (k >= rz.KI && k < rz.KF);
 	double ux = 0.0, uy = 0.0, amsx = 0.0, amsy = 0.0, dxp = 0.0, dxm = 0.0, dyp = 0.0, dym = 0.0;
@@ -566,7 +594,8 @@ namespace mithra
    * non-zero) and leave the box empty for the next deposit.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
-  clear_current_box (const FieldDev f, double* __restrict__ jn, Box* __restrict__ jbox, unsigned int* __restrict__ done)
+  clear_current_box (const FieldDev f, double* __restrict__ jn, Box* __restrict__ jbox, unsigned int* __restrict__ done,
+		     const unsigned char* __restrict__ jmask)
   {
     const Box b = *jbox;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
@@ -581,7 +610,10 @@ namespace mithra
 	    const int c = (int) (w / ((long) ni * nk)); long r = w - (long) c * ni * nk;
 	    const int k = b.lo[2] + (int) (r / ni), i = b.lo[0] + (int) (r % ni);
 	    double* row = jn + fidx(f.Pp, f.np, f.N1, c, k, i, b.lo[1]);
-	    for (int j = lane; j < nj; j += 32) row[j] = 0.0;
+	    /* only the pencils that can hold a deposit (SourceMask); every plane that takes the neighbours' deposits   */
+	    const bool all = !jmask || ( f.size > 1 && ( k == f.kb || k >= f.np - 3 ) );
+	    const unsigned char* mrow = jmask ? jmask + (long) (k >> 5) * f.P + (long) i * f.N1 + b.lo[1] : 0;
+	    for (int j = lane; j < nj; j += 32) if (all || mrow[j]) row[j] = 0.0;
 	  }
       }
     /* the last block to finish empties the box                                                          */
