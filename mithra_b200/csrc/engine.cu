@@ -867,7 +867,7 @@ extern "C" int mithra_gpu_get_time (MithraGpu* h, double* time, double* time_bun
 /* ---------------------------------------------------------------------------------------------------- */
 /* the time march                                                                                        */
 
-/* the pencil mask that bounds the J of the last deposit (kernels_field.cuh SourceMask), or 0: the box alone            */
+/* the pencil mask that bounds the J of the last deposit (kernels_field.cuh source_planes), or 0: the box alone            */
 static const unsigned char* source_mask (const MithraGpu* h)
 {
   static const bool off = getenv("MITHRA_NO_JMASK") != 0;

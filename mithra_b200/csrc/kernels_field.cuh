@@ -602,15 +602,17 @@ namespace mithra
     if (ni > 0 && nj > 0 && nk > 0)
       {
 	/* one warp per row of the box (nj contiguous nodes): full sectors whatever the width of the box          */
-	const long rows = (long) ni * nk * f.ncomp;
-	const int  lane = threadIdx.x & 31;
-	const long wstride = ((long) gridDim.x * blockDim.x) >> 5;
-	for (long w = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < rows; w += wstride)
+	/* 32-bit row arithmetic (a slab has fewer than 2^31 rows): the 64-bit divisions were a good part of the kernel      */
+	const long rows64 = (long) ni * nk * f.ncomp;
+	const int  rows = rows64 < 0x7fffffffL ? (int) rows64 : 0x7fffffff;
+	const int  lane = threadIdx.x & 31, per = ni * nk;
+	const int  wstride = (int) (((long) gridDim.x * blockDim.x) >> 5);
+	for (int w = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < rows; w += wstride)
 	  {
-	    const int c = (int) (w / ((long) ni * nk)); long r = w - (long) c * ni * nk;
-	    const int k = b.lo[2] + (int) (r / ni), i = b.lo[0] + (int) (r % ni);
+	    const int c = w / per, r = w - c * per;
+	    const int k = b.lo[2] + r / ni, i = b.lo[0] + r % ni;
 	    double* row = jn + fidx(f.Pp, f.np, f.N1, c, k, i, b.lo[1]);
-	    /* only the pencils that can hold a deposit (SourceMask); every plane that takes the neighbours' deposits   */
+	    /* only the pencils that can hold a deposit (source_planes); every plane that takes the neighbours' deposits   */
 	    const bool all = !jmask || ( f.size > 1 && ( k == f.kb || k >= f.np - 3 ) );
 	    const unsigned char* mrow = jmask ? jmask + (long) (k >> 5) * f.P + (long) i * f.N1 + b.lo[1] : 0;
 	    for (int j = lane; j < nj; j += 32) if (all || mrow[j]) row[j] = 0.0;

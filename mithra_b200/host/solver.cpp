@@ -1092,6 +1092,16 @@ namespace MITHRA
       {
 	bunchUpdate();
 	screenProfile();
+	/* the bunch samplers of the first loop, solver.cpp:1253-1270                                                  */
+	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
+	if ( bunch_.bunchVTK_ && fmod(time_ + mesh_.timeShift_, bunch_.bunchVTKRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchVisualize();
+	if ( bunch_.bunchProfile_ )
+	  {
+	    for (unsigned int i = 0; i < bunch_.bunchProfileTime_.size(); i++)
+	      if ( time_ - bunch_.bunchProfileTime_[i] < mesh_.timeStep_ && time_ > bunch_.bunchProfileTime_[i] ) bunchProfile();
+	    if ( fmod(time_ + mesh_.timeShift_, bunch_.bunchProfileRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) && ( bunch_.bunchProfileRhythm_ != 0.0 ) )
+	      bunchProfile();
+	  }
 	for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_begin(g));
 	for (MithraGpu* g : gpu_) check(mithra_gpu_migrate_end(g));
 	advance();

@@ -261,6 +261,15 @@ int main (int argc, char* argv[])
       for (auto iter = s.chargeVectorn_.begin(); iter != s.chargeVectorn_.end(); iter++) iter->rnm = iter->rnp;
       for (Double t = 0.0; t < s.nUpdateBunch_; t += 1.0) { s.bunchUpdate(); s.timeBunch_ += bunch.timeStep_; ++s.nTimeBunch_; }
       s.screenProfile();
+      /* the bunch samplers of the first loop, solver.cpp:1253-1270                                   */
+      if (bunch.sampling_ && fmod(s.time_ + mesh.timeShift_, bunch.rhythm_) < mesh.timeStep_ && (s.time_ + mesh.timeShift_ > 0.0)) s.bunchSample();
+      if (bunch.bunchVTK_ && fmod(s.time_ + mesh.timeShift_, bunch.bunchVTKRhythm_) < mesh.timeStep_ && (s.time_ + mesh.timeShift_ > 0.0)) s.bunchVisualize();
+      if (bunch.bunchProfile_)
+	{
+	  for (unsigned int i = 0; i < bunch.bunchProfileTime_.size(); i++)
+	    if (s.time_ - bunch.bunchProfileTime_[i] < mesh.timeStep_ && s.time_ > bunch.bunchProfileTime_[i]) s.bunchProfile();
+	  if (fmod(s.time_ + mesh.timeShift_, bunch.bunchProfileRhythm_) < mesh.timeStep_ && (s.time_ + mesh.timeShift_ > 0.0) && (bunch.bunchProfileRhythm_ != 0.0)) s.bunchProfile();
+	}
       s.recycleParticles();
       s.timem1_ += mesh.timeStep_; s.time_ += mesh.timeStep_; s.timep1_ += mesh.timeStep_; ++s.nTime_;
     }

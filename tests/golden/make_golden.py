@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 from oracle import binding  # noqa: E402
 
 JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
-EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
+EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
 

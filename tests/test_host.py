@@ -262,3 +262,37 @@ def test_executable_writes_the_bunch_visualization_files(gpus, tmp_path):
                     np.testing.assert_allclose(np.sort(G[sl], axis=0), np.sort(R[sl], axis=0), rtol=2e-4, atol=2e-4 * np.abs(R[sl]).max())
             else:
                 np.testing.assert_allclose(G, R, rtol=2e-4, atol=2e-4 * np.abs(R).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_runs_the_particle_only_loop_before_the_time_origin(gpus, tmp_path):
+    """initial-time-back-shift: the first loop of Solver::solve (solver.cpp:1232-1291, 179 particle-only steps of
+    micro-backshift with the bunch samplers running) followed by 100 field steps, against the unmodified reference's
+    text files: bunch moments, bunch profiles (including those written while part of the bunch is still outside the mesh:
+    the ownership test of the profile writer) and the power rows."""
+    meta, g = helpers.load_golden("micro-backshift")
+    nsteps = int(g["t0"][2]) + 100
+    assert int(g["t0"][2]) == 179
+    subprocess.check_output([_exe(), _job("micro-backshift"), "--steps", str(nsteps), "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("txt/"))
+    assert len(want) == 7
+    for rel in want:
+        ref = np.array([float(x) for x in bytes(g["txt/" + rel]).decode().split()])
+        path = tmp_path / rel
+        assert path.exists(), rel
+        got = np.array([float(x) for x in open(path).read().split()])
+        assert got.shape == ref.shape, rel
+        if rel.startswith("bunch-sampling"):
+            ref, got = ref.reshape(-1, 13), got.reshape(-1, 13)
+            scale = np.abs(ref).max(axis=0)
+            assert np.all(np.abs(got - ref) <= 2e-4 * np.abs(ref) + 1e-6 * scale + 1e-7)
+        else:
+            assert got[0] == pytest.approx(ref[0], rel=1e-12)
+            a, b = got[1:].reshape(-1, 7), ref[1:].reshape(-1, 7)
+            if gpus > 1:
+                a, b = a[np.lexsort((a[:, 1], a[:, 3]))], b[np.lexsort((b[:, 1], b[:, 3]))]
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-12)
+    rows = np.array([[float(x) for x in ln.split()] for ln in open(tmp_path / "power-sampling" / "power-micro-0.txt").read().splitlines()])
+    assert rows.shape == (100, 2)
+    np.testing.assert_allclose(rows[:, 1], g["power"][:, 0], rtol=1e-7, atol=1e-12 * np.abs(g["power"]).max())
