@@ -267,16 +267,17 @@ def test_executable_writes_the_bunch_visualization_files(gpus, tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("gpus", [1, 2])
 def test_executable_runs_the_particle_only_loop_before_the_time_origin(gpus, tmp_path):
-    """initial-time-back-shift: the first loop of Solver::solve (solver.cpp:1232-1291, 179 particle-only steps of
+    """initial-time-back-shift: the first loop of Solver::solve (solver.cpp:1232-1291, 48 particle-only steps of
     micro-backshift with the bunch samplers running) followed by 100 field steps, against the unmodified reference's
-    text files: bunch moments, bunch profiles (including those written while part of the bunch is still outside the mesh:
-    the ownership test of the profile writer) and the power rows."""
+    text files: bunch moments, bunch profiles (one of them written before the time origin) and the power rows.
+    The shift is small enough that no particle crosses the periodic wrap of the single-rank reference, which would
+    DUPLICATE it there (self-send of solver.cpp:1544-1568 while particleInProcessor keeps the original: DESIGN.md)."""
     meta, g = helpers.load_golden("micro-backshift")
     nsteps = int(g["t0"][2]) + 100
-    assert int(g["t0"][2]) == 179
+    assert int(g["t0"][2]) == 48 and g["p0"].shape[0] == 480
     subprocess.check_output([_exe(), _job("micro-backshift"), "--steps", str(nsteps), "--gpus", str(gpus)], cwd=str(tmp_path))
     want = sorted(k[4:] for k in g.files if k.startswith("txt/"))
-    assert len(want) == 7
+    assert len(want) == 4
     for rel in want:
         ref = np.array([float(x) for x in bytes(g["txt/" + rel]).decode().split()])
         path = tmp_path / rel
