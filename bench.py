@@ -247,8 +247,8 @@ def run_oracle_sample(p_full, steps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)          # 20 warm-up + 200 timed field steps
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="fel-seeded", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="override the macro-particle count (0 = the workload's)")
