@@ -296,8 +296,11 @@ namespace mithra
       }
   }
 
+  #ifndef MITHRA_DEP_MINBLOCKS
+  #define MITHRA_DEP_MINBLOCKS 4
+  #endif
   template <bool SC>
-  __global__ void __launch_bounds__(128, SC ? 3 : 4)
+  __global__ void __launch_bounds__(128, SC ? MITHRA_DEP_MINBLOCKS - 1 : MITHRA_DEP_MINBLOCKS)
   deposit_current (const __grid_constant__ BunchDev b, ParticlesDev P, long n, double* __restrict__ jn, Box* __restrict__ jbox, int run)
   {
     const long t0 = ( (long) blockIdx.x * blockDim.x + threadIdx.x ) * run;
