@@ -259,6 +259,14 @@ int mithra_gpu_bunch_moments (MithraGpu* h, double sums[13]);
  * Ce, Cb, Ca and the text line (fdtd.cpp:914-942) stay with the host writer.                                   */
 int mithra_gpu_field_sample (MithraGpu* h, const double* pos3, size_t n, double* out9, unsigned char* mine);
 
+/* E, B (FdTd::fieldEvaluate, fdtd.cpp:818-845) and A^n at n mesh nodes, for the field visualisation writers
+ * FdTd::fieldVisualizeInPlane{X,Y,Z}Normal (fdtd.cpp:1128-1540), called where solve() calls them (solver.cpp:1332-1340).
+ * ijk3[3 t ..] = (i, j, k), k the plane index in this slab's reference numbering (global plane - k0 of the slab);
+ * out9[9 t ..] = en_[m][0..2], bn_[m][0..2] (floats, widened) and (*an_)[m][0..2]; mine[t] = 1 when the node is one of
+ * the slab's own planes (else zeros).  E/B of the mesh's two end planes are those of their interior neighbour (the
+ * reference's fieldEvaluate reads beyond its arrays there).                                                     */
+int mithra_gpu_field_nodes (MithraGpu* h, const int* ijk3, size_t n, double* out9, unsigned char* mine);
+
 int mithra_gpu_counters (MithraGpu* h, MithraGpuCounters* out);
 
 /* Per-kernel timing of the last mithra_gpu_step_profiled call (device ms by CUDA events around each

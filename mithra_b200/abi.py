@@ -92,6 +92,7 @@ SYMBOLS = (
     "mithra_gpu_counters", "mithra_gpu_step_profiled", "mithra_gpu_ipc_export", "mithra_gpu_ipc_connect",
     "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
     "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map", "mithra_gpu_bunch_moments", "mithra_gpu_field_sample",
+    "mithra_gpu_field_nodes",
 )
 
 _lib = None
@@ -140,6 +141,7 @@ def load():
     lib.mithra_gpu_fetch_power_map.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int)]
     lib.mithra_gpu_bunch_moments.argtypes = [vp, dp]
     lib.mithra_gpu_field_sample.argtypes = [vp, dp, C.c_size_t, dp, C.POINTER(C.c_ubyte)]
+    lib.mithra_gpu_field_nodes.argtypes = [vp, C.POINTER(C.c_int), C.c_size_t, dp, C.POINTER(C.c_ubyte)]
     lib.mithra_gpu_selftest_divide.argtypes = [dp, C.c_size_t, C.c_double, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib

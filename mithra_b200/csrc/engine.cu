@@ -345,7 +345,7 @@ static int preload_kernels ()
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
-  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>); PL(field_sample<true>); PL(field_sample<false>);
+  PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>); PL(field_sample<true>); PL(field_sample<false>); PL(field_nodes<true>); PL(field_nodes<false>);
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
@@ -813,6 +813,27 @@ extern "C" int mithra_gpu_field_sample (MithraGpu* h, const double* pos3, size_t
   CU(cudaMemcpyAsync(mine, d_mine, n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   cudaFree(d_pos); cudaFree(d_out); cudaFree(d_mine);
+  return 0;
+}
+
+/* E, B, A^n at a list of nodes for the field visualisation writers (fdtd.cpp:1128-1540)                              */
+extern "C" int mithra_gpu_field_nodes (MithraGpu* h, const int* ijk3, size_t n, double* out9, unsigned char* mine)
+{
+  USE(h);
+  if (n == 0) return 0;
+  if (!ijk3 || !out9 || !mine) return fail("mithra_gpu_field_nodes: null argument");
+  int* d_ijk = 0; double* d_out = 0; unsigned char* d_mine = 0;
+  CU(cudaMalloc(&d_ijk, n * 3 * sizeof(int))); CU(cudaMalloc(&d_out, n * 9 * sizeof(double))); CU(cudaMalloc(&d_mine, n));
+  CU(cudaMemcpyAsync(d_ijk, ijk3, n * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  const int grid = (int) ((n + 127) / 128);
+  if (h->fd.ncomp == 4) field_nodes<true ><<<grid, 128, 0, h->stream>>>(h->fd, h->A[h->ip1], h->A[h->in], h->eb, d_ijk, (long) n, d_out, d_mine);
+  else                  field_nodes<false><<<grid, 128, 0, h->stream>>>(h->fd, h->A[h->ip1], h->A[h->in], h->eb, d_ijk, (long) n, d_out, d_mine);
+  CU(cudaGetLastError());
+  h->cnt.kernel_launches += 1;
+  CU(cudaMemcpyAsync(out9, d_out, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(mine, d_mine, n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_ijk); cudaFree(d_out); cudaFree(d_mine);
   return 0;
 }
 

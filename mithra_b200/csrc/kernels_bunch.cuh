@@ -801,6 +801,40 @@ namespace mithra
     for (int c = 0; c < 3; c++) { o[c] = et[c]; o[3 + c] = bt[c]; o[6 + c] = at[c]; }
   }
 
+  /* ------------------------------------------------------------------------------------------------
+   * E, B (FdTd::fieldEvaluate) and A^n at a list of mesh nodes, for the host's field visualisation writers
+   * (fdtd.cpp:1128-1540).  ijk[3 t ..] = (i, j, k) with k the plane index of the reference's slab numbering of THIS slab;
+   * out[9 t ..] = en[3], bn[3] (the floats, widened) and an[3]; mine[t] = 1 when the slab holds the node as one of its
+   * own planes.  Transverse boundary nodes (i, j = 0, N-1) have no E/B in the reference either (zero there).  On the
+   * two end planes of the mesh the reference's fieldEvaluate reads beyond its arrays; here those planes take the values
+   * of their interior neighbour, like every other consumer of E/B (fdtd.cpp:754-773).
+   * ------------------------------------------------------------------------------------------------ */
+  template <bool SC>
+  __global__ void __launch_bounds__(128)
+  field_nodes (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an, const float4* __restrict__ ebn,
+	       const int* __restrict__ ijk, long n, double* __restrict__ out, unsigned char* __restrict__ mine)
+  {
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = ijk[3 * t], j = ijk[3 * t + 1], k = ijk[3 * t + 2] + f.kshift;
+    double* o = out + 9 * t;
+    #pragma unroll
+    for (int q = 0; q < 9; q++) o[q] = 0.0;
+    const bool inside = ( i >= 0 && i < f.N0 && j >= 0 && j < f.N1 && k >= 0 && k < f.np );
+    /* own planes: kb .. np-2, plus the mesh's end planes on the first / last slab                                */
+    const bool own = inside && ( ( k >= f.kb && k <= f.np - 2 ) || ( k < f.kb && f.rank == 0 ) || ( k == f.np - 1 && f.rank == f.size - 1 ) );
+    mine[t] = own ? 1 : 0;
+    if (!own) return;
+    const long cs = (long) f.np * f.Pp, ma = (long) k * f.Pp + (long) i * f.N1 + j;
+    o[6] = an[ma]; o[7] = an[cs + ma]; o[8] = an[2 * cs + ma];
+    if (i < 1 || i > f.N0 - 2 || j < 1 || j > f.N1 - 2) return;
+    int ke = k;
+    if (ke < f.kb) ke = f.kb;                         /* rank 0 only (own): plane 0 <- plane 1                      */
+    if (ke == f.np - 1) ke = f.np - 2;
+    const EB v = eval_eb_node<SC>(f, anp1, an, i, j, ke);
+    o[0] = v.e[0]; o[1] = v.e[1]; o[2] = v.e[2]; o[3] = v.b[0]; o[4] = v.b[1]; o[5] = v.b[2];
+  }
+
   __global__ void power_finish (const PowerDev pw, const double* __restrict__ partial, int nblocks, double* __restrict__ row)
   {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -68,6 +68,7 @@ namespace MITHRA
     lorentzBoostBunch();
     initializeField();
     if ( seed_.sampling_ ) initializeSeedSampling();
+    initializeSeedVTK();
     initializeBunchUpdate();
     initializePowerSample();
     initializePowerVisualize();
@@ -512,6 +513,230 @@ namespace MITHRA
 	  }
       }
     f << std::endl;
+  }
+
+  /* Solver::initializeSeedVTK, solver.cpp:938-1016: boost of rhythm and plane position, output directory, and the
+   * test that the plane lies in the mesh (with the reference's still-zero ub_.dx, dy, dz)                         */
+  void Solver::initializeSeedVTK ()
+  {
+    for (unsigned int i = 0; i < seed_.vtk_.size(); i++)
+      {
+	Seed::vtk& v = seed_.vtk_[i];
+	if ( !v.sample_ ) continue;
+	if ( v.rhythm_ == 0 )
+	  { printmessage(__FILE__, __LINE__, "The visualization rhythm of the field is zero although visualization is activated !!!"); exit(1); }
+	v.rhythm_      /= gamma_;
+	v.position_[2] *= gamma_;
+	if ( v.basename_.compare(0, 1, "/") != 0 ) v.basename_ = v.directory_ + v.basename_;
+	createDirectory(v.basename_, 0);
+	bool outside = false;
+	if ( v.type_ == INPLANE )
+	  {
+	    if      ( v.plane_ == XNORMAL ) outside = ( v.position_[0] > xmax_ - ub_.dx || v.position_[0] < xmin_ + ub_.dx );
+	    else if ( v.plane_ == YNORMAL ) outside = ( v.position_[1] > ymax_ - ub_.dy || v.position_[1] < ymin_ + ub_.dy );
+	    else if ( v.plane_ == ZNORMAL ) outside = ( v.position_[2] > zmax_ - ub_.dz || v.position_[2] < zmin_ + ub_.dz );
+	  }
+	if ( v.type_ == ALLDOMAIN )
+	  printmessage(__FILE__, __LINE__, "Note: the all-domain field visualization is not part of this build (DESIGN.md) and is skipped.");
+	if ( outside )
+	  {
+	    printmessage(__FILE__, __LINE__, "The plane does not reside in the grid. No data is saved.");
+	    seed_.vtk_.erase( seed_.vtk_.begin() + i );          /* like the reference, the loop index moves on regardless */
+	  }
+      }
+  }
+
+  /* en_[m], bn_[m], (*an_)[m] of global nodes (i, j, k) from the slab that holds each as one of its own planes        */
+  void FdTd::nodeValues (const std::vector<int>& ijk, std::vector<double>& val)
+  {
+    const size_t n = ijk.size() / 3;
+    val.assign(9 * n, 0.0);
+    std::vector<double> part(9 * n);
+    std::vector<unsigned char> mine(n), have(n, 0);
+    std::vector<int> loc(ijk);
+    for (size_t r = 0; r < gpu_.size(); r++)
+      {
+	for (size_t t = 0; t < n; t++) loc[3 * t + 2] = ijk[3 * t + 2] - slabK0_[r];
+	check(mithra_gpu_field_nodes(gpu_[r], loc.data(), n, part.data(), mine.data()));
+	for (size_t t = 0; t < n; t++)
+	  if ( mine[t] && !have[t] ) { have[t] = 1; for (int q = 0; q < 9; q++) val[9 * t + q] = part[9 * t + q]; }
+      }
+  }
+
+  namespace
+  {
+    /* column of the 9 node values a FieldType selects: en 0-2, bn 3-5, an 6-8                                       */
+    inline int fieldColumn (FieldType t)
+    { switch (t) { case Ex: return 0; case Ey: return 1; case Ez: return 2; case Bx: return 3; case By: return 4; case Bz: return 5;
+		   case Ax: return 6; case Ay: return 7; case Az: return 8; default: return -1; } }
+    /* en_, bn_ are floats in the reference: float x double products, summed in double (fdtd.cpp:1157-1165)          */
+    inline double blend (const double* a, const double* b, int col, Double d)
+    { return col < 0 ? 0.0 : a[col] * ( 1.0 - d ) + b[col] * d; }
+  }
+
+  void FdTd::fieldVisualizeInPlane (unsigned int ivtk)
+  {
+    if      ( seed_.vtk_[ivtk].plane_ == XNORMAL ) fieldVisualizeInPlaneXNormal(ivtk);
+    else if ( seed_.vtk_[ivtk].plane_ == YNORMAL ) fieldVisualizeInPlaneYNormal(ivtk);
+    else if ( seed_.vtk_[ivtk].plane_ == ZNORMAL ) fieldVisualizeInPlaneZNormal(ivtk);
+  }
+
+  /* the x- and y-normal planes share everything but the roles of i and j: one body, `xn` selects                      */
+  static void writeSidePlane (FdTd& s, unsigned int ivtk, bool xn)
+  {
+    const Seed::vtk& V = s.seed_.vtk_[ivtk];
+    const int N0 = s.N0_, N1 = s.N1_, N2 = s.N2_, NT = xn ? N1 : N0;          /* NT: nodes along the in-plane transverse axis */
+    Double c;
+    const Double dr = xn ? modf( ( V.position_[0] - s.xmin_ ) / s.mesh_.meshResolution_[0], &c )
+			 : modf( ( V.position_[1] - s.ymin_ ) / s.mesh_.meshResolution_[1], &c );
+    const int fixed = (int) c;
+    const size_t nf = V.field_.size();
+
+    /* the values: v[n][l], n = k NT + t, zero where the reference leaves them (t = 0, NT-1)                           */
+    std::vector<int> ijk; ijk.reserve((size_t) 6 * N2 * NT);
+    for (int k = 0; k < N2; k++)
+      for (int t = 1; t < NT - 1; t++)
+	{
+	  const int i = xn ? fixed : t, j = xn ? t : fixed;
+	  ijk.push_back(i); ijk.push_back(j); ijk.push_back(k);
+	  ijk.push_back(xn ? i + 1 : i); ijk.push_back(xn ? j : j + 1); ijk.push_back(k);
+	}
+    std::vector<double> val;
+    s.nodeValues(ijk, val);
+    std::vector<double> v((size_t) N2 * NT * nf, 0.0);
+    size_t q = 0;
+    for (int k = 0; k < N2; k++)
+      for (int t = 1; t < NT - 1; t++, q += 2)
+	for (size_t l = 0; l < nf; l++)
+	  v[((size_t) k * NT + t) * nf + l] = blend(&val[9 * q], &val[9 * (q + 1)], fieldColumn(V.field_[l]), dr);
+
+    std::string name = V.basename_ + "-p" + stringify(0) + "-" + stringify(s.nTime_) + ".vts";
+    {
+      std::ofstream f(name.c_str(), std::ios::trunc);
+      f.setf(std::ios::scientific);
+      f.precision(4);
+      f << "<?xml version=\"1.0\"?>" << std::endl;
+      f << "<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << std::endl;
+      if ( xn )
+	{
+	  f << "<StructuredGrid WholeExtent=\"0  0  0 " << N1 - 1 << " " << 0 << " " << N2 - 1 << "\">" << std::endl;
+	  f << "<Piece Extent=\" 0 0 0 " << N1 - 1 << " " << 0 << " " << N2 - 1 << "\">" << std::endl;
+	}
+      else
+	{
+	  f << "<StructuredGrid WholeExtent=\"0 " << N0 - 1 << " 0 0 " << 0 << " " << N2 - 1 << "\">" << std::endl;
+	  f << "<Piece Extent=\"0 " << N0 - 1 << " 0 0 " << 0 << " " << N2 - 1 << "\">" << std::endl;
+	}
+      f << "<Points>" << std::endl;
+      f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+      for (int k = 0; k < N2; k++)
+	for (int t = 0; t < NT; t++)
+	  {
+	    const long int m = (long int) k * s.N1N0_ + ( xn ? fixed : t ) * N1 + ( xn ? t : fixed );
+	    const FieldVector r1 = s.rc(m), r2 = s.rc(m + ( xn ? N1 : 1 ));
+	    f << r1[0] * ( 1.0 - dr ) + r2[0] * dr << " " << r1[1] << " " << r1[2] << std::endl;
+	  }
+      f << "</DataArray>" << std::endl;
+      f << "</Points>" << std::endl;
+      f << "<CellData>" << std::endl;
+      f << "</CellData>" << std::endl;
+      f << "<PointData Vectors = \"field\">" << std::endl;
+      f << "<DataArray type=\"Float64\" Name=\"field\" NumberOfComponents=\"" << nf << "\" format=\"ascii\">" << std::endl;
+      for (int k = 0; k < N2; k++)
+	for (int t = 0; t < NT; t++)
+	  {
+	    const size_t n = (size_t) k * NT + t;
+	    f << v[n * nf];
+	    for (size_t l = 1; l < nf; l++) f << " " << v[n * nf + l];
+	    f << std::endl;
+	  }
+      f << "</DataArray>" << std::endl;
+      f << "</PointData>" << std::endl;
+      f << "</Piece>" << std::endl;
+      f << "</StructuredGrid>" << std::endl;
+      f << "</VTKFile>" << std::endl;
+    }
+    /* the file that ties the pieces together: one piece, the single-rank layout                                      */
+    name = V.basename_ + "-" + stringify(s.nTime_) + ".pvts";
+    const std::string base = V.basename_.substr(V.basename_.find_last_of("/") + 1);
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f << "<?xml version=\"1.0\"?>" << std::endl;
+    f << "<VTKFile type=\"PStructuredGrid\" version=\"0.1\" >" << std::endl;
+    if ( xn ) f << "<PStructuredGrid WholeExtent=\" 0 0 0 " << N1 - 1 << " 0 " << N2 - 1 << "\" GhostLevel = \"0\" >" << std::endl;
+    else      f << "<PStructuredGrid WholeExtent=\"0 " << N0 - 1 << " 0 0 0 " << N2 - 1 << "\" GhostLevel = \"0\" >" << std::endl;
+    f << "<PPoints>" << std::endl;
+    f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\" />" << std::endl;
+    f << "</PPoints>" << std::endl;
+    f << "<PPointData>" << std::endl;
+    f << "<DataArray type=\"Float64\" NumberOfComponents=\"" << nf << "\" Name=\"field\" format=\"ascii\" />" << std::endl;
+    f << "</PPointData>" << std::endl;
+    const std::string piece = base + "-p" + stringify(0) + "-" + stringify(s.nTime_) + ".vts";
+    if ( xn ) f << "<Piece Extent=\"0 0 0 " << N1 - 1 << " " << 0 << " " << N2 - 2 + 1 << "\"" << " Source=\"" << piece << "\" />" << std::endl;
+    else      f << "<Piece Extent=\"0 " << N0 - 1 << " 0 0 " << 0 << " " << N2 - 2 + 1 << "\"" << " Source=\"" << piece << "\" />" << std::endl;
+    f << "</PStructuredGrid>" << std::endl;
+    f << "</VTKFile>" << std::endl;
+  }
+
+  void FdTd::fieldVisualizeInPlaneXNormal (unsigned int ivtk) { writeSidePlane(*this, ivtk, true); }
+  void FdTd::fieldVisualizeInPlaneYNormal (unsigned int ivtk) { writeSidePlane(*this, ivtk, false); }
+
+  /* fdtd.cpp:1452-1540: one piece, no .pvts; the x coordinate of the points is blended like the reference does       */
+  void FdTd::fieldVisualizeInPlaneZNormal (unsigned int ivtk)
+  {
+    const Seed::vtk& V = seed_.vtk_[ivtk];
+    Double c;
+    const Double dzr = modf( ( V.position_[2] - zmin_ ) / mesh_.meshResolution_[2], &c );
+    const int k = (int) c;
+    const size_t nf = V.field_.size();
+    std::vector<int> ijk; ijk.reserve((size_t) 6 * N0_ * N1_);
+    for (int j = 1; j < N1_ - 1; j++)
+      for (int i = 1; i < N0_ - 1; i++)
+	{ ijk.push_back(i); ijk.push_back(j); ijk.push_back(k); ijk.push_back(i); ijk.push_back(j); ijk.push_back(k + 1); }
+    std::vector<double> val;
+    nodeValues(ijk, val);
+    std::vector<double> v((size_t) N1N0_ * nf, 0.0);
+    size_t q = 0;
+    for (int j = 1; j < N1_ - 1; j++)
+      for (int i = 1; i < N0_ - 1; i++, q += 2)
+	for (size_t l = 0; l < nf; l++)
+	  v[((size_t) i * N1_ + j) * nf + l] = blend(&val[9 * q], &val[9 * (q + 1)], fieldColumn(V.field_[l]), dzr);
+
+    const std::string name = V.basename_ + "-p" + stringify(0) + "-" + stringify(nTime_) + ".vts";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    f << "<?xml version=\"1.0\"?>" << std::endl;
+    f << "<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << std::endl;
+    f << "<StructuredGrid WholeExtent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl;
+    f << "<Piece Extent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl;
+    f << "<Points>" << std::endl;
+    f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+    for (int j = 0; j < N1_; j++)
+      for (int i = 0; i < N0_; i++)
+	{
+	  const long int m = (long int) k * N1N0_ + i * N1_ + j;
+	  const FieldVector r1 = rc(m), r2 = rc(m + N1N0_);
+	  f << r1[0] * ( 1.0 - dzr ) + r2[0] * dzr << " " << r1[1] << " " << r1[2] << std::endl;
+	}
+    f << "</DataArray>" << std::endl;
+    f << "</Points>" << std::endl;
+    f << "<CellData>" << std::endl;
+    f << "</CellData>" << std::endl;
+    f << "<PointData Vectors = \"field\">" << std::endl;
+    f << "<DataArray type=\"Float64\" Name=\"field\" NumberOfComponents=\"" << nf << "\" format=\"ascii\">" << std::endl;
+    for (int j = 0; j < N1_; j++)
+      for (int i = 0; i < N0_; i++)
+	{
+	  const size_t n = (size_t) i * N1_ + j;
+	  f << v[n * nf];
+	  for (size_t l = 1; l < nf; l++) f << " " << v[n * nf + l];
+	  f << std::endl;
+	}
+    f << "</DataArray>" << std::endl;
+    f << "</PointData>" << std::endl;
+    f << "</Piece>" << std::endl;
+    f << "</StructuredGrid>" << std::endl;
+    f << "</VTKFile>" << std::endl;
   }
 
   /* solver.cpp:1050-1059 */
@@ -1128,6 +1353,8 @@ namespace MITHRA
 	    }
 	  if ( pmapGroup_ >= 0 ) gated = true;                  /* the power map is fetched from inside powerVisualize()    */
 	  if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) gated = true;
+	  for (unsigned int i = 0; i < seed_.vtk_.size(); i++)
+	    if ( seed_.vtk_[i].sample_ && fmod(time_, seed_.vtk_[i].rhythm_) < mesh_.timeStep_ && time_ > 0.0 ) gated = true;
 	}
 	if ( gpu_.size() == 1 && !gated && !getenv("MITHRA_HOST_CALL_BY_CALL") )
 	  {
@@ -1144,6 +1371,13 @@ namespace MITHRA
 	recycleParticles();
 	/* rhythm-gated field sampling, solver.cpp:1326-1328                                                           */
 	if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) fieldSample();
+	/* rhythm-gated field visualisation, solver.cpp:1332-1340                                                      */
+	for (unsigned int i = 0; i < seed_.vtk_.size(); i++)
+	  if ( seed_.vtk_[i].sample_ && fmod(time_, seed_.vtk_[i].rhythm_) < mesh_.timeStep_ && time_ > 0.0 )
+	    {
+	      if      ( seed_.vtk_[i].type_ == ALLDOMAIN ) fieldVisualizeAllDomain(i);
+	      else if ( seed_.vtk_[i].type_ == INPLANE   ) fieldVisualizeInPlane(i);
+	    }
 	/* rhythm-gated bunch samplers, solver.cpp:1352-1371                                                           */
 	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
 	if ( bunch_.bunchVTK_ && fmod(time_ + mesh_.timeShift_, bunch_.bunchVTKRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchVisualize();

@@ -57,6 +57,7 @@ namespace MITHRA
     void computeFileGamma (BunchInitialize& bunchInit);
     void initializeMesh ();
     void initializeSeedSampling ();                            /* solver.cpp:848-931 */
+    void initializeSeedVTK ();                                 /* solver.cpp:938-1016 */
     void initializeField ();
     void initializeBunchUpdate ();
     void initializeBunch ();
@@ -159,11 +160,12 @@ namespace MITHRA
     void fieldShift ();
     void fieldEvaluate (long int) {}               /* E, B are evaluated eagerly on the device (eval_eb_box)         */
     void fieldSample ();                           /* fdtd.cpp:851-950: values from mithra_gpu_field_sample, the reference's line */
-    void fieldVisualizeAllDomain (unsigned int) {}
-    void fieldVisualizeInPlane (unsigned int) {}
-    void fieldVisualizeInPlaneXNormal (unsigned int) {}
-    void fieldVisualizeInPlaneYNormal (unsigned int) {}
-    void fieldVisualizeInPlaneZNormal (unsigned int) {}
+    void fieldVisualizeAllDomain (unsigned int) {} /* not built: the reference evaluates E/B beyond its arrays there */
+    void fieldVisualizeInPlane (unsigned int ivtk);              /* fdtd.cpp:1111-1121 */
+    void fieldVisualizeInPlaneXNormal (unsigned int ivtk);       /* fdtd.cpp:1128-1285 */
+    void fieldVisualizeInPlaneYNormal (unsigned int ivtk);       /* fdtd.cpp:1292-1447 */
+    void fieldVisualizeInPlaneZNormal (unsigned int ivtk);       /* fdtd.cpp:1452-1540 */
+    void nodeValues (const std::vector<int>& ijk, std::vector<double>& val);   /* en_, bn_, an_ at global nodes */
     void fieldProfile () {}
   };
 

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 from oracle import binding  # noqa: E402
 
 JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
-EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
+EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift", "micro-fviz")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
 
@@ -100,6 +100,8 @@ def make(job):
                 for fn in sorted(os.listdir(dd)):
                     if fn.endswith(".vtu") or fn.endswith(".pvtu"):
                         out["vtu/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
+                    if fn.endswith(".pvts"):
+                        out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
                     if fn.endswith(".vts"):
                         out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
                     # bunch-sampling / bunch-profile text files exactly as the reference wrote them

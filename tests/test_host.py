@@ -297,3 +297,45 @@ def test_executable_runs_the_particle_only_loop_before_the_time_origin(gpus, tmp
     rows = np.array([[float(x) for x in ln.split()] for ln in open(tmp_path / "power-sampling" / "power-micro-0.txt").read().splitlines()])
     assert rows.shape == (100, 2)
     np.testing.assert_allclose(rows[:, 1], g["power"][:, 0], rtol=1e-7, atol=1e-12 * np.abs(g["power"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_writes_the_in_plane_field_visualization_files(gpus, tmp_path):
+    """FdTd::fieldVisualizeInPlane{X,Y,Z}Normal through the host executable (node values from mithra_gpu_field_nodes)
+    against the unmodified reference's own .vts / .pvts files: same files at the same rhythm, same XML lines, same point
+    coordinates, field values to the printed digits.  B on the two end planes of the mesh is excluded: the reference
+    evaluates it from memory in front of / behind its arrays there (fieldEvaluate at k = 0, np-1, fdtd.cpp:1146-1153)."""
+    meta, g = helpers.load_golden("micro-fviz")
+    N0, N2 = int(meta["N0"][0]), int(meta["N2"][0])
+    subprocess.check_output([_exe(), _job("micro-fviz"), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("vts/"))
+    assert len(want) == 20
+    assert sorted(os.listdir(tmp_path / "field-visualization")) == want
+    for fn in want:
+        ref = bytes(g["vts/" + fn]).decode().splitlines()
+        got = open(tmp_path / "field-visualization" / fn).read().splitlines()
+        assert len(got) == len(ref), fn
+        blocks_g, blocks_r, cur_g, cur_r = [], [], [], []
+        for a, b in zip(got, ref):
+            if b.startswith("<"):
+                assert a == b, fn
+                if cur_r:
+                    blocks_g.append(np.array(cur_g)); blocks_r.append(np.array(cur_r)); cur_g, cur_r = [], []
+            else:
+                cur_g.append([float(x) for x in a.split()]); cur_r.append([float(x) for x in b.split()])
+        if fn.endswith(".pvts"):
+            assert not blocks_r
+            continue
+        assert len(blocks_r) == 2, fn                       # points, field
+        pg, pr = blocks_g[0], blocks_r[0]
+        np.testing.assert_allclose(pg, pr, rtol=2e-4, atol=2e-4 * np.abs(pr).max(), err_msg=fn)
+        fg, fr = blocks_g[1], blocks_r[1]
+        assert fg.shape == fr.shape and np.abs(fr).max() > 0, fn
+        if fn.startswith("xz-p0"):                          # columns Ey, Bx, Az; rows k-major
+            fg, fr = fg.copy(), fr.copy()
+            fg[:N0, 1] = fr[:N0, 1] = 0.0
+            fg[-N0:, 1] = fr[-N0:, 1] = 0.0
+            assert fr.shape[0] == N0 * N2
+        scale = np.abs(fr).max(axis=0)
+        assert np.all(np.abs(fg - fr) <= 2e-4 * np.abs(fr) + 2e-4 * scale), fn
