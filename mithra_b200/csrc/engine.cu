@@ -941,7 +941,10 @@ static int launch_seed_lines (MithraGpu* h, double time, cudaStream_t st)
   return 0;
 }
 
-extern "C" int mithra_gpu_field_update (MithraGpu* h)
+/* FdTd::fieldUpdate in two halves: the potentials (stencil, rim, boundaries, ghost exchange: no particle involved) and the
+ * E/B evaluation for the bunch (needs the particle box and masks).  mithra_gpu_step enqueues the first half of the NEXT
+ * step before it blocks in the particle hand-over between slabs, so the device is not idle while the host waits.        */
+static int field_update_potentials (MithraGpu* h)
 {
   USE(h);
   const FieldDev& f = h->fd;
@@ -1029,6 +1032,17 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
 	if (exchange_potentials(h->xch, f, ap, h->ip1, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("A ghost exchange: %s", h->xch.error.c_str());
       }
   }
+  h->anp1_is_current = false;
+  h->cnt.cell_updates += (unsigned long long) (f.np - 1 - f.kb + (f.rank == 0 ? 1 : 0) + (f.rank == f.size - 1 ? 1 : 0)) * f.P;
+  return 0;
+}
+
+static int field_update_eb (MithraGpu* h)
+{
+  USE(h);
+  const FieldDev& f = h->fd;
+  double* ap = h->A[h->ip1]; const double* a = h->A[h->in];
+  const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
   {
     PhaseTimer t(h, PH_EVAL);
     const double cdt = h->prm.c0 * h->prm.dt;
@@ -1087,9 +1101,13 @@ extern "C" int mithra_gpu_field_update (MithraGpu* h)
 	if (exchange_eb(h->xch, f, h->eb, h->stream, h->num_sms, &h->cnt.kernel_launches)) return fail("E/B ghost exchange: %s", h->xch.error.c_str());
       }
   }
-  h->anp1_is_current = false;
-  h->cnt.cell_updates += (unsigned long long) (f.np - 1 - f.kb + (f.rank == 0 ? 1 : 0) + (f.rank == f.size - 1 ? 1 : 0)) * f.P;
   return 0;
+}
+
+extern "C" int mithra_gpu_field_update (MithraGpu* h)
+{
+  TRY(field_update_potentials(h));
+  return field_update_eb(h);
 }
 
 /* Counting sort of the bunch by cell (kernels_sort.cuh); the particle box of the last push / upload bounds the keys. */
@@ -1362,9 +1380,16 @@ extern "C" int mithra_gpu_advance_time (MithraGpu* h)
 extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
 {
   USE(h);
+  /* With neighbours the particle hand-over ends in a host synchronisation (the number of arrivals).  The first half of
+   * the NEXT field update needs no particle, so it is enqueued before the host blocks: the device works on the
+   * potentials while the host waits and then queues the particle phase (MITHRA_NO_LOOKAHEAD: the plain order).        */
+  static const bool lookahead = getenv("MITHRA_NO_LOOKAHEAD") == 0;
+  bool potentials_done = false;
   for (int s = 0; s < nsteps; s++)
     {
-      TRY(mithra_gpu_field_update(h));
+      if (!potentials_done) TRY(field_update_potentials(h));
+      potentials_done = false;
+      TRY(field_update_eb(h));
       TRY(housekeeping_ahead(h));
       /* the screens ride on the push (one pass over the bunch less); phase profiling keeps the two kernels apart     */
       static const bool nofuse = getenv("MITHRA_NO_FUSE") != 0;
@@ -1381,8 +1406,13 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
       TRY(mithra_gpu_current_update(h));
       TRY(mithra_gpu_current_communicate(h));
       TRY(mithra_gpu_migrate_begin(h));
+      TRY(mithra_gpu_advance_time(h));                       /* host-side counters only: nothing below reads them     */
+      if (lookahead && h->fd.size > 1 && s + 1 < nsteps && !h->profiling)
+	{
+	  TRY(field_update_potentials(h));
+	  potentials_done = true;
+	}
       TRY(mithra_gpu_migrate_end(h));
-      TRY(mithra_gpu_advance_time(h));
     }
   /* whatever was started ahead on the side stream belongs to this call: later work on the main stream (and the
    * caller's timing events) come after it                                                                        */
