@@ -4,7 +4,9 @@ the forked mini-MPI) runs jobs/<name>.job for NSTEPS field steps from its own in
 the field-sampling text file and a few scalars of initialize() -- a few KB (the particle lists and field dumps of
 make_golden.py would be tens of MB at this size).
 
-    python tests/golden/make_golden_job.py fel-ir 300        # needs /root/reference; ~2 minutes
+    python tests/golden/make_golden_job.py fel-ir 3000       # needs /root/reference; hours on one core: the radiation of the
+                                                             # shipped FEL-IR job reaches its power plane after ~2200 field steps,
+                                                             # which is why no such fixture is committed
 """
 import os
 import shutil
