@@ -308,9 +308,12 @@ namespace MITHRA
   /* EXTERNAL-FIELD, datainput.cpp:562-629 */
   void ParseDarius::readExtField (Iter& iter)
   {
+    /* one ExtField object serves every wave of the group (datainput.cpp:568): what a wave does not set -- order_ outside
+     * the super-gaussian beams -- is what the previous wave left there                                                  */
+    ExtField e;
     const std::map<std::string, std::function<void (Iter&)>> subs = {
       { "electromagnetic-wave", [&] (Iter& it) {
-	  ExtField e; e.type_ = EMWAVE;
+	  e.type_ = EMWAVE;
 	  BeamKeys b; Keys keys; b.add(keys, "beam-type");
 	  Signal d;                                     /* defaults of omitted keys, datainput.cpp:585-589               */
 	  b.a0 = e.a0_; b.offset = d.t0_; b.pulseLength = d.s_; b.wavelength = 1 / d.f0_; b.cep = d.cep_;

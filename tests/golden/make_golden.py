@@ -32,7 +32,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import binding  # noqa: E402
 
-JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz")
+JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz",
+        "micro-ics", "micro-lcls", "micro-trap", "micro-beams")
 EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift", "micro-fviz")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
