@@ -87,6 +87,8 @@ namespace mithra
     double rdx, rdy, rdz, rr2;          /* reciprocal_of(dx), (dy), (dz), (r2) for div_by                */
     double c0, gamma, beta, dt_shift;
     double r1, r2, dtb, dt_bunch, dt_field;
+    double reach[3];                    /* distance a particle can travel in one field step, in cells per axis, with a
+					   safety margin (particle_reach, kernels_bunch.cuh)                       */
     int    N0, N1, np, k0, P;          /* np, k0 internal (see FieldDev)                                */
     int    kshift;
     long   Pp;
@@ -124,15 +126,40 @@ namespace mithra
 
   __device__ __forceinline__ double div_by (double x, double d, double rd)
   {
-    const double ax = fabs(x);
     const double q = x * rd;
     const double r = __fma_rn(-q, d, x);
     double res = __fma_rn(r, rd, q);
-    if (!(ax > 1.0e-150 && ax < 1.0e150 && rd != 0.0))    /* rare: keep the straight-line path free of calls */
-      res = (ax == 0.0 && rd != 0.0) ? q : div_true(x, d); /* (+-0) rd has the sign of (+-0) / d; a real call, or
-							      the compiler runs the division's inline part speculatively */
+    /* |x| in [2^-498, 2^498) -- inside (1e-150, 1e150) -- read off the exponent field with integer instructions: the
+     * test costs the FP64 pipe nothing (three DSETP per division before)                                          */
+    const unsigned ex = ( (unsigned) __double2hiint(x) >> 20 ) & 0x7ffu;
+    if (ex - 525u >= 996u || rd == 0.0)                      /* rare: keep the straight-line path free of calls */
+      res = (x == 0.0 && rd != 0.0) ? q : div_true(x, d);    /* (+-0) rd has the sign of (+-0) / d; a real call, or
+								the compiler runs the division's inline part speculatively */
     return res;
   }
+
+  /* The same three operations without the guard, for quotients that end up in a FLOAT (the E/B evaluation): the guard
+   * only matters for |x| below 2^-969, where the residual would be subnormal -- such a quotient is far below the
+   * smallest float (and any sum it enters is unchanged by its last bit), so the float is the one IEEE division gives.
+   * (A zero keeps its value, possibly not its sign.)  mithra_gpu_create refuses divisors reciprocal_of() will not take. */
+  __device__ __forceinline__ double div_fast (double x, double d, double rd)
+  {
+    const double q = x * rd;
+    const double r = __fma_rn(-q, d, x);
+    return __fma_rn(r, rd, q);
+  }
+
+  /* ------------------------------------------------------------------------------------------------
+   * Reach mask.  The E/B evaluation, the source read of the stencil and the clear of J only have to touch the nodes a
+   * particle can gather from / deposit on during ONE field step: it travels less than c dt (|v| < c, the sub-steps add up
+   * to dt), so from its position at the start of the step it stays within the cells [lo, hi] per axis with
+   * lo = cell(r - c dt), hi = cell(r + c dt), and touches the nodes lo .. hi + 1.  The mask has one byte per CELL PENCIL
+   * (cell column (i, j) x 2^MITHRA_EB_CHUNK_LOG2 planes); a particle ORs into the byte of its own cell:
+   *   PRESENT, and which neighbouring cells / plane chunks its reach extends into (XLO .. ZHI).
+   * spread_eb_mask (kernels_field.cuh) turns the cell bytes into a node-pencil mask.
+   * ------------------------------------------------------------------------------------------------ */
+  #define MITHRA_EB_CHUNK_LOG2 3                /* planes per pencil of the masks                                       */
+  enum { REACH_PRESENT = 1, REACH_XLO = 2, REACH_XHI = 4, REACH_YLO = 8, REACH_YHI = 16, REACH_ZLO = 32, REACH_ZHI = 64 };
 
   __host__ __device__ inline long fidx (const long Pp, const int np, const int N1, int c, int k, int i, int j)
   { return ((long) c * np + k) * Pp + (long) i * N1 + j; }

@@ -58,6 +58,12 @@ struct MithraGpu
    * deposit) and the seed line table of the next time level (needed by the next field update)                */
   cudaStream_t    side;
   cudaEvent_t     ev_main, ev_clear, ev_seed;
+  /* the E/B evaluation of the nodes that depend on stencil_stream's output only runs on a third stream beside rim_update,
+   * the z faces, the edges and the ghost exchange (field_update_eb)                                              */
+  cudaStream_t    ebs;
+  cudaEvent_t     ev_stencil, ev_ebinner;
+  bool            ev_stencil_fresh;       /* recorded right after the stencil of the field update in flight          */
+  bool            potentials_ahead;       /* that field update was enqueued before the particle hand-over ended     */
   bool            overlap;                /* MITHRA_NO_OVERLAP unset                                       */
   bool            clear_ahead;            /* the box has been cleared (or is being cleared) on `side`      */
   bool            seed_ahead;             /* seed table + lines for seed_ahead_time are (being) computed   */
@@ -91,6 +97,7 @@ struct MithraGpu
   bool            emask_fresh;            /* no particle upload since the last spread                               */
   bool            jmask_valid;            /* J lies inside d_emask_nodes[jmask_buf] (plus the slab merge planes)       */
   bool            j_empty;                /* J has been cleared and nothing deposited or uploaded since               */
+  bool            j_zeroed_by_update;     /* the last field update cleared J on every plane it read it (stencil_stream + rim_update) */
   int             jmask_buf;
   size_t          emask_bytes;
 
@@ -306,6 +313,10 @@ static void fill_bunch_dev (const MithraGpuParams& p, const FieldDev& f, BunchDe
   b.rdx = reciprocal_of(b.dx); b.rdy = reciprocal_of(b.dy); b.rdz = reciprocal_of(b.dz); b.rr2 = reciprocal_of(p.r2);
   b.c0 = p.c0; b.gamma = p.gamma; b.beta = p.beta; b.dt_shift = p.dt_shift;
   b.r1 = p.r1; b.r2 = p.r2; b.dtb = p.dtb; b.dt_bunch = p.dt_bunch; b.dt_field = p.dt;
+  {
+    const double cdt = p.c0 * p.dt * ( 1.0 + 1.0e-6 );
+    b.reach[0] = cdt / p.dx + 1.0e-9; b.reach[1] = cdt / p.dy + 1.0e-9; b.reach[2] = cdt / p.dz + 1.0e-9;
+  }
   b.N0 = p.N0; b.N1 = p.N1; b.np = f.np; b.k0 = f.k0; b.kshift = f.kshift; b.P = f.P; b.Pp = f.Pp; b.ncomp = f.ncomp;
   b.size = p.size;
   b.n_und = p.n_undulators;
@@ -366,6 +377,9 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   if (params->size < 1 || params->rank < 0 || params->rank >= params->size) return fail("mithra_gpu_create: rank %d of %d slabs", params->rank, params->size);
   if (params->size > 1 && params->np < 6) return fail("mithra_gpu_create: a slab of %d planes is too thin to be split further", params->np);
 
+  for (double d : { params->dt, params->dx, params->dy, params->dz, params->r2 })
+    if (reciprocal_of(d) == 0.0) return fail("mithra_gpu_create: a cell size, the time step or r2 (%g) is outside (1e-100, 1e100) job units", d);
+
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     { cudaGetLastError(); return fail("mithra_gpu_create: no CUDA device available; this library has no CPU path"); }
@@ -387,6 +401,10 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_seed, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithPriority(&h->ebs, cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&h->ev_stencil, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_ebinner, cudaEventDisableTiming));
+    h->ev_stencil_fresh = false; h->potentials_ahead = false;
     h->overlap = !getenv("MITHRA_NO_OVERLAP");
     h->clear_ahead = false; h->seed_ahead = false; h->seed_ahead_time = 0.0;
   }
@@ -421,8 +439,8 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
   h->h_ebox_last.lo[0] = h->h_ebox_last.lo[1] = h->h_ebox_last.lo[2] = 0; h->h_ebox_last.hi[0] = h->h_ebox_last.hi[1] = h->h_ebox_last.hi[2] = -1;
 
   h->d_emask_cells = 0; h->d_emask_nodes[0] = h->d_emask_nodes[1] = 0;
-  h->emask_cur = 0; h->pushes_since_spread = 0; h->emask_fresh = false; h->jmask_valid = false; h->jmask_buf = 0; h->j_empty = true;
-  h->emask_bytes = (size_t) ((f.np + (1 << MITHRA_EB_CHUNK_LOG2) - 1) >> MITHRA_EB_CHUNK_LOG2) * f.P;
+  h->emask_cur = 0; h->pushes_since_spread = 0; h->emask_fresh = false; h->jmask_valid = false; h->jmask_buf = 0; h->j_empty = true; h->j_zeroed_by_update = false;
+  h->emask_bytes = ( (size_t) ((f.np + (1 << MITHRA_EB_CHUNK_LOG2) - 1) >> MITHRA_EB_CHUNK_LOG2) * f.P + 3 ) / 4 * 4;   /* whole 32-bit words: mark_eb_pencil */
   if (!getenv("MITHRA_NO_EBMASK"))
     {
       CU(cudaMalloc(&h->d_emask_cells, h->emask_bytes)); CU(cudaMemsetAsync(h->d_emask_cells, 0, h->emask_bytes, h->stream));
@@ -565,6 +583,9 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab); cudaFree(h->d_seedu);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ebs) { cudaStreamSynchronize(h->ebs); cudaStreamDestroy(h->ebs); }
+  if (h->ev_stencil) cudaEventDestroy(h->ev_stencil);
+  if (h->ev_ebinner) cudaEventDestroy(h->ev_ebinner);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_clear) cudaEventDestroy(h->ev_clear);
   if (h->ev_seed) cudaEventDestroy(h->ev_seed);
@@ -661,6 +682,16 @@ extern "C" int mithra_gpu_download_fields (MithraGpu* h, double* anp1, double* a
   return 0;
 }
 
+/* The reach mask (device_types.cuh) assumes that a particle crosses at most one cell face per axis transversally and
+ * stays within the neighbouring plane chunk in one field step -- true for every stable time step (c dt < dx, dy; c dt ~ dz). */
+static bool reach_mask_usable (const MithraGpu* h)
+{
+  if (!h->d_emask_nodes[0] || getenv("MITHRA_EB_BOX")) return false;
+  const double cdt = h->prm.c0 * h->prm.dt * ( 1.0 + 1.0e-6 );
+  return cdt + 1.0e-9 * h->prm.dx < h->prm.dx && cdt + 1.0e-9 * h->prm.dy < h->prm.dy &&
+	 (int) ceil(cdt / h->prm.dz) + 2 <= (1 << MITHRA_EB_CHUNK_LOG2);
+}
+
 extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsigned char* mask)
 {
   USE(h);
@@ -672,8 +703,7 @@ extern "C" int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsig
   CU(cudaMemcpy(tmp.data(), h->eb, nodes_int * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
   Box b; CU(cudaMemcpy(&b, h->d_ebox, sizeof(Box), cudaMemcpyDeviceToHost));
   std::vector<unsigned char> pencil;
-  const double cdt = h->prm.c0 * h->prm.dt;
-  if (h->d_emask_nodes[0] && !getenv("MITHRA_EB_BOX") && (int) ceil(cdt / h->prm.dz) < 16)
+  if (reach_mask_usable(h))
     { pencil.resize(h->emask_bytes); CU(cudaMemcpy(pencil.data(), h->d_emask_nodes[h->emask_cur], h->emask_bytes, cudaMemcpyDeviceToHost)); }
   for (size_t m = 0; m < nodes; m++)
     {
@@ -920,7 +950,8 @@ static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
 template <bool NSFD>
 static void launch_stencil (MithraGpu* h, bool skiprim)
 {
-  if (launch_stencil_stream<NSFD>(h, skiprim)) return;
+  h->j_zeroed_by_update = false;
+  if (launch_stencil_stream<NSFD>(h, skiprim)) { h->j_zeroed_by_update = true; return; }
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
   dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);
@@ -980,6 +1011,9 @@ static int field_update_potentials (MithraGpu* h)
     if (f.nsfd) launch_stencil<true>(h, rim); else launch_stencil<false>(h, rim);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 1;
+    h->ev_stencil_fresh = false;
+    if (h->overlap && !h->profiling && rim && h->j_zeroed_by_update)
+      { CU(cudaEventRecord(h->ev_stencil, h->stream)); h->ev_stencil_fresh = true; }
   }
   {
     PhaseTimer t(h, PH_BOUNDARY);
@@ -988,8 +1022,8 @@ static int field_update_potentials (MithraGpu* h)
 	const int per = 4 * (f.N1 - 2) + 4 * (f.N0 - 6);
 	static const int KC = getenv("MITHRA_RIM_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_RIM_KC")))) : 64;   /* planes per CTA (fitting the grid to whole waves changes nothing: measured) */
 	dim3 grid((unsigned) ((per + 127) / 128), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h));
-	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h));
+	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
+	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
 	h->cnt.kernel_launches += 1;
 	if (h->d_seed && (zlo || zhi))
 	  {
@@ -1047,7 +1081,8 @@ static int field_update_eb (MithraGpu* h)
     PhaseTimer t(h, PH_EVAL);
     const double cdt = h->prm.c0 * h->prm.dt;
     const int padx = (int) ceil(cdt / h->prm.dx), pady = (int) ceil(cdt / h->prm.dy), padz = (int) ceil(cdt / h->prm.dz);
-    make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
+    const bool early_box = h->ev_stencil_fresh && !h->potentials_ahead && reach_mask_usable(h) && !getenv("MITHRA_NO_EB_SPLIT");
+    if (!early_box) make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
     if (getenv("MITHRA_EB_BOX"))
       {
 	/* the node-at-a-time kernel over the whole box (the parity tests compare the two bit for bit)                  */
@@ -1056,22 +1091,43 @@ static int field_update_eb (MithraGpu* h)
       }
     else
       {
-	/* only the pencils a particle can gather from (make_eb_box's padding, per pencil instead of per box); the
-	 * mask needs less than one 32-plane chunk of motion per step in z                                          */
+	/* only the node pencils within some particle's reach (device_types.cuh "Reach mask")                          */
 	const unsigned char* mask = 0;
-	if (h->d_emask_nodes[0] && padz < 16)
+	const bool masked = reach_mask_usable(h);
+	/* The nodes whose E/B needs nothing but stencil_stream's output go to the stream `ebs` and run beside rim_update,
+	 * the z faces, the edges and the ghost exchange of this field update; the rest follows here.  Not when this field
+	 * update was enqueued ahead of the particle hand-over (the arrivals' marks are younger than its stencil).       */
+	const bool split = h->ev_stencil_fresh && !h->potentials_ahead && masked && !getenv("MITHRA_NO_EB_SPLIT");
+	h->ev_stencil_fresh = false;
+	cudaStream_t st = h->stream;
+	if (split)
+	  {
+	    st = h->ebs;
+	    CU(cudaStreamWaitEvent(st, h->ev_stencil, 0));
+	    make_eb_box<<<1, 1, 0, st>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
+	    h->cnt.kernel_launches += 1;
+	  }
+	if (masked)
 	  {
 	    /* into the buffer the source mask of this step's stencil and clear is NOT (they may still be reading it)  */
 	    h->emask_cur ^= 1;
 	    unsigned char* nodes = h->d_emask_nodes[h->emask_cur];
-	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, nodes, h->d_ebox, padx, pady);
+	    spread_eb_mask<<<h->num_sms * 8, 256, 0, st>>>(f, h->d_emask_cells, nodes, h->d_ebox);
 	    h->cnt.kernel_launches += 1;
 	    mask = nodes;
 	    h->emask_fresh = true; h->pushes_since_spread = 0;
 	  }
 	else h->emask_fresh = false;
-	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
-	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
+	if (split)
+	  {
+	    if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, st>>>(f, ap, a, h->eb, h->d_ebox, mask, 1);
+	    else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, st>>>(f, ap, a, h->eb, h->d_ebox, mask, 1);
+	    h->cnt.kernel_launches += 1;
+	    CU(cudaEventRecord(h->ev_ebinner, st));
+	    CU(cudaStreamWaitEvent(h->stream, h->ev_ebinner, 0));
+	  }
+	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask, split ? 2 : 0);
+	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask, split ? 2 : 0);
 	if (zlo || zhi)
 	  {
 	    /* planes 0 / np-1 of the global ends copy planes 1 / np-2 (fdtd.cpp:754-773)                               */
@@ -1106,6 +1162,7 @@ static int field_update_eb (MithraGpu* h)
 
 extern "C" int mithra_gpu_field_update (MithraGpu* h)
 {
+  h->potentials_ahead = false;
   TRY(field_update_potentials(h));
   return field_update_eb(h);
 }
@@ -1273,8 +1330,9 @@ extern "C" int mithra_gpu_current_reset (MithraGpu* h)
       h->clear_ahead = false;
       return 0;
     }
-  clear_current_box<<<h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done, source_mask(h));
+  clear_current_box<<<h->j_zeroed_by_update ? h->num_sms : h->num_sms * 8, 256, 0, h->stream>>>(h->fd, h->J, h->d_jbox, h->d_done, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
   h->jmask_valid = false; h->j_empty = true;             /* J is zero: whatever is put there next decides            */
+  h->j_zeroed_by_update = false;
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   return 0;
@@ -1289,8 +1347,8 @@ static int housekeeping_ahead (MithraGpu* h)
   if (!h->ev_main_fresh) CU(cudaEventRecord(h->ev_main, h->stream));
   h->ev_main_fresh = false;
   CU(cudaStreamWaitEvent(h->side, h->ev_main, 0));
-  clear_current_box<<<h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done, source_mask(h));
-  h->jmask_valid = false; h->j_empty = true;
+  clear_current_box<<<h->j_zeroed_by_update ? h->num_sms : h->num_sms * 8, 256, 0, h->side>>>(f, h->J, h->d_jbox, h->d_done, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
+  h->jmask_valid = false; h->j_empty = true; h->j_zeroed_by_update = false;
   CU(cudaGetLastError());
   h->cnt.kernel_launches += 1;
   CU(cudaEventRecord(h->ev_clear, h->side));
@@ -1387,6 +1445,7 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
   bool potentials_done = false;
   for (int s = 0; s < nsteps; s++)
     {
+      h->potentials_ahead = potentials_done;
       if (!potentials_done) TRY(field_update_potentials(h));
       potentials_done = false;
       TRY(field_update_eb(h));
@@ -1425,6 +1484,7 @@ extern "C" int mithra_gpu_synchronize (MithraGpu* h)
   USE(h);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaStreamSynchronize(h->side));
+  CU(cudaStreamSynchronize(h->ebs));
   CU(cudaGetLastError());
   if (h->xch.d_err)
     {

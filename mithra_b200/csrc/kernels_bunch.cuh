@@ -48,10 +48,40 @@ namespace mithra
    * Bounding box (cell indices) of the particles that will gather mesh fields, used to size the E/B
    * evaluation of the next step.  The host pads it by the distance a particle can travel in one field step.
    * ------------------------------------------------------------------------------------------------ */
-  /* the pencil (cell column x 32 planes) of a particle in the mask spread_eb_mask reads (kernels_field.cuh)       */
-  __device__ __forceinline__ void mark_eb_pencil (const BunchDev& b, unsigned char* __restrict__ emask, int i, int j, int k)
+  /* Reach of a particle at (x, y, z) during the next field step (device_types.cuh "Reach mask"): its cell (i, j, k) -- k a
+   * local plane index --, clamped into the mesh, and the byte it ORs into the cell-pencil mask.  false: nothing of the
+   * mesh's gather / deposit region is within reach.  The margin is c dt plus a relative 1e-6 and a 1e-9 of the cell, far
+   * above the rounding of the index arithmetic.                                                                      */
+  __device__ __forceinline__ bool particle_reach (const BunchDev& b, double x, double y, double z, int& i, int& j, int& k, unsigned int& bits)
   {
-    if (emask && k >= 0 && k < b.np) emask[((long) (k >> 5) * b.N0 + i) * b.N1 + j] = 1;
+    const double cdt = b.c0 * b.dt_field * ( 1.0 + 1.0e-6 );
+    const double mx = cdt + 1.0e-9 * b.dx, my = cdt + 1.0e-9 * b.dy, mz = cdt + 1.0e-9 * b.dz;
+    if (!( x + mx > b.xmin + b.dx && x - mx < b.xmax - b.dx && y + my > b.ymin + b.dy && y - my < b.ymax - b.dy &&
+	   z + mz >= b.zmin && z - mz < b.zmax )) return false;
+    /* position in cells (the quotient the cell index is the floor of), the margin in cells from the host               */
+    const double qx = div_by( x - b.xmin, b.dx, b.rdx ), qy = div_by( y - b.ymin, b.dy, b.rdy ), qz = div_by( z - b.zmin, b.dz, b.rdz );
+    const int ic = (int) floor( qx ), jc = (int) floor( qy ), kc = (int) floor( qz ) - b.k0;
+    const int ilo = (int) floor( qx - b.reach[0] ), ihi = (int) floor( qx + b.reach[0] );
+    const int jlo = (int) floor( qy - b.reach[1] ), jhi = (int) floor( qy + b.reach[1] );
+    const int klo = (int) floor( qz - b.reach[2] ) - b.k0, khi = (int) floor( qz + b.reach[2] ) - b.k0;
+    i = min(max(ic, 0), b.N0 - 2); j = min(max(jc, 0), b.N1 - 2); k = min(max(kc, 0), b.np - 1);
+    constexpr int L = MITHRA_EB_CHUNK_LOG2;
+    bits = REACH_PRESENT;
+    if (ilo < i) bits |= REACH_XLO;
+    if (ihi > i) bits |= REACH_XHI;
+    if (jlo < j) bits |= REACH_YLO;
+    if (jhi > j) bits |= REACH_YHI;
+    if ((max(klo, 0) >> L) < (k >> L)) bits |= REACH_ZLO;
+    if ((min(khi + 1, b.np - 1) >> L) > (k >> L)) bits |= REACH_ZHI;
+    return true;
+  }
+
+  /* OR the reach byte into the cell-pencil mask (one 32-bit reduction; the byte array is a multiple of 4 bytes long)  */
+  __device__ __forceinline__ void mark_eb_pencil (const BunchDev& b, unsigned char* __restrict__ emask, int i, int j, int k, unsigned int bits)
+  {
+    if (!emask) return;
+    const long idx = ((long) (k >> MITHRA_EB_CHUNK_LOG2) * b.N0 + i) * b.N1 + j;
+    atomicOr(reinterpret_cast<unsigned int*>(emask + (idx & ~3L)), bits << (8 * (int) (idx & 3L)));
   }
 
   __global__ void __launch_bounds__(256)
@@ -64,15 +94,9 @@ namespace mithra
 	bool valid = false; int i = 0, j = 0, k = 0;
 	if (t < n)
 	  {
-	    const double x = P.r[0][t], y = P.r[1][t], z = P.r[2][t];
-	    if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
-	      {
-		i = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
-		j = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
-		k = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
-		valid = true;
-		mark_eb_pencil(b, emask, i, j, k);
-	      }
+	    unsigned int bits;
+	    valid = particle_reach(b, P.r[0][t], P.r[1][t], P.r[2][t], i, j, k, bits);
+	    if (valid) mark_eb_pencil(b, emask, i, j, k, bits);
 	  }
 	warp_box_merge(box, valid, i, i, j, j, k, k);
       }
@@ -497,14 +521,10 @@ namespace mithra
 	    if (any) screen_records_call(b, scr, P.rm[0][t], P.rm[1][t], zm0, x, y, z, gx, gy, gz, P.id[t]);
 	  }
 
-	if (x < b.xmax - b.dx && x > b.xmin + b.dx && y < b.ymax - b.dy && y > b.ymin + b.dy && z < b.zmax && z >= b.zmin)
-	  {
-	    bi = (int) floor( div_by( x - b.xmin, b.dx, b.rdx ) );
-	    bj = (int) floor( div_by( y - b.ymin, b.dy, b.rdy ) );
-	    bk = (int) floor( div_by( z - b.zmin, b.dz, b.rdz ) ) - b.k0;
-	    boxvalid = true;
-	    mark_eb_pencil(b, emask, bi, bj, bk);
-	  }
+	/* where the particle can gather and deposit during the NEXT field step                                          */
+	unsigned int bits;
+	boxvalid = particle_reach(b, x, y, z, bi, bj, bk, bits);
+	if (boxvalid) mark_eb_pencil(b, emask, bi, bj, bk, bits);
       }
     warp_box_merge(pbox, boxvalid, bi, bi, bj, bj, bk, bk);
   }

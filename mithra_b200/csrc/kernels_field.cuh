@@ -21,7 +21,7 @@ namespace mithra
 {
   /* ------------------------------------------------------------------------------------------------
    * Pencil mask of the source term.  J is non-zero only where the deposit of the last step put it: inside the box
-   * `jbox`, and there only on the node pencils (node column x 32 planes, see spread_eb_mask) the particles could reach
+   * `jbox`, and there only on the node pencils (node column x 8 planes, see spread_eb_mask) the particles could reach
    * -- the mask the E/B evaluation of the same step was given, because both ends of a particle's path of this step lie
    * within the padding around its cell at the start of the step.  On a slab with neighbours the planes kb, np-3 and
    * np-2 also receive the neighbours' deposits (exchange.cuh exchange_current) and are always taken.  jmask = 0: box only.
@@ -36,7 +36,7 @@ namespace mithra
     int chunk = -1; bool on = true;
     for (int k = max(ks, bx.lo[2]); k < ke && k <= bx.hi[2]; k++)
       {
-	if (mask && (k >> 5) != chunk) { chunk = k >> 5; on = mask[(long) chunk * f.P + p] != 0; }
+	if (mask && (k >> MITHRA_EB_CHUNK_LOG2) != chunk) { chunk = k >> MITHRA_EB_CHUNK_LOG2; on = mask[(long) chunk * f.P + p] != 0; }
 	if (on || ( f.size > 1 && ( k == f.kb || k >= f.np - 3 ) )) en |= 1ull << (k - ks);
       }
     return en;
@@ -193,7 +193,7 @@ namespace mithra
   template <bool NSFD, int T, int NB>
   __global__ void __launch_bounds__(T + 32, 2)
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		  const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
+		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
 		  const unsigned char* __restrict__ jmask)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 2 && NB <= 16, "stages: a power of two");
@@ -277,14 +277,22 @@ namespace mithra
     take(P1, vm1);                                        /* plane ks with A^{n-1}(ks)                        */
 
     int k = ks;
+    /* The source term.  J is loaded one plane ahead (its DRAM latency hides behind a whole plane of work) through the
+     * non-coherent path: an ordinary load still in flight would hold up the release of the ring stage in take().  J's only
+     * reader also clears it (FdTd::currentReset): the thread that loaded a value stores the zero afterwards, data-dependent
+     * on the load, and nothing else touches that address during the launch.                                          */
+    double srcn = 0.0;
+    if (srcon & 1ull) srcn = __ldg(jn + off);
     /* one plane: Z is plane k, M plane k-1, the new plane k+1 lands in Pn                                         */
     #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
       {                                                                                                         \
-	double src = 0.0;                                                                                       \
-	if (srcon & 1ull) src = __ldg(jn + off);                                                                \
+	const double src = srcn;                                                                                \
 	srcon >>= 1;                                                                                            \
+	srcn = 0.0;                                                                                             \
+	if (srcon & 1ull) srcn = __ldg(jn + off + Pp);                                                          \
 	take(Pn, vnext);                                                                                        \
 	if (interior) anp1[off] = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);    \
+	if (src != 0.0) jn[off] = src * 0.0;                     /* a (signed) zero, ordered after the load */ \
 	vm1 = vnext; off += Pp; ++k;                                                                            \
       }
     while (true)
@@ -331,8 +339,8 @@ namespace mithra
   template <bool NSFD>
   __global__ void __launch_bounds__(128, MITHRA_RIM_MINBLOCKS)
   rim_update (const FieldDev f, const RimDev rz, double* __restrict__ anp1, const double* __restrict__ an,
-	      const double* __restrict__ anm1, const double* __restrict__ jn, const Box* __restrict__ jbox, int KC,
-	      const unsigned char* __restrict__ jmask)
+	      const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC,
+	      const unsigned char* __restrict__ jmask, int zero_j)
   {
     const int N0 = f.N0, N1 = f.N1;
     const int nr = N1 - 2, nrows = 4 * nr, per = nrows + 4 * (N0 - 6);
@@ -350,7 +358,7 @@ namespace mithra
     const double* A  = an   + nb;
     const double* Am = anm1 + nb;
     double*       Ap = anp1 + nb;
-    const double* Jn = jn   + nb;
+    double*       Jn = jn   + nb;
 
     const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
     const double as = (c < 3) ? f.a[4] : f.a[5];
@@ -380,7 +388,8 @@ namespace mithra
 	const Cross Pn = cross_at(k + 1);
 	const double vm1 = Am[ko];
 	double src = 0.0;
-	if (srcon & 1ull) src = Jn[ko];
+	const bool hadj = srcon & 1ull;
+	if (hadj) src = Jn[ko];
 	srcon >>= 1;
 	/* loads of the fused work, issued with the rest                                                          */
 	const bool seedk = (k >= rz.KI && k < rz.KF);
@@ -396,6 +405,8 @@ namespace mithra
 	if (syl >= 0 && seedk)
 	  { const double S = seed_assemble_comp(uy, polc, rz.ni, rz.supergaussian, c == 2, rz.gamma); r = syminus ? r - a2 * S : r + a2 * S; }
 	Ap[ko] = r;
+	if (hadj && zero_j) Jn[ko] = 0.0;                        /* J's only reader clears it (with the other stores: a store
+								    next to the load would split the batch of loads above) */
 	if (dsx != 0)
 	  {
 	    const bool lo = dsx < 0;
@@ -595,10 +606,15 @@ namespace mithra
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
   clear_current_box (const FieldDev f, double* __restrict__ jn, Box* __restrict__ jbox, unsigned int* __restrict__ done,
-		     const unsigned char* __restrict__ jmask)
+		     const unsigned char* __restrict__ jmask, int ends_only)
   {
     const Box b = *jbox;
-    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
+    const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
+    /* ends_only: stencil_stream and rim_update have cleared what they read -- every plane this slab updates; what is
+     * left are the planes below kb (ghosts whose deposits went to the neighbour; the z face on the first slab) and np-1:
+     * the planes lo[2] .. min(hi[2], kb-1), then np-1 if the box reaches it                                         */
+    const int nlow = ends_only ? max(0, min(b.hi[2], f.kb - 1) - b.lo[2] + 1) : 0;
+    const int nk = ends_only ? nlow + ( ( b.hi[2] >= f.np - 1 && b.lo[2] <= f.np - 1 ) ? 1 : 0 ) : b.hi[2] - b.lo[2] + 1;
     if (ni > 0 && nj > 0 && nk > 0)
       {
 	/* one warp per row of the box (nj contiguous nodes): full sectors whatever the width of the box          */
@@ -610,11 +626,12 @@ namespace mithra
 	for (int w = (int) (((long) blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < rows; w += wstride)
 	  {
 	    const int c = w / per, r = w - c * per;
-	    const int k = b.lo[2] + r / ni, i = b.lo[0] + r % ni;
+	    const int kr = r / ni, i = b.lo[0] + r % ni;
+	    const int k = ends_only ? ( kr < nlow ? b.lo[2] + kr : f.np - 1 ) : b.lo[2] + kr;
 	    double* row = jn + fidx(f.Pp, f.np, f.N1, c, k, i, b.lo[1]);
 	    /* only the pencils that can hold a deposit (source_planes); every plane that takes the neighbours' deposits   */
 	    const bool all = !jmask || ( f.size > 1 && ( k == f.kb || k >= f.np - 3 ) );
-	    const unsigned char* mrow = jmask ? jmask + (long) (k >> 5) * f.P + (long) i * f.N1 + b.lo[1] : 0;
+	    const unsigned char* mrow = jmask ? jmask + (long) (k >> MITHRA_EB_CHUNK_LOG2) * f.P + (long) i * f.N1 + b.lo[1] : 0;
 	    for (int j = lane; j < nj; j += 32) if (all || mrow[j]) row[j] = 0.0;
 	  }
       }
@@ -652,19 +669,19 @@ namespace mithra
     EB o;
     {
       float e;
-      e = (float) div_by( p0, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q0, mdt, f.rmdt ) ); o.e[0] = e;
-      e = (float) div_by( p1, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q1, mdt, f.rmdt ) ); o.e[1] = e;
-      e = (float) div_by( p2, mdt, f.rmdt ); e = (float) ( (double) e - div_by( q2, mdt, f.rmdt ) ); o.e[2] = e;
+      e = (float) div_fast( p0, mdt, f.rmdt ); e = (float) ( (double) e - div_fast( q0, mdt, f.rmdt ) ); o.e[0] = e;
+      e = (float) div_fast( p1, mdt, f.rmdt ); e = (float) ( (double) e - div_fast( q1, mdt, f.rmdt ) ); o.e[1] = e;
+      e = (float) div_fast( p2, mdt, f.rmdt ); e = (float) ( (double) e - div_fast( q2, mdt, f.rmdt ) ); o.e[2] = e;
     }
     if (SC)
       {
-	o.e[0] = (float) ( (double) o.e[0] - div_by( g0, f.dx2, f.rdx2 ) );
-	o.e[1] = (float) ( (double) o.e[1] - div_by( g1, f.dy2, f.rdy2 ) );
-	o.e[2] = (float) ( (double) o.e[2] - div_by( g2, f.dz2, f.rdz2 ) );
+	o.e[0] = (float) ( (double) o.e[0] - div_fast( g0, f.dx2, f.rdx2 ) );
+	o.e[1] = (float) ( (double) o.e[1] - div_fast( g1, f.dy2, f.rdy2 ) );
+	o.e[2] = (float) ( (double) o.e[2] - div_fast( g2, f.dz2, f.rdz2 ) );
       }
-    o.b[0] = (float) ( 0.5 * ( div_by( azy, f.dy2, f.rdy2 ) - div_by( ayz, f.dz2, f.rdz2 ) + div_by( pzy, f.dy2, f.rdy2 ) - div_by( pyz, f.dz2, f.rdz2 ) ) );
-    o.b[1] = (float) ( 0.5 * ( div_by( axz, f.dz2, f.rdz2 ) - div_by( azx, f.dx2, f.rdx2 ) + div_by( pxz, f.dz2, f.rdz2 ) - div_by( pzx, f.dx2, f.rdx2 ) ) );
-    o.b[2] = (float) ( 0.5 * ( div_by( ayx, f.dx2, f.rdx2 ) - div_by( axy, f.dy2, f.rdy2 ) + div_by( pyx, f.dx2, f.rdx2 ) - div_by( pxy, f.dy2, f.rdy2 ) ) );
+    o.b[0] = (float) ( 0.5 * ( div_fast( azy, f.dy2, f.rdy2 ) - div_fast( ayz, f.dz2, f.rdz2 ) + div_fast( pzy, f.dy2, f.rdy2 ) - div_fast( pyz, f.dz2, f.rdz2 ) ) );
+    o.b[1] = (float) ( 0.5 * ( div_fast( axz, f.dz2, f.rdz2 ) - div_fast( azx, f.dx2, f.rdx2 ) + div_fast( pxz, f.dz2, f.rdz2 ) - div_fast( pzx, f.dx2, f.rdx2 ) ) );
+    o.b[2] = (float) ( 0.5 * ( div_fast( ayx, f.dx2, f.rdx2 ) - div_fast( axy, f.dy2, f.rdy2 ) + div_fast( pyx, f.dx2, f.rdx2 ) - div_fast( pxy, f.dy2, f.rdy2 ) ) );
     return o;
   }
 
@@ -738,17 +755,25 @@ namespace mithra
    * Work items (32-plane chunk, i tile, j tile) are strided over a grid of fixed size because the box lives on the
    * device; pencils that the mask (spread_eb_mask below) leaves unmarked are skipped.
    * ------------------------------------------------------------------------------------------------ */
-  #define MITHRA_EB_CHUNK_LOG2 5                /* planes per pencil of the E/B mask = planes per work item of the march */
+  #define MITHRA_MARCH_LOG2 5                   /* planes per work item of the march (four mask pencils)               */
 
-  #ifndef MITHRA_MARCH_MINBLOCKS
-  #define MITHRA_MARCH_MINBLOCKS 3                      /* 85 registers, 24 warps per SM: measured against 2 and 4           */
+  #ifndef MITHRA_MARCH_BARRIER
+  #define MITHRA_MARCH_BARRIER 1
   #endif
+  #ifndef MITHRA_MARCH_MINBLOCKS
+  #define MITHRA_MARCH_MINBLOCKS 2                      /* 128 registers: all 30 loads of a node in flight before the arithmetic
+							   (2.8 ms on FEL-LCLS; at 85 registers the scheduler sinks them: 3.5 ms) */
+  #endif
+  /* part: 0 = every node of the box; 1 = only the nodes whose E/B depends on nothing but stencil_stream's output --
+   * i in [4, N0-5], j in [4, N1-5], k in [kb+3, np-5]: one node away from the rim rows / columns and from the two planes
+   * per mesh end that the z shell of the seed, the z faces and the ghost exchange write -- so that this launch can run
+   * BESIDE rim_update and everything else of the field update that follows the stencil; 2 = the rest of the box, after them. */
   template <bool SC>
   __global__ void __launch_bounds__(256, MITHRA_MARCH_MINBLOCKS)
   eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
-		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask)
+		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask, int part)
   {
-    constexpr int L = MITHRA_EB_CHUNK_LOG2;
+    constexpr int L = MITHRA_MARCH_LOG2, LM = MITHRA_EB_CHUNK_LOG2, NS = 1 << (L - LM);
     const Box b = *boxp;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
     const int kfirst = max(b.lo[2], f.kb), klast = min(b.hi[2], f.np - 2);
@@ -760,39 +785,73 @@ namespace mithra
     const long N1 = f.N1, Pp = f.Pp, cs = (long) f.np * Pp;
     const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs, * fn = an + 3 * cs;
     const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
+    const int nch = (f.np + (1 << LM) - 1) >> LM;
 
     for (long w = blockIdx.x; w < nwork; w += gridDim.x)
       {
 	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), c = cfirst + (int) (w / ((long) njt * nit));
 	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
 	if (j > b.hi[1] || i > b.hi[0]) continue;
-	if (mask && !mask[((long) c * f.N0 + i) * N1 + j]) continue;       /* no particle can gather from this pencil */
-	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
-	long m = (long) ks * Pp + (long) i * N1 + j;              /* the node in the planar potentials            */
-	long e = (long) ks * f.P + (long) i * N1 + j;             /* ... and in the E/B array                      */
-
-	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z                                            */
-	double axm = ax[m - Pp], ax0 = ax[m], aym = ay[m - Pp], ay0 = ay[m];
-	double pxm = px[m - Pp], px0 = px[m], pym = py[m - Pp], py0 = py[m];
-	double fm = 0.0, f0 = 0.0;
-	if (SC) { fm = fn[m - Pp]; f0 = fn[m]; }
-
-	for (int k = ks; k < ke; k++, m += Pp, e += f.P)
+	/* the four mask pencils of this column within the work item; no mask: everything                              */
+	unsigned int on = (1u << NS) - 1u;
+	if (mask)
 	  {
-	    const double axp = ax[m + Pp], ayp = ay[m + Pp], pxp = px[m + Pp], pyp = py[m + Pp];
-	    const double q2 = az[m], p2 = pz[m];
+	    on = 0u;
+	    #pragma unroll
+	    for (int s = 0; s < NS; s++)
+	      { const int cm = (c << (L - LM)) + s; if (cm < nch && mask[((long) cm * f.N0 + i) * N1 + j]) on |= 1u << s; }
+	    if (!on) continue;                                 /* no particle can gather from this column here           */
+	  }
+	const bool inner = ( i >= 4 && i <= f.N0 - 5 && j >= 4 && j <= f.N1 - 5 );
+	if (part == 1 && !inner) continue;
+	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
+
+	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z; `have`: they hold the planes below k         */
+	double axm = 0.0, ax0 = 0.0, aym = 0.0, ay0 = 0.0, pxm = 0.0, px0 = 0.0, pym = 0.0, py0 = 0.0, fm = 0.0, f0 = 0.0;
+	bool have = false;
+	/* the node in plane ks: one pointer per array, advanced by a plane per step (the compiler's own addressing of
+	 * 26 loads through a recomputed 64-bit index was half of the kernel's instructions)                            */
+	const long m0 = (long) ks * Pp + (long) i * N1 + j;
+	const double* qax = ax + m0; const double* qay = ay + m0; const double* qaz = az + m0;
+	const double* qpx = px + m0; const double* qpy = py + m0; const double* qpz = pz + m0;
+	const double* qfn = fn + m0;
+	float4* qe = eb + 2 * ( (long) ks * f.P + (long) i * N1 + j );
+	const long eP = 2L * f.P;
+	for (int k = ks; k < ke; k++, qax += Pp, qay += Pp, qaz += Pp, qpx += Pp, qpy += Pp, qpz += Pp, qfn += Pp, qe += eP)
+	  {
+	    bool take = ( on >> ( ( k >> LM ) - ( c << (L - LM) ) ) ) & 1u;
+	    if (part != 0)
+	      {
+		const bool zinner = ( k >= f.kb + 3 && k <= f.np - 5 );
+		take = take && ( part == 1 ? zinner : !( inner && zinner ) );
+	      }
+	    if (!take) { have = false; continue; }
+	    if (!have)
+	      {
+		axm = qax[-Pp]; ax0 = qax[0]; aym = qay[-Pp]; ay0 = qay[0];
+		pxm = qpx[-Pp]; px0 = qpx[0]; pym = qpy[-Pp]; py0 = qpy[0];
+		if (SC) { fm = qfn[-Pp]; f0 = qfn[0]; }
+		have = true;
+	      }
+	    const double axp = qax[Pp], ayp = qay[Pp], pxp = qpx[Pp], pyp = qpy[Pp];
+	    const double q2 = qaz[0], p2 = qpz[0];
 	    double fp = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-	    if (SC) { fp = fn[m + Pp]; g0 = fn[m + N1] - fn[m - N1]; g1 = fn[m + 1] - fn[m - 1]; g2 = fp - fm; }
-	    const double azy = az[m + 1 ] - az[m - 1 ], pzy = pz[m + 1 ] - pz[m - 1 ];
-	    const double azx = az[m + N1] - az[m - N1], pzx = pz[m + N1] - pz[m - N1];
-	    const double ayx = ay[m + N1] - ay[m - N1], pyx = py[m + N1] - py[m - N1];
-	    const double axy = ax[m + 1 ] - ax[m - 1 ], pxy = px[m + 1 ] - px[m - 1 ];
+	    if (SC) { fp = qfn[Pp]; g0 = qfn[N1] - qfn[-N1]; g1 = qfn[1] - qfn[-1]; g2 = fp - fm; }
+	    const double azy = qaz[1 ] - qaz[-1 ], pzy = qpz[1 ] - qpz[-1 ];
+	    const double azx = qaz[N1] - qaz[-N1], pzx = qpz[N1] - qpz[-N1];
+	    const double ayx = qay[N1] - qay[-N1], pyx = qpy[N1] - qpy[-N1];
+	    const double axy = qax[1 ] - qax[-1 ], pxy = qpx[1 ] - qpx[-1 ];
+	    /* every load of the node is in flight before the arithmetic starts: left alone, the scheduler sinks each load
+	     * to its first use to save registers and the kernel runs at the latency of one load after the other          */
+	    #if MITHRA_MARCH_BARRIER
+	    __syncwarp(__activemask());
+	    #endif
 	    const EB o = eb_assemble<SC>(f, px0, py0, p2, ax0, ay0, q2, g0, g1, g2,
 					 azy, ayp - aym, pzy, pyp - pym,
 					 axp - axm, azx, pxp - pxm, pzx,
 					 ayx, axy, pyx, pxy);
-	    eb[2 * e]     = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
-	    eb[2 * e + 1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+	    qe[0] = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
+	    qe[1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
 	    axm = ax0; ax0 = axp; aym = ay0; ay0 = ayp; pxm = px0; px0 = pxp; pym = py0; py0 = pyp;
 	    if (SC) { fm = f0; f0 = fp; }
 	  }
@@ -800,16 +859,17 @@ namespace mithra
   }
 
   /* ------------------------------------------------------------------------------------------------
-   * Pencil mask of the E/B evaluation.  The padded particle box is a bounding box: for a bunch with Gaussian tails
-   * (FEL-LCLS: sigma 7.5 cells, truncation at 45) most of its columns hold no particle at all.  The push (and every
-   * other kernel that extends the particle box) marks the pencil -- cell column (i, j) x 32 planes -- of each particle
-   * in `cells`; here the marks are spread to the NODES a particle of that pencil can gather from during the next field
-   * step: the two nodes of its cell per axis plus the cells it can cross (padx, pady; less than one 32-plane chunk in
-   * z), which is exactly how make_eb_box pads the bounding box.  eval_eb_march skips the pencils left unmarked.
+   * Node-pencil mask from the cell-pencil reach bytes (device_types.cuh "Reach mask"; the push and particle_box write
+   * them).  The padded particle box is a bounding box: for a bunch with Gaussian tails (FEL-LCLS: sigma 7.5 cells,
+   * truncation at 45, a particle per 25 cells) most of its nodes are out of every particle's reach.  Node pencil
+   * (c, i, j) -- node column (i, j) x 8 planes -- is marked when some cell pencil (cc, ii, jj) holds a particle whose
+   * reach covers it: the two node columns of its own cell per axis, one more column / the neighbouring plane chunk
+   * where a particle of that pencil sits within c dt of the cell's face (the XLO .. ZHI bits).  eval_eb_march, the source
+   * read of the next field update and the clear of J skip everything unmarked.
    * ------------------------------------------------------------------------------------------------ */
   __global__ void __launch_bounds__(256)
   spread_eb_mask (const FieldDev f, const unsigned char* __restrict__ cells, unsigned char* __restrict__ nodes,
-		  const Box* __restrict__ eboxp, int padx, int pady)
+		  const Box* __restrict__ eboxp)
   {
     constexpr int L = MITHRA_EB_CHUNK_LOG2;
     const Box b = *eboxp;
@@ -822,9 +882,19 @@ namespace mithra
 	const int j = b.lo[1] + (int) (t % nj), i = b.lo[0] + (int) ((t / nj) % ni), c = c0 + (int) (t / ((long) nj * ni));
 	unsigned int any = 0u;
 	for (int cc = max(0, c - 1); cc <= min(nch - 1, c + 1); cc++)
-	  for (int ii = max(0, i - 1 - padx); ii <= min(f.N0 - 1, i + padx); ii++)
-	    for (int jj = max(0, j - 1 - pady); jj <= min(f.N1 - 1, j + pady); jj++)
-	      any |= cells[((long) cc * f.N0 + ii) * f.N1 + jj];
+	  {
+	    const unsigned int zneed = (cc == c) ? 0u : (cc < c ? (unsigned) REACH_ZHI : (unsigned) REACH_ZLO);
+	    for (int ii = max(0, i - 2); ii <= min(f.N0 - 2, i + 1); ii++)
+	      {
+		const unsigned int xneed = (ii == i + 1) ? (unsigned) REACH_XLO : (ii == i - 2) ? (unsigned) REACH_XHI : 0u;
+		for (int jj = max(0, j - 2); jj <= min(f.N1 - 2, j + 1); jj++)
+		  {
+		    const unsigned int v = cells[((long) cc * f.N0 + ii) * f.N1 + jj];
+		    const unsigned int need = zneed | xneed | ( (jj == j + 1) ? (unsigned) REACH_YLO : (jj == j - 2) ? (unsigned) REACH_YHI : 0u );
+		    any |= ( v != 0u && ( v & need ) == need ) ? 1u : 0u;
+		  }
+	      }
+	  }
 	nodes[((long) c * f.N0 + i) * f.N1 + j] = any ? 1 : 0;
       }
   }
