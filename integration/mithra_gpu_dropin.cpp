@@ -1,0 +1,228 @@
+/* mithra_gpu_dropin.cpp -- INTEGRATION.md option B made real: the file a maintainer of the reference adds to route the
+ * time march through libmithra_gpu.so.  It is compiled against the UNMODIFIED reference headers and linked with the
+ * UNMODIFIED reference objects (mithra.cpp's main, readdata, datainput, classes, database, stdinclude, solver.cpp with its
+ * own initialize() and solve() loop, radiation.cpp with its own initializePowerSample) by `make -C oracle ref_gpu`; it
+ *   - REPLACES src/fdtd.cpp and src/fdtdSC.cpp: the constructors and the thirteen virtuals of FdTd / FdTdSC
+ *     (solver.h:139-178) call the C ABI of include/mithra_gpu.h;
+ *   - OVERRIDES the four non-virtual Solver methods of the loop that touch particles or fields -- bunchUpdate
+ *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450): the
+ *     build weakens those four symbols in the reference objects (objcopy --weaken-symbol), the linker takes these.
+ * Nothing of the reference is edited or copied.  Rhythm-gated dumps (field / bunch sampling, visualisation, profiles)
+ * are not part of this stub -- mithra_b200/host has them over the same ABI -- and a job that asks for one stops with a
+ * message, the reference's own error convention.
+ *
+ * This is test infrastructure of the repository (it proves the drop-in claim against the reference's own main and
+ * loop); the product is the library.
+ */
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "fdtd.h"
+#include "fdtdSC.h"
+#include "../include/mithra_gpu.h"
+
+namespace MITHRA
+{
+  namespace
+  {
+    MithraGpu* gpu = 0;
+    int        subStep = 0;                        /* calls of bunchUpdate within the current field step (solver.cpp:1316) */
+
+    void check (int rc)
+    {
+      if (rc) { printmessage(std::string(__FILE__), __LINE__, std::string("GPU time march: ") + mithra_gpu_last_error()); exit(1); }
+    }
+
+    void refuse (const char* what)
+    {
+      printmessage(std::string(__FILE__), __LINE__, std::string(what) + " is not routed by this stub (mithra_b200/host writes it over the same ABI).");
+      exit(1);
+    }
+
+    template <class B>
+    void fillBeam (MithraBeam& d, const B& b)
+    {
+      d.seed_type = (int) b.seedType_;
+      for (int c = 0; c < 3; c++) { d.position[c] = b.position_[c]; d.direction[c] = b.direction_[c]; d.polarization[c] = b.polarization_[c]; }
+      d.amplitude = b.amplitude_;
+      d.radius[0] = b.radius_.size() > 0 ? b.radius_[0] : 0.0; d.radius[1] = b.radius_.size() > 1 ? b.radius_[1] : 0.0;
+      d.l = b.l_;
+      d.zR[0] = b.zR_.size() > 0 ? b.zR_[0] : 0.0; d.zR[1] = b.zR_.size() > 1 ? b.zR_[1] : 0.0;
+      d.order[0] = b.order_.size() > 0 ? b.order_[0] : 0; d.order[1] = b.order_.size() > 1 ? b.order_[1] : 0;
+      d.signal.type = (int) b.signal_.signalType_;
+      d.signal.t0 = b.signal_.t0_; d.signal.s = b.signal_.s_; d.signal.f0 = b.signal_.f0_; d.signal.cep = b.signal_.cep_;
+      d.signal.nR = (int) b.signal_.nR_;
+      d.signal.sigma_inv_g[0] = b.signal_.sigmaInvG_.size() > 0 ? b.signal_.sigmaInvG_[0] : 0.0;
+      d.signal.sigma_inv_g[1] = b.signal_.sigmaInvG_.size() > 1 ? b.signal_.sigmaInvG_[1] : 0.0;
+    }
+
+    /* Create the device solver from the state Solver::initialize() left behind: every scalar and table of the parameter
+     * block is a member of the reference's Solver (all public, solver.h:23-345), the potentials are an_ / anm1_ (with the
+     * seed already in them, solver.cpp:828-839), the bunch is chargeVectorn_.                                          */
+    void attach (Solver& s)
+    {
+      if (gpu) return;
+      if (s.size_ != 1) refuse("A run with more than one MPI rank");
+      if (s.seed_.sampling_ || s.seed_.vtk_.size() > 0 || s.seed_.profile_) refuse("Field sampling / visualization / profile");
+      if (s.bunch_.sampling_ || s.bunch_.bunchVTK_ || s.bunch_.bunchProfile_) refuse("Bunch sampling / visualization / profile");
+
+      MithraGpuParams p; memset(&p, 0, sizeof(p));
+      p.abi_version = MITHRA_GPU_ABI_VERSION;
+      p.N0 = s.N0_; p.N1 = s.N1_; p.N2 = s.N2_; p.np = s.np_; p.k0 = s.k0_; p.rank = 0; p.size = 1;             /* solver.cpp:610-641 */
+      p.dx = s.mesh_.meshResolution_[0]; p.dy = s.mesh_.meshResolution_[1]; p.dz = s.mesh_.meshResolution_[2]; p.dt = s.mesh_.timeStep_;
+      p.xmin = s.xmin_; p.xmax = s.xmax_; p.ymin = s.ymin_; p.ymax = s.ymax_; p.zmin = s.zmin_; p.zmax = s.zmax_; /* :661-666 */
+      p.zp[0] = s.zp_[0]; p.zp[1] = s.zp_[1]; p.Lz = s.mesh_.meshLength_[2];                                       /* :677-680 */
+      p.solver = (int) s.mesh_.solver_; p.space_charge = s.mesh_.spaceCharge_ ? 1 : 0; p.truncation_order = s.mesh_.truncationOrder_;
+      memcpy(p.a, s.uf_.a, sizeof(p.a)); p.alpha = s.uf_.af.alpha_; p.beta_nsfd = s.uf_.af.beta_;                 /* :729-739 */
+      memcpy(p.bB, s.uf_.bB, sizeof(p.bB)); memcpy(p.cB, s.uf_.cB, sizeof(p.cB)); memcpy(p.dB, s.uf_.dB, sizeof(p.dB));
+      memcpy(p.eE, s.uf_.eE, sizeof(p.eE)); memcpy(p.fE, s.uf_.fE, sizeof(p.fE)); memcpy(p.gE, s.uf_.gE, sizeof(p.gE));
+      memcpy(p.hC, s.uf_.hC, sizeof(p.hC));                                                                       /* :745-824 */
+      p.c0 = s.c0_; p.gamma = s.gamma_; p.beta = s.beta_; p.dt_shift = s.dt_;
+      p.dt_bunch = s.bunch_.timeStep_;
+      p.n_update_bunch = 0;
+      for (Double t = 0.0; t < s.nUpdateBunch_; t += 1.0) ++p.n_update_bunch;                                     /* the loop of :1316 */
+      p.r1 = s.ub_.r1; p.r2 = s.ub_.r2; p.dtb = s.ub_.dtb;                                                        /* :1053-1059 */
+
+      if (s.undulator_.size() > MITHRA_MAX_UNDULATORS || s.extField_.size() > MITHRA_MAX_EXTFIELDS) refuse("That many undulator modules / external fields");
+      p.n_undulators = (int) s.undulator_.size();
+      for (size_t u = 0; u < s.undulator_.size(); u++)
+	{
+	  const Undulator& U = s.undulator_[u];
+	  MithraUndulator& D = p.undulator[u];
+	  D.type = (int) U.type_; D.k = U.k_; D.lu = U.lu_; D.rb = U.rb_; D.theta = U.theta_; D.length = U.length_; D.dist = U.dist_;
+	  fillBeam(D.beam, U);
+	}
+      p.n_ext_fields = (int) s.extField_.size();
+      for (size_t u = 0; u < s.extField_.size(); u++) fillBeam(p.ext_field[u], s.extField_[u]);
+      p.seed_enabled = ( fabs(s.seed_.amplitude_) > 1.0e-50 ) ? 1 : 0;                                            /* fdtd.cpp:307 */
+      fillBeam(p.seed, s.seed_);
+
+      for (unsigned jf = 0; jf < s.FEL_.size(); jf++)
+	{
+	  if (s.FEL_[jf].vtkPower_.sampling_) refuse("Power visualization");
+	  if (s.FEL_[jf].radiationPower_.sampling_)
+	    {
+	      if (p.power.enabled) refuse("A second radiation-power group");
+	      const SampleRadiationPower& S = s.rp_[jf];                                                          /* radiation.cpp:18-121 */
+	      if (S.N > MITHRA_MAX_POWER_PLANES || S.Nl > MITHRA_MAX_POWER_LAMBDAS) refuse("That many power planes / frequencies");
+	      p.power.enabled = 1; p.power.N = S.N; p.power.Nl = S.Nl; p.power.Nf = S.Nf; p.power.pc = S.pc;
+	      for (unsigned i = 0; i < S.N; i++)  p.power.z[i] = s.FEL_[jf].radiationPower_.z_[i];
+	      for (unsigned i = 0; i < S.Nl; i++) p.power.w[i] = S.w[i];
+	    }
+	  if (s.FEL_[jf].screenProfile_.sampling_)
+	    {
+	      if (p.screens.enabled) refuse("A second screen group");
+	      const std::vector<Double>& pos = s.FEL_[jf].screenProfile_.pos_;
+	      if (pos.size() > MITHRA_MAX_SCREENS) refuse("That many screens");
+	      p.screens.enabled = 1; p.screens.N = (int) pos.size();
+	      for (size_t i = 0; i < pos.size(); i++) p.screens.pos[i] = pos[i];
+	    }
+	}
+      p.device = -1;
+      p.max_particles = s.chargeVectorn_.size() + 1024;
+      p.max_screen_records = s.chargeVectorn_.size() + 4096;
+      check(mithra_gpu_create(&p, &gpu));
+      check(mithra_gpu_set_time(gpu, s.time_, s.timeBunch_, s.nTime_));
+
+      /* FieldVector<double> is double[3] (fieldvector.h:22), std::vector<Double> for phi                            */
+      const bool sc = s.mesh_.spaceCharge_;
+      check(mithra_gpu_upload_fields(gpu, &(*s.an_)[0][0], &(*s.anm1_)[0][0], 0, sc ? &(*s.fn_)[0] : 0, sc ? &(*s.fnm1_)[0] : 0, 0));
+      std::vector<double> q; q.reserve(11 * s.chargeVectorn_.size());                                             /* Charge, stdinclude.h:130-144 */
+      for (auto it = s.chargeVectorn_.begin(); it != s.chargeVectorn_.end(); ++it)
+	{
+	  q.push_back(it->q);
+	  for (int d = 0; d < 3; d++) q.push_back(it->rnp[d]);
+	  for (int d = 0; d < 3; d++) q.push_back(it->rnm[d]);
+	  for (int d = 0; d < 3; d++) q.push_back(it->gb[d]);
+	  q.push_back(it->e);
+	}
+      check(mithra_gpu_upload_particles(gpu, q.empty() ? 0 : &q[0], s.chargeVectorn_.size()));
+    }
+
+    /* the reference's loop keeps the clocks (solver.cpp:1396-1399, :1318-1319); the library follows them                */
+    void follow (Solver& s)
+    {
+      attach(s);
+      if (subStep == 0) check(mithra_gpu_set_time(gpu, s.time_, s.timeBunch_, s.nTime_));
+    }
+  }
+
+  /* ---- Solver: the four methods of the loop that are not virtual ------------------------------------------------- */
+
+  /* solve() calls this nUpdateBunch_ times per field step and advances timeBunch_ after each call; the library runs all
+   * the sub-steps of a field step in one launch (rnm = rnp included), on the first of those calls                   */
+  void Solver::bunchUpdate ()
+  {
+    follow(*this);
+    if (subStep == 0) check(mithra_gpu_bunch_update(gpu));
+    int trips = 0;
+    for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) ++trips;
+    if (++subStep >= trips) subStep = 0;
+  }
+
+  void Solver::screenProfile ()
+  {
+    follow(*this);
+    check(mithra_gpu_screen_profile(gpu));
+    for (unsigned jf = 0; jf < FEL_.size(); jf++)
+      {
+	if (!FEL_[jf].screenProfile_.sampling_) continue;
+	for (unsigned i = 0; i < FEL_[jf].screenProfile_.pos_.size(); i++)
+	  {
+	    size_t n = 0;
+	    check(mithra_gpu_fetch_screen(gpu, (int) i, 0, 0, &n));
+	    if (n == 0) continue;
+	    std::vector<double> rec(6 * n);
+	    check(mithra_gpu_fetch_screen(gpu, (int) i, &rec[0], n, &n));
+	    for (size_t r = 0; r < n; r++)                                                                       /* solver.cpp:2229-2252 */
+	      {
+		for (int c = 0; c < 5; c++) *scrp_[jf].files[i] << rec[6 * r + c] << "\t";
+		*scrp_[jf].files[i] << rec[6 * r + 5] << std::endl;
+	      }
+	  }
+      }
+  }
+
+  void Solver::powerSample ()
+  {
+    follow(*this);
+    for (unsigned jf = 0; jf < FEL_.size(); jf++)
+      {
+	if (!FEL_[jf].radiationPower_.sampling_) continue;
+	check(mithra_gpu_power_sample(gpu));
+	size_t n = 0;
+	check(mithra_gpu_fetch_power(gpu, &rp_[jf].pG[0], 1, &n));
+	for (unsigned l = 0; l < rp_[jf].Nl; l++)                                                               /* radiation.cpp:222-230 */
+	  {
+	    for (unsigned k = 0; k < rp_[jf].N; ++k)
+	      *(rp_[jf].file[l]) << gamma_ * ( FEL_[jf].radiationPower_.z_[k] + beta_ * c0_ * ( timeBunch_ + dt_ ) ) << "\t" << rp_[jf].pG[k * rp_[jf].Nl + l] << "\t";
+	    *(rp_[jf].file[l]) << std::endl;
+	  }
+      }
+  }
+
+  void Solver::powerVisualize () {}                /* attach() refuses jobs with a power-visualization group          */
+
+  /* ---- FdTd / FdTdSC: in place of src/fdtd.cpp and src/fdtdSC.cpp ------------------------------------------------ */
+
+  #define MITHRA_GPU_FIELD_SOLVER(CLASS)                                                                                          \
+    CLASS::CLASS (Mesh& mesh, Bunch& bunch, Seed& seed, std::vector<Undulator>& undulator, std::vector<ExtField>& extField,     \
+		  std::vector<FreeElectronLaser>& FEL) : Solver ( mesh, bunch, seed, undulator, extField, FEL ) {}               \
+    void CLASS::fieldUpdate ()        { follow(*this); check(mithra_gpu_field_update(gpu)); }                                    \
+    void CLASS::fieldShift ()         { check(mithra_gpu_field_shift(gpu)); }                                                    \
+    void CLASS::fieldEvaluate (long int) {}       /* lazy in the reference (solver.cpp:1471-1478), eager on the device */       \
+    void CLASS::currentReset ()       { check(mithra_gpu_current_reset(gpu)); }                                                  \
+    void CLASS::currentUpdate ()      { check(mithra_gpu_current_update(gpu)); }                                                 \
+    void CLASS::currentCommunicate () { check(mithra_gpu_current_communicate(gpu)); }                                            \
+    void CLASS::fieldSample ()                             { refuse("Field sampling"); }                                         \
+    void CLASS::fieldVisualizeAllDomain (unsigned int)      { refuse("Field visualization"); }                                    \
+    void CLASS::fieldVisualizeInPlane (unsigned int)        { refuse("Field visualization"); }                                    \
+    void CLASS::fieldVisualizeInPlaneXNormal (unsigned int) { refuse("Field visualization"); }                                    \
+    void CLASS::fieldVisualizeInPlaneYNormal (unsigned int) { refuse("Field visualization"); }                                    \
+    void CLASS::fieldVisualizeInPlaneZNormal (unsigned int) { refuse("Field visualization"); }                                    \
+    void CLASS::fieldProfile ()                            { refuse("Field profile"); }
+
+  MITHRA_GPU_FIELD_SOLVER(FdTd)
+  MITHRA_GPU_FIELD_SOLVER(FdTdSC)
+}

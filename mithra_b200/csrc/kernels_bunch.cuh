@@ -26,6 +26,8 @@ namespace mithra
     return x;
   }
 
+  __device__ __forceinline__ void prefetch_l1 (const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
   __device__ __forceinline__ void warp_box_merge (Box* box, bool valid, int i0, int i1, int j0, int j1, int k0, int k1)
   {
     const unsigned full = 0xffffffffu;
@@ -39,8 +41,15 @@ namespace mithra
       }
     if ((threadIdx.x & 31) == 0 && hi0 >= lo0)
       {
-	atomicMin(&box->lo[0], lo0); atomicMin(&box->lo[1], lo1); atomicMin(&box->lo[2], lo2);
-	atomicMax(&box->hi[0], hi0); atomicMax(&box->hi[1], hi1); atomicMax(&box->hi[2], hi2);
+	/* the box only grows during a launch: a (possibly stale) look at it tells most warps that they have nothing to add,
+	 * and the six same-address reductions of every warp of a large bunch do not queue up in one L2 slice            */
+	const volatile Box* g = box;
+	if (lo0 < g->lo[0]) atomicMin(&box->lo[0], lo0);
+	if (lo1 < g->lo[1]) atomicMin(&box->lo[1], lo1);
+	if (lo2 < g->lo[2]) atomicMin(&box->lo[2], lo2);
+	if (hi0 > g->hi[0]) atomicMax(&box->hi[0], hi0);
+	if (hi1 > g->hi[1]) atomicMax(&box->hi[1], hi1);
+	if (hi2 > g->hi[2]) atomicMax(&box->hi[2], hi2);
       }
   }
 
@@ -393,6 +402,19 @@ namespace mithra
 	    const bool b1x = ( x < b.xmax - b.dx && x > b.xmin + b.dx );
 	    const bool b1y = ( y < b.ymax - b.dy && y > b.ymin + b.dy );
 	    const bool b1z = ( b.size == 1 ) ? ( z < b.zp1 && z >= b.zp0 ) : ( z < b.zmax && z >= b.zmin );
+
+	    /* The eight E/B nodes of the cell (one 32-byte sector each) are asked for NOW, while the analytic undulator /
+	     * beam fields below are computed (some hundred FP64 instructions): the gather further down then finds them in
+	     * L1 instead of waiting for DRAM twice.  A prefetch takes no register and returns nothing.                  */
+	    if (e == 1.0 && b1x && b1y && b1z)
+	      {
+		const int pi = (int) div_by( x - b.xmin, b.dx, b.rdx ), pj = (int) div_by( y - b.ymin, b.dy, b.rdy );
+		const int pk = (int) div_by( z - b.zmin, b.dz, b.rdz ) - b.k0;
+		const float4* q = eb + 2 * ( (long) pk * b.P + (long) pi * b.N1 + pj );
+		const long sN = 2L * b.N1, sP = 2L * b.P;
+		prefetch_l1(q);          prefetch_l1(q + 2);          prefetch_l1(q + sN);      prefetch_l1(q + sN + 2);
+		prefetch_l1(q + sP);     prefetch_l1(q + sP + 2);     prefetch_l1(q + sP + sN); prefetch_l1(q + sP + sN + 2);
+	      }
 
 	    V3 et = v3(0.0, 0.0, 0.0), bt = v3(0.0, 0.0, 0.0);
 

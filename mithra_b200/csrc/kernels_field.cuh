@@ -792,6 +792,12 @@ namespace mithra
 	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), c = cfirst + (int) (w / ((long) njt * nit));
 	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
 	if (j > b.hi[1] || i > b.hi[0]) continue;
+	if (part == 2)
+	  {
+	    /* a work item whose 32 x 8 x 32 nodes are all inner has nothing left for this pass (uniform over the CTA)     */
+	    const int j0 = b.lo[1] + (jt << 5), i0 = b.lo[0] + (it << 3);
+	    if (i0 >= 4 && i0 + 7 <= f.N0 - 5 && j0 >= 4 && j0 + 31 <= f.N1 - 5 && (c << L) >= f.kb + 3 && ((c + 1) << L) - 1 <= f.np - 5) continue;
+	  }
 	/* the four mask pencils of this column within the work item; no mask: everything                              */
 	unsigned int on = (1u << NS) - 1u;
 	if (mask)
@@ -805,6 +811,7 @@ namespace mithra
 	const bool inner = ( i >= 4 && i <= f.N0 - 5 && j >= 4 && j <= f.N1 - 5 );
 	if (part == 1 && !inner) continue;
 	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
+	if (part == 2 && inner && ks >= f.kb + 3 && ke - 1 <= f.np - 5) continue;      /* all done by the inner pass   */
 
 	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z; `have`: they hold the planes below k         */
 	double axm = 0.0, ax0 = 0.0, aym = 0.0, ay0 = 0.0, pxm = 0.0, px0 = 0.0, pym = 0.0, py0 = 0.0, fm = 0.0, f0 = 0.0;

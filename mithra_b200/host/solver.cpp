@@ -67,6 +67,11 @@ namespace MITHRA
     initializeMesh();
     lorentzBoostBunch();
     initializeField();
+    if ( seed_.profile_ )
+      {
+	printmessage(__FILE__, __LINE__, "The field profile output (FIELD / field-profile) is not part of this build: the reference prints en_ / bn_ as its lazy evaluation last left them (fdtd.cpp:1546-1594), stale on every node no particle is near. Use field-sampling or the in-plane visualization.");
+	exit(1);
+      }
     if ( seed_.sampling_ ) initializeSeedSampling();
     initializeSeedVTK();
     initializeBunchUpdate();
@@ -537,7 +542,11 @@ namespace MITHRA
 	    else if ( v.plane_ == ZNORMAL ) outside = ( v.position_[2] > zmax_ - ub_.dz || v.position_[2] < zmin_ + ub_.dz );
 	  }
 	if ( v.type_ == ALLDOMAIN )
-	  printmessage(__FILE__, __LINE__, "Note: the all-domain field visualization is not part of this build (DESIGN.md) and is skipped.");
+	  {
+	    /* the reference's error convention: say why and stop (a job must not run to its end and silently write nothing) */
+	    printmessage(__FILE__, __LINE__, "The all-domain field visualization is not part of this build: the reference evaluates E/B beyond its arrays on the end planes there (fdtd.cpp:956-1105), there is nothing to be identical to. Use the in-plane visualization.");
+	    exit(1);
+	  }
 	if ( outside )
 	  {
 	    printmessage(__FILE__, __LINE__, "The plane does not reside in the grid. No data is saved.");

@@ -79,7 +79,8 @@ namespace MITHRA
     void bunchVisualize ();                        /* solver.cpp:1647-1757: .vtu / .pvtu of the particle cloud          */
     void bunchProfile ();
     void powerVisualize ();
-    void energySample () {}
+    void energySample () {}                        /* unreachable in the reference too: its parser stores a radiation-energy group in
+						      radiationPower_ (datainput.cpp:706-717), radiationEnergy_.sampling_ stays false */
 
     /* ---- the thirteen virtuals, solver.h:139-178 ------------------------------------------------------------ */
     virtual void currentReset () = 0;
@@ -160,13 +161,15 @@ namespace MITHRA
     void fieldShift ();
     void fieldEvaluate (long int) {}               /* E, B are evaluated eagerly on the device (eval_eb_box)         */
     void fieldSample ();                           /* fdtd.cpp:851-950: values from mithra_gpu_field_sample, the reference's line */
-    void fieldVisualizeAllDomain (unsigned int) {} /* not built: the reference evaluates E/B beyond its arrays there */
+    void fieldVisualizeAllDomain (unsigned int)    /* not built; initializeSeedVTK stops a job that asks for it */
+    { printmessage(__FILE__, __LINE__, "The all-domain field visualization is not part of this build."); exit(1); }
     void fieldVisualizeInPlane (unsigned int ivtk);              /* fdtd.cpp:1111-1121 */
     void fieldVisualizeInPlaneXNormal (unsigned int ivtk);       /* fdtd.cpp:1128-1285 */
     void fieldVisualizeInPlaneYNormal (unsigned int ivtk);       /* fdtd.cpp:1292-1447 */
     void fieldVisualizeInPlaneZNormal (unsigned int ivtk);       /* fdtd.cpp:1452-1540 */
     void nodeValues (const std::vector<int>& ijk, std::vector<double>& val);   /* en_, bn_, an_ at global nodes */
-    void fieldProfile () {}
+    void fieldProfile ()                           /* not built; initialize() stops a job that asks for it */
+    { printmessage(__FILE__, __LINE__, "The field profile output is not part of this build."); exit(1); }
   };
 
   /* identical forwarding: the library switches to the A + phi kernels when MithraGpuParams.space_charge is set     */

@@ -1,0 +1,55 @@
+"""The drop-in claim, proven against the reference's own program: oracle/_ref/mithra_ref_gpu is the UNMODIFIED reference
+main() (src/mithra.cpp), job parser, parameter classes and Solver -- its own initialize() and its own solve() loop
+(src/solver.cpp:1212-1418) -- linked with integration/mithra_gpu_dropin.cpp in place of src/fdtd.cpp / src/fdtdSC.cpp
+and with libmithra_gpu.so (oracle/Makefile target ref_gpu; INTEGRATION.md option B).  It runs tests/jobs/micro-dropin.job
+(Gaussian-beam seed with TF/SF injection, static undulator, three screens, power sampling, 203 field steps) and must
+write the files the unmodified reference wrote for the same job on the CPU (tests/golden/micro-dropin.npz, made by
+tests/golden/make_golden_dropin.py): same names, same number of lines, power within 1e-8, screen records within 1e-9."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "mithra_ref_gpu")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "micro-dropin.npz")
+
+
+def _numbers(raw):
+    return [np.array([float(t) for t in line.split()]) for line in bytes(raw).decode().splitlines()]
+
+
+def test_golden_of_the_dropin_job_is_the_references_output():
+    g = np.load(GOLDEN)
+    names = sorted(g.files)
+    assert names == ["txt/power-sampling/power-micro-0.txt"] + ["txt/screens/profile-p0-screen%d.txt" % i for i in range(3)]
+    rows = _numbers(g[names[0]])
+    assert len(rows) == 203 and all(r.size == 2 for r in rows)
+    assert max(r[1] for r in rows) > 0.0                      # the seed reaches the power plane within the run
+    assert all(len(_numbers(g[n])) > 100 for n in names[1:])   # most of the bunch crosses every screen
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_main_and_loop_over_the_library(tmp_path):
+    if not os.path.exists(EXE):
+        pytest.fail("oracle/_ref/mithra_ref_gpu is missing: `make -C oracle ref_gpu` where /root/reference exists "
+                    "(it travels with the gpurun snapshot)")
+    out = subprocess.run([EXE, os.path.join(ROOT, "tests", "jobs", "micro-dropin.job")], cwd=str(tmp_path),
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert out.returncode == 0, out.stdout.decode()[-2000:]
+    g = np.load(GOLDEN)
+    for key in sorted(g.files):
+        rel = key[len("txt/"):]
+        fn = tmp_path / rel
+        assert fn.exists(), rel
+        got, want = _numbers(open(fn, "rb").read()), _numbers(g[key])
+        assert len(got) == len(want), rel
+        if "power" in rel:
+            G, W = np.array(got), np.array(want)
+            np.testing.assert_allclose(G[:, 0], W[:, 0], rtol=1e-14, err_msg=rel)          # abscissae: the reference's own clocks
+            np.testing.assert_allclose(G[:, 1], W[:, 1], rtol=1e-8, atol=1e-12 * np.abs(W[:, 1]).max(), err_msg=rel)
+        else:
+            # the reference writes the crossings of a step in list order; so does the library (upload index)
+            G, W = np.array(got), np.array(want)
+            np.testing.assert_allclose(G, W, rtol=1e-9, atol=1e-12, err_msg=rel)

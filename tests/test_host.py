@@ -5,6 +5,7 @@ the whole initial bunch the unmodified reference's own initialize() produced for
 and `p0` of tests/golden/*.npz, written by oracle/_ref/ref_dump), and the parser must reject what the reference rejects.
 GPU part: the executable runs a job end to end and writes the reference's power / screen text files."""
 import os
+import re
 import subprocess
 import sys
 
@@ -97,6 +98,23 @@ def test_unknown_key_and_group_exit_like_the_reference(tmp_path):
     assert r.returncode == 1 and "NONSENSE is not a defined group." in r.stdout
     r = subprocess.run([_exe(), str(tmp_path / "missing.job")], capture_output=True, text=True)
     assert r.returncode == 1 and "Unable to open file" in r.stdout
+
+
+def test_outputs_that_are_not_built_stop_the_job_with_a_message(tmp_path):
+    """A job that asks for the all-domain field visualization or the field profile must not run to its end and write
+    nothing: message + exit(1), the reference's error convention (--dump-params runs Solver::initialize() only)."""
+    text = open(_job("micro-fviz")).read()
+    job = tmp_path / "alldomain.job"
+    new, n = re.subn(r"(type\s*=\s*)in-plane", r"\1all-domain", text, count=1)
+    assert n == 1
+    job.write_text(new)
+    r = subprocess.run([_exe(), str(job), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 1 and "all-domain field visualization is not part of this build" in r.stdout
+    text = open(_job("micro-nsfd")).read()
+    job = tmp_path / "profile.job"
+    job.write_text(text.replace("UNDULATOR", "FIELD\n{\n  field-profile\n  {\n    sample = true\n    directory = ./\n    base-name = fp/f\n    rhythm = 10\n  }\n}\n\nUNDULATOR", 1))
+    r = subprocess.run([_exe(), str(job), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 1 and "field profile output" in r.stdout, r.stdout[-600:]
 
 
 def test_without_gpu_the_executable_fails_loudly(tmp_path):
