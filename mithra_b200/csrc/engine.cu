@@ -58,12 +58,6 @@ struct MithraGpu
    * deposit) and the seed line table of the next time level (needed by the next field update)                */
   cudaStream_t    side;
   cudaEvent_t     ev_main, ev_clear, ev_seed;
-  /* the E/B evaluation of the nodes that depend on stencil_stream's output only runs on a third stream beside rim_update,
-   * the z faces, the edges and the ghost exchange (field_update_eb)                                              */
-  cudaStream_t    ebs;
-  cudaEvent_t     ev_stencil, ev_ebinner;
-  bool            ev_stencil_fresh;       /* recorded right after the stencil of the field update in flight          */
-  bool            potentials_ahead;       /* that field update was enqueued before the particle hand-over ended     */
   bool            overlap;                /* MITHRA_NO_OVERLAP unset                                       */
   bool            clear_ahead;            /* the box has been cleared (or is being cleared) on `side`      */
   bool            seed_ahead;             /* seed table + lines for seed_ahead_time are (being) computed   */
@@ -401,10 +395,6 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
     CU(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_seed, cudaEventDisableTiming));
-    CU(cudaStreamCreateWithPriority(&h->ebs, cudaStreamNonBlocking, lo));
-    CU(cudaEventCreateWithFlags(&h->ev_stencil, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_ebinner, cudaEventDisableTiming));
-    h->ev_stencil_fresh = false; h->potentials_ahead = false;
     h->overlap = !getenv("MITHRA_NO_OVERLAP");
     h->clear_ahead = false; h->seed_ahead = false; h->seed_ahead_time = 0.0;
   }
@@ -583,9 +573,6 @@ extern "C" void mithra_gpu_destroy (MithraGpu* h)
   cudaFree(h->d_scr_pos); cudaFree(h->d_scr_rec); cudaFree(h->d_scr_cur); cudaFree(h->d_seed); cudaFree(h->d_seed_tab); cudaFree(h->d_seedu);
   cudaEventDestroy(h->pev[0]); cudaEventDestroy(h->pev[1]);
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
-  if (h->ebs) { cudaStreamSynchronize(h->ebs); cudaStreamDestroy(h->ebs); }
-  if (h->ev_stencil) cudaEventDestroy(h->ev_stencil);
-  if (h->ev_ebinner) cudaEventDestroy(h->ev_ebinner);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_clear) cudaEventDestroy(h->ev_clear);
   if (h->ev_seed) cudaEventDestroy(h->ev_seed);
@@ -1011,9 +998,6 @@ static int field_update_potentials (MithraGpu* h)
     if (f.nsfd) launch_stencil<true>(h, rim); else launch_stencil<false>(h, rim);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 1;
-    h->ev_stencil_fresh = false;
-    if (h->overlap && !h->profiling && rim && h->j_zeroed_by_update)
-      { CU(cudaEventRecord(h->ev_stencil, h->stream)); h->ev_stencil_fresh = true; }
   }
   {
     PhaseTimer t(h, PH_BOUNDARY);
@@ -1081,8 +1065,7 @@ static int field_update_eb (MithraGpu* h)
     PhaseTimer t(h, PH_EVAL);
     const double cdt = h->prm.c0 * h->prm.dt;
     const int padx = (int) ceil(cdt / h->prm.dx), pady = (int) ceil(cdt / h->prm.dy), padz = (int) ceil(cdt / h->prm.dz);
-    const bool early_box = h->ev_stencil_fresh && !h->potentials_ahead && reach_mask_usable(h) && !getenv("MITHRA_NO_EB_SPLIT");
-    if (!early_box) make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
+    make_eb_box<<<1, 1, 0, h->stream>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
     if (getenv("MITHRA_EB_BOX"))
       {
 	/* the node-at-a-time kernel over the whole box (the parity tests compare the two bit for bit)                  */
@@ -1094,40 +1077,19 @@ static int field_update_eb (MithraGpu* h)
 	/* only the node pencils within some particle's reach (device_types.cuh "Reach mask")                          */
 	const unsigned char* mask = 0;
 	const bool masked = reach_mask_usable(h);
-	/* The nodes whose E/B needs nothing but stencil_stream's output go to the stream `ebs` and run beside rim_update,
-	 * the z faces, the edges and the ghost exchange of this field update; the rest follows here.  Not when this field
-	 * update was enqueued ahead of the particle hand-over (the arrivals' marks are younger than its stencil).       */
-	const bool split = h->ev_stencil_fresh && !h->potentials_ahead && masked && !getenv("MITHRA_NO_EB_SPLIT");
-	h->ev_stencil_fresh = false;
-	cudaStream_t st = h->stream;
-	if (split)
-	  {
-	    st = h->ebs;
-	    CU(cudaStreamWaitEvent(st, h->ev_stencil, 0));
-	    make_eb_box<<<1, 1, 0, st>>>(h->d_pbox, h->d_ebox, (Box*) 0, padx, pady, padz, f.N0, f.N1, f.np);
-	    h->cnt.kernel_launches += 1;
-	  }
 	if (masked)
 	  {
 	    /* into the buffer the source mask of this step's stencil and clear is NOT (they may still be reading it)  */
 	    h->emask_cur ^= 1;
 	    unsigned char* nodes = h->d_emask_nodes[h->emask_cur];
-	    spread_eb_mask<<<h->num_sms * 8, 256, 0, st>>>(f, h->d_emask_cells, nodes, h->d_ebox);
+	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, nodes, h->d_ebox);
 	    h->cnt.kernel_launches += 1;
 	    mask = nodes;
 	    h->emask_fresh = true; h->pushes_since_spread = 0;
 	  }
 	else h->emask_fresh = false;
-	if (split)
-	  {
-	    if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, st>>>(f, ap, a, h->eb, h->d_ebox, mask, 1);
-	    else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, st>>>(f, ap, a, h->eb, h->d_ebox, mask, 1);
-	    h->cnt.kernel_launches += 1;
-	    CU(cudaEventRecord(h->ev_ebinner, st));
-	    CU(cudaStreamWaitEvent(h->stream, h->ev_ebinner, 0));
-	  }
-	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask, split ? 2 : 0);
-	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask, split ? 2 : 0);
+	if (f.ncomp == 4) eval_eb_march<true ><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
+	else              eval_eb_march<false><<<h->num_sms * 8, 256, 0, h->stream>>>(f, ap, a, h->eb, h->d_ebox, mask);
 	if (zlo || zhi)
 	  {
 	    /* planes 0 / np-1 of the global ends copy planes 1 / np-2 (fdtd.cpp:754-773)                               */
@@ -1162,7 +1124,6 @@ static int field_update_eb (MithraGpu* h)
 
 extern "C" int mithra_gpu_field_update (MithraGpu* h)
 {
-  h->potentials_ahead = false;
   TRY(field_update_potentials(h));
   return field_update_eb(h);
 }
@@ -1445,7 +1406,6 @@ extern "C" int mithra_gpu_step (MithraGpu* h, int nsteps)
   bool potentials_done = false;
   for (int s = 0; s < nsteps; s++)
     {
-      h->potentials_ahead = potentials_done;
       if (!potentials_done) TRY(field_update_potentials(h));
       potentials_done = false;
       TRY(field_update_eb(h));
@@ -1484,7 +1444,6 @@ extern "C" int mithra_gpu_synchronize (MithraGpu* h)
   USE(h);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaStreamSynchronize(h->side));
-  CU(cudaStreamSynchronize(h->ebs));
   CU(cudaGetLastError());
   if (h->xch.d_err)
     {

@@ -764,14 +764,10 @@ namespace mithra
   #define MITHRA_MARCH_MINBLOCKS 2                      /* 128 registers: all 30 loads of a node in flight before the arithmetic
 							   (2.8 ms on FEL-LCLS; at 85 registers the scheduler sinks them: 3.5 ms) */
   #endif
-  /* part: 0 = every node of the box; 1 = only the nodes whose E/B depends on nothing but stencil_stream's output --
-   * i in [4, N0-5], j in [4, N1-5], k in [kb+3, np-5]: one node away from the rim rows / columns and from the two planes
-   * per mesh end that the z shell of the seed, the z faces and the ghost exchange write -- so that this launch can run
-   * BESIDE rim_update and everything else of the field update that follows the stencil; 2 = the rest of the box, after them. */
   template <bool SC>
   __global__ void __launch_bounds__(256, MITHRA_MARCH_MINBLOCKS)
   eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
-		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask, int part)
+		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask)
   {
     constexpr int L = MITHRA_MARCH_LOG2, LM = MITHRA_EB_CHUNK_LOG2, NS = 1 << (L - LM);
     const Box b = *boxp;
@@ -792,12 +788,6 @@ namespace mithra
 	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), c = cfirst + (int) (w / ((long) njt * nit));
 	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
 	if (j > b.hi[1] || i > b.hi[0]) continue;
-	if (part == 2)
-	  {
-	    /* a work item whose 32 x 8 x 32 nodes are all inner has nothing left for this pass (uniform over the CTA)     */
-	    const int j0 = b.lo[1] + (jt << 5), i0 = b.lo[0] + (it << 3);
-	    if (i0 >= 4 && i0 + 7 <= f.N0 - 5 && j0 >= 4 && j0 + 31 <= f.N1 - 5 && (c << L) >= f.kb + 3 && ((c + 1) << L) - 1 <= f.np - 5) continue;
-	  }
 	/* the four mask pencils of this column within the work item; no mask: everything                              */
 	unsigned int on = (1u << NS) - 1u;
 	if (mask)
@@ -808,10 +798,7 @@ namespace mithra
 	      { const int cm = (c << (L - LM)) + s; if (cm < nch && mask[((long) cm * f.N0 + i) * N1 + j]) on |= 1u << s; }
 	    if (!on) continue;                                 /* no particle can gather from this column here           */
 	  }
-	const bool inner = ( i >= 4 && i <= f.N0 - 5 && j >= 4 && j <= f.N1 - 5 );
-	if (part == 1 && !inner) continue;
 	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
-	if (part == 2 && inner && ks >= f.kb + 3 && ke - 1 <= f.np - 5) continue;      /* all done by the inner pass   */
 
 	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z; `have`: they hold the planes below k         */
 	double axm = 0.0, ax0 = 0.0, aym = 0.0, ay0 = 0.0, pxm = 0.0, px0 = 0.0, pym = 0.0, py0 = 0.0, fm = 0.0, f0 = 0.0;
@@ -826,12 +813,7 @@ namespace mithra
 	const long eP = 2L * f.P;
 	for (int k = ks; k < ke; k++, qax += Pp, qay += Pp, qaz += Pp, qpx += Pp, qpy += Pp, qpz += Pp, qfn += Pp, qe += eP)
 	  {
-	    bool take = ( on >> ( ( k >> LM ) - ( c << (L - LM) ) ) ) & 1u;
-	    if (part != 0)
-	      {
-		const bool zinner = ( k >= f.kb + 3 && k <= f.np - 5 );
-		take = take && ( part == 1 ? zinner : !( inner && zinner ) );
-	      }
+	    const bool take = ( on >> ( ( k >> LM ) - ( c << (L - LM) ) ) ) & 1u;
 	    if (!take) { have = false; continue; }
 	    if (!have)
 	      {
