@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: a whole shipped job on the GPU (minutes); MITHRA_SKIP_SLOW=1 skips it")
 
 
 def _have_gpu():
