@@ -764,12 +764,20 @@ namespace mithra
   #define MITHRA_MARCH_MINBLOCKS 2                      /* 128 registers: all 30 loads of a node in flight before the arithmetic
 							   (2.8 ms on FEL-LCLS; at 85 registers the scheduler sinks them: 3.5 ms) */
   #endif
+  /* Work distribution: a work item is a tile of 32 x 8 node columns x 32 planes (four mask pencils per column).  With a
+   * mask the marked (column, pencil) pairs of the tile are first COMPACTED into a list in shared memory, ordered by
+   * pencil, then row, then column -- so that consecutive lanes still walk consecutive nodes of a row -- and the 256
+   * threads take the list 256 units at a time: on a bunch with Gaussian tails (FEL-LCLS) only 39 % of the lanes of the
+   * column-per-thread version had a marked pencil.  A unit is the 8 planes of one pencil: planes k-1, k of what is
+   * differenced along z are loaded at its start (L1 hits when the pencil below belongs to the same column).           */
   template <bool SC>
   __global__ void __launch_bounds__(256, MITHRA_MARCH_MINBLOCKS)
   eval_eb_march (const FieldDev f, const double* __restrict__ anp1, const double* __restrict__ an,
 		 float4* __restrict__ eb, const Box* __restrict__ boxp, const unsigned char* __restrict__ mask)
   {
     constexpr int L = MITHRA_MARCH_LOG2, LM = MITHRA_EB_CHUNK_LOG2, NS = 1 << (L - LM);
+    __shared__ unsigned short unit[256 * NS];           /* (pencil << 8) | column                                    */
+    __shared__ int wcount[NS][8], ubase[NS + 1];
     const Box b = *boxp;
     const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
     const int kfirst = max(b.lo[2], f.kb), klast = min(b.hi[2], f.np - 2);
@@ -782,68 +790,95 @@ namespace mithra
     const double* ax = an,   * ay = an   + cs, * az = an   + 2 * cs, * fn = an + 3 * cs;
     const double* px = anp1, * py = anp1 + cs, * pz = anp1 + 2 * cs;
     const int nch = (f.np + (1 << LM) - 1) >> LM;
+    const long eP = 2L * f.P;
 
     for (long w = blockIdx.x; w < nwork; w += gridDim.x)
       {
 	const int jt = (int) (w % njt), it = (int) ((w / njt) % nit), c = cfirst + (int) (w / ((long) njt * nit));
-	const int j = b.lo[1] + (jt << 5) + tj, i = b.lo[0] + (it << 3) + ti;
-	if (j > b.hi[1] || i > b.hi[0]) continue;
-	/* the four mask pencils of this column within the work item; no mask: everything                              */
-	unsigned int on = (1u << NS) - 1u;
-	if (mask)
+	const int i0 = b.lo[0] + (it << 3), j0 = b.lo[1] + (jt << 5);
+	/* the pencils of this thread's column that are marked (no mask: all of them)                                */
+	unsigned int on = 0u;
+	{
+	  const int j = j0 + tj, i = i0 + ti;
+	  if (j <= b.hi[1] && i <= b.hi[0])
+	    {
+	      #pragma unroll
+	      for (int s = 0; s < NS; s++)
+		{ const int cm = (c << (L - LM)) + s; if (cm < nch && (!mask || mask[((long) cm * f.N0 + i) * N1 + j])) on |= 1u << s; }
+	    }
+	}
+	/* compaction: per pencil the marked columns in (row, column) order                                          */
+	unsigned int bal[NS];
+	#pragma unroll
+	for (int s = 0; s < NS; s++)
 	  {
-	    on = 0u;
+	    bal[s] = __ballot_sync(0xffffffffu, (on >> s) & 1u);
+	    if (tj == 0) wcount[s][ti] = __popc(bal[s]);
+	  }
+	__syncthreads();
+	if (threadIdx.x == 0)
+	  {
+	    int acc = 0;
 	    #pragma unroll
 	    for (int s = 0; s < NS; s++)
-	      { const int cm = (c << (L - LM)) + s; if (cm < nch && mask[((long) cm * f.N0 + i) * N1 + j]) on |= 1u << s; }
-	    if (!on) continue;                                 /* no particle can gather from this column here           */
-	  }
-	const int ks = max(kfirst, c << L), ke = min(klast + 1, (c + 1) << L);
-
-	/* planes k-1 (m), k (0), k+1 (p) of what is differenced along z; `have`: they hold the planes below k         */
-	double axm = 0.0, ax0 = 0.0, aym = 0.0, ay0 = 0.0, pxm = 0.0, px0 = 0.0, pym = 0.0, py0 = 0.0, fm = 0.0, f0 = 0.0;
-	bool have = false;
-	/* the node in plane ks: one pointer per array, advanced by a plane per step (the compiler's own addressing of
-	 * 26 loads through a recomputed 64-bit index was half of the kernel's instructions)                            */
-	const long m0 = (long) ks * Pp + (long) i * N1 + j;
-	const double* qax = ax + m0; const double* qay = ay + m0; const double* qaz = az + m0;
-	const double* qpx = px + m0; const double* qpy = py + m0; const double* qpz = pz + m0;
-	const double* qfn = fn + m0;
-	float4* qe = eb + 2 * ( (long) ks * f.P + (long) i * N1 + j );
-	const long eP = 2L * f.P;
-	for (int k = ks; k < ke; k++, qax += Pp, qay += Pp, qaz += Pp, qpx += Pp, qpy += Pp, qpz += Pp, qfn += Pp, qe += eP)
-	  {
-	    const bool take = ( on >> ( ( k >> LM ) - ( c << (L - LM) ) ) ) & 1u;
-	    if (!take) { have = false; continue; }
-	    if (!have)
 	      {
-		axm = qax[-Pp]; ax0 = qax[0]; aym = qay[-Pp]; ay0 = qay[0];
-		pxm = qpx[-Pp]; px0 = qpx[0]; pym = qpy[-Pp]; py0 = qpy[0];
-		if (SC) { fm = qfn[-Pp]; f0 = qfn[0]; }
-		have = true;
+		ubase[s] = acc;
+		for (int q = 0; q < 8; q++) { const int n = wcount[s][q]; wcount[s][q] = acc; acc += n; }
 	      }
-	    const double axp = qax[Pp], ayp = qay[Pp], pxp = qpx[Pp], pyp = qpy[Pp];
-	    const double q2 = qaz[0], p2 = qpz[0];
-	    double fp = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-	    if (SC) { fp = qfn[Pp]; g0 = qfn[N1] - qfn[-N1]; g1 = qfn[1] - qfn[-1]; g2 = fp - fm; }
-	    const double azy = qaz[1 ] - qaz[-1 ], pzy = qpz[1 ] - qpz[-1 ];
-	    const double azx = qaz[N1] - qaz[-N1], pzx = qpz[N1] - qpz[-N1];
-	    const double ayx = qay[N1] - qay[-N1], pyx = qpy[N1] - qpy[-N1];
-	    const double axy = qax[1 ] - qax[-1 ], pxy = qpx[1 ] - qpx[-1 ];
-	    /* every load of the node is in flight before the arithmetic starts: left alone, the scheduler sinks each load
-	     * to its first use to save registers and the kernel runs at the latency of one load after the other          */
-	    #if MITHRA_MARCH_BARRIER
-	    __syncwarp(__activemask());
-	    #endif
-	    const EB o = eb_assemble<SC>(f, px0, py0, p2, ax0, ay0, q2, g0, g1, g2,
-					 azy, ayp - aym, pzy, pyp - pym,
-					 axp - axm, azx, pxp - pxm, pzx,
-					 ayx, axy, pyx, pxy);
-	    qe[0] = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
-	    qe[1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
-	    axm = ax0; ax0 = axp; aym = ay0; ay0 = ayp; pxm = px0; px0 = pxp; pym = py0; py0 = pyp;
-	    if (SC) { fm = f0; f0 = fp; }
+	    ubase[NS] = acc;
 	  }
+	__syncthreads();
+	#pragma unroll
+	for (int s = 0; s < NS; s++)
+	  if ((on >> s) & 1u) unit[wcount[s][ti] + __popc(bal[s] & ((1u << tj) - 1u))] = (unsigned short) ((s << 8) | threadIdx.x);
+	__syncthreads();
+	const int nunits = ubase[NS];
+
+	for (int u = threadIdx.x; u < nunits; u += 256)
+	  {
+	    const int code = unit[u], s = code >> 8, col = code & 255;
+	    const int i = i0 + (col >> 5), j = j0 + (col & 31);
+	    const int cm = (c << (L - LM)) + s;
+	    const int ks = max(kfirst, cm << LM), ke = min(klast + 1, (cm + 1) << LM);
+	    if (ks >= ke) continue;
+	    /* the node in plane ks: one pointer per array, advanced by a plane per step (the compiler's own addressing of
+	     * 26 loads through a recomputed 64-bit index was half of the kernel's instructions)                        */
+	    const long m0 = (long) ks * Pp + (long) i * N1 + j;
+	    const double* qax = ax + m0; const double* qay = ay + m0; const double* qaz = az + m0;
+	    const double* qpx = px + m0; const double* qpy = py + m0; const double* qpz = pz + m0;
+	    const double* qfn = fn + m0;
+	    float4* qe = eb + 2 * ( (long) ks * f.P + (long) i * N1 + j );
+	    /* planes k-1 (m), k (0), k+1 (p) of what is differenced along z                                            */
+	    double axm = qax[-Pp], ax0 = qax[0], aym = qay[-Pp], ay0 = qay[0];
+	    double pxm = qpx[-Pp], px0 = qpx[0], pym = qpy[-Pp], py0 = qpy[0];
+	    double fm = 0.0, f0 = 0.0;
+	    if (SC) { fm = qfn[-Pp]; f0 = qfn[0]; }
+	    for (int k = ks; k < ke; k++, qax += Pp, qay += Pp, qaz += Pp, qpx += Pp, qpy += Pp, qpz += Pp, qfn += Pp, qe += eP)
+	      {
+		const double axp = qax[Pp], ayp = qay[Pp], pxp = qpx[Pp], pyp = qpy[Pp];
+		const double q2 = qaz[0], p2 = qpz[0];
+		double fp = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+		if (SC) { fp = qfn[Pp]; g0 = qfn[N1] - qfn[-N1]; g1 = qfn[1] - qfn[-1]; g2 = fp - fm; }
+		const double azy = qaz[1 ] - qaz[-1 ], pzy = qpz[1 ] - qpz[-1 ];
+		const double azx = qaz[N1] - qaz[-N1], pzx = qpz[N1] - qpz[-N1];
+		const double ayx = qay[N1] - qay[-N1], pyx = qpy[N1] - qpy[-N1];
+		const double axy = qax[1 ] - qax[-1 ], pxy = qpx[1 ] - qpx[-1 ];
+		/* every load of the node is in flight before the arithmetic starts: left alone, the scheduler sinks each
+		 * load to its first use to save registers and the kernel runs at the latency of one load after the other   */
+		#if MITHRA_MARCH_BARRIER
+		__syncwarp(__activemask());
+		#endif
+		const EB o = eb_assemble<SC>(f, px0, py0, p2, ax0, ay0, q2, g0, g1, g2,
+					     azy, ayp - aym, pzy, pyp - pym,
+					     axp - axm, azx, pxp - pxm, pzx,
+					     ayx, axy, pyx, pxy);
+		qe[0] = make_float4(o.e[0], o.e[1], o.e[2], 0.f);
+		qe[1] = make_float4(o.b[0], o.b[1], o.b[2], 0.f);
+		axm = ax0; ax0 = axp; aym = ay0; ay0 = ayp; pxm = px0; px0 = pxp; pym = py0; py0 = pyp;
+		if (SC) { fm = f0; f0 = fp; }
+	      }
+	  }
+	__syncthreads();                                   /* the list is rewritten by the next work item            */
       }
   }
 
