@@ -1082,7 +1082,8 @@ static int field_update_eb (MithraGpu* h)
 	    /* into the buffer the source mask of this step's stencil and clear is NOT (they may still be reading it)  */
 	    h->emask_cur ^= 1;
 	    unsigned char* nodes = h->d_emask_nodes[h->emask_cur];
-	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, nodes, h->d_ebox);
+	    CU(cudaMemsetAsync(nodes, 0, h->emask_bytes, h->stream));
+	    spread_eb_mask<<<h->num_sms * 8, 256, 0, h->stream>>>(f, h->d_emask_cells, nodes, (long) h->emask_bytes);
 	    h->cnt.kernel_launches += 1;
 	    mask = nodes;
 	    h->emask_fresh = true; h->pushes_since_spread = 0;
