@@ -302,6 +302,7 @@ def slab_cross_check(p, wl, dist, rank, world, local_rank, nsteps=20):
         rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
         out = {"what": "%d slabs on %d GPUs against 1 slab, %d x %d x %d nodes, %d macro-particles, %d field steps" % (
                    world, world, pg.N0, pg.N1, pg.N2, n, nsteps),
+               "sum_A2": float(want[0]), "sum_J2": float(want[1]),
                "rel_diff_sum_A2": float(rel[0]), "rel_diff_sum_J2": float(rel[1]), "particles": [int(got[2]), int(want[2])],
                "rel_diff_charge_centre_z": float(abs(got[3] / got[4] - want[3] / want[4]) / abs(pg.zmax - pg.zmin)),
                "ok": bool(rel[0] < 1e-9 and rel[1] < 1e-6 and int(got[2]) == int(want[2]))}
