@@ -67,13 +67,9 @@ namespace MITHRA
     initializeMesh();
     lorentzBoostBunch();
     initializeField();
-    if ( seed_.profile_ )
-      {
-	printmessage(__FILE__, __LINE__, "The field profile output (FIELD / field-profile) is not part of this build: the reference prints en_ / bn_ as its lazy evaluation last left them (fdtd.cpp:1546-1594), stale on every node no particle is near. Use field-sampling or the in-plane visualization.");
-	exit(1);
-      }
     if ( seed_.sampling_ ) initializeSeedSampling();
     initializeSeedVTK();
+    if ( seed_.profile_ ) initializeSeedProfile();
     initializeBunchUpdate();
     initializePowerSample();
     initializePowerVisualize();
@@ -541,12 +537,6 @@ namespace MITHRA
 	    else if ( v.plane_ == YNORMAL ) outside = ( v.position_[1] > ymax_ - ub_.dy || v.position_[1] < ymin_ + ub_.dy );
 	    else if ( v.plane_ == ZNORMAL ) outside = ( v.position_[2] > zmax_ - ub_.dz || v.position_[2] < zmin_ + ub_.dz );
 	  }
-	if ( v.type_ == ALLDOMAIN )
-	  {
-	    /* the reference's error convention: say why and stop (a job must not run to its end and silently write nothing) */
-	    printmessage(__FILE__, __LINE__, "The all-domain field visualization is not part of this build: the reference evaluates E/B beyond its arrays on the end planes there (fdtd.cpp:956-1105), there is nothing to be identical to. Use the in-plane visualization.");
-	    exit(1);
-	  }
 	if ( outside )
 	  {
 	    printmessage(__FILE__, __LINE__, "The plane does not reside in the grid. No data is saved.");
@@ -746,6 +736,141 @@ namespace MITHRA
     f << "</Piece>" << std::endl;
     f << "</StructuredGrid>" << std::endl;
     f << "</VTKFile>" << std::endl;
+  }
+
+  /* FdTd::fieldVisualizeAllDomain, fdtd.cpp:956-1105: the requested fields on every node of the mesh as one ASCII .vts piece
+   * (single-rank naming, "-p0-") plus the .pvts.  The reference evaluates E/B on every node with 1 <= i <= N0-2,
+   * 1 <= j <= N1-2 at this moment (its lazy flags are bypassed) and leaves the transverse boundary nodes at zero: the
+   * same here, node by node through mithra_gpu_field_nodes.  On the two end planes of the mesh the reference's
+   * fieldEvaluate reads beyond its arrays; here they carry the E/B of their interior neighbour plane, like everywhere
+   * else in this build (fdtd.cpp:754-773) -- the A columns are the reference's on every node.                         */
+  void FdTd::fieldVisualizeAllDomain (unsigned int ivtk)
+  {
+    const Seed::vtk& V = seed_.vtk_[ivtk];
+    const size_t nf = V.field_.size();
+    const std::string name = V.basename_ + "-p" + stringify(0) + "-" + stringify(nTime_) + ".vts";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    f << "<?xml version=\"1.0\"?>" << std::endl;
+    f << "<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << std::endl;
+    f << "<StructuredGrid WholeExtent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << N2_ - 2 + 1 << "\">" << std::endl;
+    f << "<Piece Extent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << N2_ - 2 + 1 << "\">" << std::endl;
+    f << "<Points>" << std::endl;
+    f << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+    for (int k = 0; k < N2_; k++)
+      for (int j = 0; j < N1_; j++)
+	for (int i = 0; i < N0_; i++)
+	  {
+	    const FieldVector r = rc((long int) k * N1N0_ + i * N1_ + j);
+	    f << r[0] << " " << r[1] << " " << r[2] << std::endl;
+	  }
+    f << "</DataArray>" << std::endl;
+    f << "</Points>" << std::endl;
+    f << "<CellData>" << std::endl;
+    f << "</CellData>" << std::endl;
+    f << "<PointData Vectors = \"field\">" << std::endl;
+    f << "<DataArray type=\"Float64\" Name=\"field\" NumberOfComponents=\"" << nf << "\" format=\"ascii\">" << std::endl;
+    /* a few planes at a time: nine doubles per node come back from the device                                        */
+    const int chunk = std::max(1, (int) ( 2000000L / N1N0_ ));
+    std::vector<int> ijk; std::vector<double> val;
+    for (int k0 = 0; k0 < N2_; k0 += chunk)
+      {
+	const int k1 = std::min(N2_, k0 + chunk);
+	ijk.clear();
+	for (int k = k0; k < k1; k++)
+	  for (int j = 0; j < N1_; j++)
+	    for (int i = 0; i < N0_; i++) { ijk.push_back(i); ijk.push_back(j); ijk.push_back(k); }
+	nodeValues(ijk, val);
+	size_t q = 0;
+	for (int k = k0; k < k1; k++)
+	  for (int j = 0; j < N1_; j++)
+	    for (int i = 0; i < N0_; i++, q++)
+	      {
+		/* vf_.v stays zero on the transverse boundary, A included (the loop of fdtd.cpp:969-971 skips it)         */
+		const bool inner = ( i >= 1 && i <= N0_ - 2 && j >= 1 && j <= N1_ - 2 );
+		for (size_t l = 0; l < nf; l++)
+		  {
+		    const int col = fieldColumn(V.field_[l]);
+		    const double v = ( inner && col >= 0 ) ? ( col < 6 ? (double) (float) val[9 * q + col] : val[9 * q + col] ) : 0.0;
+		    f << ( l ? " " : "" ) << v;
+		  }
+		f << std::endl;
+	      }
+      }
+    f << "</DataArray>" << std::endl;
+    f << "</PointData>" << std::endl;
+    f << "</Piece>" << std::endl;
+    f << "</StructuredGrid>" << std::endl;
+    f << "</VTKFile>" << std::endl;
+    f.close();
+
+    const std::string pname = V.basename_ + "-" + stringify(nTime_) + ".pvts";
+    const std::string base = V.basename_.substr(V.basename_.find_last_of("/") + 1);
+    std::ofstream g(pname.c_str(), std::ios::trunc);
+    g << "<?xml version=\"1.0\"?>" << std::endl;
+    g << "<VTKFile type=\"PStructuredGrid\" version=\"0.1\" >" << std::endl;
+    g << "<PStructuredGrid WholeExtent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " 0 " << N2_ - 1 << "\" GhostLevel = \"0\" >" << std::endl;
+    g << "<PPoints>" << std::endl;
+    g << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\" />" << std::endl;
+    g << "</PPoints>" << std::endl;
+    g << "<PPointData>" << std::endl;
+    g << "<DataArray type=\"Float64\" NumberOfComponents=\"" << nf << "\" Name=\"field\" format=\"ascii\" />" << std::endl;
+    g << "</PPointData>" << std::endl;
+    g << "<Piece Extent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << N2_ - 2 + 1 << "\"" << " Source=\""
+      << base + "-p" + stringify(0) + "-" + stringify(nTime_) + ".vts" << "\" />" << std::endl;
+    g << "</PStructuredGrid>" << std::endl;
+    g << "</VTKFile>" << std::endl;
+  }
+
+  /* Solver::initializeSeedProfile, solver.cpp:1022-1044 */
+  void Solver::initializeSeedProfile ()
+  {
+    if ( seed_.profileRhythm_ == 0 && seed_.profileTime_.size() == 0 )
+      { printmessage(__FILE__, __LINE__, "The profiling rhythm of the field is zero and no time is set although profiling of the field is activated !!!"); exit(1); }
+    seed_.profileRhythm_ /= gamma_;
+    for (unsigned i = 0; i < seed_.profileTime_.size(); i++) seed_.profileTime_[i] /= gamma_;
+    if ( seed_.profileBasename_.compare(0, 1, "/") != 0 ) seed_.profileBasename_ = seed_.profileDirectory_ + seed_.profileBasename_;
+    createDirectory(seed_.profileBasename_, 0);
+  }
+
+  /* FdTd::fieldProfile, fdtd.cpp:1546-1594: x y z and the requested fields of every node, i outermost, one text file
+   * ("-p0-").  The reference prints en_ / bn_ as its lazy evaluation last left them -- fresh only on the nodes a particle
+   * or a sampler touched in this step, stale or zero elsewhere; this build prints the E/B of THIS step on every node
+   * (zero on the transverse boundary, where the reference never evaluates either).  The A columns are the reference's.  */
+  void FdTd::fieldProfile ()
+  {
+    const std::string name = seed_.profileBasename_ + "-p" + stringify(0) + "-" + stringify(nTime_) + ".txt";
+    std::ofstream f(name.c_str(), std::ios::trunc);
+    f.setf(std::ios::scientific);
+    f.precision(4);
+    const size_t nf = seed_.profileField_.size();
+    std::vector<int> ijk; std::vector<double> val;
+    const int chunk = std::max(1, (int) ( 2000000L / ( (long) N1_ * N2_ ) ));          /* rows i at a time          */
+    for (int i0 = 0; i0 < N0_; i0 += chunk)
+      {
+	const int i1 = std::min(N0_, i0 + chunk);
+	ijk.clear();
+	for (int i = i0; i < i1; i++)
+	  for (int j = 0; j < N1_; j++)
+	    for (int k = 0; k < N2_; k++) { ijk.push_back(i); ijk.push_back(j); ijk.push_back(k); }
+	nodeValues(ijk, val);
+	size_t q = 0;
+	for (int i = i0; i < i1; i++)
+	  for (int j = 0; j < N1_; j++)
+	    for (int k = 0; k < N2_; k++, q++)
+	      {
+		const FieldVector r = rc((long int) k * N1N0_ + i * N1_ + j);
+		f << r[0] << "\t" << r[1] << "\t" << r[2] << "\t";
+		for (size_t l = 0; l < nf; l++)
+		  {
+		    const int col = fieldColumn(seed_.profileField_[l]);
+		    if ( col < 0 ) continue;
+		    if ( col < 6 ) f << (float) val[9 * q + col] << "\t"; else f << val[9 * q + col] << "\t";
+		  }
+		f << std::endl;
+	      }
+      }
   }
 
   /* solver.cpp:1050-1059 */
@@ -1364,6 +1489,12 @@ namespace MITHRA
 	  if ( seed_.sampling_ && fmod(time_, seed_.samplingRhythm_) < mesh_.timeStep_ && time_ > 0.0 ) gated = true;
 	  for (unsigned int i = 0; i < seed_.vtk_.size(); i++)
 	    if ( seed_.vtk_[i].sample_ && fmod(time_, seed_.vtk_[i].rhythm_) < mesh_.timeStep_ && time_ > 0.0 ) gated = true;
+	  if ( seed_.profile_ )
+	    {
+	      for (unsigned int i = 0; i < seed_.profileTime_.size(); i++)
+		if ( time_ - seed_.profileTime_[i] < mesh_.timeStep_ && time_ > seed_.profileTime_[i] ) gated = true;
+	      if ( fmod(time_, seed_.profileRhythm_) < mesh_.timeStep_ && time_ > 0.0 && seed_.profileRhythm_ != 0 ) gated = true;
+	    }
 	}
 	if ( gpu_.size() == 1 && !gated && !getenv("MITHRA_HOST_CALL_BY_CALL") )
 	  {
@@ -1387,6 +1518,13 @@ namespace MITHRA
 	      if      ( seed_.vtk_[i].type_ == ALLDOMAIN ) fieldVisualizeAllDomain(i);
 	      else if ( seed_.vtk_[i].type_ == INPLANE   ) fieldVisualizeInPlane(i);
 	    }
+	/* field profile at the given times and at the rhythm, solver.cpp:1344-1351                                    */
+	if ( seed_.profile_ )
+	  {
+	    for (unsigned int i = 0; i < seed_.profileTime_.size(); i++)
+	      if ( time_ - seed_.profileTime_[i] < mesh_.timeStep_ && time_ > seed_.profileTime_[i] ) fieldProfile();
+	    if ( fmod(time_, seed_.profileRhythm_) < mesh_.timeStep_ && time_ > 0.0 && seed_.profileRhythm_ != 0 ) fieldProfile();
+	  }
 	/* rhythm-gated bunch samplers, solver.cpp:1352-1371                                                           */
 	if ( bunch_.sampling_ && fmod(time_ + mesh_.timeShift_, bunch_.rhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchSample();
 	if ( bunch_.bunchVTK_ && fmod(time_ + mesh_.timeShift_, bunch_.bunchVTKRhythm_) < mesh_.timeStep_ && ( time_ + mesh_.timeShift_ > 0.0 ) ) bunchVisualize();

@@ -57,7 +57,8 @@ namespace MITHRA
     void computeFileGamma (BunchInitialize& bunchInit);
     void initializeMesh ();
     void initializeSeedSampling ();                            /* solver.cpp:848-931 */
-    void initializeSeedVTK ();                                 /* solver.cpp:938-1016 */
+    void initializeSeedVTK ();
+    void initializeSeedProfile ();                 /* solver.cpp:1022-1044 */                                 /* solver.cpp:938-1016 */
     void initializeField ();
     void initializeBunchUpdate ();
     void initializeBunch ();
@@ -161,15 +162,13 @@ namespace MITHRA
     void fieldShift ();
     void fieldEvaluate (long int) {}               /* E, B are evaluated eagerly on the device (eval_eb_box)         */
     void fieldSample ();                           /* fdtd.cpp:851-950: values from mithra_gpu_field_sample, the reference's line */
-    void fieldVisualizeAllDomain (unsigned int)    /* not built; initializeSeedVTK stops a job that asks for it */
-    { printmessage(__FILE__, __LINE__, "The all-domain field visualization is not part of this build."); exit(1); }
+    void fieldVisualizeAllDomain (unsigned int ivtk);            /* fdtd.cpp:956-1105 */
     void fieldVisualizeInPlane (unsigned int ivtk);              /* fdtd.cpp:1111-1121 */
     void fieldVisualizeInPlaneXNormal (unsigned int ivtk);       /* fdtd.cpp:1128-1285 */
     void fieldVisualizeInPlaneYNormal (unsigned int ivtk);       /* fdtd.cpp:1292-1447 */
     void fieldVisualizeInPlaneZNormal (unsigned int ivtk);       /* fdtd.cpp:1452-1540 */
     void nodeValues (const std::vector<int>& ijk, std::vector<double>& val);   /* en_, bn_, an_ at global nodes */
-    void fieldProfile ()                           /* not built; initialize() stops a job that asks for it */
-    { printmessage(__FILE__, __LINE__, "The field profile output is not part of this build."); exit(1); }
+    void fieldProfile ();                                        /* fdtd.cpp:1546-1594 */
   };
 
   /* identical forwarding: the library switches to the A + phi kernels when MithraGpuParams.space_charge is set     */

@@ -34,7 +34,7 @@ from oracle import binding  # noqa: E402
 
 JOBS = ("micro-nsfd", "micro-fd", "micro-o1", "micro-sc", "micro-seeded", "micro-optical", "micro-pviz",
         "micro-ics", "micro-lcls", "micro-trap", "micro-beams")
-EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift", "micro-fviz")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
+EXTRA_JOBS = ("micro-bsample", "micro-fsample", "micro-fline", "micro-bvtk", "micro-backshift", "micro-fviz", "micro-fall")        # host-writer fixtures only (same physics as micro-nsfd), not in tests/helpers.JOBS
 NSTEPS = 100
 NSAMPLE = 1024
 
@@ -106,7 +106,7 @@ def make(job):
                     if fn.endswith(".vts"):
                         out["vts/" + fn] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
                     # bunch-sampling / bunch-profile text files exactly as the reference wrote them
-                    if d in ("bunch-sampling", "bunch-profile", "field-sampling") and fn.endswith(".txt"):
+                    if d in ("bunch-sampling", "bunch-profile", "field-sampling", "field-profile") and fn.endswith(".txt"):
                         out["txt/%s/%s" % (d, fn)] = np.frombuffer(open(os.path.join(dd, fn), "rb").read(), dtype=np.uint8)
         scr_dir = os.path.join(work, "screens")
         if os.path.isdir(scr_dir):

@@ -100,23 +100,6 @@ def test_unknown_key_and_group_exit_like_the_reference(tmp_path):
     assert r.returncode == 1 and "Unable to open file" in r.stdout
 
 
-def test_outputs_that_are_not_built_stop_the_job_with_a_message(tmp_path):
-    """A job that asks for the all-domain field visualization or the field profile must not run to its end and write
-    nothing: message + exit(1), the reference's error convention (--dump-params runs Solver::initialize() only)."""
-    text = open(_job("micro-fviz")).read()
-    job = tmp_path / "alldomain.job"
-    new, n = re.subn(r"(type\s*=\s*)in-plane", r"\1all-domain", text, count=1)
-    assert n == 1
-    job.write_text(new)
-    r = subprocess.run([_exe(), str(job), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True, cwd=str(tmp_path))
-    assert r.returncode == 1 and "all-domain field visualization is not part of this build" in r.stdout
-    text = open(_job("micro-nsfd")).read()
-    job = tmp_path / "profile.job"
-    job.write_text(text.replace("UNDULATOR", "FIELD\n{\n  field-profile\n  {\n    sample = true\n    directory = ./\n    base-name = fp/f\n    rhythm = 10\n  }\n}\n\nUNDULATOR", 1))
-    r = subprocess.run([_exe(), str(job), "--dump-params", str(tmp_path / "x")], capture_output=True, text=True, cwd=str(tmp_path))
-    assert r.returncode == 1 and "field profile output" in r.stdout, r.stdout[-600:]
-
-
 def test_without_gpu_the_executable_fails_loudly(tmp_path):
     from mithra_b200 import abi
     if abi.load().mithra_gpu_device_count() > 0:
@@ -357,6 +340,64 @@ def test_executable_writes_the_in_plane_field_visualization_files(gpus, tmp_path
             assert fr.shape[0] == N0 * N2
         scale = np.abs(fr).max(axis=0)
         assert np.all(np.abs(fg - fr) <= 2e-4 * np.abs(fr) + 2e-4 * scale), fn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_executable_writes_the_all_domain_visualization_and_the_field_profile(gpus, tmp_path):
+    """FdTd::fieldVisualizeAllDomain (fdtd.cpp:956-1105) and FdTd::fieldProfile (fdtd.cpp:1546-1594) through the host
+    executable against the unmodified reference's own files (tests/golden/micro-fall.npz): same files at the same rhythm,
+    same XML lines and point coordinates.  All-domain: every value to the printed digits except E/B on the two end planes
+    of the mesh (the reference's fieldEvaluate reads beyond its arrays there).  Profile: the coordinates and the A column
+    on every node; the E/B columns wherever the reference's lazily evaluated en_ / bn_ were evaluated in THAT step --
+    a node whose value is fresh in the reference equals this build's, the others are the reference's leftovers (zero or
+    an earlier step's), which this build replaces by the current field."""
+    meta, g = helpers.load_golden("micro-fall")
+    N0, N1, N2 = int(meta["N0"][0]), int(meta["N1"][0]), int(meta["N2"][0])
+    subprocess.check_output([_exe(), _job("micro-fall"), "--steps", "100", "--gpus", str(gpus)], cwd=str(tmp_path))
+    want = sorted(k[4:] for k in g.files if k.startswith("vts/"))
+    assert want == ["all-49.pvts", "all-98.pvts", "all-p0-49.vts", "all-p0-98.vts"]
+    assert sorted(os.listdir(tmp_path / "field-visualization")) == want
+    for fn in want:
+        ref = bytes(g["vts/" + fn]).decode().splitlines()
+        got = open(tmp_path / "field-visualization" / fn).read().splitlines()
+        assert len(got) == len(ref), fn
+        blocks_g, blocks_r, cur_g, cur_r = [], [], [], []
+        for a, b in zip(got, ref):
+            if b.startswith("<"):
+                assert a == b, fn
+                if cur_r:
+                    blocks_g.append(np.array(cur_g)); blocks_r.append(np.array(cur_r)); cur_g, cur_r = [], []
+            else:
+                cur_g.append([float(x) for x in a.split()]); cur_r.append([float(x) for x in b.split()])
+        if fn.endswith(".pvts"):
+            continue
+        assert len(blocks_r) == 2, fn
+        np.testing.assert_allclose(blocks_g[0], blocks_r[0], rtol=2e-4, atol=2e-4 * np.abs(blocks_r[0]).max(), err_msg=fn)
+        fg, fr = blocks_g[1].copy(), blocks_r[1].copy()                  # rows k-major, then j, then i; columns Ey, Bx, Ay, Az
+        assert fg.shape == fr.shape == (N0 * N1 * N2, 4) and np.abs(fr).max(axis=0).min() > 0, fn
+        plane = N0 * N1
+        for col in (0, 1):                                              # E/B on the end planes: not comparable
+            fg[:plane, col] = fr[:plane, col] = 0.0
+            fg[-plane:, col] = fr[-plane:, col] = 0.0
+        scale = np.abs(fr).max(axis=0)
+        assert np.all(np.abs(fg - fr) <= 2e-4 * np.abs(fr) + 2e-4 * scale), fn
+    names = sorted(k for k in g.files if k.startswith("txt/field-profile/"))
+    assert len(names) == 1
+    fn = names[0][len("txt/field-profile/"):]
+    assert sorted(os.listdir(tmp_path / "field-profile")) == [fn]
+    R = np.array([[float(x) for x in ln.split()] for ln in bytes(g[names[0]]).decode().splitlines()])
+    G = np.array([[float(x) for x in ln.split()] for ln in open(tmp_path / "field-profile" / fn).read().splitlines()])
+    assert R.shape == G.shape == (N0 * N1 * N2, 7)                       # x y z Ay Ey Bx Az, i outermost, k fastest
+    scale = np.abs(R).max(axis=0)
+    for col in (0, 1, 2, 3, 6):
+        assert np.all(np.abs(G[:, col] - R[:, col]) <= 2e-4 * np.abs(R[:, col]) + 2e-4 * scale[col]), col
+    # E/B: wherever the two agree the value is this step's; that must be the bulk of the nodes the bunch touches, and
+    # this build never prints a zero where the reference printed a fresh value
+    for col in (4, 5):
+        same = np.abs(G[:, col] - R[:, col]) <= 2e-4 * np.abs(R[:, col]) + 2e-4 * scale[col]
+        assert same[R[:, col] != 0.0].mean() > 0.5, col
+        assert np.all(G[(R[:, col] != 0.0) & same, col] != 0.0)
 
 
 @pytest.mark.gpu
