@@ -16,7 +16,14 @@
  *
  * Write-after-read safety needs no extra handshake: a neighbour can only overwrite a ghost (or mailbox) of step n+1
  * after it has waited for this slab's put of step n+1, which this slab enqueues after every reader of step n.
- * The three rotating levels of A make the same argument hold for the potentials three steps apart.
+ * The three rotating levels of A make the same argument hold for the potentials three steps apart.  The particle inboxes
+ * are the exception -- the particle-only loop before the time origin has no other exchange to order them -- and exist
+ * twice, one per parity of the hand-over: put(n + 2) follows this slab's put(n + 1), which follows its unpack(n).
+ *
+ * One process may drive several slabs (the host executable with --gpus larger than the number of devices, the one-GPU
+ * tests): every handle owns two streams and some of their kernels spin on a neighbour's flag, so the process asks for 32
+ * hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, set before the context exists: host/main.cpp, abi.py) -- with the default 8
+ * the streams of more than four slabs on one device share queues and a spinning wait can sit in front of the put it waits for.
  */
 #ifndef MITHRA_EXCHANGE_CUH_
 #define MITHRA_EXCHANGE_CUH_
@@ -29,7 +36,14 @@
 
 namespace mithra
 {
-  #define MITHRA_WAIT_TIMEOUT_NS 10000000000ull      /* 10 s */
+  /* a wait on a neighbour's flag gives up after this long and raises the slab's error flag: 10 s, or MITHRA_WAIT_TIMEOUT_S
+   * seconds (a rank that stalls in long output I/O must not make its neighbours fail)                                */
+  static inline unsigned long long wait_timeout_ns ()
+  {
+    static const unsigned long long t = [] { const char* e = getenv("MITHRA_WAIT_TIMEOUT_S"); const double s = e ? atof(e) : 10.0;
+					     return (unsigned long long) ( ( s > 0.0 ? s : 10.0 ) * 1.0e9 ); } ();
+    return t;
+  }
 
   enum { XF_A_PREV = 0, XF_A_NEXT, XF_EB_PREV, XF_EB_NEXT, XF_J_PREV, XF_J_NEXT, XF_P_PREV, XF_P_NEXT, XF_COUNT = 16 };
 
@@ -37,15 +51,14 @@ namespace mithra
   struct ArenaHeader
   {
     unsigned long long flag[XF_COUNT];     /* "data from prev / next of sequence s has arrived"             */
-    unsigned int       in_count[2];        /* particles in inbox_from_prev / inbox_from_next                */
-    int                pad[2];
+    unsigned int       in_count[2][2];     /* [parity][from prev / from next]: particles in that inbox          */
     Box                jbox_from_prev;     /* x-y-z extent (sender's internal numbering) of the J mail      */
     Box                jbox_from_next;
   };
 
   struct ArenaLayout
   {
-    size_t header, jmail_prev, jmail_next, inbox_prev, inbox_next, bytes;
+    size_t header, jmail_prev, jmail_next, inbox_prev[2], inbox_next[2], bytes;   /* inboxes: one per parity of the hand-over */
     size_t plane_doubles;                  /* ncomp * Pp                                                    */
     unsigned int inbox_cap;
   };
@@ -59,8 +72,11 @@ namespace mithra
     L.header = o;     o += (sizeof(ArenaHeader) + 255) / 256 * 256;
     L.jmail_prev = o; o += 1 * L.plane_doubles * sizeof(double);           /* their plane np-1 -> my plane kb     */
     L.jmail_next = o; o += 2 * L.plane_doubles * sizeof(double);           /* their planes 0,1 -> my np-3, np-2   */
-    L.inbox_prev = o; o += (size_t) inbox_cap * 11 * sizeof(double);
-    L.inbox_next = o; o += (size_t) inbox_cap * 11 * sizeof(double);
+    for (int b = 0; b < 2; b++)
+      {
+	L.inbox_prev[b] = o; o += (size_t) inbox_cap * 11 * sizeof(double);
+	L.inbox_next[b] = o; o += (size_t) inbox_cap * 11 * sizeof(double);
+      }
     L.bytes = (o + 255) / 256 * 256;
     return L;
   }
@@ -180,14 +196,14 @@ namespace mithra
   }
 
   /* err receives (first failure only) the flag index + 1 in the low byte and the awaited sequence above it  */
-  __global__ void wait_flag (const unsigned long long* flag, unsigned long long seq, int* err, int id)
+  __global__ void wait_flag (const unsigned long long* flag, unsigned long long seq, int* err, int id, unsigned long long timeout_ns)
   {
     unsigned long long t0, t1;
     asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*((volatile const unsigned long long*) flag) < seq)
       {
 	asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-	if (t1 - t0 > MITHRA_WAIT_TIMEOUT_NS) { atomicCAS(err, 0, (int) (( seq << 8 ) | (unsigned) ( id + 1 ))); break; }
+	if (t1 - t0 > timeout_ns) { atomicCAS(err, 0, (int) (( seq << 8 ) | (unsigned) ( id + 1 ))); break; }
 	__nanosleep(200);
       }
     __threadfence_system();
@@ -416,8 +432,8 @@ namespace mithra
 	signal_flag<<<1, 1, 0, s>>>(&hdr(x.next.arena)->flag[XF_A_PREV], x.seqA);
 	*launches += 2;
       }
-    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_PREV], x.seqA, x.d_err, XF_A_PREV); *launches += 1; }
-    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_NEXT], x.seqA, x.d_err, XF_A_NEXT); *launches += 1; }
+    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_PREV], x.seqA, x.d_err, XF_A_PREV, wait_timeout_ns()); *launches += 1; }
+    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_A_NEXT], x.seqA, x.d_err, XF_A_NEXT, wait_timeout_ns()); *launches += 1; }
     XCU(cudaGetLastError());
     return 0;
   }
@@ -439,8 +455,8 @@ namespace mithra
 	signal_flag<<<1, 1, 0, s>>>(&hdr(x.next.arena)->flag[XF_EB_PREV], x.seqEB);
 	*launches += 2;
       }
-    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_PREV], x.seqEB, x.d_err, XF_EB_PREV); *launches += 1; }
-    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_NEXT], x.seqEB, x.d_err, XF_EB_NEXT); *launches += 1; }
+    if (x.prev.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_PREV], x.seqEB, x.d_err, XF_EB_PREV, wait_timeout_ns()); *launches += 1; }
+    if (x.next.chain) { wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_EB_NEXT], x.seqEB, x.d_err, XF_EB_NEXT, wait_timeout_ns()); *launches += 1; }
     XCU(cudaGetLastError());
     return 0;
   }
@@ -467,7 +483,7 @@ namespace mithra
       }
     if (x.prev.chain)
       {
-	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_PREV], x.seqJ, x.d_err, XF_J_PREV);
+	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_PREV], x.seqJ, x.d_err, XF_J_PREV, wait_timeout_ns());
 	/* the sender's plane np-1 is my plane kb                                                          */
 	add_jmail<<<sms, 256, 0, s>>>(jn, (const double*) (x.arena + x.L.jmail_prev), &hdr(x.arena)->jbox_from_prev, jbox,
 					f.ncomp, f.Pp, f.N1, f.np, x.prev.np - 1, f.kb, 1);
@@ -475,7 +491,7 @@ namespace mithra
       }
     if (x.next.chain)
       {
-	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_NEXT], x.seqJ, x.d_err, XF_J_NEXT);
+	wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_J_NEXT], x.seqJ, x.d_err, XF_J_NEXT, wait_timeout_ns());
 	/* the sender's planes kb-2, kb-1 are my planes np-3, np-2                                         */
 	add_jmail<<<sms, 256, 0, s>>>(jn, (const double*) (x.arena + x.L.jmail_next), &hdr(x.arena)->jbox_from_next, jbox,
 					f.ncomp, f.Pp, f.N1, f.np, x.next.kb - 2, f.np - 3, 2);
@@ -496,9 +512,12 @@ namespace mithra
 	*launches += 1;
       }
     /* to prev: it receives "from next"; to next: it receives "from prev"                                    */
-    put_outbox<<<sms, 256, 0, s>>>(x.outbox[0], x.d_cursor + 0, (double*) (x.prev.arena + x.L.inbox_next), &hdr(x.prev.arena)->in_count[1], x.L.inbox_cap);
+    /* the inbox of this hand-over's parity: the neighbour may still be unpacking the other one (in the particle-only
+     * loop before the time origin nothing else orders its unpack of hand-over n before this put of n + 1)           */
+    const int par = (int) (x.seqP & 1ull);
+    put_outbox<<<sms, 256, 0, s>>>(x.outbox[0], x.d_cursor + 0, (double*) (x.prev.arena + x.L.inbox_next[par]), &hdr(x.prev.arena)->in_count[par][1], x.L.inbox_cap);
     signal_flag<<<1, 1, 0, s>>>(&hdr(x.prev.arena)->flag[XF_P_NEXT], x.seqP);
-    put_outbox<<<sms, 256, 0, s>>>(x.outbox[1], x.d_cursor + 1, (double*) (x.next.arena + x.L.inbox_prev), &hdr(x.next.arena)->in_count[0], x.L.inbox_cap);
+    put_outbox<<<sms, 256, 0, s>>>(x.outbox[1], x.d_cursor + 1, (double*) (x.next.arena + x.L.inbox_prev[par]), &hdr(x.next.arena)->in_count[par][0], x.L.inbox_cap);
     signal_flag<<<1, 1, 0, s>>>(&hdr(x.next.arena)->flag[XF_P_PREV], x.seqP);
     *launches += 4;
     XCU(cudaGetLastError());
@@ -509,11 +528,12 @@ namespace mithra
    * multi-slab field step), close the holes and append the arrivals.  Updates pn.                          */
   static inline int migrate_end (Exchange& x, ParticlesDev P, size_t* pn, size_t pcap, unsigned int* next_id, cudaStream_t s, unsigned long long* launches)
   {
-    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_PREV], x.seqP, x.d_err, XF_P_PREV);
-    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_NEXT], x.seqP, x.d_err, XF_P_NEXT);
+    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_PREV], x.seqP, x.d_err, XF_P_PREV, wait_timeout_ns());
+    wait_flag<<<1, 1, 0, s>>>(&hdr(x.arena)->flag[XF_P_NEXT], x.seqP, x.d_err, XF_P_NEXT, wait_timeout_ns());
     *launches += 2;
     XCU(cudaMemcpyAsync(x.h_counts + 0, x.d_cursor, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-    XCU(cudaMemcpyAsync(x.h_counts + 4, hdr(x.arena)->in_count, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    const int par = (int) (x.seqP & 1ull);
+    XCU(cudaMemcpyAsync(x.h_counts + 4, hdr(x.arena)->in_count[par], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     XCU(cudaMemcpyAsync(x.h_counts + 6, x.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     XCU(cudaStreamSynchronize(s));
     if (x.h_counts[6])
@@ -537,12 +557,12 @@ namespace mithra
     if (n + in_prev + in_next > pcap) { x.error = "particle capacity exceeded by arrivals from the neighbouring slabs"; return 1; }
     if (in_prev > 0)
       {
-	unpack_inbox<<<(in_prev + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_prev), (int) in_prev, *next_id);
+	unpack_inbox<<<(in_prev + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_prev[par]), (int) in_prev, *next_id);
 	n += in_prev; *next_id += in_prev; *launches += 1;
       }
     if (in_next > 0)
       {
-	unpack_inbox<<<(in_next + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_next), (int) in_next, *next_id);
+	unpack_inbox<<<(in_next + 255) / 256, 256, 0, s>>>(P, (long) n, (const double*) (x.arena + x.L.inbox_next[par]), (int) in_next, *next_id);
 	n += in_next; *next_id += in_next; *launches += 1;
       }
     XCU(cudaGetLastError());

@@ -29,6 +29,9 @@ int main (int argc, char* argv[])
       else { std::cout << argv[a] << " is not a known option." << std::endl; return 1; }
     }
 
+  /* several slabs per device: two streams each, some kernels spin on flags (csrc/exchange.cuh)                    */
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+
   timeval t0, t1;
   gettimeofday(&t0, NULL);
 
