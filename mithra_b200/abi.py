@@ -111,8 +111,6 @@ def load():
                            "There is no CPU fallback." % LIB_PATH)
     # see preload_kernels() in engine.cu; harmless if CUDA is already initialised
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-    # several slabs per device: two streams each, some kernels spin on flags (csrc/exchange.cuh)
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     lib = C.CDLL(LIB_PATH)
     dp, fp, vp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p
     lib.mithra_gpu_last_error.restype = C.c_char_p

@@ -21,9 +21,10 @@
  * twice, one per parity of the hand-over: put(n + 2) follows this slab's put(n + 1), which follows its unpack(n).
  *
  * One process may drive several slabs (the host executable with --gpus larger than the number of devices, the one-GPU
- * tests): every handle owns two streams and some of their kernels spin on a neighbour's flag, so the process asks for 32
- * hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, set before the context exists: host/main.cpp, abi.py) -- with the default 8
- * the streams of more than four slabs on one device share queues and a spinning wait can sit in front of the put it waits for.
+ * tests): every handle owns two streams and some of their kernels spin on a neighbour's flag, so a process that
+ * drives more than four slabs asks for 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, set before the context exists:
+ * host/main.cpp) -- with the default 8 the streams of more than four slabs on one device share queues and a spinning wait
+ * can sit in front of the put it waits for.
  */
 #ifndef MITHRA_EXCHANGE_CUH_
 #define MITHRA_EXCHANGE_CUH_

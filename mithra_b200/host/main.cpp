@@ -29,8 +29,6 @@ int main (int argc, char* argv[])
       else { std::cout << argv[a] << " is not a known option." << std::endl; return 1; }
     }
 
-  /* several slabs per device: two streams each, some kernels spin on flags (csrc/exchange.cuh)                    */
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 
   timeval t0, t1;
   gettimeofday(&t0, NULL);
@@ -48,6 +46,10 @@ int main (int argc, char* argv[])
   ParseDarius parser (jobFile, mesh, bunch, seed, undulator, extField, FEL);
   parser.setJobParameters();
   mesh.show(); bunch.show();
+
+  /* more than four slabs in this process: two streams each, some kernels spin on flags (csrc/exchange.cuh) -- ask for
+   * more hardware queues than the default 8 before the context exists (it makes context creation slower: only then)  */
+  if ( gpus > 4 ) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 
   Solver* solver = mesh.spaceCharge_ ? (Solver*) new FdTdSC (mesh, bunch, seed, undulator, extField, FEL)
 				     : (Solver*) new FdTd   (mesh, bunch, seed, undulator, extField, FEL);
