@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MITHRA_GPU_ABI_VERSION      3
+#define MITHRA_GPU_ABI_VERSION      4
 #define MITHRA_MAX_UNDULATORS       16
 #define MITHRA_MAX_EXTFIELDS        8
 #define MITHRA_MAX_POWER_PLANES     256
@@ -192,6 +192,46 @@ int mithra_gpu_download_eb (MithraGpu* h, float* en, float* bn, unsigned char* m
 /* Solver::initializeField, solver.cpp:828-839: an_, anm1_ = Seed::fields(node, time_ / timem1_) inside the total-field
  * box; no-op without a seed. Call after mithra_gpu_set_time.                                          */
 int mithra_gpu_seed_initial (MithraGpu* h);
+
+/* ---- the bunch of Solver::initialize() on the device ----------------------------------------------
+ * A MithraGpuBunch is a particle list double[n][11] (Charge: q, rnp[3], rnm[3], gb[3], e; stdinclude.h:130-144) in device
+ * memory that exists before any slab does: generated, boosted and back-projected on the device, then handed to the
+ * slabs without touching the host.  Formulas and operation order are the reference's; only the libm differs (CUDA's log /
+ * cos / sin against glibc's, last ulp), so the list equals the reference's to 1e-15, not bit for bit.                 */
+typedef struct MithraGpuBunch MithraGpuBunch;
+
+/* The members of BunchInitialize that Bunch::initializeEllipsoid reads (classes.h, classes.cpp:104-298), for ONE bunch
+ * position (position_[ia]) with the Halton generator and without shot noise.                                         */
+typedef struct MithraBunchEllipsoid
+{
+  unsigned int number_of_particles;   /* numberOfParticles_, already rounded up to a multiple of four (classes.cpp:107-113) */
+  unsigned int index_offset;          /* Np0: size of the charge vector before this bunch (Halton index offset)        */
+  double       cloud_charge;          /* cloudCharge_                                                                  */
+  double       initial_gamma;         /* initialGamma_                                                                 */
+  double       beta_vector[3];        /* betaVector_                                                                   */
+  double       position[3];           /* position_[ia]                                                                 */
+  double       sigma_position[3];     /* sigmaPosition_                                                                */
+  double       sigma_gamma_beta[3];   /* sigmaGammaBeta_                                                               */
+  double       tran_trun, long_trun;  /* tranTrun_, longTrun_                                                          */
+  double       lambda;                /* lambda_: bunching wavelength, 0 = no undulator (single particles, no copies)  */
+  double       bunching_factor;       /* bF_                                                                           */
+  double       bunching_phase;        /* bFP_ [degree]                                                                 */
+  int          distribution;          /* 0 = uniform (with Gaussian tapers), 1 = gaussian                              */
+  int          device;                /* CUDA device ordinal, -1 = current                                             */
+} MithraBunchEllipsoid;
+
+/* Bunch::initializeEllipsoid, classes.cpp:104-298 (rank 0 of 1): n = number of macro-particles generated.            */
+int  mithra_gpu_bunch_generate    (const MithraBunchEllipsoid* init, MithraGpuBunch** out, size_t* n);
+/* Solver::lorentzBoostBunch, solver.cpp:294-302: rnp[2] *= gamma, gb[2] = gamma g (bz - beta); zmax = max rnp[2] (zmaxG). */
+int  mithra_gpu_bunch_boost       (MithraGpuBunch* b, double gamma, double beta, double* zmax);
+/* solver.cpp:340-346: rnp += gb / g (rnp[2] - zu) beta.                                                               */
+int  mithra_gpu_bunch_backproject (MithraGpuBunch* b, double zu, double beta);
+/* the list in its order, for dumps and tests (n x 11 doubles).                                                        */
+int  mithra_gpu_bunch_download    (MithraGpuBunch* b, double* aos11, size_t capacity, size_t* n);
+void mithra_gpu_bunch_destroy     (MithraGpuBunch* b);
+/* Solver::distributeParticles, solver.cpp:429-487, for the slab of `h`: the particles whose wrapped z lies in [zp0, zp1)
+ * become the slab's bunch, in list order -- mithra_gpu_upload_particles without the host.                             */
+int  mithra_gpu_upload_particles_device (MithraGpu* h, const MithraGpuBunch* b);
 
 /* chargeVectorn_ (solver.h:271). */
 int mithra_gpu_upload_particles   (MithraGpu* h, const double* aos11, size_t n);

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_UNDULATORS, MAX_EXTFIELDS = 16, 8
 MAX_POWER_PLANES, MAX_POWER_LAMBDAS, MAX_SCREENS = 256, 64, 64
 NPHASES = 8
@@ -93,6 +93,8 @@ SYMBOLS = (
     "mithra_gpu_migrate_begin", "mithra_gpu_migrate_end", "mithra_gpu_selftest_divide",
     "mithra_gpu_power_visualize", "mithra_gpu_fetch_power_map", "mithra_gpu_bunch_moments", "mithra_gpu_field_sample",
     "mithra_gpu_field_nodes",
+    "mithra_gpu_bunch_generate", "mithra_gpu_bunch_boost", "mithra_gpu_bunch_backproject", "mithra_gpu_bunch_download",
+    "mithra_gpu_bunch_destroy", "mithra_gpu_upload_particles_device",
 )
 
 _lib = None

@@ -25,6 +25,7 @@
 #include "kernels_sort.cuh"
 #include "kernels_seed.cuh"
 #include "exchange.cuh"
+#include "kernels_init.cuh"
 
 using namespace mithra;
 
@@ -161,6 +162,14 @@ struct MithraGpu
   bool            profiling;
   cudaEvent_t     pev[2];
   float           pms[MITHRA_GPU_NPHASES];
+};
+
+/* a particle list that exists before any slab does (kernels_init.cuh)                                  */
+struct MithraGpuBunch
+{
+  int     device;
+  double* aos;                            /* [n][11]                                                        */
+  size_t  n;
 };
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -354,6 +363,7 @@ static int preload_kernels ()
   PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
+  PL(ellipsoid_count); PL(scan_block_counts); PL(ellipsoid_write); PL(bunch_boost); PL(bunch_backproject); PL(owned_count); PL(owned_copy);
   #undef PL
   if (e != cudaSuccess) return fail("preloading the kernels failed: %s", cudaGetErrorString(e));
   return 0;
@@ -734,15 +744,12 @@ static int refresh_particle_box (MithraGpu* h)
 }
 
 /* The copy the sort is not using at the moment doubles as the staging buffer of the AoS transfers.           */
-extern "C" int mithra_gpu_upload_particles (MithraGpu* h, const double* aos11, size_t n)
+/* the n particles staged as double[n][11] in the idle copy become the slab's bunch                              */
+static int adopt_staged_particles (MithraGpu* h, size_t n)
 {
-  USE(h);
-  if (n > h->pcap) return fail("mithra_gpu_upload_particles: %zu particles exceed the capacity %zu (MithraGpuParams.max_particles)", n, h->pcap);
   if (n)
     {
-      double* stage = h->Palt.q;
-      CU(cudaMemcpyAsync(stage, aos11, n * 11 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      aos_to_particles<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(stage, h->P, (long) n);
+      aos_to_particles<<<(int) ((n + 255) / 256), 256, 0, h->stream>>>(h->Palt.q, h->P, (long) n);
       CU(cudaGetLastError());
       h->cnt.kernel_launches += 1;
     }
@@ -750,6 +757,153 @@ extern "C" int mithra_gpu_upload_particles (MithraGpu* h, const double* aos11, s
   h->steps_since_sort = 1 << 30;                        /* sort before the next push (if sorting is on)             */
   TRY(refresh_particle_box(h));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int mithra_gpu_upload_particles (MithraGpu* h, const double* aos11, size_t n)
+{
+  USE(h);
+  if (n > h->pcap) return fail("mithra_gpu_upload_particles: %zu particles exceed the capacity %zu (MithraGpuParams.max_particles)", n, h->pcap);
+  if (n) CU(cudaMemcpyAsync(h->Palt.q, aos11, n * 11 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return adopt_staged_particles(h, n);
+}
+
+/* Solver::distributeParticles (solver.cpp:429-487) without the host: the particles of the device-resident list that this
+ * slab owns, in list order.  The list may live on another device of the box (peer copy).                           */
+extern "C" int mithra_gpu_upload_particles_device (MithraGpu* h, const MithraGpuBunch* b)
+{
+  USE(h);
+  if (!b) return fail("mithra_gpu_upload_particles_device: null bunch");
+  const MithraGpuParams& p = h->prm;
+  size_t n = 0;
+  if (b->n > 0)
+    {
+      const double* src = b->aos;
+      double* tmp = 0;
+      if (b->device != h->device)
+	{
+	  CU(cudaMalloc(&tmp, b->n * 11 * sizeof(double)));
+	  CU(cudaMemcpyPeer(tmp, h->device, b->aos, b->device, b->n * 11 * sizeof(double)));
+	  src = tmp;
+	}
+      const unsigned int nblocks = (unsigned int) ((b->n + 255) / 256);
+      unsigned int* d_cnt = 0; unsigned long long* d_tot = 0;
+      CU(cudaMalloc(&d_cnt, (size_t) nblocks * sizeof(unsigned int))); CU(cudaMalloc(&d_tot, sizeof(unsigned long long)));
+      owned_count<<<nblocks, 256, 0, h->stream>>>(src, b->n, p.zmin, p.Lz, p.zp[0], p.zp[1], d_cnt);
+      scan_block_counts<<<1, 1024, 0, h->stream>>>(d_cnt, nblocks, d_tot);
+      CU(cudaGetLastError());
+      unsigned long long own = 0;
+      CU(cudaMemcpyAsync(&own, d_tot, sizeof(own), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      n = (size_t) own;
+      if (n > h->pcap)
+	{ cudaFree(d_cnt); cudaFree(d_tot); cudaFree(tmp); return fail("mithra_gpu_upload_particles_device: %zu particles exceed the capacity %zu (MithraGpuParams.max_particles)", n, h->pcap); }
+      if (n) owned_copy<<<nblocks, 256, 0, h->stream>>>(src, b->n, p.zmin, p.Lz, p.zp[0], p.zp[1], d_cnt, h->Palt.q);
+      CU(cudaGetLastError());
+      h->cnt.kernel_launches += 3;
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(d_cnt); cudaFree(d_tot); cudaFree(tmp);
+    }
+  return adopt_staged_particles(h, n);
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* the bunch of Solver::initialize() on the device (kernels_init.cuh)                                    */
+
+extern "C" void mithra_gpu_bunch_destroy (MithraGpuBunch* b)
+{
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaFree(b->aos);
+  delete b;
+}
+
+extern "C" int mithra_gpu_bunch_generate (const MithraBunchEllipsoid* init, MithraGpuBunch** out, size_t* n)
+{
+  if (!init || !out) return fail("mithra_gpu_bunch_generate: null argument");
+  if (init->number_of_particles % 4 != 0) return fail("mithra_gpu_bunch_generate: the number of particles must be a multiple of four (classes.cpp:107-113)");
+  if (init->bunching_factor > 2.0 || init->bunching_factor < 0.0) return fail("mithra_gpu_bunch_generate: the bunching factor can not be larger than one or a negative value");
+  if (init->distribution != 0 && init->distribution != 1) return fail("mithra_gpu_bunch_generate: unknown longitudinal distribution");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    { cudaGetLastError(); return fail("mithra_gpu_bunch_generate: no CUDA device available; this library has no CPU path"); }
+  MithraGpuBunch* b = new MithraGpuBunch();
+  b->device = init->device; b->aos = 0; b->n = 0;
+  if (b->device < 0) CU(cudaGetDevice(&b->device));
+  CU(cudaSetDevice(b->device));
+  const double PI = 3.1415926535;                        /* stdinclude.h:43 */
+  const unsigned int ng = ( init->lambda == 0.0 ) ? 1u : 4u;
+  const unsigned int nbody = init->number_of_particles / ng;
+  /* body + the tapers of a uniform profile, classes.cpp:203,268 */
+  unsigned int ncand = nbody;
+  if (init->distribution == 0)
+    ncand = std::max(nbody, (unsigned int) ( nbody * ( 1.0 + 2.0 * init->lambda * sqrt( 2.0 * PI ) / ( 2.0 * init->sigma_position[2] ) ) ));
+  const unsigned int nblocks = (ncand + 255u) / 256u;
+  unsigned int* d_cnt = 0; unsigned long long* d_tot = 0;
+  CU(cudaMalloc(&d_cnt, (size_t) std::max(1u, nblocks) * sizeof(unsigned int))); CU(cudaMalloc(&d_tot, sizeof(unsigned long long)));
+  unsigned long long accepted = 0;
+  if (ncand > 0)
+    {
+      ellipsoid_count<<<nblocks, 256>>>(*init, ncand, d_cnt);
+      scan_block_counts<<<1, 1024>>>(d_cnt, nblocks, d_tot);
+      CU(cudaGetLastError());
+      CU(cudaMemcpy(&accepted, d_tot, sizeof(accepted), cudaMemcpyDeviceToHost));
+    }
+  b->n = (size_t) accepted * ng;
+  if (b->n > 0)
+    {
+      CU(cudaMalloc(&b->aos, b->n * 11 * sizeof(double)));
+      ellipsoid_write<<<nblocks, 256>>>(*init, ncand, d_cnt, b->aos);
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+    }
+  cudaFree(d_cnt); cudaFree(d_tot);
+  if (n) *n = b->n;
+  *out = b;
+  return 0;
+}
+
+extern "C" int mithra_gpu_bunch_boost (MithraGpuBunch* b, double gamma, double beta, double* zmax)
+{
+  if (!b) return fail("mithra_gpu_bunch_boost: null bunch");
+  CU(cudaSetDevice(b->device));
+  double zm = -1.0e100;
+  if (b->n > 0)
+    {
+      const unsigned int nblocks = (unsigned int) ((b->n + 255) / 256);
+      double* d_z = 0; CU(cudaMalloc(&d_z, (size_t) nblocks * sizeof(double)));
+      bunch_boost<<<nblocks, 256>>>(b->aos, b->n, gamma, beta, d_z);
+      CU(cudaGetLastError());
+      std::vector<double> z(nblocks);
+      CU(cudaMemcpy(z.data(), d_z, (size_t) nblocks * sizeof(double), cudaMemcpyDeviceToHost));
+      cudaFree(d_z);
+      for (double v : z) zm = std::max(zm, v);
+    }
+  if (zmax) *zmax = zm;
+  return 0;
+}
+
+extern "C" int mithra_gpu_bunch_backproject (MithraGpuBunch* b, double zu, double beta)
+{
+  if (!b) return fail("mithra_gpu_bunch_backproject: null bunch");
+  CU(cudaSetDevice(b->device));
+  if (b->n > 0)
+    {
+      bunch_backproject<<<(unsigned int) ((b->n + 255) / 256), 256>>>(b->aos, b->n, zu, beta);
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+    }
+  return 0;
+}
+
+extern "C" int mithra_gpu_bunch_download (MithraGpuBunch* b, double* aos11, size_t capacity, size_t* n)
+{
+  if (!b) return fail("mithra_gpu_bunch_download: null bunch");
+  if (n) *n = b->n;
+  if (!aos11) return 0;
+  if (capacity < b->n) return fail("mithra_gpu_bunch_download: capacity %zu < %zu particles", capacity, b->n);
+  CU(cudaSetDevice(b->device));
+  if (b->n > 0) CU(cudaMemcpy(aos11, b->aos, b->n * 11 * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
 

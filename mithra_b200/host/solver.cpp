@@ -29,6 +29,7 @@ namespace MITHRA
       nTime_(0), nTimeBunch_(0), Nc_(0), nUpdateBunch_(1.0), maxSteps_(-1), powerGroup_(-1), screenGroup_(-1), pmapGroup_(-1), bunchSampleFile_(0), fieldSampleFile_(0), sfCe_(0.0), sfCb_(0.0), sfCa_(0.0), spaceChargeSolver_(false)
   {
     zp_[0] = zp_[1] = 0.0;
+    deviceBunch_ = 0;
     memset(&uf_, 0, sizeof(uf_)); memset(&uc_, 0, sizeof(uc_)); memset(&ub_, 0, sizeof(ub_));
     /* light speed, vacuum permeability and permittivity in the job's units, solver.cpp:59-61                    */
     c0_ = C0 / mesh_.lengthScale_ * mesh_.timeScale_;
@@ -243,9 +244,44 @@ namespace MITHRA
   }
 
   /* solver.cpp:1130-1178; the process generates the whole bunch (rank 0 of 1)                                    */
+  bool Solver::wantDeviceBunch () const
+  {
+    if ( getenv("MITHRA_HOST_BUNCH") || bunch_.bunchInit_.size() != 1 ) return false;
+    const BunchInitialize& b = bunch_.bunchInit_[0];
+    if ( b.bunchType_ != "ellipsoid" || b.generator_ != "halton" || b.shotNoise_ || b.position_.size() > 1 ) return false;
+    if ( b.distribution_ != "uniform" && b.distribution_ != "gaussian" ) return false;
+    /* what would need sums over the bunch in the reference's (sequential) order stays on the host                   */
+    if ( mesh_.optimizePosition_ || mesh_.totalDist_ > 0.0 || mesh_.timeShift_ != 0.0 ) return false;
+    if ( b.numberOfParticles_ < ( 1u << 20 ) && !getenv("MITHRA_DEVICE_BUNCH") ) return false;
+    return mithra_gpu_device_count() > 0;
+  }
+
   void Solver::initializeBunch ()
   {
     printmessage(__FILE__, __LINE__, "[[[ Initializing the bunch and prepare the charge vector ");
+    deviceBunch_ = 0;
+    if ( wantDeviceBunch() )
+      {
+	BunchInitialize& b = bunch_.bunchInit_[0];
+	if ( b.position_.size() == 0 ) b.position_.push_back( FieldVector(0.0) );
+	if ( b.numberOfParticles_ % 4 != 0 )                     /* classes.cpp:107-113 */
+	  {
+	    b.numberOfParticles_ += 4 - b.numberOfParticles_ % 4;
+	    printmessage(__FILE__, __LINE__, "Warning: The number of particles in the bunch is not a multiple of four. It is corrected to " + stringify(b.numberOfParticles_));
+	  }
+	MithraBunchEllipsoid e; memset(&e, 0, sizeof(e));
+	e.number_of_particles = b.numberOfParticles_; e.index_offset = 0;
+	e.cloud_charge = b.cloudCharge_; e.initial_gamma = b.initialGamma_;
+	for (int c = 0; c < 3; c++)
+	  { e.beta_vector[c] = b.betaVector_[c]; e.position[c] = b.position_[0][c]; e.sigma_position[c] = b.sigmaPosition_[c]; e.sigma_gamma_beta[c] = b.sigmaGammaBeta_[c]; }
+	e.tran_trun = b.tranTrun_; e.long_trun = b.longTrun_; e.lambda = b.lambda_; e.bunching_factor = b.bF_; e.bunching_phase = b.bFP_;
+	e.distribution = ( b.distribution_ == "uniform" ) ? 0 : 1;
+	e.device = -1;
+	size_t n = 0;
+	check(mithra_gpu_bunch_generate(&e, &deviceBunch_, &n));
+	printmessage(__FILE__, __LINE__, "The bunch (" + stringify(n) + " macro-particles) is generated on the device. ]]]");
+	return;
+      }
     std::list<Charge> qv;
     for (BunchInitialize& b : bunch_.bunchInit_)
       {
@@ -285,6 +321,7 @@ namespace MITHRA
 	q.gb[2]   = gamma_ * g * ( bz - beta_ );
 	zmaxG     = std::max( zmaxG , q.rnp[2] );
       }
+    if ( deviceBunch_ ) check(mithra_gpu_bunch_boost(deviceBunch_, gamma_, beta_, &zmaxG));
 
     /* at bunch time zero the bunch head is undulator_[0].dist_ (lab frame) in front of the entrance              */
     if ( undulator_.size() > 0 )
@@ -308,6 +345,7 @@ namespace MITHRA
 	q.rnp[1] += q.gb[1] / g * ( q.rnp[2] - bunch_.zu_ ) * beta_;
 	q.rnp[2] += q.gb[2] / g * ( q.rnp[2] - bunch_.zu_ ) * beta_;
       }
+    if ( deviceBunch_ ) check(mithra_gpu_bunch_backproject(deviceBunch_, bunch_.zu_, beta_));
 
     if ( mesh_.optimizePosition_ && undulator_.size() > 0 )
       {
@@ -326,6 +364,7 @@ namespace MITHRA
 
     distributeParticles(chargeVectorn_);
     Nc_ = chargeVectorn_.size();
+    if ( deviceBunch_ ) { size_t n = 0; check(mithra_gpu_bunch_download(deviceBunch_, 0, 0, &n)); Nc_ = n; }
     printmessage(__FILE__, __LINE__, "The total number of macro-particles is equal to " + stringify(Nc_) + " .");
 
     if ( mesh_.totalDist_ > 0.0 )
@@ -1130,8 +1169,8 @@ namespace MITHRA
 	p.device = r % ndev;
 	const size_t n = rows[r].size() / 11;
 	/* room for the particles that migrate in: the whole bunch fits on any slab                                   */
-	p.max_particles = ( size_ == 1 ) ? n + 1024 : chargeVectorn_.size() + 1024;
-	p.max_screen_records = std::max<size_t>(chargeVectorn_.size(), 4096);
+	p.max_particles = ( size_ == 1 && !deviceBunch_ ) ? n + 1024 : (size_t) Nc_ + 1024;
+	p.max_screen_records = std::max<size_t>(Nc_, 4096);
 	check(mithra_gpu_create(&p, &gpu_[r]));
       }
     if ( size_ > 1 )
@@ -1148,9 +1187,11 @@ namespace MITHRA
     for (int r = 0; r < size_; r++)
       {
 	check(mithra_gpu_set_time(gpu_[r], time_, timeBunch_, nTime_));
-	check(mithra_gpu_upload_particles(gpu_[r], rows[r].data(), rows[r].size() / 11));
+	if ( deviceBunch_ ) check(mithra_gpu_upload_particles_device(gpu_[r], deviceBunch_));      /* distributeParticles on the device */
+	else                check(mithra_gpu_upload_particles(gpu_[r], rows[r].data(), rows[r].size() / 11));
 	check(mithra_gpu_seed_initial(gpu_[r]));
       }
+    if ( deviceBunch_ ) { mithra_gpu_bunch_destroy(deviceBunch_); deviceBunch_ = 0; }
   }
 
   /* ========================================================================================================== */
@@ -1639,6 +1680,11 @@ namespace MITHRA
     w.d("time", time_); w.d("timem1", timem1_); w.d("timep1", timep1_); w.d("timeBunch", timeBunch_);
     w.i("nTime", (int) nTime_); w.i("nTimeBunch", (int) nTimeBunch_);
     std::vector<double> rows; rows.reserve(chargeVectorn_.size() * 11);
+    if ( deviceBunch_ )
+      {
+	size_t n = 0; check(mithra_gpu_bunch_download(deviceBunch_, 0, 0, &n));
+	rows.resize(n * 11); check(mithra_gpu_bunch_download(deviceBunch_, rows.data(), n, &n));
+      }
     for (const Charge& q : chargeVectorn_)
       {
 	rows.push_back(q.q);

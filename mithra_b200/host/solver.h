@@ -136,6 +136,11 @@ namespace MITHRA
     std::vector<SampleRadiationPower> rp_;
     std::vector<SampleScreenProfile>  scrp_;
     ChargeVector chargeVectorn_;
+    /* Large Halton ellipsoids are generated, boosted and back-projected on the device and handed to the slabs there
+     * (mithra_gpu_bunch_*): chargeVectorn_ then stays empty.  MITHRA_DEVICE_BUNCH=1 forces it for any size,
+     * MITHRA_HOST_BUNCH=1 keeps the host path (bit-identical to the reference's list; the device list is to 1e-15). */
+    MithraGpuBunch* deviceBunch_;
+    bool wantDeviceBunch () const;
 
     std::vector<MithraGpu*> gpu_;                  /* one handle per slab / GPU                                      */
 
