@@ -248,7 +248,7 @@ namespace MITHRA
   {
     if ( getenv("MITHRA_HOST_BUNCH") || bunch_.bunchInit_.size() != 1 ) return false;
     const BunchInitialize& b = bunch_.bunchInit_[0];
-    if ( b.bunchType_ != "ellipsoid" || b.generator_ != "halton" || b.shotNoise_ || b.position_.size() > 1 ) return false;
+    if ( b.bunchType_ != "ellipsoid" || b.generator_ == "random" || b.shotNoise_ || b.position_.size() > 1 ) return false;
     if ( b.distribution_ != "uniform" && b.distribution_ != "gaussian" ) return false;
     /* what would need sums over the bunch in the reference's (sequential) order stays on the host                   */
     if ( mesh_.optimizePosition_ || mesh_.totalDist_ > 0.0 || mesh_.timeShift_ != 0.0 ) return false;
