@@ -73,7 +73,8 @@ struct MithraGpu
   double*         J;
   double*         d_stage;                /* AoS staging of the field transfers (field_stage)              */
   size_t          stage_bytes;
-  bool            stream_configured[2];   /* stencil_stream<NSFD>: dynamic shared memory limit raised on this device */
+  bool            stream_configured[2][2][2]; /* stencil_stream<NSFD, T, .., FACES>: dynamic shared memory limit raised on this device */
+  int             face_slots[2];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
   Box*            d_jbox;
   unsigned int*   d_done;
 
@@ -355,7 +356,8 @@ static int preload_kernels ()
   #define PL(k) do { cudaError_t r_ = preload(k); if (r_ != cudaSuccess) e = r_; } while (0)
   PL(aos_to_planar); PL(planar_to_aos); PL(aos_to_particles); PL(particles_to_aos); PL(set_box); PL(make_eb_box);
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
-  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8>)); PL((stencil_stream<false, 512, 8>));
+  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8, false>)); PL((stencil_stream<false, 512, 8, false>)); PL((stencil_stream<true, 512, 8, true>)); PL((stencil_stream<false, 512, 8, true>));
+  PL((stencil_stream<true, 480, 8, false>)); PL((stencil_stream<false, 480, 8, false>)); PL((stencil_stream<true, 448, 8, true>)); PL((stencil_stream<false, 448, 8, true>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
@@ -428,7 +430,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       }
   }
   h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
-  h->stream_configured[0] = h->stream_configured[1] = false;
+  memset(h->stream_configured, 0, sizeof(h->stream_configured)); h->face_slots[0] = h->face_slots[1] = -1;
   h->d_stage = 0; h->stage_bytes = 0;
   CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
   CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
@@ -1066,33 +1068,51 @@ static const unsigned char* source_mask (const MithraGpu* h)
   return (h->jmask_valid && !off) ? h->d_emask_nodes[h->jmask_buf] : 0;
 }
 
-/* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory */
-template <bool NSFD>
-static bool launch_stencil_stream (MithraGpu* h, bool skiprim)
+/* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory.
+ * faces: the variant that also does the x and y absorbing faces (no rim_update afterwards)                         */
+template <bool NSFD, bool FACES, int T>
+static bool launch_stencil_stream_t (MithraGpu* h, bool skiprim)
 {
   const FieldDev& f = h->fd;
-  constexpr int T = 512, NB = 8;
+  constexpr int NB = 8;
   static const int KC = getenv("MITHRA_STENCIL_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_STENCIL_KC")))) : 64;   /* <= 64: source_planes */
-  if (getenv("MITHRA_STENCIL_PLAIN")) return false;
-  const size_t smem = stencil_stream_smem(T, f.N1, NB);
-  if (smem > 200 * 1024) return false;
+  if (FACES && h->face_slots[T == 512] < 0) h->face_slots[T == 512] = stencil_stream_face_slots(f.N0, f.N1, T);
+  const int NR = FACES ? h->face_slots[T == 512] : 0;
+  const size_t smem = stencil_stream_smem(T, f.N1, NB, FACES, NR);
+  if (smem > (FACES ? 110 : 200) * 1024) return false;      /* with the faces: two CTAs per SM or not at all             */
   /* the attribute belongs to the device: one process may drive several (one handle per slab)                */
-  if (!h->stream_configured[NSFD])
+  if (!h->stream_configured[NSFD][FACES][T == 512])
     {
-      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
-      h->stream_configured[NSFD] = true;
+      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB, FACES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+      h->stream_configured[NSFD][FACES][T == 512] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB><<<grid, T + 32, smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h));
+  stencil_stream<NSFD, T, NB, FACES><<<grid, T + (FACES ? 64 : 32), smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h), NR);
   return true;
 }
 
-/* the plain-load interior kernel always covers every interior node (rim_update afterwards simply rewrites the rim) */
-template <bool NSFD>
-static void launch_stencil (MithraGpu* h, bool skiprim)
+/* Tile sizes: the consumer loop must not spill (a reload from local memory in it costs more than a plane of the march), and
+ * two CTAs share an SM: 480 consumers + the producer warp leave 64 registers per thread, with the face warp 448 do.
+ * MITHRA_STREAM_T=512: the 512-node tiles of round 1 (56 registers, a few spilled words) for comparison.               */
+template <bool NSFD, bool FACES>
+static bool launch_stencil_stream_as (MithraGpu* h, bool skiprim)
 {
+  if (getenv("MITHRA_STENCIL_PLAIN")) return false;
+  static const bool t512 = getenv("MITHRA_STREAM_T") && atoi(getenv("MITHRA_STREAM_T")) == 512;
+  if (t512) return launch_stencil_stream_t<NSFD, FACES, 512>(h, skiprim);
+  return launch_stencil_stream_t<NSFD, FACES, FACES ? 448 : 480>(h, skiprim);
+}
+
+/* the interior sweep; *faces: in, the x / y faces may be fused into it (a rim path without seed); out, they were.
+ * The plain-load interior kernel always covers every interior node (rim_update afterwards simply rewrites the rim) */
+template <bool NSFD>
+static void launch_stencil (MithraGpu* h, bool skiprim, bool* faces)
+{
+  h->j_zeroed_by_update = true;
+  if (*faces && launch_stencil_stream_as<NSFD, true>(h, false)) return;
+  *faces = false;
+  if (launch_stencil_stream_as<NSFD, false>(h, skiprim)) return;
   h->j_zeroed_by_update = false;
-  if (launch_stencil_stream<NSFD>(h, skiprim)) { h->j_zeroed_by_update = true; return; }
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
   dim3 grid((f.P + BX - 1) / BX, (f.np - 1 - f.kb + KC - 1) / KC, f.ncomp);
@@ -1128,6 +1148,9 @@ static int field_update_potentials (MithraGpu* h)
    * faces, the edges and the corners.  MITHRA_NO_FUSE keeps the reference's three passes apart (the parity tests
    * compare the two bit for bit).                                                                              */
   const bool rim = f.N0 >= 8 && f.N1 >= 8 && f.np >= 8 && !getenv("MITHRA_NO_FUSE");
+  /* without a seed the x / y faces are all rim_update would add to the interior value: stencil_stream does them itself
+   * (MITHRA_NO_FACEWARP: stencil_stream + rim_update as for seeded jobs)                                            */
+  bool faces = rim && !h->d_seed && !getenv("MITHRA_NO_FACEWARP");
   RimDev rz; memset(&rz, 0, sizeof(rz));
   if (rim && h->d_seed)
     {
@@ -1149,7 +1172,7 @@ static int field_update_potentials (MithraGpu* h)
     }
   {
     PhaseTimer t(h, PH_STENCIL);
-    if (f.nsfd) launch_stencil<true>(h, rim); else launch_stencil<false>(h, rim);
+    if (f.nsfd) launch_stencil<true>(h, rim, &faces); else launch_stencil<false>(h, rim, &faces);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 1;
   }
@@ -1157,12 +1180,15 @@ static int field_update_potentials (MithraGpu* h)
     PhaseTimer t(h, PH_BOUNDARY);
     if (rim)
       {
+	if (!faces)
+	  {
 	const int per = 4 * (f.N1 - 2) + 4 * (f.N0 - 6);
 	static const int KC = getenv("MITHRA_RIM_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_RIM_KC")))) : 64;   /* planes per CTA (fitting the grid to whole waves changes nothing: measured) */
 	dim3 grid((unsigned) ((per + 127) / 128), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
 	if (f.nsfd) rim_update<true ><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
 	else        rim_update<false><<<grid, 128, 0, h->stream>>>(f, rz, ap, a, am, h->J, h->d_jbox, KC, source_mask(h), h->j_zeroed_by_update ? 1 : 0);
 	h->cnt.kernel_launches += 1;
+	  }
 	if (h->d_seed && (zlo || zhi))
 	  {
 	    const long tot = 4L * (f.N0 - 4) * (f.N1 - 4);

@@ -165,9 +165,35 @@ namespace mithra
   __device__ __forceinline__ void mbar_arrive (unsigned long long* b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
 
-  /* shared memory of one CTA: 2 * NB mbarriers, then NB stages of (T + 2 N1e) doubles of A^n and T doubles of A^{n-1} */
-  static inline size_t stencil_stream_smem (int T, int N1, int NB)
-  { const int N1e = (N1 + 1) & ~1; return 256 + (size_t) NB * ( (size_t) T + 2 * N1e + T ) * sizeof(double); }
+  /* shared memory of one CTA: a header (mbarriers, FACES: the counters of the task list), then NB stages, each
+   * (T + 2 H) doubles of A^n, T + 2 HM doubles of A^{n-1} and -- FACES -- NR hand-over slots; FACES: then the task list.
+   * H: halo of the A^n stage, N1e (FACES: N1e + 2); HM: 0 (FACES: H)                                                       */
+  static inline size_t stencil_stream_smem (int T, int N1, int NB, bool faces = false, int NR = 0)
+  {
+    const int N1e = (N1 + 1) & ~1;
+    if (!faces) return 256 + (size_t) NB * ( (size_t) T + 2 * N1e + T ) * sizeof(double);
+    const int H = N1e + 2;
+    return 1024 + (size_t) NB * ( 2 * ( (size_t) T + 2 * H ) + NR ) * sizeof(double) + (size_t) 2 * NR * sizeof(int);
+  }
+
+  /* the nodes of a tile that sit next to an x or y face (the inward neighbours n of the face nodes): their largest number
+   * over the tiles of T consecutive in-plane positions -- the hand-over slots a CTA of stencil_stream<.., FACES> needs    */
+  static inline int stencil_stream_face_slots (int N0, int N1, int T)
+  {
+    const long P = (long) N0 * N1;
+    int worst = 0;
+    for (long p0 = 0; p0 < P; p0 += T)
+      {
+	int n = 0;
+	for (long p = p0; p < p0 + T && p < P; p++)
+	  {
+	    const int i = (int) (p / N1), j = (int) (p - (long) i * N1);
+	    if (i >= 1 && i <= N0 - 2 && j >= 1 && j <= N1 - 2 && (i == 1 || i == N0 - 2 || j == 1 || j == N1 - 2)) n++;
+	  }
+	if (n > worst) worst = n;
+      }
+    return (worst + 1) & ~1;
+  }
 
   /* the 5-point cross of one plane around the thread's node                                                    */
   struct Cross { double c, xp, xm, yp, ym; };
@@ -189,129 +215,9 @@ namespace mithra
 	   as * src;
   }
 
-  /* T consumer threads (one in-plane position each) + one producer warp                                        */
-  template <bool NSFD, int T, int NB>
-  __global__ void __launch_bounds__(T + 32, 2)
-  stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
-		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
-		  const unsigned char* __restrict__ jmask)
-  {
-    static_assert((NB & (NB - 1)) == 0 && NB >= 2 && NB <= 16, "stages: a power of two");
-    extern __shared__ __align__(128) unsigned char smraw[];
-    unsigned long long* full  = reinterpret_cast<unsigned long long*>(smraw);
-    unsigned long long* empty = full + NB;
-    const int  N1 = f.N1, N1e = (N1 + 1) & ~1;
-    const int  W  = T + 2 * N1e;                          /* doubles of one A^n stage                       */
-    double* stA = reinterpret_cast<double*>(smraw + 256);
-    double* stM = stA + (size_t) NB * W;
-
-    const int  tid = threadIdx.x, c = blockIdx.z;
-    const long p0  = (long) blockIdx.x * T;
-    const int  ks  = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);      /* planes ks .. ke-1            */
-    if (ks >= ke) return;
-    const long Pp = f.Pp, cb = (long) c * f.np * Pp;
-    const int  nq = ke - ks + 2;                          /* planes ks-1 .. ke travel through the ring       */
-
-    if (tid == 0)
-      {
-	for (int s = 0; s < NB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], T / 32); }
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-    __syncthreads();
-
-    if (tid >= T)
-      {
-	/* ---- producer warp: one lane feeds the ring ---------------------------------------------------- */
-	if (tid != T) return;
-	/* source range of an A^n stage, clipped to the plane; both ends are even                              */
-	const long lo = max(0L, p0 - N1e), hi = min(Pp, p0 + T + N1e);
-	const int  dstoff = (int) (lo - (p0 - N1e));
-	const unsigned bytesA = (unsigned) ((hi - lo) * sizeof(double));
-	const unsigned bytesM = (unsigned) ((min(Pp, p0 + T) - p0) * sizeof(double));
-	const double* srcA = an   + cb + (long) (ks - 1) * Pp + lo;
-	const double* srcM = anm1 + cb + (long) (ks - 1) * Pp + p0;
-	for (int q = 0; q < nq; q++, srcA += Pp, srcM += Pp)
-	  {
-	    const int s = q & (NB - 1);
-	    if (q >= NB) mbar_wait(&empty[s], (unsigned) (((q / NB) - 1) & 1));
-	    const bool needM = (q >= 1 && q < nq - 1);     /* A^{n-1} rides along for the planes that are updated */
-	    mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
-	    bulk_g2s(stA + (size_t) s * W + dstoff, srcA, bytesA, &full[s]);
-	    if (needM) bulk_g2s(stM + (size_t) s * T, srcM, bytesM, &full[s]);
-	  }
-	return;
-      }
-
-    /* ---- consumers -------------------------------------------------------------------------------------- */
-    const long p = p0 + tid;
-    const int  i = (int) (p / N1), j = (int) (p - (long) i * N1);
-    /* skiprim: the two outermost interior node layers in x and y belong to rim_update                          */
-    const int  rim = skiprim ? 2 : 0;
-    const bool interior = (p < f.P && i >= 1 + rim && i <= f.N0 - 2 - rim && j >= 1 + rim && j <= f.N1 - 2 - rim);
-    const bool lane0 = (tid & 31) == 0;
-
-    const double a0 = f.a[0], a1 = f.a[1], a2 = f.a[2], a3 = f.a[3];
-    const double as = (c < 3) ? f.a[4] : f.a[5];
-    const double alpha = f.alpha, beta = f.beta;
-    const Box bx = *jbox;
-    unsigned long long srcon = interior ? source_planes(f, bx, jmask, i, j, p, ks, ke) : 0ull;      /* bit 0 = the next plane */
-    long off = cb + p + (long) ks * Pp;                   /* the node in plane k, in A^{n+1} and J             */
-    const double* myA = stA + N1e + tid;
-    const double* myM = stM + tid;
-
-    int q = 0;                                            /* ring position of the next plane to take          */
-    /* take plane q out of the ring: its cross, the A^{n-1} value that came with it; then hand the stage back     */
-    auto take = [&] (Cross& x, double& vm) {
-      const int s = q & (NB - 1);
-      mbar_wait(&full[s], (unsigned) ((q / NB) & 1));
-      const double* a = myA + (size_t) s * W;
-      x.c = a[0]; x.xp = a[N1]; x.xm = a[-N1]; x.yp = a[1]; x.ym = a[-1];
-      vm = myM[(size_t) s * T];
-      __syncwarp();
-      if (lane0) mbar_arrive(&empty[s]);
-      ++q; };
-
-    Cross P0, P1, P2;
-    double vm1, vnext, dummy;
-    take(P0, dummy);                                      /* plane ks-1                                       */
-    take(P1, vm1);                                        /* plane ks with A^{n-1}(ks)                        */
-
-    int k = ks;
-    /* The source term.  J is loaded one plane ahead (its DRAM latency hides behind a whole plane of work) through the
-     * non-coherent path: an ordinary load still in flight would hold up the release of the ring stage in take().  J's only
-     * reader also clears it (FdTd::currentReset): the thread that loaded a value stores the zero afterwards, data-dependent
-     * on the load, and nothing else touches that address during the launch.                                          */
-    double srcn = 0.0;
-    if (srcon & 1ull) srcn = __ldg(jn + off);
-    /* one plane: Z is plane k, M plane k-1, the new plane k+1 lands in Pn                                         */
-    #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
-      {                                                                                                         \
-	const double src = srcn;                                                                                \
-	srcon >>= 1;                                                                                            \
-	srcn = 0.0;                                                                                             \
-	if (srcon & 1ull) srcn = __ldg(jn + off + Pp);                                                          \
-	take(Pn, vnext);                                                                                        \
-	if (interior) anp1[off] = stencil_value<NSFD>(M, Z, Pn, vm1, src, a0, a1, a2, a3, as, alpha, beta);    \
-	if (src != 0.0) jn[off] = src * 0.0;                     /* a (signed) zero, ordered after the load */ \
-	vm1 = vnext; off += Pp; ++k;                                                                            \
-      }
-    while (true)
-      {
-	MITHRA_STREAM_STEP(P0, P1, P2); if (k >= ke) break;
-	MITHRA_STREAM_STEP(P1, P2, P0); if (k >= ke) break;
-	MITHRA_STREAM_STEP(P2, P0, P1); if (k >= ke) break;
-      }
-    #undef MITHRA_STREAM_STEP
-  }
-
-  #ifndef MITHRA_RIM_MINBLOCKS
-  #define MITHRA_RIM_MINBLOCKS 6                        /* 80 registers: the kernel is pure load latency, 6 beats 5 and 8    */
-  #endif
-
-  /* AdvanceField::advanceBoundary{F,S} (database.cpp:137-176) for the face node s from the thread of its inward
-   * neighbour n, same association order as face_update below:
+  /* AdvanceField::advanceBoundary{F,S} (database.cpp:137-176) for the face node s with its inward neighbour n:
    *   apn = A+_n, ams = A-_s, amn = A-_n, as_ = A_s, an_ = A_n, then the four tangential neighbours along t1 in the
-   *   order (n+, n-, s+, s-) and likewise along z                                                               */
+   *   order (n+, n-, s+, s-) and likewise along z -- the association order of face_update below                     */
   __device__ __forceinline__ double face_value (const double* B, double ams, double apn, double amn, double as_, double an_,
 						double n1p, double n1m, double s1p, double s1m,
 						double n2p, double n2m, double s2p, double s2m)
@@ -322,6 +228,273 @@ namespace mithra
 	   B[3] * ( n1p + n1m + s1p + s1m ) +
 	   B[4] * ( n2p + n2m + s2p + s2m );
   }
+
+  /* T consumer threads (one in-plane position each) + one producer warp (+ one face warp)
+   *
+   * FACES (meshes without a TF/SF seed; N0, N1, np >= 8): the x and y absorbing faces (fdtd.cpp:377-520) are done here as
+   * well, and rim_update is not launched at all.  A face node s needs A+ of its inward neighbour n -- computed by a
+   * consumer thread of this very CTA -- and, of A^n and A^{n-1}, only values the ring already holds: s, n and their
+   * in-plane neighbours in plane k, s and n in the planes k-1 and k+1.  Doing the face in the consumer thread of n puts one
+   * or two face lanes into most warps of a row-major tile, and every such warp then runs the face code (round 1: +1 ms);
+   * so the faces get a WARP OF THEIR OWN: the consumers of the nodes n drop their result for plane k into a slot of the
+   * stage they have just taken (plane k+1) and all consumer warps arrive on `rdone` of that stage; the face warp waits
+   * there, takes the 13 other values out of the stages of the planes k-1, k, k+1 (it holds the oldest of them back:
+   * `empty` counts it in), and stores A+_s.  The faces cost a CTA about one warp-step per plane instead of a DRAM round
+   * trip over sectors that hold 1-4 rim nodes each (rim_update: 6.6 GB per step on FEL-LCLS for 2.8 GB of rim nodes).
+   * Stages carry two more doubles of halo (the in-plane neighbours of a face node one row off the tile) and the A^{n-1}
+   * stage the row of face nodes that lies outside the tile, where there is one.  Same operations in the same order as
+   * face_update: bit-identical.
+   * Shared memory is addressed as 32-bit shared-space addresses throughout (one base per stage, constant offsets): the
+   * consumer loop has to fit 56 registers without a spill -- a reload from local memory in it costs more than a plane.  */
+  __device__ __forceinline__ double lds_f64 (unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+  __device__ __forceinline__ void   sts_f64 (unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+  __device__ __forceinline__ void mbar_wait_a (unsigned b, unsigned parity)
+  {
+    unsigned done;
+    while (true)
+      {
+	asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+		     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+	if (done) break;
+	__nanosleep(32);
+      }
+  }
+  __device__ __forceinline__ void mbar_arrive_a (unsigned b)
+  { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory"); }
+
+  template <bool NSFD, int T, int NB, bool FACES>
+  __global__ void __launch_bounds__(T + (FACES ? 64 : 32), 2)
+  stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
+		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
+		  const unsigned char* __restrict__ jmask, int NR)
+  {
+    static_assert((NB & (NB - 1)) == 0 && NB >= 4 && NB <= 16, "stages: a power of two");
+    static_assert(T % 32 == 0 && T <= 1024, "whole consumer warps, one prefix entry per lane of the face warp");
+    constexpr int NW = T / 32;                            /* consumer warps                                            */
+    constexpr int HDR = FACES ? 1024 : 256;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* full  = reinterpret_cast<unsigned long long*>(smraw);
+    unsigned long long* empty = full + NB;
+    unsigned long long* rdone = empty + NB;               /* FACES: the results of plane k are in the slots of stage k+1 */
+    int* wc = reinterpret_cast<int*>(smraw + 384);        /* FACES: [5][NW] counts -> prefixes, then the task count     */
+    const int  N0 = f.N0, N1 = f.N1, N1e = (N1 + 1) & ~1;
+    const int  H  = FACES ? N1e + 2 : N1e;                /* doubles of halo either side of an A^n stage               */
+    const int  W  = T + 2 * H;                            /* doubles of the A^n part of a stage             */
+    const int  HM = FACES ? H : 0, WM = T + 2 * HM;       /* the same for A^{n-1}                                      */
+    const int  S  = W + WM + (FACES ? NR : 0);            /* doubles of a stage                                        */
+    double* st = reinterpret_cast<double*>(smraw + HDR);
+    int*    tasks = reinterpret_cast<int*>(st + (size_t) NB * S);         /* FACES: node | type << 12 | slot << 16     */
+    const unsigned bars = smem_u32(smraw), st0 = smem_u32(st);
+    const unsigned SB = (unsigned) S * 8u;                /* bytes of a stage                                          */
+
+    const int  tid = threadIdx.x, c = blockIdx.z;
+    const int  p0  = blockIdx.x * T;
+    const int  ks  = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);      /* planes ks .. ke-1            */
+    if (ks >= ke) return;
+    const long Pp = f.Pp, cb = (long) c * f.np * Pp;
+    const int  nq = ke - ks + 2;                          /* planes ks-1 .. ke travel through the ring       */
+
+    if (tid == 0)
+      {
+	for (int s = 0; s < NB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW + (FACES ? 1 : 0)); if (FACES) mbar_init(&rdone[s], NW); }
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+
+    /* the node of a consumer thread                                                                             */
+    const int  p = p0 + tid;
+    const int  i = p / N1, j = p - i * N1;
+    /* skiprim: the two outermost interior node layers in x and y belong to rim_update                          */
+    const int  rim = (skiprim && !FACES) ? 2 : 0;
+    const bool interior = (tid < T && p < f.P && i >= 1 + rim && i <= N0 - 2 - rim && j >= 1 + rim && j <= N1 - 2 - rim);
+
+    /* FACES: slot of every node next to a face (in node order) and the list of the faces by type (x low, x high, y low,
+     * y high; each in node order so that the stores of an x face are contiguous): ballots, per-warp counts, one scan by
+     * the face warp, and every consumer writes its own entries                                                      */
+    int myslot = -1;
+    if (FACES)
+      {
+	const unsigned below = (1u << (tid & 31)) - 1u;
+	const int warp = tid >> 5;
+	unsigned bal[5]; bool on[5];
+	on[1] = interior && i == 1; on[2] = interior && i == N0 - 2; on[3] = interior && j == 1; on[4] = interior && j == N1 - 2;
+	on[0] = on[1] || on[2] || on[3] || on[4];
+	if (tid < T)
+	  {
+	    #pragma unroll
+	    for (int e = 0; e < 5; e++) { bal[e] = __ballot_sync(0xffffffffu, on[e]); if ((tid & 31) == 0) wc[e * NW + warp] = __popc(bal[e]); }
+	  }
+	__syncthreads();
+	if (tid >= T + 32)
+	  {
+	    /* exclusive prefixes: the slots over wc[0][.], the tasks over wc[1..4][.] (type-major); NW <= 32            */
+	    const int lane = tid & 31;
+	    int v = lane < NW ? wc[lane] : 0, x = v;
+	    #pragma unroll
+	    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+	    if (lane < NW) wc[lane] = x - v;
+	    int carry = 0;
+	    #pragma unroll
+	    for (int e = 1; e < 5; e++)
+	      {
+		v = lane < NW ? wc[e * NW + lane] : 0; x = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+		if (lane < NW) wc[e * NW + lane] = carry + x - v;
+		carry += __shfl_sync(0xffffffffu, x, 31);
+	      }
+	    if (lane == 0) wc[5 * NW] = carry;
+	  }
+	__syncthreads();
+	if (tid < T && on[0])
+	  {
+	    myslot = wc[warp] + __popc(bal[0] & below);
+	    #pragma unroll
+	    for (int e = 1; e < 5; e++)
+	      if (on[e]) tasks[wc[e * NW + warp] + __popc(bal[e] & below)] = tid | ((e - 1) << 12) | (myslot << 16);
+	  }
+      }
+    __syncthreads();
+
+    if (tid >= T)
+      {
+	if (FACES && tid >= T + 32)
+	  {
+	    /* ---- face warp ------------------------------------------------------------------------------------- */
+	    const int lane = tid & 31, nt = wc[5 * NW];
+	    mbar_wait(&full[0], 0u); mbar_wait(&full[1], 0u);           /* the planes ks-1, ks                         */
+	    double* out = anp1 + cb + (long) ks * Pp + p0;
+	    for (int k = ks, q = 1; k < ke; k++, q++, out += Pp)          /* q: ring position of plane k                 */
+	      {
+		const int sp = (q + 1) & (NB - 1);
+		mbar_wait(&rdone[sp], (unsigned) (((q - 1) / NB) & 1));
+		mbar_wait(&full[sp], (unsigned) (((q + 1) / NB) & 1));      /* complete: the consumers have taken it       */
+		const double* Sk = st + (size_t) (q & (NB - 1)) * S + H;
+		const double* Sm = st + (size_t) ((q - 1) & (NB - 1)) * S + H;
+		const double* Sp = st + (size_t) sp * S + H;
+		const double* Mk = Sk + (W - H) + HM;
+		const double* Rk = Sp + (W - H) + WM;
+		for (int t = lane; t < nt; t += 32)
+		  {
+		    const int w = tasks[t], n = w & 0xfff, type = (w >> 12) & 3, slot = w >> 16;
+		    const int ds = (type == 0) ? -N1 : (type == 1) ? N1 : (type == 2) ? -1 : 1;
+		    const int d1 = (type < 2) ? 1 : N1;
+		    const int s = n + ds;
+		    const double apn = Rk[slot], ams = Mk[s], amn = Mk[n];
+		    const double as_ = Sk[s], an_ = Sk[n];
+		    const double n1p = Sk[n + d1], n1m = Sk[n - d1], s1p = Sk[s + d1], s1m = Sk[s - d1];
+		    const double n2p = Sp[n], n2m = Sm[n], s2p = Sp[s], s2m = Sm[s];
+		    const double r = (type < 2) ? face_value(f.bB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m)
+						: face_value(f.cB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m);
+		    out[s] = r;
+		  }
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty[(q - 1) & (NB - 1)]);
+	      }
+	    return;
+	  }
+	/* ---- producer warp: one lane feeds the ring ---------------------------------------------------- */
+	if (tid != T) return;
+	/* source range of an A^n stage, clipped to the plane; both ends are even                              */
+	const long lo = max(0L, (long) p0 - H), hi = min(Pp, (long) p0 + T + H);
+	const int  dstoff = (int) (lo - (p0 - H));
+	const unsigned bytesA = (unsigned) ((hi - lo) * sizeof(double));
+	/* A^{n-1}: the tile; FACES: two more either side (a y face node across the end of the tile), a whole row where the
+	 * tile holds nodes of row 1 / N0-2 whose x face nodes lie outside of it                                          */
+	long mlo = p0, mhi = min(Pp, (long) p0 + T);
+	if (FACES)
+	  {
+	    const int ifirst = p0 / N1, ilast = (min(p0 + T, f.P) - 1) / N1;
+	    mlo = max(0L,  (long) p0 - ( (ifirst <= 1 && 1 <= ilast) ? H : 2 ));
+	    mhi = min(Pp, (long) p0 + T + ( (ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 ));
+	  }
+	const int  dstoffM = W + (int) (mlo - (p0 - HM));
+	const unsigned bytesM = (unsigned) ((mhi - mlo) * sizeof(double));
+	const double* srcA = an   + cb + (long) (ks - 1) * Pp + lo;
+	const double* srcM = anm1 + cb + (long) (ks - 1) * Pp + mlo;
+	for (int q = 0; q < nq; q++, srcA += Pp, srcM += Pp)
+	  {
+	    const int s = q & (NB - 1);
+	    if (q >= NB) mbar_wait(&empty[s], (unsigned) (((q / NB) - 1) & 1));
+	    const bool needM = (q >= 1 && q < nq - 1);     /* A^{n-1} rides along for the planes that are updated */
+	    mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
+	    bulk_g2s(st + (size_t) s * S + dstoff, srcA, bytesA, &full[s]);
+	    if (needM) bulk_g2s(st + (size_t) s * S + dstoffM, srcM, bytesM, &full[s]);
+	  }
+	return;
+      }
+
+    /* ---- consumers -------------------------------------------------------------------------------------- */
+    const bool lane0 = (tid & 31) == 0;
+    const double as = (c < 3) ? f.a[4] : f.a[5];
+    unsigned long long srcon;                             /* bit 0 = the next plane                          */
+    { const Box bx = *jbox; srcon = interior ? source_planes(f, bx, jmask, i, j, p, ks, ke) : 0ull; }
+    /* the node in plane k, in A^{n+1} and J: a base the whole CTA shares and a 32-bit offset (at most 64 planes)      */
+    double* const apc = anp1 + cb + (long) ks * Pp + p0;
+    double* const jnc = jn   + cb + (long) ks * Pp + p0;
+    const unsigned PpU = (unsigned) Pp;
+    unsigned off = (unsigned) tid;
+    const unsigned mine = st0 + (unsigned) (H + tid) * 8u;                    /* this node in the A^n part of stage 0  */
+    const unsigned n1b  = (unsigned) N1 * 8u;
+    const unsigned dM   = (unsigned) (W - H + HM) * 8u;                       /* from there to its A^{n-1} value       */
+    const unsigned dR   = (unsigned) (W - H - tid + WM + myslot) * 8u;        /* FACES: and to its hand-over slot      */
+
+    int q = 0;                                            /* ring position of the next plane to take          */
+    /* take plane q out of the ring: its cross; returns the node's address in that stage.  The stage is handed back one
+     * step later, after the A^{n-1} value that came with it has been read where it is needed (one live double less)      */
+    auto take = [&] (Cross& x) -> unsigned {
+      const unsigned s = (unsigned) q & (NB - 1);
+      mbar_wait_a(bars + s * 8u, (unsigned) ((q / NB) & 1));
+      const unsigned a = mine + s * SB;
+      x.c = lds_f64(a); x.xp = lds_f64(a + n1b); x.xm = lds_f64(a - n1b); x.yp = lds_f64(a + 8u); x.ym = lds_f64(a - 8u);
+      ++q;
+      return a; };
+    /* hand the stage of ring position qq back (every lane of the warp has read what it needs of it)                     */
+    auto release = [&] (unsigned qq) { __syncwarp(); if (lane0) mbar_arrive_a(bars + NB * 8u + (qq & (NB - 1)) * 8u); };
+
+    Cross P0, P1, P2;
+    take(P0);                                             /* plane ks-1                                       */
+    release(0u);
+    take(P1);                                             /* plane ks                                         */
+
+    /* The source term.  J is loaded one plane ahead (its DRAM latency hides behind a whole plane of work) through the
+     * non-coherent path: an ordinary load still in flight would hold up the release of the ring stage.  J's only
+     * reader also clears it (FdTd::currentReset): the thread that loaded a value stores the zero afterwards, data-dependent
+     * on the load, and nothing else touches that address during the launch.                                          */
+    double srcn = 0.0;
+    if (srcon & 1ull) srcn = __ldg(jnc + off);
+    /* one plane: Z is plane k (ring position q - 1 on entry), M plane k-1, the new plane k+1 lands in Pn           */
+    #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
+      {                                                                                                         \
+	const double src = srcn;                                                                                \
+	srcon >>= 1;                                                                                            \
+	srcn = 0.0;                                                                                             \
+	if (srcon & 1ull) srcn = __ldg(jnc + (off + PpU));                                                      \
+	const unsigned a = take(Pn);                                                                            \
+	const double vm1 = lds_f64(mine + (((unsigned) q - 2u) & (NB - 1)) * SB + dM);   /* A^{n-1} of plane k */    \
+	release((unsigned) q - 2u);                                                                             \
+	const double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, f.a[0], f.a[1], f.a[2], f.a[3], as, f.alpha, f.beta); \
+	if (FACES)                                               /* A+ of plane k rides in the stage of plane k+1 */ \
+	  {                                                                                                     \
+	    if (myslot >= 0) sts_f64(a + dR, r);                                                                \
+	    __syncwarp();                                                                                       \
+	    if (lane0) mbar_arrive_a(bars + 2 * NB * 8u + (((unsigned) q - 1u) & (NB - 1)) * 8u);               \
+	  }                                                                                                     \
+	if (interior) apc[off] = r;                                                                             \
+	if (src != 0.0) jnc[off] = src * 0.0;                    /* a (signed) zero, ordered after the load */ \
+	off += PpU;                                                                                             \
+      }
+    while (true)
+      {
+	MITHRA_STREAM_STEP(P0, P1, P2); if (q >= nq) break;
+	MITHRA_STREAM_STEP(P1, P2, P0); if (q >= nq) break;
+	MITHRA_STREAM_STEP(P2, P0, P1); if (q >= nq) break;
+      }
+    #undef MITHRA_STREAM_STEP
+  }
+
+  #ifndef MITHRA_RIM_MINBLOCKS
+  #define MITHRA_RIM_MINBLOCKS 6                        /* 80 registers: the kernel is pure load latency, 6 beats 5 and 8    */
+  #endif
 
   /* ------------------------------------------------------------------------------------------------
    * Rim of every plane: rows i = 1, 2, N0-3, N0-2 and columns j = 1, 2, N1-3, N1-2 (N0, N1 >= 8).

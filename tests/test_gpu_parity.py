@@ -246,12 +246,18 @@ def _resized(job, N0, N1, npl):
 
 @pytest.mark.parametrize("job,shape", [("micro-seeded", (14, 14, 242)), ("micro-seeded", (37, 85, 70)), ("micro-seeded", (80, 41, 9)),
                                        ("micro-seeded", (8, 200, 12)), ("micro-seeded", (31, 8, 75)), ("micro-sc", (29, 53, 66)),
-                                       ("micro-o1", (33, 101, 40)), ("micro-fd", (64, 9, 130)), ("micro-nsfd", (85, 85, 70))])
+                                       ("micro-o1", (33, 101, 40)), ("micro-fd", (64, 9, 130)), ("micro-nsfd", (85, 85, 70)),
+                                       ("micro-nsfd", (102, 102, 40)), ("micro-nsfd", (20, 73, 30)), ("micro-fd", (40, 27, 33)),
+                                       ("micro-sc", (8, 200, 12)), ("micro-o1", (31, 8, 75)), ("micro-nsfd", (14, 14, 242)),
+                                       ("micro-sc", (9, 513, 20)), ("micro-nsfd", (140, 73, 12)), ("micro-fd", (40, 39, 20))])
 def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
-    """The production path -- stencil_stream on the inner nodes + rim_update (interior value, x / y shell seed terms and
-    x / y faces of the two outer node layers in one pass) -- against the reference's three passes as separate kernels
-    (MITHRA_NO_FUSE) and against the plain-load stencil (MITHRA_STENCIL_PLAIN): bit-identical potentials, on meshes
-    whose 512-node tiles cut through rows and down to the smallest mesh the rim path takes (8 nodes across)."""
+    """The production path -- seeded jobs: stencil_stream on the inner nodes + rim_update (interior value, x / y shell seed
+    terms and x / y faces of the two outer node layers in one pass); jobs without a seed: stencil_stream with its face
+    warp (interior value of every node and the x / y faces in one kernel) -- against the reference's three passes as
+    separate kernels (MITHRA_NO_FUSE), against stencil_stream + rim_update (MITHRA_NO_FACEWARP) and against the plain-load
+    stencil (MITHRA_STENCIL_PLAIN): bit-identical potentials, on meshes whose 448- / 480-node tiles cut through rows (102:
+    the FEL-LCLS row; 140 x 73: a tile starts on the node next to a y face; 39: a tile ends on one; 513: a tile inside
+    row 1) and down to the smallest mesh the rim path takes (8 nodes across)."""
     p, g = _resized(job, *shape)
     rng = np.random.default_rng(11)
     n = p.N0 * p.N1 * p.np
@@ -270,7 +276,8 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
     bunch[:, 10] = 1.0
     names = ("anp1", "an", "anm1") + (("fnp1", "fn", "fnm1") if p.space_charge else ())
     out = {}
-    for mode in ("fused", "MITHRA_NO_FUSE", "MITHRA_STENCIL_PLAIN"):
+    modes = ("MITHRA_NO_FUSE", "MITHRA_NO_FACEWARP", "MITHRA_STENCIL_PLAIN")
+    for mode in ("fused",) + modes:
         if mode != "fused":
             monkeypatch.setenv(mode, "1")
         s = abi.GpuSolver(p)
@@ -287,7 +294,7 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
         if mode != "fused":
             monkeypatch.delenv(mode)
     assert np.abs(out["fused"]["anp1"]).max() > 0
-    for mode in ("MITHRA_NO_FUSE", "MITHRA_STENCIL_PLAIN"):
+    for mode in modes:
         for k in names:
             np.testing.assert_array_equal(out["fused"][k], out[mode][k], err_msg="%s %s" % (mode, k))
 
