@@ -162,22 +162,62 @@ namespace mithra
 		 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
   }
 
+  /* for a warp whose wait is on the critical path of the whole CTA: no back-off between the tries                      */
+  #ifndef MITHRA_SVC_SPIN
+  #define MITHRA_SVC_SPIN 1
+  #endif
+  #ifndef MITHRA_SVC_EARLY
+  #define MITHRA_SVC_EARLY 1
+  #endif
+  __device__ __forceinline__ void mbar_wait_now (unsigned long long* b, unsigned parity)
+  {
+  #if MITHRA_SVC_SPIN
+    unsigned done;
+    do
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+		   : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    while (!done);
+  #else
+    mbar_wait(b, parity);
+  #endif
+  }
   __device__ __forceinline__ void mbar_arrive (unsigned long long* b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
 
+  /* 1: the consumers of rows 1 and N0-2 also do the x faces behind them (measured: the two tiles that hold those rows then
+   * run at less than half speed, 0.6 ms per FEL-LCLS step); 0: boundary_faces does the x faces afterwards (0.2 ms)         */
+  #ifndef MITHRA_STREAM_XFACES
+  #define MITHRA_STREAM_XFACES 0
+  #endif
   /* shared memory of one CTA: a header (mbarriers, FACES: the counters of the task list), then NB stages, each
    * (T + 2 H) doubles of A^n, T + 2 HM doubles of A^{n-1} and -- FACES -- NR hand-over slots; FACES: then the task list.
    * H: halo of the A^n stage, N1e (FACES: N1e + 2); HM: 0 (FACES: H)                                                       */
-  static inline size_t stencil_stream_smem (int T, int N1, int NB, bool faces = false, int NR = 0)
+  static inline size_t stencil_stream_smem (int T, int N1, int NB, bool faces = false, int NR = 0, int WM = 0)
   {
     const int N1e = (N1 + 1) & ~1;
     if (!faces) return 256 + (size_t) NB * ( (size_t) T + 2 * N1e + T ) * sizeof(double);
     const int H = N1e + 2;
-    return 1024 + (size_t) NB * ( 2 * ( (size_t) T + 2 * H ) + NR ) * sizeof(double) + (size_t) 2 * NR * sizeof(int);
+    return 1024 + (size_t) NB * ( (size_t) T + 2 * H + WM + NR ) * sizeof(double) + (size_t) 2 * NR * sizeof(int);
   }
 
-  /* the nodes of a tile that sit next to an x or y face (the inward neighbours n of the face nodes): their largest number
-   * over the tiles of T consecutive in-plane positions -- the hand-over slots a CTA of stencil_stream<.., FACES> needs    */
+  /* FACES: doubles of the A^{n-1} part of a stage -- the tile, two more either side, and a row (H = N1e + 2) instead on the
+   * side where the tile holds nodes of row 1 / N0-2 (their x face nodes may lie outside of it): the widest over the tiles */
+  static inline int stencil_stream_m_width (int N0, int N1, int T)
+  {
+    const long P = (long) N0 * N1;
+    const int H = ((N1 + 1) & ~1) + 2;
+    int worst = 0;
+    for (long p0 = 0; p0 < P; p0 += T)
+      {
+	const int ifirst = (int) (p0 / N1), ilast = (int) ((std::min(p0 + T, P) - 1) / N1);
+	const int w = T + ( (MITHRA_STREAM_XFACES && ifirst <= 1 && 1 <= ilast) ? H : 2 ) + ( (MITHRA_STREAM_XFACES && ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 );
+	if (w > worst) worst = w;
+      }
+    return worst;
+  }
+
+  /* the nodes of a tile that sit next to a y face (the inward neighbours n of its nodes): their largest number over the
+   * tiles of T consecutive in-plane positions -- the hand-over slots a CTA of stencil_stream<.., FACES> needs            */
   static inline int stencil_stream_face_slots (int N0, int N1, int T)
   {
     const long P = (long) N0 * N1;
@@ -188,7 +228,7 @@ namespace mithra
 	for (long p = p0; p < p0 + T && p < P; p++)
 	  {
 	    const int i = (int) (p / N1), j = (int) (p - (long) i * N1);
-	    if (i >= 1 && i <= N0 - 2 && j >= 1 && j <= N1 - 2 && (i == 1 || i == N0 - 2 || j == 1 || j == N1 - 2)) n++;
+	    if (i >= 1 && i <= N0 - 2 && j >= 1 && j <= N1 - 2 && (j == 1 || j == N1 - 2)) n++;
 	  }
 	if (n > worst) worst = n;
       }
@@ -262,11 +302,16 @@ namespace mithra
   __device__ __forceinline__ void mbar_arrive_a (unsigned b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory"); }
 
+  #ifdef MITHRA_DBG_NORDONE
+  #define MITHRA_DBG_NORDONE_V 1
+  #else
+  #define MITHRA_DBG_NORDONE_V 0
+  #endif
   template <bool NSFD, int T, int NB, bool FACES>
-  __global__ void __launch_bounds__(T + (FACES ? 64 : 32), 2)
+  __global__ void __launch_bounds__(T + (FACES ? 64 : 32), (T > 512 ? 1 : 2))
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
 		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
-		  const unsigned char* __restrict__ jmask, int NR)
+		  const unsigned char* __restrict__ jmask, int NR, int WMF)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 4 && NB <= 16, "stages: a power of two");
     static_assert(T % 32 == 0 && T <= 1024, "whole consumer warps, one prefix entry per lane of the face warp");
@@ -280,7 +325,13 @@ namespace mithra
     const int  N0 = f.N0, N1 = f.N1, N1e = (N1 + 1) & ~1;
     const int  H  = FACES ? N1e + 2 : N1e;                /* doubles of halo either side of an A^n stage               */
     const int  W  = T + 2 * H;                            /* doubles of the A^n part of a stage             */
-    const int  HM = FACES ? H : 0, WM = T + 2 * HM;       /* the same for A^{n-1}                                      */
+    /* the A^{n-1} part: the tile; FACES: two more either side (a y face node across the end of the tile), a whole row H
+     * on the side where the tile holds nodes of row 1 / N0-2 whose x face nodes lie outside of it (WMF: the widest tile)  */
+    const int  p0  = blockIdx.x * T;
+    const int  ifirst = p0 / N1, ilast = (min(p0 + T, f.P) - 1) / N1;
+    const int  HM  = FACES ? ( (MITHRA_STREAM_XFACES && ifirst <= 1 && 1 <= ilast) ? H : 2 ) : 0;                  /* low side  */
+    const int  HMh = FACES ? ( (MITHRA_STREAM_XFACES && ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 ) : 0;        /* high side */
+    const int  WM  = FACES ? WMF : T;
     const int  S  = W + WM + (FACES ? NR : 0);            /* doubles of a stage                                        */
     double* st = reinterpret_cast<double*>(smraw + HDR);
     int*    tasks = reinterpret_cast<int*>(st + (size_t) NB * S);         /* FACES: node | type << 12 | slot << 16     */
@@ -288,7 +339,6 @@ namespace mithra
     const unsigned SB = (unsigned) S * 8u;                /* bytes of a stage                                          */
 
     const int  tid = threadIdx.x, c = blockIdx.z;
-    const int  p0  = blockIdx.x * T;
     const int  ks  = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);      /* planes ks .. ke-1            */
     if (ks >= ke) return;
     const long Pp = f.Pp, cb = (long) c * f.np * Pp;
@@ -315,18 +365,17 @@ namespace mithra
       {
 	const unsigned below = (1u << (tid & 31)) - 1u;
 	const int warp = tid >> 5;
-	unsigned bal[5]; bool on[5];
-	on[1] = interior && i == 1; on[2] = interior && i == N0 - 2; on[3] = interior && j == 1; on[4] = interior && j == N1 - 2;
-	on[0] = on[1] || on[2] || on[3] || on[4];
+	unsigned bal[3]; bool on[3];
+	on[1] = interior && j == 1; on[2] = interior && j == N1 - 2; on[0] = on[1] || on[2];
 	if (tid < T)
 	  {
 	    #pragma unroll
-	    for (int e = 0; e < 5; e++) { bal[e] = __ballot_sync(0xffffffffu, on[e]); if ((tid & 31) == 0) wc[e * NW + warp] = __popc(bal[e]); }
+	    for (int e = 0; e < 3; e++) { bal[e] = __ballot_sync(0xffffffffu, on[e]); if ((tid & 31) == 0) wc[e * NW + warp] = __popc(bal[e]); }
 	  }
 	__syncthreads();
 	if (tid >= T + 32)
 	  {
-	    /* exclusive prefixes: the slots over wc[0][.], the tasks over wc[1..4][.] (type-major); NW <= 32            */
+	    /* exclusive prefixes: the slots over wc[0][.], the tasks over wc[1..2][.] (type-major); NW <= 32            */
 	    const int lane = tid & 31;
 	    int v = lane < NW ? wc[lane] : 0, x = v;
 	    #pragma unroll
@@ -334,7 +383,7 @@ namespace mithra
 	    if (lane < NW) wc[lane] = x - v;
 	    int carry = 0;
 	    #pragma unroll
-	    for (int e = 1; e < 5; e++)
+	    for (int e = 1; e < 3; e++)
 	      {
 		v = lane < NW ? wc[e * NW + lane] : 0; x = v;
 		#pragma unroll
@@ -342,14 +391,14 @@ namespace mithra
 		if (lane < NW) wc[e * NW + lane] = carry + x - v;
 		carry += __shfl_sync(0xffffffffu, x, 31);
 	      }
-	    if (lane == 0) wc[5 * NW] = carry;
+	    if (lane == 0) wc[3 * NW] = carry;
 	  }
 	__syncthreads();
 	if (tid < T && on[0])
 	  {
 	    myslot = wc[warp] + __popc(bal[0] & below);
 	    #pragma unroll
-	    for (int e = 1; e < 5; e++)
+	    for (int e = 1; e < 3; e++)
 	      if (on[e]) tasks[wc[e * NW + warp] + __popc(bal[e] & below)] = tid | ((e - 1) << 12) | (myslot << 16);
 	  }
       }
@@ -357,68 +406,92 @@ namespace mithra
 
     if (tid >= T)
       {
-	if (FACES && tid >= T + 32)
-	  {
-	    /* ---- face warp ------------------------------------------------------------------------------------- */
-	    const int lane = tid & 31, nt = wc[5 * NW];
-	    mbar_wait(&full[0], 0u); mbar_wait(&full[1], 0u);           /* the planes ks-1, ks                         */
-	    double* out = anp1 + cb + (long) ks * Pp + p0;
-	    for (int k = ks, q = 1; k < ke; k++, q++, out += Pp)          /* q: ring position of plane k                 */
-	      {
-		const int sp = (q + 1) & (NB - 1);
-		mbar_wait(&rdone[sp], (unsigned) (((q - 1) / NB) & 1));
-		mbar_wait(&full[sp], (unsigned) (((q + 1) / NB) & 1));      /* complete: the consumers have taken it       */
-		const double* Sk = st + (size_t) (q & (NB - 1)) * S + H;
-		const double* Sm = st + (size_t) ((q - 1) & (NB - 1)) * S + H;
-		const double* Sp = st + (size_t) sp * S + H;
-		const double* Mk = Sk + (W - H) + HM;
-		const double* Rk = Sp + (W - H) + WM;
-		for (int t = lane; t < nt; t += 32)
-		  {
-		    const int w = tasks[t], n = w & 0xfff, type = (w >> 12) & 3, slot = w >> 16;
-		    const int ds = (type == 0) ? -N1 : (type == 1) ? N1 : (type == 2) ? -1 : 1;
-		    const int d1 = (type < 2) ? 1 : N1;
-		    const int s = n + ds;
-		    const double apn = Rk[slot], ams = Mk[s], amn = Mk[n];
-		    const double as_ = Sk[s], an_ = Sk[n];
-		    const double n1p = Sk[n + d1], n1m = Sk[n - d1], s1p = Sk[s + d1], s1m = Sk[s - d1];
-		    const double n2p = Sp[n], n2m = Sm[n], s2p = Sp[s], s2m = Sm[s];
-		    const double r = (type < 2) ? face_value(f.bB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m)
-						: face_value(f.cB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m);
-		    out[s] = r;
-		  }
-		__syncwarp();
-		if (lane == 0) mbar_arrive(&empty[(q - 1) & (NB - 1)]);
-	      }
-	    return;
-	  }
-	/* ---- producer warp: one lane feeds the ring ---------------------------------------------------- */
-	if (tid != T) return;
+	/* ---- service warp: lane 0 feeds the ring; FACES: all lanes do the y faces -------------------------------- */
+	const int lane = tid & 31;
 	/* source range of an A^n stage, clipped to the plane; both ends are even                              */
 	const long lo = max(0L, (long) p0 - H), hi = min(Pp, (long) p0 + T + H);
 	const int  dstoff = (int) (lo - (p0 - H));
 	const unsigned bytesA = (unsigned) ((hi - lo) * sizeof(double));
-	/* A^{n-1}: the tile; FACES: two more either side (a y face node across the end of the tile), a whole row where the
-	 * tile holds nodes of row 1 / N0-2 whose x face nodes lie outside of it                                          */
-	long mlo = p0, mhi = min(Pp, (long) p0 + T);
-	if (FACES)
-	  {
-	    const int ifirst = p0 / N1, ilast = (min(p0 + T, f.P) - 1) / N1;
-	    mlo = max(0L,  (long) p0 - ( (ifirst <= 1 && 1 <= ilast) ? H : 2 ));
-	    mhi = min(Pp, (long) p0 + T + ( (ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 ));
-	  }
+	const long mlo = max(0L, (long) p0 - HM), mhi = min(Pp, (long) p0 + T + HMh);
 	const int  dstoffM = W + (int) (mlo - (p0 - HM));
 	const unsigned bytesM = (unsigned) ((mhi - mlo) * sizeof(double));
 	const double* srcA = an   + cb + (long) (ks - 1) * Pp + lo;
 	const double* srcM = anm1 + cb + (long) (ks - 1) * Pp + mlo;
-	for (int q = 0; q < nq; q++, srcA += Pp, srcM += Pp)
+	/* plane of ring position q into its stage (the stage is free)                                                */
+	auto produce = [&] (int q) {
+	  const int s = q & (NB - 1);
+	  const bool needM = (q >= 1 && q < nq - 1);       /* A^{n-1} rides along for the planes that are updated */
+	  mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
+	  bulk_g2s(st + (size_t) s * S + dstoff, srcA + (long) q * Pp, bytesA, &full[s]);
+	  if (needM) bulk_g2s(st + (size_t) s * S + dstoffM, srcM + (long) q * Pp, bytesM, &full[s]); };
+
+	if (tid < T + 32)
 	  {
-	    const int s = q & (NB - 1);
-	    if (q >= NB) mbar_wait(&empty[s], (unsigned) (((q / NB) - 1) & 1));
-	    const bool needM = (q >= 1 && q < nq - 1);     /* A^{n-1} rides along for the planes that are updated */
-	    mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
-	    bulk_g2s(st + (size_t) s * S + dstoff, srcA, bytesA, &full[s]);
-	    if (needM) bulk_g2s(st + (size_t) s * S + dstoffM, srcM, bytesM, &full[s]);
+	    /* ---- producer warp: one lane feeds the ring ------------------------------------------------------ */
+	    if (lane != 0) return;
+	    for (int q = 0; q < nq; q++)
+	      {
+		if (q >= NB) mbar_wait_now(&empty[q & (NB - 1)], (unsigned) (((q / NB) - 1) & 1));
+		produce(q);
+	      }
+	    return;
+	  }
+
+	/* ---- FACES, face warp: per plane k it waits for the consumers' A+ of the nodes next to a y face, does those faces
+	 * from the stages of the planes k-1, k, k+1 and hands the oldest stage it held back (`empty` counts it in)          */
+	const int nt = wc[3 * NW];
+	mbar_wait(&full[0], 0u); mbar_wait(&full[1], 0u);           /* the planes ks-1, ks                         */
+	double* out = anp1 + cb + (long) ks * Pp + p0;
+	/* one face: node n of the tile, its face node s = n -+ 1 (type 0 / 1), the slot with A+_n; zn, zs: A_n and A_s of
+	 * plane k-1 on entry, of plane k on return                                                                    */
+	auto face = [&] (int w, const double* Sk, const double* Sp, const double* Mk, const double* Rk, double& zn, double& zs) {
+	  const int n = w & 0xfff, s = n + (((w >> 12) & 1) ? 1 : -1), slot = w >> 16;
+	  const double apn = Rk[slot], ams = Mk[s], amn = Mk[n];
+	  const double as_ = Sk[s], an_ = Sk[n];
+	  const double n1p = Sk[n + N1], n1m = Sk[n - N1], s1p = Sk[s + N1], s1m = Sk[s - N1];
+	  const double n2p = Sp[n], n2m = zn, s2p = Sp[s], s2m = zs;
+	  out[s] = face_value(f.cB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m);
+	  zn = an_; zs = as_; };
+	/* The usual case, at most a face per lane: its task is decoded once and the two values of plane k-1 it needs are the
+	 * ones it read as plane k one step earlier -- kept in registers, so the warp needs the stages of the planes k and k+1
+	 * only and hands stage k back at the end of step k (a plane of look-ahead more for the ring).  More faces than lanes
+	 * (rows shorter than 30 nodes): the planes k-1 are read from their stage, which is handed back a step later.        */
+	const bool early = MITHRA_SVC_EARLY && nt <= 32;
+	const int w0 = lane < nt ? tasks[lane] : -1;
+	double zn = 0.0, zs = 0.0;
+	if (w0 >= 0) { const int n = w0 & 0xfff, s = n + (((w0 >> 12) & 1) ? 1 : -1); zn = st[H + n]; zs = st[H + s]; }   /* plane ks-1: stage 0 */
+	auto recycle = [&] (int qr) { mbar_arrive(&empty[qr & (NB - 1)]); };      /* hand the stage of ring position qr back */
+	for (int k = ks, q = 1; k < ke; k++, q++, out += Pp)          /* q: ring position of plane k                 */
+	  {
+	    const int sp = (q + 1) & (NB - 1);
+	    #ifndef MITHRA_DBG_NORDONE
+	    mbar_wait_now(&rdone[sp], (unsigned) (((q - 1) / NB) & 1));
+	    #endif
+	    mbar_wait_now(&full[sp], (unsigned) (((q + 1) / NB) & 1));  /* complete: the consumers have taken it       */
+	    const double* Sk = st + (size_t) (q & (NB - 1)) * S + H;
+	    const double* Sp = st + (size_t) sp * S + H;
+	    const double* Mk = Sk + (W - H) + HM;
+	    const double* Rk = Sp + (W - H) + WM;
+	    #ifndef MITHRA_DBG_NOFACE
+	    if (w0 >= 0) face(w0, Sk, Sp, Mk, Rk, zn, zs);
+	    #endif
+	    if (!early)
+	      {
+		const double* Sm = st + (size_t) ((q - 1) & (NB - 1)) * S + H;
+		for (int t = lane + 32; t < nt; t += 32)
+		  {
+		    const int w = tasks[t], n = w & 0xfff, s = n + (((w >> 12) & 1) ? 1 : -1);
+		    double yn = Sm[n], ys = Sm[s];
+		    face(w, Sk, Sp, Mk, Rk, yn, ys);
+		  }
+	      }
+	    __syncwarp();
+	    if (lane == 0)
+	      {
+		if (early) { if (q == 1) recycle(0); recycle(q); }
+		else       recycle(q - 1);
+	      }
+	    __syncwarp();
 	  }
 	return;
       }
@@ -437,6 +510,9 @@ namespace mithra
     const unsigned n1b  = (unsigned) N1 * 8u;
     const unsigned dM   = (unsigned) (W - H + HM) * 8u;                       /* from there to its A^{n-1} value       */
     const unsigned dR   = (unsigned) (W - H - tid + WM + myslot) * 8u;        /* FACES: and to its hand-over slot      */
+    /* FACES: the x face node behind this node (rows 1 and N0-2: whole warps, so the consumers do these themselves from
+     * the crosses they hold and three more values of the stage of plane k, which is still theirs): its offset in bytes  */
+    const int dsx = (FACES && interior && MITHRA_STREAM_XFACES) ? ( i == 1 ? -(int) n1b : i == N0 - 2 ? (int) n1b : 0 ) : 0;
 
     int q = 0;                                            /* ring position of the next plane to take          */
     /* take plane q out of the ring: its cross; returns the node's address in that stage.  The stage is handed back one
@@ -468,18 +544,31 @@ namespace mithra
 	const double src = srcn;                                                                                \
 	srcon >>= 1;                                                                                            \
 	srcn = 0.0;                                                                                             \
-	if (srcon & 1ull) srcn = __ldg(jnc + (off + PpU));                                                      \
+	if (srcon & 1ull)                                                                                       \
+	  {                                                                                                     \
+	    const double* jq = jnc + (off + PpU);                                                               \
+	    srcn = __ldg(jq);                                                                                   \
+	    asm volatile("prefetch.global.L2 [%0];" :: "l"(jq + 2u * PpU));   /* pencils are 8 planes tall: two planes on, the load then hits L2 */ \
+	  }                                                                                                     \
 	const unsigned a = take(Pn);                                                                            \
-	const double vm1 = lds_f64(mine + (((unsigned) q - 2u) & (NB - 1)) * SB + dM);   /* A^{n-1} of plane k */    \
-	release((unsigned) q - 2u);                                                                             \
+	const unsigned az = mine + (((unsigned) q - 2u) & (NB - 1)) * SB;        /* the node in the stage of plane k */ \
+	const double vm1 = lds_f64(az + dM);                                             /* A^{n-1} of plane k */    \
 	const double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, f.a[0], f.a[1], f.a[2], f.a[3], as, f.alpha, f.beta); \
-	if (FACES)                                               /* A+ of plane k rides in the stage of plane k+1 */ \
+	if (FACES && !MITHRA_DBG_NORDONE_V)                      /* A+ of plane k rides in the stage of plane k+1 */ \
 	  {                                                                                                     \
 	    if (myslot >= 0) sts_f64(a + dR, r);                                                                \
 	    __syncwarp();                                                                                       \
 	    if (lane0) mbar_arrive_a(bars + 2 * NB * 8u + (((unsigned) q - 1u) & (NB - 1)) * 8u);               \
 	  }                                                                                                     \
 	if (interior) apc[off] = r;                                                                             \
+	if (FACES && MITHRA_STREAM_XFACES && dsx != 0)                                                          \
+	  {                                                                                                     \
+	    const bool lo = dsx < 0;                                                                            \
+	    const double ams = lds_f64(az + dsx + dM), s1p = lds_f64(az + dsx + 8u), s1m = lds_f64(az + dsx - 8u); \
+	    apc[(int) off + (dsx >> 3)] = face_value(f.bB, ams, r, vm1, lo ? Z.xm : Z.xp, Z.c, Z.yp, Z.ym, s1p, s1m, \
+						      Pn.c, M.c, lo ? Pn.xm : Pn.xp, lo ? M.xm : M.xp);           \
+	  }                                                                                                     \
+	release((unsigned) q - 2u);                                                                             \
 	if (src != 0.0) jnc[off] = src * 0.0;                    /* a (signed) zero, ordered after the load */ \
 	off += PpU;                                                                                             \
       }
@@ -623,8 +712,10 @@ namespace mithra
     const long ny = (long) (f.N0 - 2) * nk;
     const long nz = (long) (f.N0 - 2) * (f.N1 - 2);
     const bool zlo = (f.rank == 0), zhi = (f.rank == f.size - 1);
-    const long first = zonly ? 2 * nx + 2 * ny : 0;       /* zonly: rim_update has done the x and y faces    */
-    const long per = 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0) - first;
+    /* zonly = 1: rim_update (or stencil_stream) has done the x and y faces; 2: the x faces alone (stencil_stream does the
+     * y faces and leaves these: whole rows, as cheap here as anywhere)                                                  */
+    const long first = zonly == 1 ? 2 * nx + 2 * ny : 0;
+    const long per = zonly == 2 ? 2 * nx : 2 * nx + 2 * ny + (zlo ? nz : 0) + (zhi ? nz : 0) - first;
     const long tot = per * f.ncomp;
     const long N1 = f.N1, Pp = f.Pp;
 
@@ -1073,26 +1164,35 @@ namespace mithra
   {
     constexpr int L = MITHRA_EB_CHUNK_LOG2;
     const int nch = (f.np + (1 << L) - 1) >> L;
-    const long nwords = nbytes >> 2;                       /* the arrays are whole 32-bit words (mark_eb_pencil)     */
-    const unsigned int* cw = reinterpret_cast<const unsigned int*>(cells);
-    for (long w = (long) blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long) gridDim.x * blockDim.x)
+    /* the arrays are whole 16-byte words (engine.cu emask_bytes); sixteen cell bytes per load, nearly all of them zero:
+     * the loop over the words is the whole cost of the kernel (32-bit counters; a slab has fewer than 2^31 cell pencils)  */
+    const unsigned int nquads = (unsigned int) (nbytes >> 4);
+    const uint4* cq = reinterpret_cast<const uint4*>(cells);
+    const unsigned int P = (unsigned int) f.P, N1 = (unsigned int) f.N1;
+    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nquads; w += gridDim.x * blockDim.x)
       {
-	unsigned int word = cw[w];
-	if (!word) continue;
-	for (int q = 0; q < 4; q++, word >>= 8)
+	const uint4 quad = __ldg(cq + w);
+	if (!(quad.x | quad.y | quad.z | quad.w)) continue;
+	#pragma unroll
+	for (int h = 0; h < 4; h++)
 	  {
-	    const unsigned int v = word & 0xffu;
-	    if (!v) continue;
-	    const long t = 4 * w + q;
-	    const int cc = (int) (t / f.P), r = (int) (t - (long) cc * f.P), ii = r / f.N1, jj = r - ii * f.N1;
-	    if (cc >= nch) continue;
-	    const int c0 = (v & REACH_ZLO) ? max(cc - 1, 0) : cc, c1 = (v & REACH_ZHI) ? min(cc + 1, nch - 1) : cc;
-	    const int i0 = (v & REACH_XLO) ? max(ii - 1, 0) : ii, i1 = min((v & REACH_XHI) ? ii + 2 : ii + 1, f.N0 - 1);
-	    const int j0 = (v & REACH_YLO) ? max(jj - 1, 0) : jj, j1 = min((v & REACH_YHI) ? jj + 2 : jj + 1, f.N1 - 1);
-	    for (int c = c0; c <= c1; c++)
-	      for (int i = i0; i <= i1; i++)
-		for (int j = j0; j <= j1; j++)
-		  nodes[((long) c * f.N0 + i) * f.N1 + j] = 1;
+	    unsigned int word = h == 0 ? quad.x : h == 1 ? quad.y : h == 2 ? quad.z : quad.w;
+	    if (!word) continue;
+	    for (int q = 0; q < 4; q++, word >>= 8)
+	      {
+		const unsigned int v = word & 0xffu;
+		if (!v) continue;
+		const unsigned int t = 16u * w + 4u * h + q;
+		const int cc = (int) (t / P), r = (int) (t - (unsigned int) cc * P), ii = r / (int) N1, jj = r - ii * (int) N1;
+		if (cc >= nch) continue;
+		const int c0 = (v & REACH_ZLO) ? max(cc - 1, 0) : cc, c1 = (v & REACH_ZHI) ? min(cc + 1, nch - 1) : cc;
+		const int i0 = (v & REACH_XLO) ? max(ii - 1, 0) : ii, i1 = min((v & REACH_XHI) ? ii + 2 : ii + 1, f.N0 - 1);
+		const int j0 = (v & REACH_YLO) ? max(jj - 1, 0) : jj, j1 = min((v & REACH_YHI) ? jj + 2 : jj + 1, f.N1 - 1);
+		for (int c = c0; c <= c1; c++)
+		  for (int i = i0; i <= i1; i++)
+		    for (int j = j0; j <= j1; j++)
+		      nodes[((long) c * f.N0 + i) * f.N1 + j] = 1;
+	      }
 	  }
       }
   }
