@@ -74,7 +74,7 @@ struct MithraGpu
   double*         d_stage;                /* AoS staging of the field transfers (field_stage)              */
   size_t          stage_bytes;
   bool            stream_configured[2][2][3]; /* stencil_stream<NSFD, T, .., FACES>: dynamic shared memory limit raised on this device */
-  int             face_slots[3];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
+  int             face_nodes[2];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
   Box*            d_jbox;
   unsigned int*   d_done;
 
@@ -356,8 +356,8 @@ static int preload_kernels ()
   #define PL(k) do { cudaError_t r_ = preload(k); if (r_ != cudaSuccess) e = r_; } while (0)
   PL(aos_to_planar); PL(planar_to_aos); PL(aos_to_particles); PL(particles_to_aos); PL(set_box); PL(make_eb_box);
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
-  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8, false>)); PL((stencil_stream<false, 512, 8, false>)); PL((stencil_stream<true, 512, 8, true>)); PL((stencil_stream<false, 512, 8, true>));
-  PL((stencil_stream<true, 480, 8, false>)); PL((stencil_stream<false, 480, 8, false>)); PL((stencil_stream<true, 448, 8, true>)); PL((stencil_stream<false, 448, 8, true>)); PL((stencil_stream<true, 672, 16, true>)); PL((stencil_stream<false, 672, 16, true>));
+  PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8, false>)); PL((stencil_stream<false, 512, 8, false>));
+  PL((stencil_stream<true, 480, 8, false>)); PL((stencil_stream<false, 480, 8, false>)); PL((stencil_stream<true, 448, 8, true>)); PL((stencil_stream<false, 448, 8, true>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
@@ -430,7 +430,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       }
   }
   h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
-  memset(h->stream_configured, 0, sizeof(h->stream_configured)); h->face_slots[0] = h->face_slots[1] = h->face_slots[2] = -1;
+  memset(h->stream_configured, 0, sizeof(h->stream_configured)); h->face_nodes[0] = h->face_nodes[1] = -1;
   h->d_stage = 0; h->stage_bytes = 0;
   CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
   CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
@@ -1074,35 +1074,36 @@ template <bool NSFD, bool FACES, int T, int NB>
 static bool launch_stencil_stream_t (MithraGpu* h, bool skiprim)
 {
   const FieldDev& f = h->fd;
-  constexpr int slot = (T == 512) ? 1 : (T == 672) ? 2 : 0;
+  constexpr int slot = (T == 512) ? 1 : 0;
   static const int KC = getenv("MITHRA_STENCIL_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_STENCIL_KC")))) : 64;   /* <= 64: source_planes */
-  if (FACES && h->face_slots[slot] < 0) h->face_slots[slot] = stencil_stream_face_slots(f.N0, f.N1, T);
-  const int NR = FACES ? h->face_slots[slot] : 0, WM = FACES ? stencil_stream_m_width(f.N0, f.N1, T) : 0;
-  const size_t smem = stencil_stream_smem(T, f.N1, NB, FACES, NR, WM);
-  /* two CTAs per SM (tiles of up to 512 nodes) or one with a deeper ring                                        */
-  if (smem > (size_t) (T > 512 ? 226 : FACES ? 112 : 200) * 1024) return false;
+  if (FACES)
+    {
+      /* a lane of the face warp for every node next to a y face                                                   */
+      if (h->face_nodes[slot] < 0) h->face_nodes[slot] = stencil_stream_face_nodes(f.N0, f.N1, T);
+      if (h->face_nodes[slot] > 32) return false;
+    }
+  const size_t smem = stencil_stream_smem(T, f.N1, NB, FACES);
+  if (smem > (size_t) (FACES ? 112 : 200) * 1024) return false;      /* with the faces: two CTAs per SM or not at all     */
   /* the attribute belongs to the device: one process may drive several (one handle per slab)                */
   if (!h->stream_configured[NSFD][FACES][slot])
     {
-      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB, FACES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB, FACES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
       h->stream_configured[NSFD][FACES][slot] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB, FACES><<<grid, T + (FACES ? 64 : 32), smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h), NR, WM);
+  stencil_stream<NSFD, T, NB, FACES><<<grid, T + (FACES ? 64 : 32), smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h));
   return true;
 }
 
 /* Tile sizes: the consumer loop must not spill (a reload from local memory in it costs more than a plane of the march), and
- * two CTAs share an SM: 480 consumers + the service warp leave 64 registers per thread.
- * MITHRA_STREAM_T=512: the 512-node tiles of round 1 (56 registers, a few spilled words) for comparison;
- * MITHRA_STREAM_T=704: one CTA per SM with a ring of 16 stages (experiment).                                           */
+ * two CTAs share an SM: 480 consumers + the producer warp leave 64 registers per thread, so do 448 + the producer and
+ * the face warp.  MITHRA_STREAM_T=512: the 512-node tiles of round 1 (56 registers, a few spilled words) for comparison. */
 template <bool NSFD, bool FACES>
 static bool launch_stencil_stream_as (MithraGpu* h, bool skiprim)
 {
   if (getenv("MITHRA_STENCIL_PLAIN")) return false;
   static const int tsel = getenv("MITHRA_STREAM_T") ? atoi(getenv("MITHRA_STREAM_T")) : 0;
-  if (tsel == 512) return launch_stencil_stream_t<NSFD, FACES, 512, 8>(h, skiprim);
-  if (tsel == 704 && FACES && launch_stencil_stream_t<NSFD, FACES, 672, 16>(h, skiprim)) return true;
+  if (tsel == 512 && !FACES) return launch_stencil_stream_t<NSFD, FACES, 512, 8>(h, skiprim);
   return launch_stencil_stream_t<NSFD, FACES, FACES ? 448 : 480, 8>(h, skiprim);
 }
 
@@ -1183,7 +1184,7 @@ static int field_update_potentials (MithraGpu* h)
     PhaseTimer t(h, PH_BOUNDARY);
     if (rim)
       {
-	if (faces && !MITHRA_STREAM_XFACES)
+	if (faces)
 	  {
 	    /* stencil_stream has done the y faces; the x faces are whole rows: one coalesced pass                       */
 	    const long nface = 2L * (f.N1 - 2) * (f.np - 1 - f.kb) * f.ncomp;

@@ -162,63 +162,23 @@ namespace mithra
 		 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
   }
 
-  /* for a warp whose wait is on the critical path of the whole CTA: no back-off between the tries                      */
-  #ifndef MITHRA_SVC_SPIN
-  #define MITHRA_SVC_SPIN 1
-  #endif
-  #ifndef MITHRA_SVC_EARLY
-  #define MITHRA_SVC_EARLY 1
-  #endif
-  __device__ __forceinline__ void mbar_wait_now (unsigned long long* b, unsigned parity)
-  {
-  #if MITHRA_SVC_SPIN
-    unsigned done;
-    do
-      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-		   : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    while (!done);
-  #else
-    mbar_wait(b, parity);
-  #endif
-  }
   __device__ __forceinline__ void mbar_arrive (unsigned long long* b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
 
-  /* 1: the consumers of rows 1 and N0-2 also do the x faces behind them (measured: the two tiles that hold those rows then
-   * run at less than half speed, 0.6 ms per FEL-LCLS step); 0: boundary_faces does the x faces afterwards (0.2 ms)         */
-  #ifndef MITHRA_STREAM_XFACES
-  #define MITHRA_STREAM_XFACES 0
-  #endif
-  /* shared memory of one CTA: a header (mbarriers, FACES: the counters of the task list), then NB stages, each
-   * (T + 2 H) doubles of A^n, T + 2 HM doubles of A^{n-1} and -- FACES -- NR hand-over slots; FACES: then the task list.
-   * H: halo of the A^n stage, N1e (FACES: N1e + 2); HM: 0 (FACES: H)                                                       */
-  static inline size_t stencil_stream_smem (int T, int N1, int NB, bool faces = false, int NR = 0, int WM = 0)
+  /* shared memory of one CTA: a header (mbarriers, FACES: the counters of the face list), then NB stages, each
+   * (T + 2 H) doubles of A^n and T + 2 HM doubles of A^{n-1}; FACES: then the face list.
+   * H: halo of the A^n stage, N1e (FACES: N1e + 2); HM: 0 (FACES: 2)                                                       */
+  static inline size_t stencil_stream_smem (int T, int N1, int NB, bool faces = false)
   {
     const int N1e = (N1 + 1) & ~1;
     if (!faces) return 256 + (size_t) NB * ( (size_t) T + 2 * N1e + T ) * sizeof(double);
-    const int H = N1e + 2;
-    return 1024 + (size_t) NB * ( (size_t) T + 2 * H + WM + NR ) * sizeof(double) + (size_t) 2 * NR * sizeof(int);
-  }
-
-  /* FACES: doubles of the A^{n-1} part of a stage -- the tile, two more either side, and a row (H = N1e + 2) instead on the
-   * side where the tile holds nodes of row 1 / N0-2 (their x face nodes may lie outside of it): the widest over the tiles */
-  static inline int stencil_stream_m_width (int N0, int N1, int T)
-  {
-    const long P = (long) N0 * N1;
-    const int H = ((N1 + 1) & ~1) + 2;
-    int worst = 0;
-    for (long p0 = 0; p0 < P; p0 += T)
-      {
-	const int ifirst = (int) (p0 / N1), ilast = (int) ((std::min(p0 + T, P) - 1) / N1);
-	const int w = T + ( (MITHRA_STREAM_XFACES && ifirst <= 1 && 1 <= ilast) ? H : 2 ) + ( (MITHRA_STREAM_XFACES && ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 );
-	if (w > worst) worst = w;
-      }
-    return worst;
+    return 1024 + (size_t) NB * ( 2 * (size_t) T + 2 * (N1e + 2) + 4 ) * sizeof(double) + 32 * sizeof(int);
   }
 
   /* the nodes of a tile that sit next to a y face (the inward neighbours n of its nodes): their largest number over the
-   * tiles of T consecutive in-plane positions -- the hand-over slots a CTA of stencil_stream<.., FACES> needs            */
-  static inline int stencil_stream_face_slots (int N0, int N1, int T)
+   * tiles of T consecutive in-plane positions; stencil_stream<.., FACES> gives each of them a lane of its face warp, so
+   * it takes meshes with at most 32                                                                                   */
+  static inline int stencil_stream_face_nodes (int N0, int N1, int T)
   {
     const long P = (long) N0 * N1;
     int worst = 0;
@@ -232,7 +192,7 @@ namespace mithra
 	  }
 	if (n > worst) worst = n;
       }
-    return (worst + 1) & ~1;
+    return worst;
   }
 
   /* the 5-point cross of one plane around the thread's node                                                    */
@@ -269,25 +229,24 @@ namespace mithra
 	   B[4] * ( n2p + n2m + s2p + s2m );
   }
 
-  /* T consumer threads (one in-plane position each) + one producer warp (+ one face warp)
+  /* T consumer threads (one in-plane position each) + one producer warp (+ FACES: one face warp)
    *
-   * FACES (meshes without a TF/SF seed; N0, N1, np >= 8): the x and y absorbing faces (fdtd.cpp:377-520) are done here as
-   * well, and rim_update is not launched at all.  A face node s needs A+ of its inward neighbour n -- computed by a
-   * consumer thread of this very CTA -- and, of A^n and A^{n-1}, only values the ring already holds: s, n and their
-   * in-plane neighbours in plane k, s and n in the planes k-1 and k+1.  Doing the face in the consumer thread of n puts one
-   * or two face lanes into most warps of a row-major tile, and every such warp then runs the face code (round 1: +1 ms);
-   * so the faces get a WARP OF THEIR OWN: the consumers of the nodes n drop their result for plane k into a slot of the
-   * stage they have just taken (plane k+1) and all consumer warps arrive on `rdone` of that stage; the face warp waits
-   * there, takes the 13 other values out of the stages of the planes k-1, k, k+1 (it holds the oldest of them back:
-   * `empty` counts it in), and stores A+_s.  The faces cost a CTA about one warp-step per plane instead of a DRAM round
-   * trip over sectors that hold 1-4 rim nodes each (rim_update: 6.6 GB per step on FEL-LCLS for 2.8 GB of rim nodes).
-   * Stages carry two more doubles of halo (the in-plane neighbours of a face node one row off the tile) and the A^{n-1}
-   * stage the row of face nodes that lies outside the tile, where there is one.  Same operations in the same order as
-   * face_update: bit-identical.
-   * Shared memory is addressed as 32-bit shared-space addresses throughout (one base per stage, constant offsets): the
-   * consumer loop has to fit 56 registers without a spill -- a reload from local memory in it costs more than a plane.  */
+   * FACES (meshes without a TF/SF seed; N0, N1, np >= 8; at most 32 nodes next to a y face per tile): the y absorbing
+   * faces (fdtd.cpp:449-520) are done here as well, the x faces -- whole rows -- by one coalesced pass of boundary_faces
+   * afterwards, and rim_update is not launched at all.  A y face node s needs A+ of its inward neighbour n and, of A^n
+   * and A^{n-1}, only values the ring holds anyway: s, n and their in-plane neighbours in plane k, s and n in the planes
+   * k-1 and k+1 -- nearly all of them in the cross of n.  Doing the face in the consumer thread of n puts one or two
+   * face lanes into most warps of a row-major tile, and every such warp then runs the face code (round 1: +1 ms); so the
+   * nodes next to a y face get a WARP OF THEIR OWN: lane l of the face warp owns the l-th such node of the tile as a
+   * consumer would (its consumer thread idles) -- interior value with the source term, store -- and then the face node
+   * behind it from the same crosses plus three more values of the stage of plane k.  The face warp is one more consumer
+   * to the ring (`empty` counts it in); nothing is handed over between warps.  rim_update moved 6.6 GB per FEL-LCLS step
+   * for 2.8 GB of rim nodes; here the faces add nothing to the traffic of the sweep.  Stages carry two more doubles of
+   * halo (the in-plane neighbours of a face node one row off the tile; the face node across the end of the tile in
+   * A^{n-1}).  Same operations in the same order as face_update: bit-identical.
+   * Shared memory is addressed as 32-bit shared-space addresses (one base per stage, constant offsets): the consumer loop
+   * has to fit its registers without a spill -- a reload from local memory in it costs more than a plane.             */
   __device__ __forceinline__ double lds_f64 (unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
-  __device__ __forceinline__ void   sts_f64 (unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
   __device__ __forceinline__ void mbar_wait_a (unsigned b, unsigned parity)
   {
     unsigned done;
@@ -302,16 +261,11 @@ namespace mithra
   __device__ __forceinline__ void mbar_arrive_a (unsigned b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory"); }
 
-  #ifdef MITHRA_DBG_NORDONE
-  #define MITHRA_DBG_NORDONE_V 1
-  #else
-  #define MITHRA_DBG_NORDONE_V 0
-  #endif
   template <bool NSFD, int T, int NB, bool FACES>
-  __global__ void __launch_bounds__(T + (FACES ? 64 : 32), (T > 512 ? 1 : 2))
+  __global__ void __launch_bounds__(T + (FACES ? 64 : 32), 2)
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
 		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
-		  const unsigned char* __restrict__ jmask, int NR, int WMF)
+		  const unsigned char* __restrict__ jmask)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 4 && NB <= 16, "stages: a power of two");
     static_assert(T % 32 == 0 && T <= 1024, "whole consumer warps, one prefix entry per lane of the face warp");
@@ -320,25 +274,19 @@ namespace mithra
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned long long* full  = reinterpret_cast<unsigned long long*>(smraw);
     unsigned long long* empty = full + NB;
-    unsigned long long* rdone = empty + NB;               /* FACES: the results of plane k are in the slots of stage k+1 */
-    int* wc = reinterpret_cast<int*>(smraw + 384);        /* FACES: [5][NW] counts -> prefixes, then the task count     */
+    int* wc = reinterpret_cast<int*>(smraw + 512);        /* FACES: [NW] counts -> prefixes, then the number of faces   */
     const int  N0 = f.N0, N1 = f.N1, N1e = (N1 + 1) & ~1;
-    const int  H  = FACES ? N1e + 2 : N1e;                /* doubles of halo either side of an A^n stage               */
-    const int  W  = T + 2 * H;                            /* doubles of the A^n part of a stage             */
-    /* the A^{n-1} part: the tile; FACES: two more either side (a y face node across the end of the tile), a whole row H
-     * on the side where the tile holds nodes of row 1 / N0-2 whose x face nodes lie outside of it (WMF: the widest tile)  */
-    const int  p0  = blockIdx.x * T;
-    const int  ifirst = p0 / N1, ilast = (min(p0 + T, f.P) - 1) / N1;
-    const int  HM  = FACES ? ( (MITHRA_STREAM_XFACES && ifirst <= 1 && 1 <= ilast) ? H : 2 ) : 0;                  /* low side  */
-    const int  HMh = FACES ? ( (MITHRA_STREAM_XFACES && ifirst <= N0 - 2 && N0 - 2 <= ilast) ? H : 2 ) : 0;        /* high side */
-    const int  WM  = FACES ? WMF : T;
-    const int  S  = W + WM + (FACES ? NR : 0);            /* doubles of a stage                                        */
+    const int  H  = FACES ? N1e + 2 : N1e;                /* doubles of halo either side of the A^n part of a stage    */
+    const int  W  = T + 2 * H;                            /* doubles of the A^n part                        */
+    const int  HM = FACES ? 2 : 0, WM = T + 2 * HM;       /* the same for A^{n-1}                                      */
+    const int  S  = W + WM;                               /* doubles of a stage                                        */
     double* st = reinterpret_cast<double*>(smraw + HDR);
-    int*    tasks = reinterpret_cast<int*>(st + (size_t) NB * S);         /* FACES: node | type << 12 | slot << 16     */
+    int*    faces = reinterpret_cast<int*>(st + (size_t) NB * S);         /* FACES: node | high side << 12              */
     const unsigned bars = smem_u32(smraw), st0 = smem_u32(st);
     const unsigned SB = (unsigned) S * 8u;                /* bytes of a stage                                          */
 
     const int  tid = threadIdx.x, c = blockIdx.z;
+    const int  p0  = blockIdx.x * T;
     const int  ks  = f.kb + blockIdx.y * KC, ke = min(ks + KC, f.np - 1);      /* planes ks .. ke-1            */
     if (ks >= ke) return;
     const long Pp = f.Pp, cb = (long) c * f.np * Pp;
@@ -346,157 +294,79 @@ namespace mithra
 
     if (tid == 0)
       {
-	for (int s = 0; s < NB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW + (FACES ? 1 : 0)); if (FACES) mbar_init(&rdone[s], NW); }
+	for (int s = 0; s < NB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW + (FACES ? 1 : 0)); }
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
 
-    /* the node of a consumer thread                                                                             */
-    const int  p = p0 + tid;
-    const int  i = p / N1, j = p - i * N1;
+    /* the node of a thread: a consumer's is its position in the tile                                            */
+    int  node = tid;
+    int  p = p0 + node, i = p / N1, j = p - i * N1;
     /* skiprim: the two outermost interior node layers in x and y belong to rim_update                          */
     const int  rim = (skiprim && !FACES) ? 2 : 0;
-    const bool interior = (tid < T && p < f.P && i >= 1 + rim && i <= N0 - 2 - rim && j >= 1 + rim && j <= N1 - 2 - rim);
+    bool interior = (tid < T && p < f.P && i >= 1 + rim && i <= N0 - 2 - rim && j >= 1 + rim && j <= N1 - 2 - rim);
+    int  fs = 0;                                          /* FACES: offset in bytes of the y face node behind the node */
 
-    /* FACES: slot of every node next to a face (in node order) and the list of the faces by type (x low, x high, y low,
-     * y high; each in node order so that the stores of an x face are contiguous): ballots, per-warp counts, one scan by
-     * the face warp, and every consumer writes its own entries                                                      */
-    int myslot = -1;
     if (FACES)
       {
+	/* the nodes next to a y face, in node order, one per lane of the face warp: ballots, per-warp counts, a scan    */
 	const unsigned below = (1u << (tid & 31)) - 1u;
 	const int warp = tid >> 5;
-	unsigned bal[3]; bool on[3];
-	on[1] = interior && j == 1; on[2] = interior && j == N1 - 2; on[0] = on[1] || on[2];
-	if (tid < T)
-	  {
-	    #pragma unroll
-	    for (int e = 0; e < 3; e++) { bal[e] = __ballot_sync(0xffffffffu, on[e]); if ((tid & 31) == 0) wc[e * NW + warp] = __popc(bal[e]); }
-	  }
+	const bool on = interior && (j == 1 || j == N1 - 2);
+	unsigned bal = 0u;
+	if (tid < T) { bal = __ballot_sync(0xffffffffu, on); if ((tid & 31) == 0) wc[warp] = __popc(bal); }
 	__syncthreads();
 	if (tid >= T + 32)
 	  {
-	    /* exclusive prefixes: the slots over wc[0][.], the tasks over wc[1..2][.] (type-major); NW <= 32            */
 	    const int lane = tid & 31;
 	    int v = lane < NW ? wc[lane] : 0, x = v;
 	    #pragma unroll
 	    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
 	    if (lane < NW) wc[lane] = x - v;
-	    int carry = 0;
-	    #pragma unroll
-	    for (int e = 1; e < 3; e++)
-	      {
-		v = lane < NW ? wc[e * NW + lane] : 0; x = v;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-		if (lane < NW) wc[e * NW + lane] = carry + x - v;
-		carry += __shfl_sync(0xffffffffu, x, 31);
-	      }
-	    if (lane == 0) wc[3 * NW] = carry;
+	    if (lane == 31) wc[NW] = x;
 	  }
 	__syncthreads();
-	if (tid < T && on[0])
+	if (on) { faces[wc[warp] + __popc(bal & below)] = tid | ((j == 1 ? 0 : 1) << 12); interior = false; }    /* the face warp's */
+	__syncthreads();
+	if (tid >= T + 32)
 	  {
-	    myslot = wc[warp] + __popc(bal[0] & below);
-	    #pragma unroll
-	    for (int e = 1; e < 3; e++)
-	      if (on[e]) tasks[wc[e * NW + warp] + __popc(bal[e] & below)] = tid | ((e - 1) << 12) | (myslot << 16);
+	    const int lane = tid & 31;
+	    if (lane < wc[NW])
+	      {
+		const int w = faces[lane];
+		node = w & 0xfff; fs = (w >> 12) ? 8 : -8;
+		p = p0 + node; i = p / N1; j = p - i * N1; interior = true;
+	      }
+	    else node = 0;
 	  }
       }
-    __syncthreads();
+    else __syncthreads();
 
-    if (tid >= T)
+    if (tid >= T && tid < T + 32)
       {
-	/* ---- service warp: lane 0 feeds the ring; FACES: all lanes do the y faces -------------------------------- */
-	const int lane = tid & 31;
-	/* source range of an A^n stage, clipped to the plane; both ends are even                              */
+	/* ---- producer warp: one lane feeds the ring -------------------------------------------------------- */
+	if (tid != T) return;
+	/* source range of the A^n part of a stage, clipped to the plane; both ends are even                          */
 	const long lo = max(0L, (long) p0 - H), hi = min(Pp, (long) p0 + T + H);
 	const int  dstoff = (int) (lo - (p0 - H));
 	const unsigned bytesA = (unsigned) ((hi - lo) * sizeof(double));
-	const long mlo = max(0L, (long) p0 - HM), mhi = min(Pp, (long) p0 + T + HMh);
+	const long mlo = max(0L, (long) p0 - HM), mhi = min(Pp, (long) p0 + T + HM);
 	const int  dstoffM = W + (int) (mlo - (p0 - HM));
 	const unsigned bytesM = (unsigned) ((mhi - mlo) * sizeof(double));
 	const double* srcA = an   + cb + (long) (ks - 1) * Pp + lo;
 	const double* srcM = anm1 + cb + (long) (ks - 1) * Pp + mlo;
-	/* plane of ring position q into its stage (the stage is free)                                                */
-	auto produce = [&] (int q) {
-	  const int s = q & (NB - 1);
-	  const bool needM = (q >= 1 && q < nq - 1);       /* A^{n-1} rides along for the planes that are updated */
-	  mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
-	  bulk_g2s(st + (size_t) s * S + dstoff, srcA + (long) q * Pp, bytesA, &full[s]);
-	  if (needM) bulk_g2s(st + (size_t) s * S + dstoffM, srcM + (long) q * Pp, bytesM, &full[s]); };
-
-	if (tid < T + 32)
+	for (int q = 0; q < nq; q++, srcA += Pp, srcM += Pp)
 	  {
-	    /* ---- producer warp: one lane feeds the ring ------------------------------------------------------ */
-	    if (lane != 0) return;
-	    for (int q = 0; q < nq; q++)
-	      {
-		if (q >= NB) mbar_wait_now(&empty[q & (NB - 1)], (unsigned) (((q / NB) - 1) & 1));
-		produce(q);
-	      }
-	    return;
-	  }
-
-	/* ---- FACES, face warp: per plane k it waits for the consumers' A+ of the nodes next to a y face, does those faces
-	 * from the stages of the planes k-1, k, k+1 and hands the oldest stage it held back (`empty` counts it in)          */
-	const int nt = wc[3 * NW];
-	mbar_wait(&full[0], 0u); mbar_wait(&full[1], 0u);           /* the planes ks-1, ks                         */
-	double* out = anp1 + cb + (long) ks * Pp + p0;
-	/* one face: node n of the tile, its face node s = n -+ 1 (type 0 / 1), the slot with A+_n; zn, zs: A_n and A_s of
-	 * plane k-1 on entry, of plane k on return                                                                    */
-	auto face = [&] (int w, const double* Sk, const double* Sp, const double* Mk, const double* Rk, double& zn, double& zs) {
-	  const int n = w & 0xfff, s = n + (((w >> 12) & 1) ? 1 : -1), slot = w >> 16;
-	  const double apn = Rk[slot], ams = Mk[s], amn = Mk[n];
-	  const double as_ = Sk[s], an_ = Sk[n];
-	  const double n1p = Sk[n + N1], n1m = Sk[n - N1], s1p = Sk[s + N1], s1m = Sk[s - N1];
-	  const double n2p = Sp[n], n2m = zn, s2p = Sp[s], s2m = zs;
-	  out[s] = face_value(f.cB, ams, apn, amn, as_, an_, n1p, n1m, s1p, s1m, n2p, n2m, s2p, s2m);
-	  zn = an_; zs = as_; };
-	/* The usual case, at most a face per lane: its task is decoded once and the two values of plane k-1 it needs are the
-	 * ones it read as plane k one step earlier -- kept in registers, so the warp needs the stages of the planes k and k+1
-	 * only and hands stage k back at the end of step k (a plane of look-ahead more for the ring).  More faces than lanes
-	 * (rows shorter than 30 nodes): the planes k-1 are read from their stage, which is handed back a step later.        */
-	const bool early = MITHRA_SVC_EARLY && nt <= 32;
-	const int w0 = lane < nt ? tasks[lane] : -1;
-	double zn = 0.0, zs = 0.0;
-	if (w0 >= 0) { const int n = w0 & 0xfff, s = n + (((w0 >> 12) & 1) ? 1 : -1); zn = st[H + n]; zs = st[H + s]; }   /* plane ks-1: stage 0 */
-	auto recycle = [&] (int qr) { mbar_arrive(&empty[qr & (NB - 1)]); };      /* hand the stage of ring position qr back */
-	for (int k = ks, q = 1; k < ke; k++, q++, out += Pp)          /* q: ring position of plane k                 */
-	  {
-	    const int sp = (q + 1) & (NB - 1);
-	    #ifndef MITHRA_DBG_NORDONE
-	    mbar_wait_now(&rdone[sp], (unsigned) (((q - 1) / NB) & 1));
-	    #endif
-	    mbar_wait_now(&full[sp], (unsigned) (((q + 1) / NB) & 1));  /* complete: the consumers have taken it       */
-	    const double* Sk = st + (size_t) (q & (NB - 1)) * S + H;
-	    const double* Sp = st + (size_t) sp * S + H;
-	    const double* Mk = Sk + (W - H) + HM;
-	    const double* Rk = Sp + (W - H) + WM;
-	    #ifndef MITHRA_DBG_NOFACE
-	    if (w0 >= 0) face(w0, Sk, Sp, Mk, Rk, zn, zs);
-	    #endif
-	    if (!early)
-	      {
-		const double* Sm = st + (size_t) ((q - 1) & (NB - 1)) * S + H;
-		for (int t = lane + 32; t < nt; t += 32)
-		  {
-		    const int w = tasks[t], n = w & 0xfff, s = n + (((w >> 12) & 1) ? 1 : -1);
-		    double yn = Sm[n], ys = Sm[s];
-		    face(w, Sk, Sp, Mk, Rk, yn, ys);
-		  }
-	      }
-	    __syncwarp();
-	    if (lane == 0)
-	      {
-		if (early) { if (q == 1) recycle(0); recycle(q); }
-		else       recycle(q - 1);
-	      }
-	    __syncwarp();
+	    const int s = q & (NB - 1);
+	    if (q >= NB) mbar_wait(&empty[s], (unsigned) (((q / NB) - 1) & 1));
+	    const bool needM = (q >= 1 && q < nq - 1);     /* A^{n-1} rides along for the planes that are updated */
+	    mbar_expect_tx(&full[s], bytesA + (needM ? bytesM : 0u));
+	    bulk_g2s(st + (size_t) s * S + dstoff, srcA, bytesA, &full[s]);
+	    if (needM) bulk_g2s(st + (size_t) s * S + dstoffM, srcM, bytesM, &full[s]);
 	  }
 	return;
       }
 
-    /* ---- consumers -------------------------------------------------------------------------------------- */
+    /* ---- consumers (and the face warp, whose lanes are consumers of the nodes next to a y face) -------------- */
     const bool lane0 = (tid & 31) == 0;
     const double as = (c < 3) ? f.a[4] : f.a[5];
     unsigned long long srcon;                             /* bit 0 = the next plane                          */
@@ -505,25 +375,20 @@ namespace mithra
     double* const apc = anp1 + cb + (long) ks * Pp + p0;
     double* const jnc = jn   + cb + (long) ks * Pp + p0;
     const unsigned PpU = (unsigned) Pp;
-    unsigned off = (unsigned) tid;
-    const unsigned mine = st0 + (unsigned) (H + tid) * 8u;                    /* this node in the A^n part of stage 0  */
+    unsigned off = (unsigned) node;
+    const unsigned mine = st0 + (unsigned) (H + node) * 8u;                   /* this node in the A^n part of stage 0  */
     const unsigned n1b  = (unsigned) N1 * 8u;
     const unsigned dM   = (unsigned) (W - H + HM) * 8u;                       /* from there to its A^{n-1} value       */
-    const unsigned dR   = (unsigned) (W - H - tid + WM + myslot) * 8u;        /* FACES: and to its hand-over slot      */
-    /* FACES: the x face node behind this node (rows 1 and N0-2: whole warps, so the consumers do these themselves from
-     * the crosses they hold and three more values of the stage of plane k, which is still theirs): its offset in bytes  */
-    const int dsx = (FACES && interior && MITHRA_STREAM_XFACES) ? ( i == 1 ? -(int) n1b : i == N0 - 2 ? (int) n1b : 0 ) : 0;
 
     int q = 0;                                            /* ring position of the next plane to take          */
     /* take plane q out of the ring: its cross; returns the node's address in that stage.  The stage is handed back one
      * step later, after the A^{n-1} value that came with it has been read where it is needed (one live double less)      */
-    auto take = [&] (Cross& x) -> unsigned {
+    auto take = [&] (Cross& x) {
       const unsigned s = (unsigned) q & (NB - 1);
       mbar_wait_a(bars + s * 8u, (unsigned) ((q / NB) & 1));
       const unsigned a = mine + s * SB;
       x.c = lds_f64(a); x.xp = lds_f64(a + n1b); x.xm = lds_f64(a - n1b); x.yp = lds_f64(a + 8u); x.ym = lds_f64(a - 8u);
-      ++q;
-      return a; };
+      ++q; };
     /* hand the stage of ring position qq back (every lane of the warp has read what it needs of it)                     */
     auto release = [&] (unsigned qq) { __syncwarp(); if (lane0) mbar_arrive_a(bars + NB * 8u + (qq & (NB - 1)) * 8u); };
 
@@ -550,23 +415,17 @@ namespace mithra
 	    srcn = __ldg(jq);                                                                                   \
 	    asm volatile("prefetch.global.L2 [%0];" :: "l"(jq + 2u * PpU));   /* pencils are 8 planes tall: two planes on, the load then hits L2 */ \
 	  }                                                                                                     \
-	const unsigned a = take(Pn);                                                                            \
+	take(Pn);                                                                                               \
 	const unsigned az = mine + (((unsigned) q - 2u) & (NB - 1)) * SB;        /* the node in the stage of plane k */ \
 	const double vm1 = lds_f64(az + dM);                                             /* A^{n-1} of plane k */    \
 	const double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, f.a[0], f.a[1], f.a[2], f.a[3], as, f.alpha, f.beta); \
-	if (FACES && !MITHRA_DBG_NORDONE_V)                      /* A+ of plane k rides in the stage of plane k+1 */ \
-	  {                                                                                                     \
-	    if (myslot >= 0) sts_f64(a + dR, r);                                                                \
-	    __syncwarp();                                                                                       \
-	    if (lane0) mbar_arrive_a(bars + 2 * NB * 8u + (((unsigned) q - 1u) & (NB - 1)) * 8u);               \
-	  }                                                                                                     \
 	if (interior) apc[off] = r;                                                                             \
-	if (FACES && MITHRA_STREAM_XFACES && dsx != 0)                                                          \
+	if (FACES && fs != 0)                                            /* face warp: the y face node behind */  \
 	  {                                                                                                     \
-	    const bool lo = dsx < 0;                                                                            \
-	    const double ams = lds_f64(az + dsx + dM), s1p = lds_f64(az + dsx + 8u), s1m = lds_f64(az + dsx - 8u); \
-	    apc[(int) off + (dsx >> 3)] = face_value(f.bB, ams, r, vm1, lo ? Z.xm : Z.xp, Z.c, Z.yp, Z.ym, s1p, s1m, \
-						      Pn.c, M.c, lo ? Pn.xm : Pn.xp, lo ? M.xm : M.xp);           \
+	    const bool lo = fs < 0;                                                                             \
+	    const double ams = lds_f64(az + fs + dM), s1p = lds_f64(az + fs + n1b), s1m = lds_f64(az + fs - n1b); \
+	    apc[(int) off + (fs >> 3)] = face_value(f.cB, ams, r, vm1, lo ? Z.ym : Z.yp, Z.c, Z.xp, Z.xm, s1p, s1m, \
+						     Pn.c, M.c, lo ? Pn.ym : Pn.yp, lo ? M.ym : M.yp);           \
 	  }                                                                                                     \
 	release((unsigned) q - 2u);                                                                             \
 	if (src != 0.0) jnc[off] = src * 0.0;                    /* a (signed) zero, ordered after the load */ \
