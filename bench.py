@@ -513,12 +513,15 @@ def main():
     cell_b, npush = BYTES_PER_CELL[sc], npart_local * pl.n_update_bunch
     algo_step = cell_b * nodes_local + BYTES_PER_PUSH * npush + 56 * npart_local          # bytes one field step must move
     achieved_step = algo_step / (step_ms * 1e-3) / 1e9
-    # the dominant kernel, stencil_stream: one launch advances the nodes that are not on the rim (the two outer interior
-    # layers in x and y belong to rim_update, timed under "boundary"), (N0-6)(N1-6) nodes of each of the np-2 updated planes
+    # the dominant kernel, stencil_stream.  Seeded jobs: one launch advances the nodes that are not on the rim (the two outer
+    # interior layers in x and y belong to rim_update, timed under "boundary"), (N0-6)(N1-6) nodes of each of the np-2 updated
+    # planes.  Jobs without a seed: every interior node and the y faces, (N0-2) N1 nodes per plane (the x faces are the pass of
+    # boundary_faces timed under "boundary").
     stencil_ms = per["stencil"]
     rim = pl.N0 >= 8 and pl.N1 >= 8 and pl.np >= 8
     planes = pl.np - 2
-    stencil_nodes = ((pl.N0 - 6) * (pl.N1 - 6) if rim else (pl.N0 - 2) * (pl.N1 - 2)) * planes
+    faces_fused = rim and not pl.seed_enabled
+    stencil_nodes = ((pl.N0 - 2) * pl.N1 if faces_fused else (pl.N0 - 6) * (pl.N1 - 6) if rim else (pl.N0 - 2) * (pl.N1 - 2)) * planes
     stencil_bytes = cell_b * stencil_nodes
     field_ms = per["stencil"] + per["boundary"]
     traffic, traffic_src = None, None
@@ -541,7 +544,7 @@ def main():
             "stencil_stream": {"ms": stencil_ms, "algorithmic_bytes": stencil_bytes, "units": stencil_nodes,
                                "achieved": gbs(stencil_bytes, stencil_ms), "frac": gbs(stencil_bytes, stencil_ms) / pk["hbm_gbs"],
                                "share_of_step": stencil_ms / max(1e-9, sum(per.values()))},
-            "field_update": {"what": "whole fieldUpdate (seed table, stencil_stream, rim_update, z shell / faces, edges, corners) over all nodes",
+            "field_update": {"what": "whole fieldUpdate (seed table, stencil_stream, rim_update or the x faces, z shell / faces, edges, corners) over all nodes",
                              "ms": field_ms, "achieved": gbs(cell_b * nodes_local, field_ms), "frac": gbs(cell_b * nodes_local, field_ms) / pk["hbm_gbs"]},
             "push_particles": {"ms": per["push"], "achieved": gbs(BYTES_PER_PUSH * npush, per["push"]), "bytes_per_push": BYTES_PER_PUSH},
             "deposit_current": {"ms": per["deposit"], "achieved": gbs(56 * npart_local, per["deposit"]), "bytes_per_particle": 56},
