@@ -74,7 +74,7 @@ struct MithraGpu
   double*         d_stage;                /* AoS staging of the field transfers (field_stage)              */
   size_t          stage_bytes;
   bool            stream_configured[2][2][3]; /* stencil_stream<NSFD, T, .., FACES>: dynamic shared memory limit raised on this device */
-  int             face_nodes[2];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
+  int             face_nodes[3];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
   Box*            d_jbox;
   unsigned int*   d_done;
 
@@ -357,12 +357,12 @@ static int preload_kernels ()
   PL(aos_to_planar); PL(planar_to_aos); PL(aos_to_particles); PL(particles_to_aos); PL(set_box); PL(make_eb_box);
   PL(sort_zero); PL(sort_count); PL(scan_chunk_sums); PL(scan_sums); PL(scan_chunks); PL(sort_permute);
   PL((stencil_interior<true, 128, 32>)); PL((stencil_interior<false, 128, 32>)); PL((stencil_stream<true, 512, 8, false>)); PL((stencil_stream<false, 512, 8, false>));
-  PL((stencil_stream<true, 480, 8, false>)); PL((stencil_stream<false, 480, 8, false>)); PL((stencil_stream<true, 448, 8, true>)); PL((stencil_stream<false, 448, 8, true>));
+  PL((stencil_stream<true, 480, 8, false>)); PL((stencil_stream<false, 480, 8, false>)); PL((stencil_stream<true, 448, 8, true>)); PL((stencil_stream<false, 448, 8, true>)); PL((stencil_stream<true, 384, 8, true, true>)); PL((stencil_stream<false, 384, 8, true, true>));
   PL(boundary_faces); PL(boundary_edges); PL(boundary_corners); PL(clear_current_box);
   PL(eval_eb_box<true>); PL(eval_eb_box<false>); PL(eval_eb_march<true>); PL(eval_eb_march<false>); PL(spread_eb_mask);
   PL(particle_box); PL(particle_cells); PL(bunch_moments); PL(push_particles<true>); PL(push_particles<false>); PL(deposit_current<true>); PL(deposit_current<false>);
   PL(screen_cross); PL(power_dft<true>); PL(power_dft<false>); PL(power_finish); PL(power_map<true>); PL(power_map<false>); PL(field_sample<true>); PL(field_sample<false>); PL(field_nodes<true>); PL(field_nodes<false>);
-  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
+  PL(seed_inject_scan); PL(seed_inject_shell); PL(seed_lines); PL(seed_xshell_rows); PL(seed_inject_zshell); PL(rim_update<true>); PL(rim_update<false>); PL(seed_initial_kernel); PL(seed_plane_table);
   PL(put_planes); PL(put_eb); PL(put_jmail); PL(add_jmail); PL(signal_flag); PL(wait_flag);
   PL(migrate_pack); PL(put_outbox); PL(fill_holes); PL(unpack_inbox);
   PL(ellipsoid_count); PL(scan_block_counts); PL(ellipsoid_write); PL(bunch_boost); PL(bunch_backproject); PL(owned_count); PL(owned_copy);
@@ -430,7 +430,7 @@ extern "C" int mithra_gpu_create (const MithraGpuParams* params, MithraGpu** out
       }
   }
   h->ip1 = 0; h->in = 1; h->im1 = 2; h->anp1_is_current = true;
-  memset(h->stream_configured, 0, sizeof(h->stream_configured)); h->face_nodes[0] = h->face_nodes[1] = -1;
+  memset(h->stream_configured, 0, sizeof(h->stream_configured)); h->face_nodes[0] = h->face_nodes[1] = h->face_nodes[2] = -1;
   h->d_stage = 0; h->stage_bytes = 0;
   CU(cudaMalloc(&h->d_jbox, sizeof(Box))); CU(cudaMalloc(&h->d_pbox, sizeof(Box))); CU(cudaMalloc(&h->d_ebox, sizeof(Box)));
   CU(cudaMalloc(&h->d_done, sizeof(unsigned int))); CU(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
@@ -1070,16 +1070,16 @@ static const unsigned char* source_mask (const MithraGpu* h)
 
 /* bulk-async plane pipeline (kernels_field.cuh stencil_stream); false when its stages do not fit in shared memory.
  * faces: the variant that also does the x and y absorbing faces (no rim_update afterwards)                         */
-template <bool NSFD, bool FACES, int T, int NB>
-static bool launch_stencil_stream_t (MithraGpu* h, bool skiprim)
+template <bool NSFD, bool FACES, int T, int NB, bool SEED>
+static bool launch_stencil_stream_t (MithraGpu* h, bool skiprim, const RimDev& rz)
 {
   const FieldDev& f = h->fd;
-  constexpr int slot = (T == 512) ? 1 : 0;
+  constexpr int slot = (T == 512) ? 1 : SEED ? 2 : 0;
   static const int KC = getenv("MITHRA_STENCIL_KC") ? std::min(64, std::max(1, atoi(getenv("MITHRA_STENCIL_KC")))) : 64;   /* <= 64: source_planes */
   if (FACES)
     {
       /* a lane of the face warp for every node next to a y face                                                   */
-      if (h->face_nodes[slot] < 0) h->face_nodes[slot] = stencil_stream_face_nodes(f.N0, f.N1, T);
+      if (h->face_nodes[slot] < 0) h->face_nodes[slot] = stencil_stream_face_nodes(f.N0, f.N1, T, SEED);
       if (h->face_nodes[slot] > 32) return false;
     }
   const size_t smem = stencil_stream_smem(T, f.N1, NB, FACES);
@@ -1087,35 +1087,37 @@ static bool launch_stencil_stream_t (MithraGpu* h, bool skiprim)
   /* the attribute belongs to the device: one process may drive several (one handle per slab)                */
   if (!h->stream_configured[NSFD][FACES][slot])
     {
-      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB, FACES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (cudaFuncSetAttribute((const void*) stencil_stream<NSFD, T, NB, FACES, SEED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
       h->stream_configured[NSFD][FACES][slot] = true;
     }
   dim3 grid((unsigned) ((f.P + T - 1) / T), (unsigned) ((f.np - 1 - f.kb + KC - 1) / KC), (unsigned) f.ncomp);
-  stencil_stream<NSFD, T, NB, FACES><<<grid, T + (FACES ? 64 : 32), smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h));
+  stencil_stream<NSFD, T, NB, FACES, SEED><<<grid, T + (FACES ? 64 : 32), smem, h->stream>>>(f, h->A[h->ip1], h->A[h->in], h->A[h->im1], h->J, h->d_jbox, KC, skiprim ? 1 : 0, source_mask(h), rz);
   return true;
 }
 
 /* Tile sizes: the consumer loop must not spill (a reload from local memory in it costs more than a plane of the march), and
  * two CTAs share an SM: 480 consumers + the producer warp leave 64 registers per thread, so do 448 + the producer and
- * the face warp.  MITHRA_STREAM_T=512: the 512-node tiles of round 1 (56 registers, a few spilled words) for comparison. */
+ * the face warp; with a seed the face warp carries the seed scalars of the next plane as well: 384 consumers, 72 registers.
+ * MITHRA_STREAM_T=512: the 512-node tiles of round 1 (56 registers, a few spilled words) for comparison. */
 template <bool NSFD, bool FACES>
-static bool launch_stencil_stream_as (MithraGpu* h, bool skiprim)
+static bool launch_stencil_stream_as (MithraGpu* h, bool skiprim, const RimDev& rz)
 {
   if (getenv("MITHRA_STENCIL_PLAIN")) return false;
   static const int tsel = getenv("MITHRA_STREAM_T") ? atoi(getenv("MITHRA_STREAM_T")) : 0;
-  if (tsel == 512 && !FACES) return launch_stencil_stream_t<NSFD, FACES, 512, 8>(h, skiprim);
-  return launch_stencil_stream_t<NSFD, FACES, FACES ? 448 : 480, 8>(h, skiprim);
+  if (tsel == 512 && !FACES) return launch_stencil_stream_t<NSFD, FACES, 512, 8, false>(h, skiprim, rz);
+  if (FACES && rz.seed) return launch_stencil_stream_t<NSFD, FACES, FACES ? 384 : 480, 8, FACES>(h, skiprim, rz);
+  return launch_stencil_stream_t<NSFD, FACES, FACES ? 448 : 480, 8, false>(h, skiprim, rz);
 }
 
 /* the interior sweep; *faces: in, the x / y faces may be fused into it (a rim path without seed); out, they were.
  * The plain-load interior kernel always covers every interior node (rim_update afterwards simply rewrites the rim) */
 template <bool NSFD>
-static void launch_stencil (MithraGpu* h, bool skiprim, bool* faces)
+static void launch_stencil (MithraGpu* h, bool skiprim, bool* faces, const RimDev& rz)
 {
   h->j_zeroed_by_update = true;
-  if (*faces && launch_stencil_stream_as<NSFD, true>(h, false)) return;
+  if (*faces && launch_stencil_stream_as<NSFD, true>(h, false, rz)) return;
   *faces = false;
-  if (launch_stencil_stream_as<NSFD, false>(h, skiprim)) return;
+  if (launch_stencil_stream_as<NSFD, false>(h, skiprim, rz)) return;
   h->j_zeroed_by_update = false;
   const FieldDev& f = h->fd;
   constexpr int BX = 128, KC = 32;
@@ -1152,9 +1154,13 @@ static int field_update_potentials (MithraGpu* h)
    * faces, the edges and the corners.  MITHRA_NO_FUSE keeps the reference's three passes apart (the parity tests
    * compare the two bit for bit).                                                                              */
   const bool rim = f.N0 >= 8 && f.N1 >= 8 && f.np >= 8 && !getenv("MITHRA_NO_FUSE");
-  /* without a seed the x / y faces are all rim_update would add to the interior value: stencil_stream does them itself
-   * (MITHRA_NO_FACEWARP: stencil_stream + rim_update as for seeded jobs)                                            */
-  bool faces = rim && !h->d_seed && !getenv("MITHRA_NO_FACEWARP");
+  /* Without a seed stencil_stream does the y faces itself and one pass over whole rows the x faces (MITHRA_NO_FACEWARP:
+   * stencil_stream on the inner nodes + rim_update, as for seeded jobs).  With a seed the same split works -- the face warp
+   * owns the four y-shell nodes of every row and applies their seed terms, seed_xshell_rows the x-shell terms of the rows
+   * in between -- and is bit-identical, but it LOSES on FEL-SEEDED (sweep 1.58 ms against 0.76 + 0.23 of rim_update saved:
+   * the face warp needs 72 registers, so 384-node tiles, a third fewer bytes in flight per SM, and it is the slowest
+   * consumer of every stage): opt-in with MITHRA_SEEDWARP=1, kept for the parity tests                               */
+  bool faces = rim && !getenv("MITHRA_NO_FACEWARP") && (!h->d_seed || getenv("MITHRA_SEEDWARP"));
   RimDev rz; memset(&rz, 0, sizeof(rz));
   if (rim && h->d_seed)
     {
@@ -1176,7 +1182,7 @@ static int field_update_potentials (MithraGpu* h)
     }
   {
     PhaseTimer t(h, PH_STENCIL);
-    if (f.nsfd) launch_stencil<true>(h, rim, &faces); else launch_stencil<false>(h, rim, &faces);
+    if (f.nsfd) launch_stencil<true>(h, rim, &faces, rz); else launch_stencil<false>(h, rim, &faces, rz);
     CU(cudaGetLastError());
     h->cnt.kernel_launches += 1;
   }
@@ -1184,6 +1190,12 @@ static int field_update_potentials (MithraGpu* h)
     PhaseTimer t(h, PH_BOUNDARY);
     if (rim)
       {
+	if (faces && rz.seed)
+	  {
+	    const long tot = 4L * (f.N1 - 6) * (rz.KF - rz.KI) * 3;
+	    seed_xshell_rows<<<grid_for(tot, 128, h->num_sms * 8), 128, 0, h->stream>>>(f, rz, ap);
+	    h->cnt.kernel_launches += 1;
+	  }
 	if (faces)
 	  {
 	    /* stencil_stream has done the y faces; the x faces are whole rows: one coalesced pass                       */

@@ -177,8 +177,8 @@ namespace mithra
 
   /* the nodes of a tile that sit next to a y face (the inward neighbours n of its nodes): their largest number over the
    * tiles of T consecutive in-plane positions; stencil_stream<.., FACES> gives each of them a lane of its face warp, so
-   * it takes meshes with at most 32                                                                                   */
-  static inline int stencil_stream_face_nodes (int N0, int N1, int T)
+   * it takes meshes with at most 32.  seeded: and the nodes one further in, the other half of the y shell of a TF/SF seed  */
+  static inline int stencil_stream_face_nodes (int N0, int N1, int T, bool seeded = false)
   {
     const long P = (long) N0 * N1;
     int worst = 0;
@@ -188,7 +188,7 @@ namespace mithra
 	for (long p = p0; p < p0 + T && p < P; p++)
 	  {
 	    const int i = (int) (p / N1), j = (int) (p - (long) i * N1);
-	    if (i >= 1 && i <= N0 - 2 && j >= 1 && j <= N1 - 2 && (j == 1 || j == N1 - 2)) n++;
+	    if (i >= 1 && i <= N0 - 2 && j >= 1 && j <= N1 - 2 && (j == 1 || j == N1 - 2 || (seeded && (j == 2 || j == N1 - 3)))) n++;
 	  }
 	if (n > worst) worst = n;
       }
@@ -261,11 +261,11 @@ namespace mithra
   __device__ __forceinline__ void mbar_arrive_a (unsigned b)
   { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory"); }
 
-  template <bool NSFD, int T, int NB, bool FACES>
+  template <bool NSFD, int T, int NB, bool FACES, bool SEED = false>
   __global__ void __launch_bounds__(T + (FACES ? 64 : 32), 2)
   stencil_stream (const FieldDev f, double* __restrict__ anp1, const double* __restrict__ an,
 		  const double* __restrict__ anm1, double* __restrict__ jn, const Box* __restrict__ jbox, int KC, int skiprim,
-		  const unsigned char* __restrict__ jmask)
+		  const unsigned char* __restrict__ jmask, const RimDev rz)
   {
     static_assert((NB & (NB - 1)) == 0 && NB >= 4 && NB <= 16, "stages: a power of two");
     static_assert(T % 32 == 0 && T <= 1024, "whole consumer warps, one prefix entry per lane of the face warp");
@@ -311,7 +311,7 @@ namespace mithra
 	/* the nodes next to a y face, in node order, one per lane of the face warp: ballots, per-warp counts, a scan    */
 	const unsigned below = (1u << (tid & 31)) - 1u;
 	const int warp = tid >> 5;
-	const bool on = interior && (j == 1 || j == N1 - 2);
+	const bool on = interior && (j == 1 || j == N1 - 2 || (SEED && (j == 2 || j == N1 - 3)));
 	unsigned bal = 0u;
 	if (tid < T) { bal = __ballot_sync(0xffffffffu, on); if ((tid & 31) == 0) wc[warp] = __popc(bal); }
 	__syncthreads();
@@ -325,7 +325,7 @@ namespace mithra
 	    if (lane == 31) wc[NW] = x;
 	  }
 	__syncthreads();
-	if (on) { faces[wc[warp] + __popc(bal & below)] = tid | ((j == 1 ? 0 : 1) << 12); interior = false; }    /* the face warp's */
+	if (on) { faces[wc[warp] + __popc(bal & below)] = tid | ((j == 1 ? 0 : j == N1 - 2 ? 1 : 2) << 12); interior = false; }    /* the face warp's */
 	__syncthreads();
 	if (tid >= T + 32)
 	  {
@@ -333,13 +333,26 @@ namespace mithra
 	    if (lane < wc[NW])
 	      {
 		const int w = faces[lane];
-		node = w & 0xfff; fs = (w >> 12) ? 8 : -8;
+		node = w & 0xfff; fs = (w >> 12) == 0 ? -8 : (w >> 12) == 1 ? 8 : 0;
 		p = p0 + node; i = p / N1; j = p - i * N1; interior = true;
 	      }
 	    else node = 0;
 	  }
       }
     else __syncthreads();
+
+    /* FACES with a TF/SF seed: the x / y shell corrections (fdtd.cpp:312-350) of the nodes the face warp owns -- the four
+     * y-shell nodes of every row; the x-shell nodes between them are whole rows and go to seed_xshell_rows afterwards.
+     * Offsets into RimDev.seedu of plane 0 (line * L + index), -1: none; sign of the correction as in rim_update          */
+    int sxo = -1, syo = -1;
+    bool sxminus = false, syminus = false;
+    if (FACES && SEED && c < 3 && tid >= T + 32 && interior)
+      {
+	if (j >= 2 && j <= N1 - 3) { const int l = (i == 1) ? 1 : (i == 2) ? 0 : (i == N0 - 2) ? 2 : (i == N0 - 3) ? 3 : -1; if (l >= 0) sxo = l * rz.L + j; }
+	if (i >= 2 && i <= N0 - 3) { const int l = (j == 1) ? 5 : (j == 2) ? 4 : (j == N1 - 2) ? 6 : (j == N1 - 3) ? 7 : -1; if (l >= 0) syo = l * rz.L + i; }
+	sxminus = (i == 1 || i == N0 - 2); syminus = (j == 1 || j == N1 - 2);
+      }
+    const bool seeded = SEED && (sxo >= 0 || syo >= 0);
 
     if (tid >= T && tid < T + 32)
       {
@@ -403,6 +416,13 @@ namespace mithra
      * on the load, and nothing else touches that address during the launch.                                          */
     double srcn = 0.0;
     if (srcon & 1ull) srcn = __ldg(jnc + off);
+    double uxn = 0.0, uyn = 0.0;                          /* SEED, face warp: the seed scalars of the next plane         */
+    if (SEED && seeded && ks >= rz.KI && ks < rz.KF)
+      {
+	const double* su = rz.seedu + (long) ks * 8 * rz.L;
+	if (sxo >= 0) uxn = __ldg(su + sxo);
+	if (syo >= 0) uyn = __ldg(su + syo);
+      }
     /* one plane: Z is plane k (ring position q - 1 on entry), M plane k-1, the new plane k+1 lands in Pn           */
     #define MITHRA_STREAM_STEP(M, Z, Pn)                                                                        \
       {                                                                                                         \
@@ -415,10 +435,35 @@ namespace mithra
 	    srcn = __ldg(jq);                                                                                   \
 	    asm volatile("prefetch.global.L2 [%0];" :: "l"(jq + 2u * PpU));   /* pencils are 8 planes tall: two planes on, the load then hits L2 */ \
 	  }                                                                                                     \
+	double ux = 0.0, uy = 0.0;                               /* face warp, seeded job: the seed scalars of plane k */ \
+	if (SEED && seeded)                                      /* loaded a plane ahead like J, L2 four planes on     */ \
+	  {                                                                                                     \
+	    ux = uxn; uy = uyn; uxn = 0.0; uyn = 0.0;                                                           \
+	    const int kn = ks + q - 1;                                                                          \
+	    if (kn >= rz.KI && kn < rz.KF)                                                                      \
+	      {                                                                                                 \
+		const double* su = rz.seedu + (long) kn * 8 * rz.L;                                             \
+		const long ahead = (kn + 4 < rz.KF) ? 32L * rz.L : 0L;                                         \
+		if (sxo >= 0) { uxn = __ldg(su + sxo); asm volatile("prefetch.global.L2 [%0];" :: "l"(su + sxo + ahead)); } \
+		if (syo >= 0) { uyn = __ldg(su + syo); asm volatile("prefetch.global.L2 [%0];" :: "l"(su + syo + ahead)); } \
+	      }                                                                                                 \
+	  }                                                                                                     \
 	take(Pn);                                                                                               \
 	const unsigned az = mine + (((unsigned) q - 2u) & (NB - 1)) * SB;        /* the node in the stage of plane k */ \
 	const double vm1 = lds_f64(az + dM);                                             /* A^{n-1} of plane k */    \
-	const double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, f.a[0], f.a[1], f.a[2], f.a[3], as, f.alpha, f.beta); \
+	double r = stencil_value<NSFD>(M, Z, Pn, vm1, src, f.a[0], f.a[1], f.a[2], f.a[3], as, f.alpha, f.beta); \
+	if (SEED && seeded)                                      /* x shell term, then y shell term (fdtd.cpp:312-350) */ \
+	  {                                                                                                     \
+	    const int k = ks + q - 3;                                                                           \
+	    if (k >= rz.KI && k < rz.KF)                                                                        \
+	      {                                                                                                 \
+		const double polc = (c == 0 ? rz.pol[0] : c == 1 ? rz.pol[1] : rz.pol[2]);                      \
+		if (sxo >= 0)                                                                                   \
+		  { const double S = seed_assemble_comp(ux, polc, rz.ni, rz.supergaussian, c == 2, rz.gamma); r = sxminus ? r - f.a[1] * S : r + f.a[1] * S; } \
+		if (syo >= 0)                                                                                   \
+		  { const double S = seed_assemble_comp(uy, polc, rz.ni, rz.supergaussian, c == 2, rz.gamma); r = syminus ? r - f.a[2] * S : r + f.a[2] * S; } \
+	      }                                                                                                 \
+	  }                                                                                                     \
 	if (interior) apc[off] = r;                                                                             \
 	if (FACES && fs != 0)                                            /* face warp: the y face node behind */  \
 	  {                                                                                                     \
@@ -438,6 +483,30 @@ namespace mithra
 	MITHRA_STREAM_STEP(P2, P0, P1); if (q >= nq) break;
       }
     #undef MITHRA_STREAM_STEP
+  }
+
+  /* The x-shell corrections of a TF/SF seed (fdtd.cpp:312-330) on the nodes stencil_stream<.., FACES> leaves to this pass:
+   * rows i = 1, 2, N0-3, N0-2, j in [3, N1-4] (the face warp has done j = 2 and N1-3, which also take a y term), planes
+   * [KI, KF): A+(1) -= a1 S(2), A+(2) += a1 S(1), A+(N0-2) -= a1 S(N0-3), A+(N0-3) += a1 S(N0-2).  Whole rows: coalesced.     */
+  __global__ void __launch_bounds__(128)
+  seed_xshell_rows (const FieldDev f, const RimDev rz, double* __restrict__ anp1)
+  {
+    const int  nj = f.N1 - 6;
+    const long per = 4L * nj, tot = per * (rz.KF - rz.KI) * 3;
+    const long cs = (long) f.np * f.Pp;
+    for (long t = (long) blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long) gridDim.x * blockDim.x)
+      {
+	const int c = (int) (t / (per * (rz.KF - rz.KI)));
+	long r = t - (long) c * per * (rz.KF - rz.KI);
+	const int k = rz.KI + (int) (r / per); r -= (long) (k - rz.KI) * per;
+	const int q = (int) (r / nj), j = 3 + (int) (r - (long) q * nj);
+	const int i = (q == 0) ? 1 : (q == 1) ? 2 : (q == 2) ? f.N0 - 3 : f.N0 - 2;
+	const int line = (q == 0) ? 1 : (q == 1) ? 0 : (q == 2) ? 3 : 2;
+	const double S = seed_assemble_comp(rz.seedu[((long) k * 8 + line) * rz.L + j], rz.pol[c], rz.ni, rz.supergaussian, c == 2, rz.gamma);
+	double* a = anp1 + (long) c * cs + (long) k * f.Pp + (long) i * f.N1 + j;
+	const double v = *a;
+	*a = (q == 0 || q == 3) ? v - f.a[1] * S : v + f.a[1] * S;
+      }
   }
 
   #ifndef MITHRA_RIM_MINBLOCKS

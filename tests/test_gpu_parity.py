@@ -249,11 +249,15 @@ def _resized(job, N0, N1, npl):
                                        ("micro-o1", (33, 101, 40)), ("micro-fd", (64, 9, 130)), ("micro-nsfd", (85, 85, 70)),
                                        ("micro-nsfd", (102, 102, 40)), ("micro-nsfd", (20, 73, 30)), ("micro-fd", (40, 27, 33)),
                                        ("micro-sc", (8, 200, 12)), ("micro-o1", (31, 8, 75)), ("micro-nsfd", (14, 14, 242)),
-                                       ("micro-sc", (9, 513, 20)), ("micro-nsfd", (140, 73, 12)), ("micro-fd", (40, 39, 20))])
+                                       ("micro-sc", (9, 513, 20)), ("micro-nsfd", (140, 73, 12)), ("micro-fd", (40, 39, 20)),
+                                       ("micro-seeded", (85, 85, 70)), ("micro-seeded", (40, 102, 30)), ("micro-seeded", (9, 513, 20)),
+                                       ("micro-seeded", (140, 73, 12))])
 def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
-    """The production path -- seeded jobs: stencil_stream on the inner nodes + rim_update (interior value, x / y shell seed
-    terms and x / y faces of the two outer node layers in one pass); jobs without a seed: stencil_stream with its face
-    warp (interior value of every node and the x / y faces in one kernel) -- against the reference's three passes as
+    """The production path -- jobs without a seed: stencil_stream with its face warp (interior value of every node and the
+    y faces in one kernel, the x faces as a pass over whole rows); seeded jobs, and meshes with more than 32 face-warp
+    nodes per tile (rows shorter than about 30 nodes): stencil_stream on the inner nodes + rim_update -- against the
+    seeded variant of the face warp (MITHRA_SEEDWARP: y-shell seed terms in the face warp, x-shell terms as a pass over
+    whole rows), against the reference's three passes as
     separate kernels (MITHRA_NO_FUSE), against stencil_stream + rim_update (MITHRA_NO_FACEWARP) and against the plain-load
     stencil (MITHRA_STENCIL_PLAIN): bit-identical potentials, on meshes whose 448- / 480-node tiles cut through rows (102:
     the FEL-LCLS row; 140 x 73: a tile starts on the node next to a y face; 39: a tile ends on one; 513: a tile inside
@@ -276,7 +280,8 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
     bunch[:, 10] = 1.0
     names = ("anp1", "an", "anm1") + (("fnp1", "fn", "fnm1") if p.space_charge else ())
     out = {}
-    modes = ("MITHRA_NO_FUSE", "MITHRA_NO_FACEWARP", "MITHRA_STENCIL_PLAIN")
+    # MITHRA_SEEDWARP: seeded jobs through stencil_stream's face warp + seed_xshell_rows (opt-in: it loses on FEL-SEEDED)
+    modes = ("MITHRA_NO_FUSE", "MITHRA_NO_FACEWARP", "MITHRA_STENCIL_PLAIN") + (("MITHRA_SEEDWARP",) if job == "micro-seeded" else ())
     for mode in ("fused",) + modes:
         if mode != "fused":
             monkeypatch.setenv(mode, "1")
