@@ -1160,7 +1160,12 @@ static int field_update_potentials (MithraGpu* h)
    * in between -- and is bit-identical, but it LOSES on FEL-SEEDED (sweep 1.58 ms against 0.76 + 0.23 of rim_update saved:
    * the face warp needs 72 registers, so 384-node tiles, a third fewer bytes in flight per SM, and it is the slowest
    * consumer of every stage): opt-in with MITHRA_SEEDWARP=1, kept for the parity tests                               */
-  bool faces = rim && !getenv("MITHRA_NO_FACEWARP") && (!h->d_seed || getenv("MITHRA_SEEDWARP"));
+  /* The face warp pays where the rim is a noticeable part of the plane: rim_update costs about ten times its share of the
+   * nodes (FEL-LCLS, 102 x 102: 3.9 % of the nodes on the perimeter, 1.64 of 6.4 ms), the face warp a fixed 10-15 % of the
+   * sweep (448- instead of 480-node tiles, one more warp per CTA).  FEL-ICS (402 x 402, 1 %): 7.2 ms per step with
+   * rim_update, 7.6 with the face warp.  MITHRA_FACEWARP=1 forces it.                                                  */
+  const bool narrow = 4.0 * (f.N0 + f.N1) >= 0.02 * (double) f.N0 * f.N1 || getenv("MITHRA_FACEWARP");
+  bool faces = rim && narrow && !getenv("MITHRA_NO_FACEWARP") && (!h->d_seed || getenv("MITHRA_SEEDWARP"));
   RimDev rz; memset(&rz, 0, sizeof(rz));
   if (rim && h->d_seed)
     {

@@ -251,7 +251,7 @@ def _resized(job, N0, N1, npl):
                                        ("micro-sc", (8, 200, 12)), ("micro-o1", (31, 8, 75)), ("micro-nsfd", (14, 14, 242)),
                                        ("micro-sc", (9, 513, 20)), ("micro-nsfd", (140, 73, 12)), ("micro-fd", (40, 39, 20)),
                                        ("micro-seeded", (85, 85, 70)), ("micro-seeded", (40, 102, 30)), ("micro-seeded", (9, 513, 20)),
-                                       ("micro-seeded", (140, 73, 12))])
+                                       ("micro-seeded", (140, 73, 12)), ("micro-nsfd", (402, 402, 10))])
 def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
     """The production path -- jobs without a seed: stencil_stream with its face warp (interior value of every node and the
     y faces in one kernel, the x faces as a pass over whole rows); seeded jobs, and meshes with more than 32 face-warp
@@ -281,7 +281,8 @@ def test_fused_stencil_equals_separate_kernels(job, shape, monkeypatch):
     names = ("anp1", "an", "anm1") + (("fnp1", "fn", "fnm1") if p.space_charge else ())
     out = {}
     # MITHRA_SEEDWARP: seeded jobs through stencil_stream's face warp + seed_xshell_rows (opt-in: it loses on FEL-SEEDED)
-    modes = ("MITHRA_NO_FUSE", "MITHRA_NO_FACEWARP", "MITHRA_STENCIL_PLAIN") + (("MITHRA_SEEDWARP",) if job == "micro-seeded" else ())
+    # MITHRA_FACEWARP: the face warp also on wide meshes (402 x 402, the FEL-ICS plane: the default there is rim_update)
+    modes = ("MITHRA_NO_FUSE", "MITHRA_NO_FACEWARP", "MITHRA_STENCIL_PLAIN", "MITHRA_FACEWARP") + (("MITHRA_SEEDWARP",) if job == "micro-seeded" else ())
     for mode in ("fused",) + modes:
         if mode != "fused":
             monkeypatch.setenv(mode, "1")
