@@ -1104,9 +1104,16 @@ static bool launch_stencil_stream_as (MithraGpu* h, bool skiprim, const RimDev& 
 {
   if (getenv("MITHRA_STENCIL_PLAIN")) return false;
   static const int tsel = getenv("MITHRA_STREAM_T") ? atoi(getenv("MITHRA_STREAM_T")) : 0;
-  if (tsel == 512 && !FACES) return launch_stencil_stream_t<NSFD, FACES, 512, 8, false>(h, skiprim, rz);
-  if (FACES && rz.seed) return launch_stencil_stream_t<NSFD, FACES, FACES ? 384 : 480, 8, FACES>(h, skiprim, rz);
-  return launch_stencil_stream_t<NSFD, FACES, FACES ? 448 : 480, 8, false>(h, skiprim, rz);
+  if constexpr (!FACES)
+    {
+      if (tsel == 512) return launch_stencil_stream_t<NSFD, false, 512, 8, false>(h, skiprim, rz);
+      return launch_stencil_stream_t<NSFD, false, 480, 8, false>(h, skiprim, rz);
+    }
+  else
+    {
+      if (rz.seed) return launch_stencil_stream_t<NSFD, true, 384, 8, true>(h, skiprim, rz);
+      return launch_stencil_stream_t<NSFD, true, 448, 8, false>(h, skiprim, rz);
+    }
 }
 
 /* the interior sweep; *faces: in, the x / y faces may be fused into it (a rim path without seed); out, they were.
