@@ -1101,25 +1101,33 @@ namespace mithra
       {
 	const uint4 quad = __ldg(cq + w);
 	if (!(quad.x | quad.y | quad.z | quad.w)) continue;
+	/* (chunk, row, column) of the first of the sixteen cell pencils: one division per load, the rest by stepping      */
+	const unsigned int t0 = 16u * w;
+	int cc = (int) (t0 / P);
+	const int r0 = (int) (t0 - (unsigned int) cc * P);
+	int ii = r0 / (int) N1, jj = r0 - ii * (int) N1;
 	#pragma unroll
 	for (int h = 0; h < 4; h++)
 	  {
 	    unsigned int word = h == 0 ? quad.x : h == 1 ? quad.y : h == 2 ? quad.z : quad.w;
-	    if (!word) continue;
+	    #pragma unroll
 	    for (int q = 0; q < 4; q++, word >>= 8)
 	      {
 		const unsigned int v = word & 0xffu;
-		if (!v) continue;
-		const unsigned int t = 16u * w + 4u * h + q;
-		const int cc = (int) (t / P), r = (int) (t - (unsigned int) cc * P), ii = r / (int) N1, jj = r - ii * (int) N1;
-		if (cc >= nch) continue;
-		const int c0 = (v & REACH_ZLO) ? max(cc - 1, 0) : cc, c1 = (v & REACH_ZHI) ? min(cc + 1, nch - 1) : cc;
-		const int i0 = (v & REACH_XLO) ? max(ii - 1, 0) : ii, i1 = min((v & REACH_XHI) ? ii + 2 : ii + 1, f.N0 - 1);
-		const int j0 = (v & REACH_YLO) ? max(jj - 1, 0) : jj, j1 = min((v & REACH_YHI) ? jj + 2 : jj + 1, f.N1 - 1);
-		for (int c = c0; c <= c1; c++)
-		  for (int i = i0; i <= i1; i++)
-		    for (int j = j0; j <= j1; j++)
-		      nodes[((long) c * f.N0 + i) * f.N1 + j] = 1;
+		if (v && cc < nch)
+		  {
+		    const int c0 = (v & REACH_ZLO) ? max(cc - 1, 0) : cc, c1 = (v & REACH_ZHI) ? min(cc + 1, nch - 1) : cc;
+		    const int i0 = (v & REACH_XLO) ? max(ii - 1, 0) : ii, i1 = min((v & REACH_XHI) ? ii + 2 : ii + 1, f.N0 - 1);
+		    const int j0 = (v & REACH_YLO) ? max(jj - 1, 0) : jj, j1 = min((v & REACH_YHI) ? jj + 2 : jj + 1, f.N1 - 1);
+		    for (int c = c0; c <= c1; c++)
+		      for (int i = i0; i <= i1; i++)
+			{
+			  unsigned char* row = nodes + ((long) c * f.N0 + i) * f.N1;
+			  for (int j = j0; j <= j1; j++) row[j] = 1;
+			}
+		  }
+		/* the next cell pencil                                                                                    */
+		if (++jj == (int) N1) { jj = 0; if (++ii == f.N0) { ii = 0; ++cc; } }
 	      }
 	  }
       }
