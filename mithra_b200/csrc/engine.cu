@@ -74,7 +74,7 @@ struct MithraGpu
   double*         d_stage;                /* AoS staging of the field transfers (field_stage)              */
   size_t          stage_bytes;
   bool            stream_configured[2][2][3]; /* stencil_stream<NSFD, T, .., FACES>: dynamic shared memory limit raised on this device */
-  int             face_nodes[3];          /* stencil_stream<.., FACES>: hand-over slots per CTA, by tile size (-1: not yet counted) */
+  int             face_nodes[3];          /* stencil_stream<.., FACES>: most nodes next to a y face in one tile, per variant (-1: not yet counted) */
   Box*            d_jbox;
   unsigned int*   d_done;
 

@@ -134,8 +134,13 @@ namespace mithra
    * cp.async.bulk (1-D bulk copy through the TMA unit, completion on an mbarrier) into a ring of NB stages, NB-1
    * planes ahead of the plane being computed, so HBM latency is covered by the ring and not by occupancy.  A thread
    * keeps the 5-point cross of planes k-1, k in registers, takes the five values of plane k+1 from shared memory
-   * and streams A^{n+1} out with a coalesced store.  Arithmetic and association order are those of
+   * and streams A^{n+1} out with a coalesced store; a stage goes back to the producer one step after it was taken, when
+   * the A^{n-1} value that came with it has been read.  Arithmetic and association order are those of
    * stencil_interior (bit-identical results).
+   * Variants (engine.cu launch_stencil_stream_as): <T = 480, FACES = false> inner nodes only, rim_update does the rim
+   * (seeded jobs, wide meshes); <448, FACES> every interior node and the y faces (narrow meshes without a seed);
+   * <384, FACES, SEED> the same with the y-shell seed terms (opt-in).  T is chosen so that two CTAs fit an SM without a
+   * spill in the consumer loop: 64 / 64 / 72 registers.
    *
    * Alignment: bulk copies need 16-byte aligned addresses and sizes; Pp is a multiple of 16 doubles, T is even and
    * the halo is rounded up to an even number of doubles (N1e), the extra element is never read.
@@ -231,7 +236,8 @@ namespace mithra
 
   /* T consumer threads (one in-plane position each) + one producer warp (+ FACES: one face warp)
    *
-   * FACES (meshes without a TF/SF seed; N0, N1, np >= 8; at most 32 nodes next to a y face per tile): the y absorbing
+   * FACES (N0, N1, np >= 8; at most 32 nodes next to a y face per tile; by default meshes without a TF/SF seed whose
+   * perimeter is at least 2 % of the plane -- engine.cu field_update_potentials): the y absorbing
    * faces (fdtd.cpp:449-520) are done here as well, the x faces -- whole rows -- by one coalesced pass of boundary_faces
    * afterwards, and rim_update is not launched at all.  A y face node s needs A+ of its inward neighbour n and, of A^n
    * and A^{n-1}, only values the ring holds anyway: s, n and their in-plane neighbours in plane k, s and n in the planes
