@@ -46,6 +46,30 @@ def test_initialize_matches_reference_bit_for_bit(job, tmp_path):
     np.testing.assert_array_equal(rec["particles"].reshape(-1, 11), g["p0"])
 
 
+INIT_JOBS = ("init-manual", "init-crystal", "init-file", "init-gauss", "init-shot", "init-shotg")
+
+
+@pytest.mark.parametrize("job", INIT_JOBS)
+def test_initialize_of_every_bunch_generator_matches_reference_bit_for_bit(job, tmp_path):
+    """The generators no time-march fixture uses -- `manual`, `3D-crystal`, `file` (with the reference's phantom last row,
+    classes.cpp:375-415), gaussian ellipsoid, bunching factor with a phase, shot noise on both profiles, several positions and
+    several bunches (Halton offset Np0) -- against the unmodified reference's initialize() (tests/golden/make_golden_init.py):
+    every scalar and table, and the whole boosted particle list, bit for bit (classes.cpp:60-420, solver.cpp:263-423, 1126-1180)."""
+    import shutil
+    shutil.copy(os.path.join(ROOT, "tests", "jobs", "init-file-bunch.txt"), str(tmp_path))
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), _job(job), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    meta, g = helpers.load_golden(job)
+    for k, v in meta.items():
+        if k.endswith(".optical") or k.endswith(".signal"):
+            continue
+        assert k in rec, k
+        np.testing.assert_array_equal(np.asarray(rec[k]), np.asarray(v), err_msg=k)
+    assert g["p0"].shape[0] > 0
+    np.testing.assert_array_equal(rec["particles"].reshape(-1, 11), g["p0"])
+
+
 @pytest.mark.parametrize("job", helpers.JOBS)
 def test_parameter_block_equals_harness_block(job, tmp_path):
     """MithraGpuParams as the host fills it == the block the parity tests build from the reference's meta record."""
