@@ -11,6 +11,7 @@
  *   <nsteps>          number of field steps of the second while loop to run (0 = only initialise)
  *   --full-at LIST    write <prefix>.full<step>.bin holding the state at the START of field step <step>
  *                     (step 0 = right after initialize()); step == nsteps is allowed (= final state)
+ *   --no-fields       ... without the field arrays (times and particles only: tools/check_shipped_jobs.py)
  *   --phases-at s     additionally write <prefix>.phase<s>.bin with the intermediate arrays of step s
  *   --bench W         CPU-baseline mode (any number of mini-MPI ranks, MINIMPI_NP): no state dumps; W untimed
  *                     warm-up steps, then <nsteps> field steps timed between two MPI_Barriers; rank 0 prints one
@@ -112,13 +113,15 @@ namespace
     w.d("timeBunch", s.timeBunch_); w.i("nTime", (int) s.nTime_); w.i("nTimeBunch", (int) s.nTimeBunch_);
   }
 
+  bool noFields = false;           /* --no-fields: the full dumps hold times and particles only              */
+
   void dumpFull (const std::string& prefix, int step, Solver& s, bool sc)
   {
     std::ostringstream nm; nm << prefix << ".full" << step << ".bin";
     Writer w(nm.str());
     w.i("step", step);
     dumpTimes(w, s);
-    dumpFields(w, s, sc, "jn");      /* at the start of a step anp1_ holds the deposited current      */
+    if (!noFields) dumpFields(w, s, sc, "jn");      /* at the start of a step anp1_ holds the deposited current      */
     std::vector<double> p = particles(s);
     w.f64("particles", p.empty() ? 0 : &p[0], (int64_t) p.size());
   }
@@ -159,6 +162,7 @@ int main (int argc, char* argv[])
       if      (!strcmp(argv[a], "--full-at")   && a + 1 < argc) fullAt = parseList(argv[++a]);
       else if (!strcmp(argv[a], "--phases-at") && a + 1 < argc) phasesAt = atoi(argv[++a]);
       else if (!strcmp(argv[a], "--quiet")) quiet = true;
+      else if (!strcmp(argv[a], "--no-fields")) noFields = true;
       else if (!strcmp(argv[a], "--bench")     && a + 1 < argc) benchWarm = atoi(argv[++a]);
     }
 

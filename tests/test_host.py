@@ -70,6 +70,35 @@ def test_initialize_of_every_bunch_generator_matches_reference_bit_for_bit(job, 
     np.testing.assert_array_equal(rec["particles"].reshape(-1, 11), g["p0"])
 
 
+def _shipped_jobs():
+    import json
+    path = os.path.join(ROOT, "tests", "golden", "shipped-jobs.json")
+    table = json.load(open(path)) if os.path.exists(path) else {}
+    return sorted(k for k, v in table.items() if "skipped" not in v), table
+
+
+@pytest.mark.parametrize("rel", _shipped_jobs()[0])
+def test_shipped_job_files_initialize_like_the_reference(rel, tmp_path):
+    """The job files the reference ships (prj/*/job-files/*.job) through the host's parser and initialize(): number of
+    particles, SHA-256 of every scalar / coefficient table and of the whole boosted particle list equal what the unmodified
+    reference produced for the same file (tests/golden/shipped-jobs.json, written by tools/check_shipped_jobs.py --write; jobs
+    whose mesh the reference cannot allocate in the build container are listed there as skipped).  The job files are read
+    from /root/reference/prj, so this runs where the reference is present (not on the GPU box)."""
+    job = os.path.join("/root/reference/prj", rel)
+    if not os.path.exists(job):
+        pytest.skip("the reference's job files are not on this machine")
+    want = _shipped_jobs()[1][rel]
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), helpers.localised_job(job, str(tmp_path)), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    assert rec["particles"].size // 11 == want["particles"]
+    assert (int(rec["N0"][0]), int(rec["N1"][0]), int(rec["N2"][0])) == (want["N0"], want["N1"], want["N2"])
+    dm, nm = helpers.digest_meta(rec)
+    assert nm == want["meta_records"]
+    assert dm == want["meta_sha256"]
+    assert helpers.digest_particles(rec["particles"]) == want["particles_sha256"]
+
+
 @pytest.mark.parametrize("job", helpers.JOBS)
 def test_parameter_block_equals_harness_block(job, tmp_path):
     """MithraGpuParams as the host fills it == the block the parity tests build from the reference's meta record."""
