@@ -11,7 +11,10 @@
  *   <nsteps>          number of field steps of the second while loop to run (0 = only initialise)
  *   --full-at LIST    write <prefix>.full<step>.bin holding the state at the START of field step <step>
  *                     (step 0 = right after initialize()); step == nsteps is allowed (= final state)
- *   --no-fields       ... without the field arrays (times and particles only: tools/check_shipped_jobs.py)
+ *   --no-fields       ... without the field arrays (times and particles only)
+ *   --init-only       write <prefix>.meta.bin and <prefix>.full0.bin (times and particles, no fields) right after
+ *                     Solver::initialize() and stop -- before the particle-only loop of a job with an
+ *                     initial-time-back-shift (tools/check_shipped_jobs.py)
  *   --phases-at s     additionally write <prefix>.phase<s>.bin with the intermediate arrays of step s
  *   --bench W         CPU-baseline mode (any number of mini-MPI ranks, MINIMPI_NP): no state dumps; W untimed
  *                     warm-up steps, then <nsteps> field steps timed between two MPI_Barriers; rank 0 prints one
@@ -156,13 +159,14 @@ int main (int argc, char* argv[])
   if (argc < 4) { fprintf(stderr, "usage: ref_dump <job> <out-prefix> <nsteps> [--full-at a,b] [--phases-at s] [--quiet]\n"); return 2; }
   const std::string prefix = argv[2];
   const int nsteps = atoi(argv[3]);
-  std::set<int> fullAt; int phasesAt = -1; bool quiet = false; int benchWarm = -1;
+  std::set<int> fullAt; int phasesAt = -1; bool quiet = false; int benchWarm = -1; bool initOnly = false;
   for (int a = 4; a < argc; a++)
     {
       if      (!strcmp(argv[a], "--full-at")   && a + 1 < argc) fullAt = parseList(argv[++a]);
       else if (!strcmp(argv[a], "--phases-at") && a + 1 < argc) phasesAt = atoi(argv[++a]);
       else if (!strcmp(argv[a], "--quiet")) quiet = true;
       else if (!strcmp(argv[a], "--no-fields")) noFields = true;
+      else if (!strcmp(argv[a], "--init-only")) initOnly = true;
       else if (!strcmp(argv[a], "--bench")     && a + 1 < argc) benchWarm = atoi(argv[++a]);
     }
 
@@ -256,6 +260,15 @@ int main (int argc, char* argv[])
       }
     dumpTimes(w, s);
   }
+
+  if (initOnly)
+    {
+      /* the state right after Solver::initialize(), before either loop of solve(): times and particles            */
+      noFields = true;
+      dumpFull(prefix, 0, s, sc);
+      MPI_Finalize();
+      return 0;
+    }
 
   std::vector<double> powerSeries;
 
