@@ -20,7 +20,9 @@ SURVEY 8(d) over ms_per_step), with the per-phase table and the dominant kernel 
 unmodified reference (oracle/_ref/ref_dump --bench on the mini-MPI ranks of all host cores) on a bounded z-slice of the
 same job; "e2e" = the same job through the C ABI with host buffers (pinned upload of potentials + bunch, per-step power
 read-back, final download inside the timed region).  With N > 1 the line also carries "check": the N-slab run of a
-reduced mesh against the 1-slab run of the same problem.
+reduced mesh against the 1-slab run of the same problem.  At N = 1 "host_binary" is one more leg: jobs/<workload>.job through
+the C++ host (mithra_b200/host/mithra_b200 --steps K+W: the reference's Solver surface over the C ABI, its own initialize()),
+step time from the host's own clock around the K steps -- the number for the path a user of the reference would run.
 
 --impl reference times the reference's own CPU implementation alone with the same keys: on the SAME mesh and bunch
 (jobs/<workload>.job) when K + W steps of it fit a few minutes of host time, else on the bounded z-slice.
@@ -224,6 +226,38 @@ def run_reference_sample(sample_job, steps, warmup, ranks=None):
     return r
 
 
+def run_host_binary(job, steps, warmup, nodes):
+    """The same job through the C++ host (mithra_b200/host/mithra_b200: the reference's main() / Solver surface over the C
+    ABI, INTEGRATION.md option A): the job file as shipped under jobs/, the host's own initialize() (bunch generated on the
+    device), `warmup` + `steps` field steps of Solver::solve(), step time from the host's own "Time march" line.  Never
+    fatal for the bench line: any failure is reported under "error"."""
+    import re
+    import shutil
+    import tempfile
+    exe = os.path.join(ROOT, "mithra_b200", "host", "mithra_b200")
+    if not os.path.exists(exe):
+        return {"error": "mithra_b200/host/mithra_b200 is not built"}
+    work = tempfile.mkdtemp(prefix="mithra-bench-host-")
+    try:
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, os.path.join(ROOT, job), "--steps", str(steps + warmup)], cwd=work, timeout=900,
+                           env=dict(os.environ, MITHRA_HOST_TIMING_SKIP=str(warmup)), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, errors="replace")
+        wall = time.perf_counter() - t0
+        m = re.findall(r"Time march: (\d+) field steps in ([0-9.eE+-]+) s", r.stdout or "")
+        if r.returncode != 0 or not m:
+            tail = (r.stdout or "").strip().splitlines()[-1:] or [""]
+            return {"error": "exit %d: %s" % (r.returncode, tail[0][-200:])}
+        n, sec = int(m[-1][0]), float(m[-1][1])
+        return {"what": "%s through the C++ host binary (Solver::solve over the C ABI, its own initialize()): %d field steps after %d warm-up steps" % (job, n, warmup),
+                "steps": n, "ms_per_step": 1e3 * sec / n, "value": nodes * n / sec, "unit": "cell-updates/s",
+                "wall_seconds_with_initialize": wall}
+    except Exception as e:                                              # noqa: BLE001 -- an extra leg must not cost the line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_oracle_sample(p_full, steps):
     """Fallback CPU baseline when oracle/_ref is absent: the C port on a thin slab (1 thread)."""
     import copy
@@ -334,6 +368,7 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="override the macro-particle count (0 = the workload's)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="repeat the timed block of K steps until this much device time is measured")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-host-binary", action="store_true", help="skip the extra leg that runs the job through the C++ host binary")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
@@ -596,6 +631,10 @@ def main():
                    sample_job, sample_frac, r["nodes"], int(r["particles"])),
                "pushes_per_s": r["pushes_per_s"]}
 
+    host = None
+    if rank == 0 and world == 1 and not args.no_host_binary:
+        host = run_host_binary(wl["job"], K, W, p.N0 * p.N1 * p.N2)
+
     nodes_max, parts_all = allmax(float(nodes_local)), allsum([npart_local])[0]
     if rank == 0:
         line = {
@@ -609,6 +648,7 @@ def main():
                 "mesh": "%d x %d x %d" % (pg.N0, pg.N1, pg.N2), "host_buffers": "pinned" if pin_ok else "pageable",
                 "initial_levels": "A^n-1 = A^n (host memory)" if tight else "A^n-1 = 0.999 A^n"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "check": check,
+            "host_binary": host,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -1508,9 +1508,18 @@ namespace MITHRA
       }
 
     gettimeofday(&t0, NULL);
-    const unsigned int nStart = nTime_;
+    unsigned int nStart = nTime_;
+    /* MITHRA_HOST_TIMING_SKIP=W: the clock of the "Time march" line below starts after W field steps (bench.py's warm-up)   */
+    const long timingSkip = getenv("MITHRA_HOST_TIMING_SKIP") ? atol(getenv("MITHRA_HOST_TIMING_SKIP")) : 0;
+    const long stepsAtStart = steps;
     while ( time_ < mesh_.totalTime_ && ( maxSteps_ < 0 || steps < maxSteps_ ) )
       {
+	if ( timingSkip > 0 && steps - stepsAtStart == timingSkip )
+	  {
+	    for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
+	    gettimeofday(&t0, NULL);
+	    nStart = nTime_;
+	  }
 	/* A step without a rhythm-gated bunch output is exactly mithra_gpu_step: the same calls in the same order, with
 	 * the library free to run its housekeeping beside the particle kernels and to test the screens inside the push.
 	 * One process driving several slabs keeps the call-by-call loop (every slab must enqueue its sends before the
@@ -1595,6 +1604,15 @@ namespace MITHRA
 	    printmessage(__FILE__, __LINE__, " Average calculation time for each time step (s) = " + stringify( dT / (double) ( nTime_ - nStart ) ));
 	    printmessage(__FILE__, __LINE__, " Estimated remaining time (min)                  = " + stringify( ( mesh_.totalTime_ / time_ - 1 ) * dT / 60 ));
 	  }
+      }
+    /* the march of this call in one line (with --steps no 0.1 % mark may have been passed; bench.py reads it)           */
+    if ( nTime_ > nStart )
+      {
+	for (MithraGpu* g : gpu_) check(mithra_gpu_synchronize(g));
+	gettimeofday(&t1, NULL);
+	const Double dT = ( t1.tv_usec - t0.tv_usec ) / 1.0e6 + ( t1.tv_sec - t0.tv_sec );
+	printmessage(__FILE__, __LINE__, " Time march: " + stringify(nTime_ - nStart) + " field steps in " + stringify(dT) +
+		     " s; average calculation time for each time step (s) = " + stringify( dT / (double) ( nTime_ - nStart ) ));
       }
     finalize();
   }
