@@ -7,13 +7,17 @@
  *   - OVERRIDES the four non-virtual Solver methods of the loop that touch particles or fields -- bunchUpdate
  *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450): the
  *     build weakens those four symbols in the reference objects (objcopy --weaken-symbol), the linker takes these.
- * Nothing of the reference is edited or copied.  Rhythm-gated dumps (field / bunch sampling, visualisation, profiles)
- * are not part of this stub -- mithra_b200/host has them over the same ABI -- and a job that asks for one stops with a
- * message, the reference's own error convention.
+ * Nothing of the reference is edited or copied.  The rhythm-gated BUNCH outputs (bunchSample, bunchVisualize, bunchProfile,
+ * solver.cpp:1582-1792) stay the reference's own code: in a field step in which one of them is due the stub copies the
+ * bunch back from the device into chargeVectorn_ (same order) before the loop reaches them.  The rhythm-gated FIELD dumps
+ * (sampling, visualisation, profile) live in fdtd.cpp, which this file replaces: they are not part of this stub --
+ * mithra_b200/host has them over the same ABI -- and a job that asks for one stops with a message, the reference's own
+ * error convention.
  *
  * This is test infrastructure of the repository (it proves the drop-in claim against the reference's own main and
  * loop); the product is the library.
  */
+#include <cmath>
 #include <cstring>
 #include <iostream>
 #include <vector>
@@ -65,7 +69,6 @@ namespace MITHRA
       if (gpu) return;
       if (s.size_ != 1) refuse("A run with more than one MPI rank");
       if (s.seed_.sampling_ || s.seed_.vtk_.size() > 0 || s.seed_.profile_) refuse("Field sampling / visualization / profile");
-      if (s.bunch_.sampling_ || s.bunch_.bunchVTK_ || s.bunch_.bunchProfile_) refuse("Bunch sampling / visualization / profile");
 
       MithraGpuParams p; memset(&p, 0, sizeof(p));
       p.abi_version = MITHRA_GPU_ABI_VERSION;
@@ -140,6 +143,41 @@ namespace MITHRA
       check(mithra_gpu_upload_particles(gpu, q.empty() ? 0 : &q[0], s.chargeVectorn_.size()));
     }
 
+    /* Will the loop call bunchSample / bunchVisualize / bunchProfile in this field step?  Its own conditions
+     * (solver.cpp:1253-1270 in the particle-only loop, :1356-1371 in the main loop), evaluated a few lines earlier.   */
+    bool bunchOutputDue (Solver& s)
+    {
+      const Double tb = s.time_ + s.mesh_.timeShift_, dt = s.mesh_.timeStep_;
+      if ( s.bunch_.sampling_ && fmod(tb, s.bunch_.rhythm_) < dt && tb > 0.0 ) return true;
+      if ( s.bunch_.bunchVTK_ && fmod(tb, s.bunch_.bunchVTKRhythm_) < dt && tb > 0.0 ) return true;
+      if ( s.bunch_.bunchProfile_ )
+	{
+	  for (unsigned int i = 0; i < s.bunch_.bunchProfileTime_.size(); i++)
+	    if ( s.time_ - s.bunch_.bunchProfileTime_[i] < dt && s.time_ > s.bunch_.bunchProfileTime_[i] ) return true;
+	  if ( fmod(tb, s.bunch_.bunchProfileRhythm_) < dt && tb > 0.0 && s.bunch_.bunchProfileRhythm_ != 0.0 ) return true;
+	}
+      return false;
+    }
+
+    /* the bunch of the device back into chargeVectorn_: mithra_gpu_download_particles returns the reference's order (the
+     * order of the upload), a single slab neither gains nor loses particles                                          */
+    void refreshBunch (Solver& s)
+    {
+      size_t n = 0;
+      check(mithra_gpu_num_particles(gpu, &n));
+      if (n != s.chargeVectorn_.size()) refuse("A bunch whose size changed on the device");
+      if (n == 0) return;
+      std::vector<double> q(11 * n);
+      check(mithra_gpu_download_particles(gpu, &q[0], n, &n));
+      const double* r = &q[0];
+      for (auto it = s.chargeVectorn_.begin(); it != s.chargeVectorn_.end(); ++it, r += 11)
+	{
+	  it->q = r[0];
+	  for (int d = 0; d < 3; d++) { it->rnp[d] = r[1 + d]; it->rnm[d] = r[4 + d]; it->gb[d] = r[7 + d]; }
+	  it->e = r[10];
+	}
+    }
+
     /* the reference's loop keeps the clocks (solver.cpp:1396-1399, :1318-1319); the library follows them                */
     void follow (Solver& s)
     {
@@ -158,7 +196,12 @@ namespace MITHRA
     if (subStep == 0) check(mithra_gpu_bunch_update(gpu));
     int trips = 0;
     for (Double t = 0.0; t < nUpdateBunch_; t += 1.0) ++trips;
-    if (++subStep >= trips) subStep = 0;
+    if (++subStep >= trips)
+      {
+	subStep = 0;
+	/* the last sub-step of the field step: the reference's own bunch writers come next in the loop                  */
+	if (bunchOutputDue(*this)) refreshBunch(*this);
+      }
   }
 
   void Solver::screenProfile ()

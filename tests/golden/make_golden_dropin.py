@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden fixture of the drop-in proof: the UNMODIFIED reference executable (oracle/_ref/mithra_ref = src/mithra.cpp's own
-main(), built by oracle/Makefile with the single-rank MPI shim) runs tests/jobs/micro-dropin.job to its end; every text
-file it writes (radiation power, screens) is kept as written.  tests/test_dropin.py runs the same job through
+main(), built by oracle/Makefile with the single-rank MPI shim) runs tests/jobs/micro-dropin.job (and micro-dropin-bunch.job, the same
+job with the three bunch outputs) to its end; every file it writes (radiation power, screens, bunch sampling / profile / .vtu) is kept as written.  tests/test_dropin.py runs the same job through
 oracle/_ref/mithra_ref_gpu -- the same main(), parser, Solver::initialize() and Solver::solve(), with
 integration/mithra_gpu_dropin.cpp in place of fdtd.cpp / fdtdSC.cpp -- and compares the files.
 
@@ -17,10 +17,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-JOB = "micro-dropin"
+JOBS = ("micro-dropin", "micro-dropin-bunch")
 
 
-def main():
+def main(JOB):
     exe = os.path.join(ROOT, "oracle", "_ref", "mithra_ref")
     if not os.path.exists(exe):
         sys.exit("oracle/_ref/mithra_ref is missing: run `make -C oracle ref` where /root/reference exists")
@@ -42,4 +42,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    for j in (sys.argv[1:] or JOBS):
+        main(j)

@@ -53,3 +53,70 @@ def test_unmodified_reference_main_and_loop_over_the_library(tmp_path):
             # the reference writes the crossings of a step in list order; so does the library (upload index)
             G, W = np.array(got), np.array(want)
             np.testing.assert_allclose(G, W, rtol=1e-9, atol=1e-12, err_msg=rel)
+
+
+GOLDEN_BUNCH = os.path.join(ROOT, "tests", "golden", "micro-dropin-bunch.npz")
+
+
+def test_golden_of_the_bunch_output_job_is_the_references_output():
+    g = np.load(GOLDEN_BUNCH)
+    dirs = sorted({k.split("/")[1] for k in g.files})
+    assert dirs == ["bunch-profile", "bunch-sampling", "bunch-visualization", "power-sampling", "screens"]
+    assert len(_numbers(g["txt/bunch-sampling/bunch.txt"])) >= 10
+    assert sum(k.endswith(".vtu") for k in g.files) == 3 and sum(k.startswith("txt/bunch-profile/") for k in g.files) == 5
+
+
+@pytest.mark.gpu
+def test_reference_bunch_writers_run_on_the_bunch_of_the_device(tmp_path):
+    """tests/jobs/micro-dropin-bunch.job = micro-dropin + bunch-sampling, bunch-profile and bunch-visualization groups, through
+    oracle/_ref/mithra_ref_gpu: bunchSample / bunchProfile / bunchVisualize are the reference's OWN code (solver.cpp:1582-1792)
+    working on chargeVectorn_, which the stub refreshes from the device in the field steps where one of them is due
+    (integration/mithra_gpu_dropin.cpp refreshBunch).  Every file the unmodified reference wrote on the CPU must come out:
+    same names, same line counts, XML lines identical, numbers to the printed digits (the positions carry the libm
+    difference of the push, 1e-9)."""
+    if not os.path.exists(EXE):
+        pytest.fail("oracle/_ref/mithra_ref_gpu is missing: `make -C oracle ref_gpu` where /root/reference exists")
+    out = subprocess.run([EXE, os.path.join(ROOT, "tests", "jobs", "micro-dropin-bunch.job")], cwd=str(tmp_path),
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert out.returncode == 0, out.stdout.decode()[-2000:]
+    g = np.load(GOLDEN_BUNCH)
+    for key in sorted(g.files):
+        rel = key[len("txt/"):]
+        fn = tmp_path / rel
+        assert fn.exists(), rel
+        ref = bytes(g[key]).decode().splitlines()
+        got = open(fn).read().splitlines()
+        assert len(got) == len(ref), rel
+        if rel.endswith(".pvtu"):
+            assert got == ref, rel
+        elif rel.endswith(".vtu"):
+            rows_g, rows_r = [], []
+            for a, b in zip(got, ref):
+                if b.startswith("<"):
+                    assert a == b, rel
+                    continue
+                ta, tb = a.split(), b.split()
+                assert len(ta) == len(tb), rel
+                if len(tb) == 3:
+                    rows_g.append([float(x) for x in ta]); rows_r.append([float(x) for x in tb])
+                else:
+                    assert ta == tb, rel                                  # connectivity, offsets, types
+            G, R = np.array(rows_g), np.array(rows_r)
+            np.testing.assert_allclose(G, R, rtol=2e-4, atol=2e-4 * np.abs(R).max(), err_msg=rel)
+        elif rel.startswith("bunch-sampling"):
+            G = np.array([[float(x) for x in l.split()] for l in got]); R = np.array([[float(x) for x in l.split()] for l in ref])
+            assert G.shape == R.shape and R.shape[1] == 13, rel
+            scale = np.abs(R).max(axis=0)
+            assert np.all(np.abs(G - R) <= 2e-4 * np.abs(R) + 1e-6 * scale + 1e-7), rel
+        elif rel.startswith("bunch-profile"):
+            assert float(got[0]) == pytest.approx(float(ref[0]), rel=1e-14)
+            G = np.array([[float(x) for x in l.split()] for l in got[1:]]); R = np.array([[float(x) for x in l.split()] for l in ref[1:]])
+            np.testing.assert_allclose(G, R, rtol=1e-8, atol=1e-12, err_msg=rel)
+        elif "power" in rel:
+            G, W = np.array(_numbers("\n".join(got).encode())), np.array(_numbers("\n".join(ref).encode()))
+            np.testing.assert_allclose(G[:, 0], W[:, 0], rtol=1e-14, err_msg=rel)
+            np.testing.assert_allclose(G[:, 1], W[:, 1], rtol=1e-8, atol=1e-12 * np.abs(W[:, 1]).max(), err_msg=rel)
+        else:
+            G, W = np.array(_numbers("\n".join(got).encode())), np.array(_numbers("\n".join(ref).encode()))
+            np.testing.assert_allclose(G, W, rtol=1e-9, atol=1e-12, err_msg=rel)
+
