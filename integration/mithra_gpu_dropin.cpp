@@ -1,18 +1,23 @@
 /* mithra_gpu_dropin.cpp -- INTEGRATION.md option B made real: the file a maintainer of the reference adds to route the
  * time march through libmithra_gpu.so.  It is compiled against the UNMODIFIED reference headers and linked with the
  * UNMODIFIED reference objects (mithra.cpp's main, readdata, datainput, classes, database, stdinclude, solver.cpp with its
- * own initialize() and solve() loop, radiation.cpp with its own initializePowerSample) by `make -C oracle ref_gpu`; it
- *   - REPLACES src/fdtd.cpp and src/fdtdSC.cpp: the constructors and the thirteen virtuals of FdTd / FdTdSC
- *     (solver.h:139-178) call the C ABI of include/mithra_gpu.h;
- *   - OVERRIDES the four non-virtual Solver methods of the loop that touch particles or fields -- bunchUpdate
- *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450): the
- *     build weakens those four symbols in the reference objects (objcopy --weaken-symbol), the linker takes these.
- * Nothing of the reference is edited or copied.  The rhythm-gated BUNCH outputs (bunchSample, bunchVisualize, bunchProfile,
- * solver.cpp:1582-1792) stay the reference's own code: in a field step in which one of them is due the stub copies the
- * bunch back from the device into chargeVectorn_ (same order) before the loop reaches them.  The rhythm-gated FIELD dumps
- * (sampling, visualisation, profile) live in fdtd.cpp, which this file replaces: they are not part of this stub --
- * mithra_b200/host has them over the same ABI -- and a job that asks for one stops with a message, the reference's own
- * error convention.
+ * own initialize() and solve() loop, radiation.cpp with its own initializePowerSample, fdtd.cpp and fdtdSC.cpp with their
+ * constructors, fieldEvaluate and field writers) by `make -C oracle ref_gpu`; it OVERRIDES
+ *   - the five time-march virtuals of FdTd / FdTdSC (solver.h:139-178): fieldUpdate, fieldShift, currentReset,
+ *     currentUpdate, currentCommunicate call the C ABI of include/mithra_gpu.h;
+ *   - the four non-virtual Solver methods of the loop that touch particles or fields -- bunchUpdate
+ *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450).
+ * The build weakens those symbols in copies of the reference objects (objcopy --weaken-symbol), the linker takes these.
+ * Nothing of the reference is edited or copied.
+ *
+ * The rhythm-gated outputs stay the reference's OWN code working on its own host arrays, which the stub refreshes from the
+ * device in a field step in which one of them is due (the loop's own conditions, evaluated at the end of the step's last
+ * bunchUpdate call, a few lines before the loop evaluates them):
+ *   - bunchSample, bunchVisualize, bunchProfile (solver.cpp:1582-1792) on chargeVectorn_  <- mithra_gpu_download_particles
+ *     (the order of the upload);
+ *   - fieldSample, fieldVisualize*, fieldProfile (fdtd.cpp:851-1594, fdtdSC.cpp) through the reference's lazy fieldEvaluate
+ *     on anp1_ / an_ (/ fnp1_ / fn_)  <- mithra_gpu_download_fields, pic_ cleared, the end planes given the E/B of their inner
+ *     neighbours as the tail of the reference's fieldUpdate does (fdtd.cpp:742-773).
  *
  * This is test infrastructure of the repository (it proves the drop-in claim against the reference's own main and
  * loop); the product is the library.
@@ -68,7 +73,6 @@ namespace MITHRA
     {
       if (gpu) return;
       if (s.size_ != 1) refuse("A run with more than one MPI rank");
-      if (s.seed_.sampling_ || s.seed_.vtk_.size() > 0 || s.seed_.profile_) refuse("Field sampling / visualization / profile");
 
       MithraGpuParams p; memset(&p, 0, sizeof(p));
       p.abi_version = MITHRA_GPU_ABI_VERSION;
@@ -178,6 +182,45 @@ namespace MITHRA
 	}
     }
 
+    /* Will the loop call fieldSample / fieldVisualize* / fieldProfile in this field step (solver.cpp:1326-1351)?        */
+    bool fieldOutputDue (Solver& s)
+    {
+      const Double dt = s.mesh_.timeStep_;
+      if ( s.seed_.sampling_ && fmod(s.time_, s.seed_.samplingRhythm_) < dt && s.time_ > 0.0 ) return true;
+      for (unsigned int i = 0; i < s.seed_.vtk_.size(); i++)
+	if ( s.seed_.vtk_[i].sample_ && fmod(s.time_, s.seed_.vtk_[i].rhythm_) < dt && s.time_ > 0.0 ) return true;
+      if ( s.seed_.profile_ )
+	{
+	  for (unsigned int i = 0; i < s.seed_.profileTime_.size(); i++)
+	    if ( s.time_ - s.seed_.profileTime_[i] < dt && s.time_ > s.seed_.profileTime_[i] ) return true;
+	  if ( fmod(s.time_, s.seed_.profileRhythm_) < dt && s.time_ > 0.0 && s.seed_.profileRhythm_ != 0 ) return true;
+	}
+      return false;
+    }
+
+    /* The potentials of the device (A^{n+1} just computed, A^n) back into the reference's host arrays, for its writers and
+     * the lazy fieldEvaluate they call: no node evaluated yet, except that the two end planes carry the E/B of the planes
+     * next to them, which the reference sets up at the end of its fieldUpdate (fdtd.cpp:742-773; one rank: both ends).   */
+    void refreshFields (Solver& s)
+    {
+      const bool sc = s.mesh_.spaceCharge_;
+      check(mithra_gpu_download_fields(gpu, &(*s.anp1_)[0][0], &(*s.an_)[0][0], &(*s.anm1_)[0][0],
+				       sc ? &(*s.fnp1_)[0] : 0, sc ? &(*s.fn_)[0] : 0, sc ? &(*s.fnm1_)[0] : 0));
+      /* the raw views the reference's fieldUpdate sets at the start of every step (fdtd.cpp:241-246, fdtdSC.cpp:270-280)  */
+      s.uf_.anp1 = &(*s.anp1_)[0][0]; s.uf_.an = &(*s.an_)[0][0]; s.uf_.anm1 = &(*s.anm1_)[0][0]; s.uf_.jn = s.uf_.anp1;
+      s.uf_.en = &s.en_[0][0]; s.uf_.bn = &s.bn_[0][0];
+      if (sc) { s.uf_.fnp1 = &(*s.fnp1_)[0]; s.uf_.fn = &(*s.fn_)[0]; s.uf_.fnm1 = &(*s.fnm1_)[0]; s.uf_.rn = s.uf_.fnp1; }
+      s.pic_.assign(s.pic_.size(), false);
+      const long P = s.N1N0_;
+      for (int i = 1; i < s.N0_ - 1; i++)
+	for (int j = 1; j < s.N1_ - 1; j++)
+	  {
+	    const long lo = P + (long) s.N1_ * i + j, hi = P * ( s.np_ - 2 ) + (long) s.N1_ * i + j;
+	    s.fieldEvaluate(lo); s.pic_[lo - P] = true; s.en_[lo - P] = s.en_[lo]; s.bn_[lo - P] = s.bn_[lo];
+	    s.fieldEvaluate(hi); s.pic_[hi + P] = true; s.en_[hi + P] = s.en_[hi]; s.bn_[hi + P] = s.bn_[hi];
+	  }
+    }
+
     /* the reference's loop keeps the clocks (solver.cpp:1396-1399, :1318-1319); the library follows them                */
     void follow (Solver& s)
     {
@@ -201,6 +244,7 @@ namespace MITHRA
 	subStep = 0;
 	/* the last sub-step of the field step: the reference's own bunch writers come next in the loop                  */
 	if (bunchOutputDue(*this)) refreshBunch(*this);
+	if (fieldOutputDue(*this)) refreshFields(*this);
       }
   }
 
@@ -247,24 +291,14 @@ namespace MITHRA
 
   void Solver::powerVisualize () {}                /* attach() refuses jobs with a power-visualization group          */
 
-  /* ---- FdTd / FdTdSC: in place of src/fdtd.cpp and src/fdtdSC.cpp ------------------------------------------------ */
+  /* ---- FdTd / FdTdSC: the five time-march virtuals (the rest of fdtd.cpp / fdtdSC.cpp stays the reference's) --------- */
 
   #define MITHRA_GPU_FIELD_SOLVER(CLASS)                                                                                          \
-    CLASS::CLASS (Mesh& mesh, Bunch& bunch, Seed& seed, std::vector<Undulator>& undulator, std::vector<ExtField>& extField,     \
-		  std::vector<FreeElectronLaser>& FEL) : Solver ( mesh, bunch, seed, undulator, extField, FEL ) {}               \
     void CLASS::fieldUpdate ()        { follow(*this); check(mithra_gpu_field_update(gpu)); }                                    \
     void CLASS::fieldShift ()         { check(mithra_gpu_field_shift(gpu)); }                                                    \
-    void CLASS::fieldEvaluate (long int) {}       /* lazy in the reference (solver.cpp:1471-1478), eager on the device */       \
     void CLASS::currentReset ()       { check(mithra_gpu_current_reset(gpu)); }                                                  \
     void CLASS::currentUpdate ()      { check(mithra_gpu_current_update(gpu)); }                                                 \
-    void CLASS::currentCommunicate () { check(mithra_gpu_current_communicate(gpu)); }                                            \
-    void CLASS::fieldSample ()                             { refuse("Field sampling"); }                                         \
-    void CLASS::fieldVisualizeAllDomain (unsigned int)      { refuse("Field visualization"); }                                    \
-    void CLASS::fieldVisualizeInPlane (unsigned int)        { refuse("Field visualization"); }                                    \
-    void CLASS::fieldVisualizeInPlaneXNormal (unsigned int) { refuse("Field visualization"); }                                    \
-    void CLASS::fieldVisualizeInPlaneYNormal (unsigned int) { refuse("Field visualization"); }                                    \
-    void CLASS::fieldVisualizeInPlaneZNormal (unsigned int) { refuse("Field visualization"); }                                    \
-    void CLASS::fieldProfile ()                            { refuse("Field profile"); }
+    void CLASS::currentCommunicate () { check(mithra_gpu_current_communicate(gpu)); }
 
   MITHRA_GPU_FIELD_SOLVER(FdTd)
   MITHRA_GPU_FIELD_SOLVER(FdTdSC)

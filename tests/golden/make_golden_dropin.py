@@ -17,7 +17,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-JOBS = ("micro-dropin", "micro-dropin-bunch")
+JOBS = ("micro-dropin", "micro-dropin-bunch", "micro-dropin-field")
 
 
 def main(JOB):
