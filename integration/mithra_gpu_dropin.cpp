@@ -6,7 +6,8 @@
  *   - the five time-march virtuals of FdTd / FdTdSC (solver.h:139-178): fieldUpdate, fieldShift, currentReset,
  *     currentUpdate, currentCommunicate call the C ABI of include/mithra_gpu.h;
  *   - the four non-virtual Solver methods of the loop that touch particles or fields -- bunchUpdate
- *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450).
+ *     (solver.cpp:1424-1576), screenProfile (:2205-2257), powerSample and powerVisualize (radiation.cpp:127-450; the power
+ *     map is accumulated on the device and written here in the reference's .vts layout).
  * The build weakens those symbols in copies of the reference objects (objcopy --weaken-symbol), the linker takes these.
  * Nothing of the reference is edited or copied.
  *
@@ -24,6 +25,7 @@
  */
 #include <cmath>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <vector>
 
@@ -107,7 +109,12 @@ namespace MITHRA
 
       for (unsigned jf = 0; jf < s.FEL_.size(); jf++)
 	{
-	  if (s.FEL_[jf].vtkPower_.sampling_) refuse("Power visualization");
+	  if (s.FEL_[jf].vtkPower_.sampling_ && s.rp_[jf].Nz == 1)                                               /* radiation.cpp:238-318, :338 */
+	    {
+	      if (p.power_map.enabled) refuse("A second power-visualization group");
+	      const SampleRadiationPower& S = s.rp_[jf];
+	      p.power_map.enabled = 1; p.power_map.Nf = S.Nf; p.power_map.z = s.FEL_[jf].vtkPower_.z_; p.power_map.w = S.w[0]; p.power_map.pc = S.pc;
+	    }
 	  if (s.FEL_[jf].radiationPower_.sampling_)
 	    {
 	      if (p.power.enabled) refuse("A second radiation-power group");
@@ -289,7 +296,52 @@ namespace MITHRA
       }
   }
 
-  void Solver::powerVisualize () {}                /* attach() refuses jobs with a power-visualization group          */
+  /* The per-pixel DFT window advances on the device in every step; at the rhythm the map comes back (pL[i N1 + j],
+   * radiation.cpp:388) and is written in the reference's .vts layout (radiation.cpp:393-447): the points of the plane
+   * between the two node planes around it, j outermost, then one power value per point in the same order.           */
+  void Solver::powerVisualize ()
+  {
+    follow(*this);
+    for (unsigned jf = 0; jf < FEL_.size(); jf++)
+      {
+	const FreeElectronLaser::RadiationVisualization& V = FEL_[jf].vtkPower_;
+	if ( !( V.sampling_ && rp_[jf].Nz == 1 ) ) continue;
+	check(mithra_gpu_power_visualize(gpu));
+	if ( !( fmod(time_, V.rhythm_) < mesh_.timeStep_ ) ) continue;
+	std::vector<double> map((size_t) N1N0_, 0.0);
+	int mine = 0;
+	check(mithra_gpu_fetch_power_map(gpu, &map[0], map.size(), &mine));
+	Double whole;
+	const Double frac  = modf( ( V.z_ - zmin_ ) / mesh_.meshResolution_[2], &whole );
+	const long   plane = (long) whole - k0_;
+	std::ofstream out((V.basename_ + "-" + stringify(nTime_) + VTS_FILE_SUFFIX).c_str(), std::ios::trunc);
+	out.setf(std::ios::scientific);
+	out.precision(4);
+	out << "<?xml version=\"1.0\"?>" << std::endl
+	    << "<VTKFile type=\"StructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << std::endl
+	    << "<StructuredGrid WholeExtent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl
+	    << "<Piece Extent=\"0 " << N0_ - 1 << " 0 " << N1_ - 1 << " " << 0 << " " << 0 << "\">" << std::endl
+	    << "<Points>" << std::endl
+	    << "<DataArray type = \"Float64\" NumberOfComponents=\"3\" format=\"ascii\">" << std::endl;
+	for (int j = 0; j < N1_; j++)
+	  for (int i = 0; i < N0_; i++)
+	    {
+	      const long node = plane * N1N0_ + (long) i * N1_ + j;
+	      FieldVector<Double> lo = rc(node), hi = rc(node + N1N0_);
+	      out << lo[0] * ( 1.0 - frac ) + hi[0] * frac << " " << lo[1] << " " << lo[2] << std::endl;
+	    }
+	out << "</DataArray>" << std::endl << "</Points>" << std::endl
+	    << "<CellData>" << std::endl << "</CellData>" << std::endl
+	    << "<PointData Vectors = \"power\">" << std::endl
+	    << "<DataArray type=\"Float64\" Name=\"power\" NumberOfComponents=\"" << 1 << "\" format=\"ascii\">" << std::endl;
+	for (int j = 0; j < N1_; j++)
+	  for (int i = 0; i < N0_; i++)
+	    out << map[(size_t) i * N1_ + j] << std::endl;
+	out << "</DataArray>" << std::endl << "</PointData>" << std::endl
+	    << "</Piece>" << std::endl << "</StructuredGrid>" << std::endl << "</VTKFile>" << std::endl;
+	out.close();
+      }
+  }
 
   /* ---- FdTd / FdTdSC: the five time-march virtuals (the rest of fdtd.cpp / fdtdSC.cpp stays the reference's) --------- */
 

@@ -61,14 +61,15 @@ GOLDEN_BUNCH = os.path.join(ROOT, "tests", "golden", "micro-dropin-bunch.npz")
 def test_golden_of_the_bunch_output_job_is_the_references_output():
     g = np.load(GOLDEN_BUNCH)
     dirs = sorted({k.split("/")[1] for k in g.files})
-    assert dirs == ["bunch-profile", "bunch-sampling", "bunch-visualization", "power-sampling", "screens"]
+    assert dirs == ["bunch-profile", "bunch-sampling", "bunch-visualization", "power-map", "power-sampling", "screens"]
+    assert sum(k.startswith("txt/power-map/") for k in g.files) == 6
     assert len(_numbers(g["txt/bunch-sampling/bunch.txt"])) >= 10
     assert sum(k.endswith(".vtu") for k in g.files) == 3 and sum(k.startswith("txt/bunch-profile/") for k in g.files) == 5
 
 
 @pytest.mark.gpu
 def test_reference_bunch_writers_run_on_the_bunch_of_the_device(tmp_path):
-    """tests/jobs/micro-dropin-bunch.job = micro-dropin + bunch-sampling, bunch-profile and bunch-visualization groups, through
+    """tests/jobs/micro-dropin-bunch.job = micro-dropin + power-visualization, bunch-sampling, bunch-profile and bunch-visualization groups, through
     oracle/_ref/mithra_ref_gpu: bunchSample / bunchProfile / bunchVisualize are the reference's OWN code (solver.cpp:1582-1792)
     working on chargeVectorn_, which the stub refreshes from the device in the field steps where one of them is due
     (integration/mithra_gpu_dropin.cpp refreshBunch).  Every file the unmodified reference wrote on the CPU must come out:
@@ -89,6 +90,9 @@ def test_reference_bunch_writers_run_on_the_bunch_of_the_device(tmp_path):
         assert len(got) == len(ref), rel
         if rel.endswith(".pvtu"):
             assert got == ref, rel
+        elif rel.startswith("power-map"):
+            # Solver::powerVisualize: the map is accumulated on the device, the .vts is the stub's writer (radiation.cpp:393-447)
+            _compare_numeric_file(got, ref, rel)
         elif rel.endswith(".vtu"):
             rows_g, rows_r = [], []
             for a, b in zip(got, ref):
