@@ -33,12 +33,18 @@ namespace MITHRA
   {
     ++iter;
     if (iter == jobFile_.end() || *iter != "{") { std::cout << "The " << what << " directory is empty" << std::endl; exit(1); }
-    for (++iter; iter != jobFile_.end() && *iter != "}"; ++iter)
+    /* the reference reads a block with do { ... } while (*iter != "}") (datainput.cpp:153-209 and every other block): the first
+     * line is taken as a key before the brace is looked at, so an EMPTY block stops with "} is not defined in ... group."      */
+    ++iter;
+    do
       {
+	if (iter == jobFile_.end()) break;
 	const Keys::const_iterator k = keys.find(parameterName(*iter));
 	if (k == keys.end()) { std::cout << parameterName(*iter) << " is not defined in " << groupName << " group." << std::endl; exit(1); }
 	k->second(*iter);
+	++iter;
       }
+    while (iter != jobFile_.end() && *iter != "}");
     if (iter == jobFile_.end()) { std::cout << "The " << what << " directory is not closed" << std::endl; exit(1); }
   }
 
@@ -46,8 +52,14 @@ namespace MITHRA
   {
     ++iter;
     if (iter == jobFile_.end() || *iter != "{") { std::cout << "The " << what << " directory is empty" << std::endl; exit(1); }
-    for (++iter; iter != jobFile_.end() && *iter != "}"; ++iter)
+    bool first = true;
+    for (++iter; iter != jobFile_.end(); ++iter)
       {
+	/* a strict group is a do { ... } while (*iter != "}") in the reference too (BUNCH, datainput.cpp:142-283): empty, it
+	 * stops at the brace with the message of its last branch; the other groups are left at the brace (the reference
+	 * runs past it there)                                                                                          */
+	if (*iter == "}" && !(strict && first)) break;
+	first = false;
 	const auto s = subs.find(*iter);
 	if (s != subs.end()) { s->second(iter); continue; }
 	if (strict) { std::cout << parameterName(*iter) << " is not defined in the " << unknownIn << " group." << std::endl; exit(1); }

@@ -99,6 +99,34 @@ def test_shipped_job_files_initialize_like_the_reference(rel, tmp_path):
     assert helpers.digest_particles(rec["particles"]) == want["particles_sha256"]
 
 
+def _parser_errors():
+    import json
+    path = os.path.join(ROOT, "tests", "golden", "parser-errors.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_parser_errors()))
+def test_malformed_jobs_stop_like_the_reference(name, tmp_path):
+    """Twenty malformed variants of micro-nsfd.job (unknown keys / groups / types, values out of range, empty blocks, a bunch
+    file whose row count does not match, ...): the host must end like the unmodified reference's parser + initialize() did on the
+    same text (tests/golden/parser-errors.json, made by tests/golden/make_golden_errors.py) -- same exit code and, when it
+    stops, the same last message (the reference's convention: print, then exit(1)).  Three of the variants are
+    accepted by the reference (an unknown bunch type, an unknown length unit, a zero bunch time step): so are they here."""
+    import re
+    import shutil
+    want = _parser_errors()[name]
+    shutil.copy(os.path.join(ROOT, "tests", "jobs", "init-file-bunch.txt"), str(tmp_path))
+    job = tmp_path / (name + ".job")
+    job.write_text(want["job"])
+    r = subprocess.run([_exe(), str(job), "--dump-params", str(tmp_path / "h")], cwd=str(tmp_path), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, errors="replace", timeout=120)
+    assert r.returncode == want["exit_code"], r.stdout[-500:]
+    if want["exit_code"]:
+        lines = [ln for ln in r.stdout.strip().splitlines() if ln.strip()]
+        last = re.sub(r"^.*?::: [A-Za-z_.]+:\d+ ::: \s*", "", lines[-1]).strip()
+        assert last == want["message"]
+
+
 @pytest.mark.parametrize("job", helpers.JOBS)
 def test_parameter_block_equals_harness_block(job, tmp_path):
     """MithraGpuParams as the host fills it == the block the parity tests build from the reference's meta record."""
