@@ -240,7 +240,7 @@ def run_host_binary(job, steps, warmup, nodes):
     work = tempfile.mkdtemp(prefix="mithra-bench-host-")
     try:
         t0 = time.perf_counter()
-        r = subprocess.run([exe, os.path.join(ROOT, job), "--steps", str(steps + warmup)], cwd=work, timeout=900,
+        r = subprocess.run([exe, os.path.join(ROOT, job), "--steps", str(steps + warmup)], cwd=work, timeout=180,
                            env=dict(os.environ, MITHRA_HOST_TIMING_SKIP=str(warmup)), stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, text=True, errors="replace")
         wall = time.perf_counter() - t0
