@@ -14,7 +14,8 @@
  *   --no-fields       ... without the field arrays (times and particles only)
  *   --init-only       write <prefix>.meta.bin and <prefix>.full0.bin (times and particles, no fields) right after
  *                     Solver::initialize() and stop -- before the particle-only loop of a job with an
- *                     initial-time-back-shift (tools/check_shipped_jobs.py)
+ *                     initial-time-back-shift (tools/check_shipped_jobs.py); with several mini-MPI ranks every rank
+ *                     writes <prefix>.rank<r>.bin instead: its slab (np, k0, zp) and its particles
  *   --phases-at s     additionally write <prefix>.phase<s>.bin with the intermediate arrays of step s
  *   --bench W         CPU-baseline mode (any number of mini-MPI ranks, MINIMPI_NP): no state dumps; W untimed
  *                     warm-up steps, then <nsteps> field steps timed between two MPI_Barriers; rank 0 prints one
@@ -265,7 +266,18 @@ int main (int argc, char* argv[])
     {
       /* the state right after Solver::initialize(), before either loop of solve(): times and particles            */
       noFields = true;
-      dumpFull(prefix, 0, s, sc);
+      if (s.size_ == 1) dumpFull(prefix, 0, s, sc);
+      else
+	{
+	  /* several ranks (MINIMPI_NP): every rank writes its slab of the partition (solver.cpp:619-641) and the particles
+	   * distributeParticles left it with (solver.cpp:429-487) to <prefix>.rank<r>.bin                                */
+	  std::ostringstream nm; nm << prefix << ".rank" << s.rank_ << ".bin";
+	  Writer w(nm.str());
+	  w.i("rank", s.rank_); w.i("size", s.size_); w.i("np", s.np_); w.i("k0", s.k0_);
+	  w.f64("zp", s.zp_, 2);
+	  std::vector<double> p = particles(s);
+	  w.f64("particles", p.empty() ? 0 : &p[0], (int64_t) p.size());
+	}
       MPI_Finalize();
       return 0;
     }

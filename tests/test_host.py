@@ -168,6 +168,40 @@ def test_two_slab_partition_matches_reference_scheme(tmp_path):
         assert (got.zp[0], got.zp[1]) == (want.zp[0], want.zp[1])
 
 
+@pytest.mark.parametrize("job,n", [("micro-nsfd", 2), ("micro-nsfd", 3), ("micro-nsfd", 4), ("micro-seeded", 2), ("micro-lcls", 3)])
+def test_slab_partition_and_particle_distribution_match_the_reference_ranks(job, n, tmp_path):
+    """GPU g of N takes the slab MPI rank g of N takes in the reference.  The unmodified reference run with N
+    mini-MPI ranks (tests/golden/init-slabs.npz, tests/golden/make_golden_slabs.py) gives for every rank np, k0 and zp
+    (solver.cpp:619-641) and the particles distributeParticles leaves it with (solver.cpp:429-487); the host's `--gpus N`
+    partition must be the same numbers, and its ownership split of the (single-rank, bit-identical) bunch the same SET of
+    particles per slab, bit for bit."""
+    import ctypes as C
+    from mithra_b200 import abi
+    g = np.load(os.path.join(ROOT, "tests", "golden", "init-slabs.npz"))
+    pre = str(tmp_path / "h")
+    subprocess.check_output([_exe(), _job(job), "--gpus", str(n), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    P = rec["particles"].reshape(-1, 11)
+    whole = abi.Params.from_buffer_copy(rec["params0"].tobytes())
+    zmin, Lz = whole.zmin, whole.Lz
+    total = 0
+    for r in range(n):
+        key = "%s/%d/%d/" % (job, n, r)
+        got = abi.Params.from_buffer_copy(rec["params%d" % r].tobytes())
+        assert (got.np, got.k0, got.rank, got.size) == (int(g[key + "slab"][0]), int(g[key + "slab"][1]), r, n)
+        assert (got.zp[0], got.zp[1]) == (g[key + "zp"][0], g[key + "zp"][1])
+        # the host's ownership rule (host/solver.cpp attachGpu = solver.cpp:1440-1441 / 2292-2300 with the periodic wrap)
+        zr = np.fmod(P[:, 3] - zmin, Lz)
+        zr = np.where(zr < 0, zr + Lz, zr) + zmin
+        mine = P[(zr >= got.zp[0]) & (zr < got.zp[1])]
+        ref = g[key + "particles"]
+        assert mine.shape == ref.shape, (r, mine.shape, ref.shape)
+        order = lambda a: a[np.lexsort(a.T[::-1])]
+        np.testing.assert_array_equal(order(mine), order(ref))
+        total += ref.shape[0]
+    assert total == P.shape[0]
+
+
 def test_unknown_key_and_group_exit_like_the_reference(tmp_path):
     text = open(_job("micro-nsfd")).read()
     bad = tmp_path / "bad.job"
