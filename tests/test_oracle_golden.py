@@ -115,3 +115,48 @@ def test_screens(run):
         assert rec.shape == ref.shape
         # the reference writes 15 significant digits (solver.cpp:2183-2187)
         np.testing.assert_allclose(rec, ref, rtol=2e-15, atol=0)
+
+
+def test_oracle_reproduces_the_files_of_the_reference_main_over_a_whole_job(tmp_path):
+    """A whole job, not 100 steps of ref_dump: tests/jobs/micro-dropin.job (TF/SF seed, static undulator, three lab-frame screens,
+    power sampling) as the UNMODIFIED reference main() ran it to its end on the CPU (tests/golden/micro-dropin.npz: the power file
+    and the three screen files as written).  The oracle starts from the host's initialize() (bit-identical to the reference's on
+    every fixture and shipped job, tests/test_host.py), marches the 203 field steps of Solver::solve and must give the numbers of
+    those files to every printed digit: power rows (radiation.cpp:222-230) and screen records (solver.cpp:2229-2252)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from mithra_b200 import abi, meta as mmeta
+    root = helpers.ROOT
+    exe = os.path.join(root, "mithra_b200", "host", "mithra_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    pre = str(tmp_path / "h")
+    subprocess.check_output([exe, os.path.join(root, "tests", "jobs", "micro-dropin.job"), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    p = abi.Params.from_buffer_copy(rec["params0"].tobytes())
+    p.max_particles = rec["particles"].size // 11 + 16
+    p.max_screen_records = 1 << 16
+    o = binding.Oracle(p)
+    o.set_time(float(rec["time"][0]), float(rec["timeBunch"][0]), int(rec["nTime"][0]))
+    o.upload_particles(rec["particles"].reshape(-1, 11))
+    o.seedInitial()
+    total, dt = float(rec["totalTime"][0]), float(rec["dt"][0])
+    time, nsteps, tb = float(rec["time"][0]), 0, []
+    while time < total:                                   # the loop condition of solver.cpp:1300 with the loop's own clock
+        helpers.solve_step(o)
+        time += dt
+        nsteps += 1
+    g = np.load(os.path.join(root, "tests", "golden", "micro-dropin.npz"))
+    want = np.array([[float(x) for x in ln.split()] for ln in bytes(g["txt/power-sampling/power-micro-0.txt"]).decode().splitlines()])
+    assert nsteps == want.shape[0] == 203
+    power = np.asarray(o.fetch_power()).reshape(nsteps, -1)
+    # the file prints 6 significant digits (default stream precision): compare at that resolution
+    np.testing.assert_allclose(power[:, 0], want[:, 1], rtol=6e-6, atol=1e-300)
+    assert want[:, 1].max() > 0.0
+    for s in range(3):
+        ref = np.array([[float(x) for x in ln.split()] for ln in bytes(g["txt/screens/profile-p0-screen%d.txt" % s]).decode().splitlines()])
+        got = np.asarray(o.fetch_screen(s)).reshape(-1, 6)
+        assert got.shape == ref.shape and ref.shape[0] > 100
+        np.testing.assert_allclose(got, ref, rtol=6e-6, atol=1e-300)
+    o.close()
