@@ -160,3 +160,44 @@ def test_oracle_reproduces_the_files_of_the_reference_main_over_a_whole_job(tmp_
         assert got.shape == ref.shape and ref.shape[0] > 100
         np.testing.assert_allclose(got, ref, rtol=6e-6, atol=1e-300)
     o.close()
+
+
+def test_oracle_reproduces_the_power_maps_of_the_reference_main(tmp_path):
+    """tests/jobs/micro-dropin-bunch.job through the unmodified reference main() (tests/golden/micro-dropin-bunch.npz): the six
+    power-visualization files power-map/pmap-<nTime>.vts (radiation.cpp:324-450, written whenever fmod(time, rhythm) < dt).  The
+    oracle marches the same job and its per-pixel map at those steps must be the printed numbers (5 significant digits), pixel by
+    pixel in the file's order (j outermost)."""
+    import os
+    import subprocess
+    from mithra_b200 import abi, meta as mmeta
+    root = helpers.ROOT
+    exe = os.path.join(root, "mithra_b200", "host", "mithra_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    pre = str(tmp_path / "h")
+    subprocess.check_output([exe, os.path.join(root, "tests", "jobs", "micro-dropin-bunch.job"), "--dump-params", pre], cwd=str(tmp_path))
+    rec = mmeta.read_records(pre + ".meta.bin")
+    p = abi.Params.from_buffer_copy(rec["params0"].tobytes())
+    assert p.power_map.enabled == 1
+    p.max_particles = rec["particles"].size // 11 + 16
+    p.max_screen_records = 1 << 16
+    g = np.load(os.path.join(root, "tests", "golden", "micro-dropin-bunch.npz"))
+    due = sorted(int(k.split("pmap-")[1].split(".")[0]) for k in g.files if k.startswith("txt/power-map/"))
+    assert due == [0, 40, 80, 120, 160, 200]
+    o = binding.Oracle(p)
+    o.set_time(float(rec["time"][0]), float(rec["timeBunch"][0]), int(rec["nTime"][0]))
+    o.upload_particles(rec["particles"].reshape(-1, 11))
+    o.seedInitial()
+    N0, N1 = p.N0, p.N1
+    seen = 0
+    for step in range(due[-1] + 1):
+        helpers.solve_step(o)                              # powerVisualize inside; the file of step n is written in step n
+        if step in due:
+            lines = bytes(g["txt/power-map/pmap-%d.vts" % step]).decode().splitlines()
+            start = [i for i, ln in enumerate(lines) if "Name=\"power\"" in ln][0] + 1
+            want = np.array([float(x) for x in lines[start:start + N0 * N1]]).reshape(N1, N0)        # j outermost, i inner
+            got = np.asarray(o.fetch_power_map()).reshape(N0, N1).T
+            np.testing.assert_allclose(got, want, rtol=6e-5, atol=1e-300, err_msg="pmap-%d" % step)
+            seen += int(np.abs(want).max() > 0.0)
+    assert seen >= 3                                       # the seed reaches the plane within the run
+    o.close()
